@@ -1,0 +1,44 @@
+// C-ABI dispatch: picks the tensor-core (bf16) or exact-fp32 kernel for GEMM and attention.
+// There is no CPU path: every entry point launches CUDA kernels on the caller's stream.
+#include <stdlib.h>
+#include "bpm_common.cuh"
+
+int bpm_gemm_simt(const bpm_gemm_t* g, cudaStream_t stream);
+int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream);
+int bpm_xattn_fwd_simt(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, cudaStream_t s);
+int bpm_xattn_bwd_simt(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                       float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t s);
+int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, cudaStream_t s);
+int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                     float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t s);
+int bpm_xattn_tc_supported(const bpm_attn_t* a);
+
+// BPM_DEBUG_FFMA=1 routes bf16 problems through the FFMA kernels too (kernel bring-up / bisecting only).
+static int debug_ffma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BPM_DEBUG_FFMA"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+
+extern "C" int bpm_gemm(const bpm_gemm_t* g, void* stream) {
+  BPM_REQUIRE(g && g->A && g->B && g->C && g->M > 0 && g->N > 0 && g->K > 0, "gemm: bad args");
+  BPM_REQUIRE(g->ab_dtype == BPM_F32 || g->ab_dtype == BPM_BF16, "gemm: bad dtype");
+  BPM_REQUIRE(!g->accumulate || g->c_dtype == BPM_F32, "gemm: accumulate needs fp32 C");
+  // tiny-M problems (the [B, D] head) are >90% tile padding on a 128-row MMA: they stay on the FFMA kernel
+  if (g->ab_dtype == BPM_F32 || debug_ffma()) return bpm_gemm_simt(g, (cudaStream_t)stream);
+  return bpm_gemm_tc(g, (cudaStream_t)stream);
+}
+
+extern "C" int bpm_xattn_fwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, void* stream) {
+  BPM_REQUIRE(a && q && k && v && out && lse, "xattn_fwd: null pointer");
+  if (a->dtype == BPM_BF16 && !debug_ffma() && bpm_xattn_tc_supported(a)) return bpm_xattn_fwd_tc(a, q, k, v, out, lse, (cudaStream_t)stream);
+  return bpm_xattn_fwd_simt(a, q, k, v, out, lse, (cudaStream_t)stream);
+}
+
+extern "C" int bpm_xattn_bwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                             float* delta, void* dq, float dq_scale, void* dk, void* dv, void* stream) {
+  BPM_REQUIRE(a && q && k && v && out && dout && lse && delta && dq && dk && dv, "xattn_bwd: null pointer");
+  if (a->dtype == BPM_BF16 && !debug_ffma() && bpm_xattn_tc_supported(a))
+    return bpm_xattn_bwd_tc(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, (cudaStream_t)stream);
+  return bpm_xattn_bwd_simt(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, (cudaStream_t)stream);
+}

@@ -1,0 +1,532 @@
+// HBM-bound elementwise / small-reduction kernels of the BPMulT trunk (sm_100a).
+// All of them are streaming kernels: 16-byte vector accesses, coalesced along the row, grid sized to a multiple of
+// the SM count (148) with a grid-stride loop.  See include/bpmult_b200.h for the contracts + reference citations.
+#include <stdarg.h>
+#include "bpm_common.cuh"
+
+// ---------------------------------------------------------------- error plumbing / device query
+static thread_local char g_err[512] = "";
+void bpm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int bpm_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    (void)cudaGetLastError();
+  }
+  return n;
+}
+extern "C" int bpm_version(void) { return 100; }
+extern "C" const char* bpm_last_error(void) { return g_err; }
+extern "C" int bpm_device_ok(int dev) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return major == 10;
+}
+
+static inline int grid_for(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)bpm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------- pack / unpack
+__device__ __forceinline__ int remap_fwd(int i, int dh, int dhp) { return dh > 0 ? (i / dh) * dhp + (i % dh) : i; }
+
+template <typename T>
+__global__ void pack_matrix_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, T* __restrict__ dst, int rows_p,
+                                   int cols_p, int row_dh, int row_dhp, int col_dh, int col_dhp) {
+  // one thread per destination element: inverse-map to the source (zero when it lands on padding)
+  int64_t n = (int64_t)rows_p * cols_p;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int rp = (int)(i / cols_p), cp = (int)(i % cols_p);
+    int r = rp, c = cp;
+    bool ok = true;
+    if (row_dh > 0) { int h = rp / row_dhp, j = rp % row_dhp; ok = ok && j < row_dh; r = h * row_dh + j; }
+    if (col_dh > 0) { int h = cp / col_dhp, j = cp % col_dhp; ok = ok && j < col_dh; c = h * col_dh + j; }
+    ok = ok && r < rows && c < cols;
+    dst[i] = from_f<T>(ok ? src[(int64_t)r * ld_src + c] : 0.f);
+  }
+}
+
+__global__ void unpack_matrix_kernel(const float* __restrict__ src_p, int cols_p, float* __restrict__ dst, int rows, int cols,
+                                     int ld_dst, int row_dh, int row_dhp, int col_dh, int col_dhp, int accumulate, float scale) {
+  int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols), c = (int)(i % cols);
+    int rp = remap_fwd(r, row_dh, row_dhp), cp = remap_fwd(c, col_dh, col_dhp);
+    float v = src_p[(int64_t)rp * cols_p + cp] * scale;
+    float* d = dst + (int64_t)r * ld_dst + c;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+extern "C" int bpm_pack_matrix(const float* src, int rows, int cols, int ld_src, void* dst, int rows_p, int cols_p, int dst_dtype,
+                               int row_dh, int row_dhp, int col_dh, int col_dhp, void* stream) {
+  BPM_REQUIRE(src && dst && rows > 0 && cols > 0 && rows_p > 0 && cols_p > 0, "pack_matrix: bad args");
+  BPM_REQUIRE((row_dh > 0 ? (rows / row_dh) * row_dhp : rows) <= rows_p && (col_dh > 0 ? (cols / col_dh) * col_dhp : cols) <= cols_p,
+              "pack_matrix: padded shape too small");
+  int64_t n = (int64_t)rows_p * cols_p;
+  int g = grid_for(n, 256);
+  if (dst_dtype == BPM_BF16)
+    pack_matrix_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld_src, (bf16*)dst, rows_p, cols_p, row_dh, row_dhp, col_dh, col_dhp);
+  else
+    pack_matrix_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld_src, (float*)dst, rows_p, cols_p, row_dh, row_dhp, col_dh, col_dhp);
+  BPM_CHECK_LAUNCH("pack_matrix");
+  return BPM_OK;
+}
+
+extern "C" int bpm_unpack_matrix(const float* src_p, int rows_p, int cols_p, float* dst, int rows, int cols, int ld_dst, int row_dh,
+                                 int row_dhp, int col_dh, int col_dhp, int accumulate, float scale, void* stream) {
+  BPM_REQUIRE(src_p && dst && rows > 0 && cols > 0, "unpack_matrix: bad args");
+  (void)rows_p;
+  unpack_matrix_kernel<<<grid_for((int64_t)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(src_p, cols_p, dst, rows, cols, ld_dst, row_dh, row_dhp,
+                                                                                          col_dh, col_dhp, accumulate, scale);
+  BPM_CHECK_LAUNCH("unpack_matrix");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- stage / unstage rows
+template <typename T>
+__global__ void stage_rows_kernel(const float* __restrict__ src, int B, int T_, int C, int64_t sb, int64_t st, int64_t sc, T* __restrict__ dst,
+                                  int Tp, int Cp, bpm_dropout_t drop) {
+  DropCtx dc = make_drop(drop);
+  int64_t n = (int64_t)B * Tp * Cp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    int64_t r = i / Cp;
+    int t = (int)(r % Tp), b = (int)(r / Tp);
+    float v = 0.f;
+    if (t < T_ && c < C) v = src[b * sb + t * st + c * sc] * drop_mult1(dc, (uint64_t)i);
+    dst[i] = from_f<T>(v);
+  }
+}
+
+__global__ void unstage_rows_kernel(const float* __restrict__ g, int B, int T_, int C, int Tp, int Cp, float* __restrict__ dsrc, int64_t sb,
+                                    int64_t st, int64_t sc, int accumulate, bpm_dropout_t drop) {
+  DropCtx dc = make_drop(drop);
+  int64_t n = (int64_t)B * T_ * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    int t = (int)(r % T_), b = (int)(r / T_);
+    int64_t e = ((int64_t)b * Tp + t) * Cp + c;
+    float v = g[e] * drop_mult1(dc, (uint64_t)e);
+    float* d = dsrc + b * sb + t * st + c * sc;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+extern "C" int bpm_stage_rows(const float* src, int B, int T, int C, int64_t sb, int64_t st, int64_t sc, void* dst, int Tp, int Cp,
+                              int dst_dtype, bpm_dropout_t drop, void* stream) {
+  BPM_REQUIRE(src && dst && B > 0 && T > 0 && C > 0, "stage_rows: bad args");
+  BPM_REQUIRE(T <= Tp, "stage_rows: sequence length %d exceeds the fixed length %d (reference: negative pad size, mmtr.py:722-732)", T, Tp);
+  BPM_REQUIRE(C <= Cp, "stage_rows: C %d > Cp %d", C, Cp);
+  int g = grid_for((int64_t)B * Tp * Cp, 256);
+  if (dst_dtype == BPM_BF16) stage_rows_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(src, B, T, C, sb, st, sc, (bf16*)dst, Tp, Cp, drop);
+  else stage_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(src, B, T, C, sb, st, sc, (float*)dst, Tp, Cp, drop);
+  BPM_CHECK_LAUNCH("stage_rows");
+  return BPM_OK;
+}
+
+extern "C" int bpm_unstage_rows(const float* g, int B, int T, int C, int Tp, int Cp, float* dsrc, int64_t sb, int64_t st, int64_t sc,
+                                int accumulate, bpm_dropout_t drop, void* stream) {
+  BPM_REQUIRE(g && dsrc && B > 0 && T > 0 && C > 0 && T <= Tp && C <= Cp, "unstage_rows: bad args");
+  unstage_rows_kernel<<<grid_for((int64_t)B * T * C, 256), 256, 0, (cudaStream_t)stream>>>(g, B, T, C, Tp, Cp, dsrc, sb, st, sc, accumulate, drop);
+  BPM_CHECK_LAUNCH("unstage_rows");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- embed
+// One thread handles 8 consecutive columns of one row (16 B of bf16 / 32 B of fp32).
+template <typename TI, typename TO>
+__global__ void embed_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ pe, int rows, int T_, int D, int Dp, float scale,
+                                 TO* __restrict__ y, bpm_dropout_t drop) {
+  DropCtx dc = make_drop(drop);
+  int vpr = Dp / 8;
+  int64_t n = (int64_t)rows * vpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / vpr;
+    int c0 = (int)(i % vpr) * 8;
+    int t = (int)(r % T_);
+    float ch0 = to_f<TI>(x[r * Dp]);
+    int pos = ch0 != 0.f ? t + 1 : 0;
+    Vec8<TI> xv; xv.load(x + r * Dp + c0);
+    Vec8<float> pv; pv.load(pe + (int64_t)pos * Dp + c0);
+    float m[8];
+    drop_mult8(dc, (uint64_t)(r * Dp + c0), m);
+    Vec8<TO> o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] = (c0 + j < D) ? (scale * xv.v[j] + pv.v[j]) * m[j] : 0.f;
+    o.store(y + r * Dp + c0);
+  }
+}
+
+__global__ void embed_bwd_kernel(const float* __restrict__ dy, int rows, int D, int Dp, float scale, float* __restrict__ dx, int accumulate,
+                                 bpm_dropout_t drop) {
+  DropCtx dc = make_drop(drop);
+  int vpr = Dp / 8;
+  int64_t n = (int64_t)rows * vpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / vpr;
+    int c0 = (int)(i % vpr) * 8;
+    Vec8<float> g; g.load(dy + r * Dp + c0);
+    float m[8];
+    drop_mult8(dc, (uint64_t)(r * Dp + c0), m);
+    Vec8<float> o;
+    if (accumulate) o.load(dx + r * Dp + c0);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) o.v[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] += (c0 + j < D) ? scale * g.v[j] * m[j] : 0.f;
+    o.store(dx + r * Dp + c0);
+  }
+}
+
+extern "C" int bpm_embed_fwd(const void* x, int x_dtype, const float* pe, int B, int T, int D, int Dp, float scale, void* y, int y_dtype,
+                             bpm_dropout_t drop, void* stream) {
+  BPM_REQUIRE(x && pe && y && B > 0 && T > 0 && D > 0 && Dp >= D && Dp % 8 == 0, "embed_fwd: bad args");
+  int rows = B * T;
+  int g = grid_for((int64_t)rows * (Dp / 8), 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x_dtype == BPM_BF16 && y_dtype == BPM_BF16) embed_fwd_kernel<bf16, bf16><<<g, 256, 0, s>>>((const bf16*)x, pe, rows, T, D, Dp, scale, (bf16*)y, drop);
+  else if (x_dtype == BPM_BF16 && y_dtype == BPM_F32) embed_fwd_kernel<bf16, float><<<g, 256, 0, s>>>((const bf16*)x, pe, rows, T, D, Dp, scale, (float*)y, drop);
+  else if (x_dtype == BPM_F32 && y_dtype == BPM_F32) embed_fwd_kernel<float, float><<<g, 256, 0, s>>>((const float*)x, pe, rows, T, D, Dp, scale, (float*)y, drop);
+  else if (x_dtype == BPM_F32 && y_dtype == BPM_BF16) embed_fwd_kernel<float, bf16><<<g, 256, 0, s>>>((const float*)x, pe, rows, T, D, Dp, scale, (bf16*)y, drop);
+  else BPM_REQUIRE(false, "embed_fwd: bad dtype");
+  BPM_CHECK_LAUNCH("embed_fwd");
+  return BPM_OK;
+}
+
+extern "C" int bpm_embed_bwd(const float* dy, int rows, int D, int Dp, float scale, float* dx, int accumulate, bpm_dropout_t drop, void* stream) {
+  BPM_REQUIRE(dy && dx && rows > 0 && Dp % 8 == 0, "embed_bwd: bad args");
+  embed_bwd_kernel<<<grid_for((int64_t)rows * (Dp / 8), 256), 256, 0, (cudaStream_t)stream>>>(dy, rows, D, Dp, scale, dx, accumulate, drop);
+  BPM_CHECK_LAUNCH("embed_bwd");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- add / axpy / cast_drop
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec8<T> va, vb; va.load(a + i * 8); vb.load(b + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; j++) va.v[j] += vb.v[j];
+    va.store(y + i * 8);
+  }
+}
+extern "C" int bpm_add(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream) {
+  BPM_REQUIRE(a && b && y && n > 0 && n % 8 == 0, "add: bad args");
+  int g = grid_for(n / 8, 256);
+  if (dtype == BPM_BF16) add_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n / 8);
+  else add_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)a, (const float*)b, (float*)y, n / 8);
+  BPM_CHECK_LAUNCH("add");
+  return BPM_OK;
+}
+
+template <typename T>
+__global__ void axpy_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n8, int accumulate) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec8<T> s; s.load(src + i * 8);
+    Vec8<float> d;
+    if (accumulate) {
+      d.load(dst + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; j++) d.v[j] += s.v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) d.v[j] = s.v[j];
+    }
+    d.store(dst + i * 8);
+  }
+}
+extern "C" int bpm_axpy_f32(const void* src, int src_dtype, float* dst, int64_t n, int accumulate, void* stream) {
+  BPM_REQUIRE(src && dst && n > 0 && n % 8 == 0, "axpy: bad args");
+  int g = grid_for(n / 8, 256);
+  if (src_dtype == BPM_BF16) axpy_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n / 8, accumulate);
+  else axpy_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, dst, n / 8, accumulate);
+  BPM_CHECK_LAUNCH("axpy");
+  return BPM_OK;
+}
+
+template <typename T>
+__global__ void cast_drop_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n8, bpm_dropout_t drop) {
+  DropCtx dc = make_drop(drop);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec8<float> s; s.load(x + i * 8);
+    float m[8];
+    drop_mult8(dc, (uint64_t)(i * 8), m);
+    Vec8<T> o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] = s.v[j] * m[j];
+    o.store(y + i * 8);
+  }
+}
+extern "C" int bpm_cast_drop(const float* x, void* y, int y_dtype, int rows, int cols, bpm_dropout_t drop, void* stream) {
+  BPM_REQUIRE(x && y && rows > 0 && cols > 0 && cols % 8 == 0, "cast_drop: bad args");
+  int64_t n8 = (int64_t)rows * cols / 8;
+  int g = grid_for(n8, 256);
+  if (y_dtype == BPM_BF16) cast_drop_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n8, drop);
+  else cast_drop_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, n8, drop);
+  BPM_CHECK_LAUNCH("cast_drop");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+// grid (col-chunks of 64, row-slabs); block 256 = 8 row lanes x 32 col-pairs... each thread owns 2 columns.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ X, int M, int N, int ld, float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][64];
+  int cl = (threadIdx.x & 31) * 2, rl = threadIdx.x >> 5;
+  int c = blockIdx.x * 64 + cl;
+  int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      s0 += to_f<T>(X[(int64_t)r * ld + c]);
+      if (c + 1 < N) s1 += to_f<T>(X[(int64_t)r * ld + c + 1]);
+    }
+  }
+  red[rl][cl] = s0; red[rl][cl + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += red[i][threadIdx.x];
+    int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < N) atomicAdd(out + cc, s);
+  }
+}
+extern "C" int bpm_colsum(const void* X, int dtype, int M, int N, int ld, float* out, void* stream) {
+  BPM_REQUIRE(X && out && M > 0 && N > 0 && ld >= N, "colsum: bad args");
+  int gx = bpm_cdiv(N, 64);
+  int slabs = max(1, min(bpm_cdiv(M, 64), (bpm_num_sms() * 4) / gx));
+  int rpb = bpm_cdiv(M, slabs);
+  dim3 grid(gx, bpm_cdiv(M, rpb));
+  if (dtype == BPM_BF16) colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)X, M, N, ld, out, rpb);
+  else colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)X, M, N, ld, out, rpb);
+  BPM_CHECK_LAUNCH("colsum");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- sequence GMU combine
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+template <typename T>
+__global__ void gmu_fwd_kernel(int features, const T* __restrict__ a1, const T* __restrict__ a2, const T* __restrict__ h1p, const T* __restrict__ h2p,
+                               const T* __restrict__ zp, const T* __restrict__ addend, int64_t n8, T* __restrict__ y, T* __restrict__ z_out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec8<T> x1, x2, h1, h2, z, ad, o;
+    h1.load(h1p + i * 8); h2.load(h2p + i * 8); z.load(zp + i * 8);
+    if (features) { x1.load(a1 + i * 8); x2.load(a2 + i * 8); }
+    if (addend) ad.load(addend + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float zz = sigmoidf_(z.v[j]), t1 = tanhf(h1.v[j]), t2 = tanhf(h2.v[j]);
+      float v = features ? zz * t1 * x1.v[j] + (1.f - zz) * t2 * x2.v[j] : zz * t1 + (1.f - zz) * t2;
+      o.v[j] = v + (addend ? ad.v[j] : 0.f);
+      z.v[j] = zz;
+    }
+    o.store(y + i * 8);
+    if (z_out) z.store(z_out + i * 8);
+  }
+}
+
+template <typename T>
+__global__ void gmu_bwd_kernel(int features, const T* __restrict__ a1, const T* __restrict__ a2, const T* __restrict__ h1p, const T* __restrict__ h2p,
+                               const T* __restrict__ zp, const float* __restrict__ dy, int64_t n8, T* __restrict__ dh1, T* __restrict__ dh2,
+                               T* __restrict__ dz, float* __restrict__ da1, float* __restrict__ da2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec8<T> x1, x2, h1, h2, z, o1, o2, oz;
+    Vec8<float> g, g1, g2;
+    h1.load(h1p + i * 8); h2.load(h2p + i * 8); z.load(zp + i * 8); g.load(dy + i * 8);
+    if (features) { x1.load(a1 + i * 8); x2.load(a2 + i * 8); g1.load(da1 + i * 8); g2.load(da2 + i * 8); }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float zz = sigmoidf_(z.v[j]), t1 = tanhf(h1.v[j]), t2 = tanhf(h2.v[j]);
+      float u1 = features ? x1.v[j] : 1.f, u2 = features ? x2.v[j] : 1.f;
+      float gy = g.v[j];
+      o1.v[j] = gy * zz * u1 * (1.f - t1 * t1);
+      o2.v[j] = gy * (1.f - zz) * u2 * (1.f - t2 * t2);
+      oz.v[j] = gy * (t1 * u1 - t2 * u2) * zz * (1.f - zz);
+      if (features) { g1.v[j] += gy * zz * t1; g2.v[j] += gy * (1.f - zz) * t2; }
+    }
+    o1.store(dh1 + i * 8); o2.store(dh2 + i * 8); oz.store(dz + i * 8);
+    if (features) { g1.store(da1 + i * 8); g2.store(da2 + i * 8); }
+  }
+}
+
+extern "C" int bpm_gmu_fwd(int dtype, int features, const void* a1, const void* a2, const void* h1pre, const void* h2pre, const void* zpre,
+                           const void* addend, int rows, int Dp, void* y, void* z_out, void* stream) {
+  BPM_REQUIRE(h1pre && h2pre && zpre && y && rows > 0 && Dp % 8 == 0 && (!features || (a1 && a2)), "gmu_fwd: bad args");
+  int64_t n8 = (int64_t)rows * Dp / 8;
+  int g = grid_for(n8, 256);
+  if (dtype == BPM_BF16)
+    gmu_fwd_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(features, (const bf16*)a1, (const bf16*)a2, (const bf16*)h1pre, (const bf16*)h2pre,
+                                                              (const bf16*)zpre, (const bf16*)addend, n8, (bf16*)y, (bf16*)z_out);
+  else
+    gmu_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(features, (const float*)a1, (const float*)a2, (const float*)h1pre, (const float*)h2pre,
+                                                               (const float*)zpre, (const float*)addend, n8, (float*)y, (float*)z_out);
+  BPM_CHECK_LAUNCH("gmu_fwd");
+  return BPM_OK;
+}
+
+extern "C" int bpm_gmu_bwd(int dtype, int features, const void* a1, const void* a2, const void* h1pre, const void* h2pre, const void* zpre,
+                           const float* dy, int rows, int Dp, void* dh1pre, void* dh2pre, void* dzpre, float* da1, float* da2, void* stream) {
+  BPM_REQUIRE(h1pre && h2pre && zpre && dy && dh1pre && dh2pre && dzpre && rows > 0 && Dp % 8 == 0 && (!features || (a1 && a2 && da1 && da2)),
+              "gmu_bwd: bad args");
+  int64_t n8 = (int64_t)rows * Dp / 8;
+  int g = grid_for(n8, 256);
+  if (dtype == BPM_BF16)
+    gmu_bwd_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(features, (const bf16*)a1, (const bf16*)a2, (const bf16*)h1pre, (const bf16*)h2pre,
+                                                              (const bf16*)zpre, dy, n8, (bf16*)dh1pre, (bf16*)dh2pre, (bf16*)dzpre, da1, da2);
+  else
+    gmu_bwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(features, (const float*)a1, (const float*)a2, (const float*)h1pre, (const float*)h2pre,
+                                                               (const float*)zpre, dy, n8, (float*)dh1pre, (float*)dh2pre, (float*)dzpre, da1, da2);
+  BPM_CHECK_LAUNCH("gmu_bwd");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- pooling (first + last time step)
+template <typename T>
+__global__ void pool_fwd_kernel(const T* __restrict__ x, int B, int T_, int Dp, float* __restrict__ out, int ld_out, int col_off) {
+  int n = B * Dp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int b = i / Dp, c = i % Dp;
+    const T* base = x + (int64_t)b * T_ * Dp + c;
+    out[(int64_t)b * ld_out + col_off + c] = to_f<T>(base[0]) + to_f<T>(base[(int64_t)(T_ - 1) * Dp]);
+  }
+}
+__global__ void pool_bwd_kernel(const float* __restrict__ dout, int ld_out, int col_off, int B, int T_, int Dp, float* __restrict__ dx) {
+  int n = B * Dp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int b = i / Dp, c = i % Dp;
+    float g = dout[(int64_t)b * ld_out + col_off + c];
+    float* base = dx + (int64_t)b * T_ * Dp + c;
+    if (T_ == 1) base[0] += 2.f * g;
+    else { base[0] += g; base[(int64_t)(T_ - 1) * Dp] += g; }
+  }
+}
+extern "C" int bpm_pool_fwd(const void* x, int dtype, int B, int T, int Dp, float* out, int ld_out, int col_off, void* stream) {
+  BPM_REQUIRE(x && out && B > 0 && T > 0 && Dp > 0, "pool_fwd: bad args");
+  int g = grid_for((int64_t)B * Dp, 256);
+  if (dtype == BPM_BF16) pool_fwd_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, T, Dp, out, ld_out, col_off);
+  else pool_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, B, T, Dp, out, ld_out, col_off);
+  BPM_CHECK_LAUNCH("pool_fwd");
+  return BPM_OK;
+}
+extern "C" int bpm_pool_bwd(const float* dout, int ld_out, int col_off, int B, int T, int Dp, float* dx, void* stream) {
+  BPM_REQUIRE(dout && dx && B > 0 && T > 0 && Dp > 0, "pool_bwd: bad args");
+  pool_bwd_kernel<<<grid_for((int64_t)B * Dp, 256), 256, 0, (cudaStream_t)stream>>>(dout, ld_out, col_off, B, T, Dp, dx);
+  BPM_CHECK_LAUNCH("pool_bwd");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- final GMU gate (TextShifting3/4)
+__global__ void tsgate_fwd_kernel(const float* __restrict__ hpre, const float* __restrict__ zpre, int n_in, int B, int Dp, float* __restrict__ fused,
+                                  float* __restrict__ z_out) {
+  int n = B * Dp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int b = i / Dp, c = i % Dp;
+    float acc = 0.f;
+    for (int k = 0; k < n_in; k++) {
+      float z = sigmoidf_(zpre[(int64_t)k * n + i]);
+      acc += z * tanhf(hpre[(int64_t)k * n + i]);
+      if (z_out) z_out[(int64_t)b * n_in * Dp + k * Dp + c] = z;
+    }
+    fused[i] = acc;
+  }
+}
+__global__ void tsgate_bwd_kernel(const float* __restrict__ hpre, const float* __restrict__ zpre, const float* __restrict__ dfused, int n_in, int B,
+                                  int Dp, float* __restrict__ dhpre, float* __restrict__ dzpre) {
+  int n = B * Dp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float g = dfused[i];
+    for (int k = 0; k < n_in; k++) {
+      float z = sigmoidf_(zpre[(int64_t)k * n + i]), t = tanhf(hpre[(int64_t)k * n + i]);
+      dhpre[(int64_t)k * n + i] = g * z * (1.f - t * t);
+      dzpre[(int64_t)k * n + i] = g * t * z * (1.f - z);
+    }
+  }
+}
+extern "C" int bpm_tsgate_fwd(const float* hpre, const float* zpre, int n_in, int B, int Dp, float* fused, float* z_out, void* stream) {
+  BPM_REQUIRE(hpre && zpre && fused && n_in > 0 && B > 0 && Dp > 0, "tsgate_fwd: bad args");
+  tsgate_fwd_kernel<<<grid_for((int64_t)B * Dp, 256), 256, 0, (cudaStream_t)stream>>>(hpre, zpre, n_in, B, Dp, fused, z_out);
+  BPM_CHECK_LAUNCH("tsgate_fwd");
+  return BPM_OK;
+}
+extern "C" int bpm_tsgate_bwd(const float* hpre, const float* zpre, const float* dfused, int n_in, int B, int Dp, float* dhpre, float* dzpre,
+                              void* stream) {
+  BPM_REQUIRE(hpre && zpre && dfused && dhpre && dzpre && n_in > 0 && B > 0 && Dp > 0, "tsgate_bwd: bad args");
+  tsgate_bwd_kernel<<<grid_for((int64_t)B * Dp, 256), 256, 0, (cudaStream_t)stream>>>(hpre, zpre, dfused, n_in, B, Dp, dhpre, dzpre);
+  BPM_CHECK_LAUNCH("tsgate_bwd");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- BCE with logits (+ gradient), single block
+__global__ void bce_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ targets, const float* __restrict__ pw, int B, int C,
+                           float grad_scale, float* __restrict__ loss, float* __restrict__ dlogits) {
+  __shared__ float red[32];
+  int n = B * C;
+  float acc = 0.f;
+  float inv = 1.f / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int b = i / C, c = i % C;
+    float x = logits[(int64_t)b * ldl + c], y = targets[i], w = pw ? pw[c] : 1.f;
+    float lw = 1.f + (w - 1.f) * y;
+    // softplus(-x) computed stably (matches ATen's log_sigmoid formulation)
+    float sp = fmaxf(-x, 0.f) + log1pf(__expf(-fabsf(x)));
+    acc += (1.f - y) * x + lw * sp;
+    float sg = 1.f / (1.f + __expf(-x));
+    dlogits[(int64_t)b * ldl + c] = ((1.f - y) - lw * (1.f - sg)) * inv * grad_scale;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) *loss = v * inv;
+  }
+}
+extern "C" int bpm_bce_fwd_bwd(const float* logits, int ldl, const float* targets, const float* pos_weight, int B, int C, float grad_scale,
+                               float* loss, float* dlogits, void* stream) {
+  BPM_REQUIRE(logits && targets && loss && dlogits && B > 0 && C > 0 && ldl >= C, "bce: bad args");
+  bce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, ldl, targets, pos_weight, B, C, grad_scale, loss, dlogits);
+  BPM_CHECK_LAUNCH("bce");
+  return BPM_OK;
+}
+
+// ---------------------------------------------------------------- Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                            float b1, float b2, float eps, float gs, const int64_t* __restrict__ step_ptr) {
+  float step = (float)(*step_ptr);
+  float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gs;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+extern "C" int bpm_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                             float grad_scale, const int64_t* step_ptr, void* stream) {
+  BPM_REQUIRE(param && grad && m && v && step_ptr && n > 0, "adam: bad args");
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, grad_scale, step_ptr);
+  BPM_CHECK_LAUNCH("adam");
+  return BPM_OK;
+}

@@ -1,0 +1,204 @@
+// LayerNorm forward / backward over the padded row layout (sm_100a).  HBM-bound: one warp per row, the row lives
+// in registers (16-byte vector loads), statistics over the D real columns only, pad columns written as zero.
+// Reference: nn.LayerNorm(embed_dim) eps 1e-5, models/transformer.py:197-202,227-229.
+// Algorithmic bytes: rows*D*(e_in + e_out) fwd; rows*D*(e_dy + e_x + 4 [+4 accumulate read]) bwd.
+#include "bpm_common.cuh"
+
+#define LN_WARPS 4
+
+template <typename TI, typename TO, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               int rows, int D, int Dp, float eps, TO* __restrict__ y, float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int nvec = Dp >> 3;
+  float invD = 1.f / (float)D;
+  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+    const TI* xr = x + (int64_t)row * Dp;
+    Vec8<TI> v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        v[i].load(xr + c * 8);
+#pragma unroll
+        for (int j = 0; j < 8; j++) s += (c * 8 + j < D) ? v[i].v[j] : 0.f;
+      }
+    }
+    float mean = warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { float d = (c * 8 + j < D) ? v[i].v[j] - mean : 0.f; q += d * d; }
+      }
+    }
+    float rstd = rsqrtf(warp_sum(q) * invD + eps);
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    TO* yr = y + (int64_t)row * Dp;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        Vec8<float> g, b; g.load(gamma + c * 8); b.load(beta + c * 8);
+        Vec8<TO> o;
+#pragma unroll
+        for (int j = 0; j < 8; j++) o.v[j] = (c * 8 + j < D) ? (v[i].v[j] - mean) * rstd * g.v[j] + b.v[j] : 0.f;
+        o.store(yr + c * 8);
+      }
+    }
+  }
+}
+
+// backward: persistent grid, each warp walks rows; dgamma/dbeta partials stay in registers until the end.
+template <typename TG, typename TX, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in, const float* __restrict__ gamma, int rows, int D,
+                                                               int Dp, float* __restrict__ dx, int accumulate, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta) {
+  extern __shared__ float sm[];  // [LN_WARPS][2][Dp]
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int nvec = Dp >> 3;
+  float invD = 1.f / (float)D;
+  float ag[NV][8], ab[NV][8];
+  Vec8<float> gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    int c = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { ag[i][j] = 0.f; ab[i][j] = 0.f; gm[i].v[j] = 0.f; }
+    if (c < nvec) gm[i].load(gamma + c * 8);
+  }
+  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+    const TG* gr = dy + (int64_t)row * Dp;
+    const TX* xr = x + (int64_t)row * Dp;
+    float mean = mean_in[row], rstd = rstd_in[row];
+    Vec8<TG> g[NV];
+    Vec8<TX> xv[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        g[i].load(gr + c * 8);
+        xv[i].load(xr + c * 8);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          bool ok = c * 8 + j < D;
+          float xh = ok ? (xv[i].v[j] - mean) * rstd : 0.f;
+          float gy = ok ? g[i].v[j] : 0.f;
+          float gh = gy * gm[i].v[j];
+          xv[i].v[j] = xh; g[i].v[j] = gh;
+          s1 += gh; s2 += gh * xh;
+          ag[i][j] += gy * xh; ab[i][j] += gy;
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    float* dr = dx + (int64_t)row * Dp;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        Vec8<float> o;
+        if (accumulate) o.load(dr + c * 8);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) o.v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) o.v[j] += (c * 8 + j < D) ? rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2) : 0.f;
+        o.store(dr + c * 8);
+      }
+    }
+  }
+  // block-level reduction of the parameter gradients, then one atomic per column per block
+  float* sg = sm + (size_t)warp * 2 * Dp;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    int c = lane + 32 * i;
+    if (c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) { sg[c * 8 + j] = ag[i][j]; sg[Dp + c * 8 + j] = ab[i][j]; }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * Dp; c += blockDim.x) {
+    int col = c % Dp;
+    if (col >= D) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; w++) s += sm[(size_t)w * 2 * Dp + c];
+    atomicAdd((c < Dp ? dgamma : dbeta) + col, s);
+  }
+}
+
+template <typename TI, typename TO>
+static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, int rows, int D, int Dp, float eps, void* y, float* mean, float* rstd,
+                         cudaStream_t s) {
+  int nv = bpm_cdiv(Dp / 8, 32);
+  int grid = min(bpm_cdiv(rows, LN_WARPS), bpm_num_sms() * 16);
+#define LNF(NV) ln_fwd_kernel<TI, TO, NV><<<grid, LN_WARPS * 32, 0, s>>>((const TI*)x, gamma, beta, rows, D, Dp, eps, (TO*)y, mean, rstd)
+  switch (nv) {
+    case 1: LNF(1); break;
+    case 2: LNF(2); break;
+    case 3: LNF(3); break;
+    case 4: LNF(4); break;
+    default: bpm_set_error("layernorm: Dp %d > 1024 unsupported", Dp); return BPM_EINVAL;
+  }
+#undef LNF
+  return BPM_OK;
+}
+
+extern "C" int bpm_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int rows, int D, int Dp, float eps, void* y,
+                                 int y_dtype, float* mean, float* rstd, void* stream) {
+  BPM_REQUIRE(x && gamma && beta && y && mean && rstd && rows > 0 && D > 0 && Dp >= D && Dp % 8 == 0, "layernorm_fwd: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if (x_dtype == BPM_F32 && y_dtype == BPM_F32) rc = ln_fwd_launch<float, float>(x, gamma, beta, rows, D, Dp, eps, y, mean, rstd, s);
+  else if (x_dtype == BPM_F32 && y_dtype == BPM_BF16) rc = ln_fwd_launch<float, bf16>(x, gamma, beta, rows, D, Dp, eps, y, mean, rstd, s);
+  else if (x_dtype == BPM_BF16 && y_dtype == BPM_BF16) rc = ln_fwd_launch<bf16, bf16>(x, gamma, beta, rows, D, Dp, eps, y, mean, rstd, s);
+  else if (x_dtype == BPM_BF16 && y_dtype == BPM_F32) rc = ln_fwd_launch<bf16, float>(x, gamma, beta, rows, D, Dp, eps, y, mean, rstd, s);
+  else BPM_REQUIRE(false, "layernorm_fwd: bad dtype");
+  if (rc) return rc;
+  BPM_CHECK_LAUNCH("layernorm_fwd");
+  return BPM_OK;
+}
+
+template <typename TG, typename TX>
+static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, int rows, int D, int Dp, float* dx,
+                         int accumulate, float* dgamma, float* dbeta, cudaStream_t s) {
+  int nv = bpm_cdiv(Dp / 8, 32);
+  int grid = min(bpm_cdiv(rows, LN_WARPS), bpm_num_sms() * 4);
+  size_t smem = (size_t)LN_WARPS * 2 * Dp * sizeof(float);
+#define LNB(NV) \
+  ln_bwd_kernel<TG, TX, NV><<<grid, LN_WARPS * 32, smem, s>>>((const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta)
+  switch (nv) {
+    case 1: LNB(1); break;
+    case 2: LNB(2); break;
+    case 3: LNB(3); break;
+    case 4: LNB(4); break;
+    default: bpm_set_error("layernorm: Dp %d > 1024 unsupported", Dp); return BPM_EINVAL;
+  }
+#undef LNB
+  return BPM_OK;
+}
+
+extern "C" int bpm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
+                                 int rows, int D, int Dp, float* dx, int accumulate, float* dgamma, float* dbeta, void* stream) {
+  BPM_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && rows > 0 && D > 0 && Dp >= D && Dp % 8 == 0, "layernorm_bwd: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if (dy_dtype == BPM_F32 && x_dtype == BPM_F32) rc = ln_bwd_launch<float, float>(dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, s);
+  else if (dy_dtype == BPM_BF16 && x_dtype == BPM_F32) rc = ln_bwd_launch<bf16, float>(dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, s);
+  else if (dy_dtype == BPM_BF16 && x_dtype == BPM_BF16) rc = ln_bwd_launch<bf16, bf16>(dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, s);
+  else if (dy_dtype == BPM_F32 && x_dtype == BPM_BF16) rc = ln_bwd_launch<float, bf16>(dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, s);
+  else BPM_REQUIRE(false, "layernorm_bwd: bad dtype");
+  if (rc) return rc;
+  BPM_CHECK_LAUNCH("layernorm_bwd");
+  return BPM_OK;
+}

@@ -1,0 +1,193 @@
+"""Thin tensor-level wrappers over the C ABI (include/bpmult_b200.h).  torch is plumbing here: it owns device memory
+and the stream; every op below is one or two launches of our own CUDA kernels on `torch.cuda.current_stream()`.
+
+`CudaOps` is the only product implementation.  (tests/emu_ops.py holds a pure-torch emulation of the same contract
+that is used ONLY to unit-test the host-side engine logic on machines without a GPU.)"""
+import ctypes as C
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from ._lib import Attn, Dropout, Gemm
+
+Drop = namedtuple("Drop", "p seed seed_ptr site")
+NO_DROP = Drop(0.0, 0, None, 0)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return _lib.BPM_F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BPM_BF16
+    raise TypeError("bpmult_b200: unsupported dtype %s" % t.dtype)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _drop(d):
+    if d is None or d.p <= 0.0:
+        return Dropout(0, None, 0, 0.0)
+    return Dropout(int(d.seed) & 0xFFFFFFFFFFFFFFFF, None if d.seed_ptr is None else d.seed_ptr.data_ptr(), int(d.site), float(d.p))
+
+
+class CudaOps:
+    """All methods write into caller-provided output tensors (no allocation, no sync)."""
+    name = "cuda"
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.BpmError("bpmult_b200: no CUDA device -- this package has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if not self.lib.bpm_device_ok(self.device.index or 0):
+            raise _lib.BpmError("bpmult_b200: device %s is not sm_100 (B200)" % self.device)
+        self.launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _s(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ck(self, rc, what):
+        self.launches += 1
+        if rc != 0:
+            _lib.check(rc, what)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ weight staging
+    def pack_matrix(self, src, dst, row_map=(0, 0), col_map=(0, 0)):
+        assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1 and dst.is_contiguous()
+        self._ck(self.lib.bpm_pack_matrix(src.data_ptr(), src.shape[0], src.shape[1], src.stride(0), dst.data_ptr(), dst.shape[0],
+                                          dst.shape[1], _dt(dst), row_map[0], row_map[1], col_map[0], col_map[1], self._s()), "pack_matrix")
+
+    def unpack_matrix(self, src_p, dst, row_map=(0, 0), col_map=(0, 0), accumulate=False, scale=1.0):
+        assert src_p.dtype == torch.float32 and dst.dtype == torch.float32 and dst.dim() == 2 and dst.stride(1) == 1
+        self._ck(self.lib.bpm_unpack_matrix(src_p.data_ptr(), src_p.shape[0], src_p.shape[1], dst.data_ptr(), dst.shape[0], dst.shape[1],
+                                            dst.stride(0), row_map[0], row_map[1], col_map[0], col_map[1], int(accumulate), float(scale),
+                                            self._s()), "unpack_matrix")
+
+    # ------------------------------------------------------------------ staging / embed
+    def stage_rows(self, src, dst, Tp, drop=None):
+        """src fp32 (B, T, C) with arbitrary strides -> dst [B*Tp, Cp]"""
+        B, T, Cc = src.shape
+        assert src.dtype == torch.float32 and dst.shape[0] == B * Tp
+        self._ck(self.lib.bpm_stage_rows(src.data_ptr(), B, T, Cc, src.stride(0), src.stride(1), src.stride(2), dst.data_ptr(), Tp,
+                                         dst.shape[1], _dt(dst), _drop(drop), self._s()), "stage_rows")
+
+    def unstage_rows(self, g, dsrc, Tp, accumulate=False, drop=None):
+        B, T, Cc = dsrc.shape
+        assert g.dtype == torch.float32 and dsrc.dtype == torch.float32
+        self._ck(self.lib.bpm_unstage_rows(g.data_ptr(), B, T, Cc, Tp, g.shape[1], dsrc.data_ptr(), dsrc.stride(0), dsrc.stride(1),
+                                           dsrc.stride(2), int(accumulate), _drop(drop), self._s()), "unstage_rows")
+
+    def embed_fwd(self, x, pe, B, T, D, scale, y, drop=None):
+        Dp = x.shape[1]
+        assert pe.shape[0] >= T + 1 and pe.shape[1] == Dp and pe.dtype == torch.float32
+        self._ck(self.lib.bpm_embed_fwd(x.data_ptr(), _dt(x), pe.data_ptr(), B, T, D, Dp, float(scale), y.data_ptr(), _dt(y), _drop(drop),
+                                        self._s()), "embed_fwd")
+
+    def embed_bwd(self, dy, D, scale, dx, accumulate, drop=None):
+        assert dy.dtype == torch.float32 and dx.dtype == torch.float32
+        self._ck(self.lib.bpm_embed_bwd(dy.data_ptr(), dy.shape[0], D, dy.shape[1], float(scale), dx.data_ptr(), int(accumulate), _drop(drop),
+                                        self._s()), "embed_bwd")
+
+    # ------------------------------------------------------------------ layernorm
+    def layernorm_fwd(self, x, gamma, beta, D, y, mean, rstd, eps=1e-5):
+        self._ck(self.lib.bpm_layernorm_fwd(x.data_ptr(), _dt(x), gamma.data_ptr(), beta.data_ptr(), x.shape[0], D, x.shape[1], float(eps),
+                                            y.data_ptr(), _dt(y), mean.data_ptr(), rstd.data_ptr(), self._s()), "layernorm_fwd")
+
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, D, dx, accumulate, dgamma, dbeta):
+        assert dx.dtype == torch.float32
+        self._ck(self.lib.bpm_layernorm_bwd(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                            x.shape[0], D, x.shape[1], dx.data_ptr(), int(accumulate), dgamma.data_ptr(), dbeta.data_ptr(),
+                                            self._s()), "layernorm_bwd")
+
+    # ------------------------------------------------------------------ gemm
+    def gemm(self, A, B, Cout, M, N, K, ta=0, tb=0, bias=None, alpha=1.0, act=0, drop=None, gate=None, gate_scale=1.0, residual=None,
+             accumulate=False, split_k=0):
+        assert A.dtype == B.dtype and A.stride(1) == 1 and B.stride(1) == 1 and Cout.stride(1) == 1
+        g = Gemm()
+        g.ab_dtype, g.ta, g.tb, g.M, g.N, g.K = _dt(A), int(ta), int(tb), M, N, K
+        g.A, g.lda, g.B, g.ldb = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
+        g.C, g.ldc, g.c_dtype = Cout.data_ptr(), Cout.stride(0), _dt(Cout)
+        g.bias, g.alpha, g.act = _ptr(bias), float(alpha), int(act)
+        g.drop = _drop(drop)
+        g.gate, g.ldg, g.gate_dtype, g.gate_scale = _ptr(gate), (gate.stride(0) if gate is not None else 0), (_dt(gate) if gate is not None else 0), float(gate_scale)
+        g.residual, g.ldr, g.res_dtype = _ptr(residual), (residual.stride(0) if residual is not None else 0), (_dt(residual) if residual is not None else 0)
+        g.accumulate, g.split_k = int(accumulate), int(split_k)
+        self._ck(self.lib.bpm_gemm(C.byref(g), self._s()), "gemm")
+
+    def colsum(self, X, N, out):
+        self._ck(self.lib.bpm_colsum(X.data_ptr(), _dt(X), X.shape[0], N, X.stride(0), out.data_ptr(), self._s()), "colsum")
+
+    # ------------------------------------------------------------------ attention
+    def _attn(self, q, B, T, S, H, dh, dhp, mask_off, key_pad, drop):
+        a = Attn()
+        a.dtype, a.B, a.T, a.S, a.H, a.dh, a.dhp, a.mask_off = _dt(q), B, T, S, H, dh, dhp, int(mask_off)
+        a.key_pad = _ptr(key_pad)
+        a.drop = _drop(drop)
+        return a
+
+    def xattn_fwd(self, q, k, v, out, lse, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None):
+        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop)
+        self._ck(self.lib.bpm_xattn_fwd(C.byref(a), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), self._s()), "xattn_fwd")
+
+    def xattn_bwd(self, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None):
+        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop)
+        self._ck(self.lib.bpm_xattn_bwd(C.byref(a), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                        delta.data_ptr(), dq.data_ptr(), float(dq_scale), dk.data_ptr(), dv.data_ptr(), self._s()), "xattn_bwd")
+
+    def xattn_weights(self, q, k, lse, w, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None):
+        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop)
+        self._ck(self.lib.bpm_xattn_weights(C.byref(a), q.data_ptr(), k.data_ptr(), lse.data_ptr(), w.data_ptr(), self._s()), "xattn_weights")
+
+    # ------------------------------------------------------------------ GMU / elementwise
+    def gmu_fwd(self, features, a1, a2, h1p, h2p, zp, addend, y, z_out=None):
+        self._ck(self.lib.bpm_gmu_fwd(_dt(h1p), int(features), _ptr(a1), _ptr(a2), h1p.data_ptr(), h2p.data_ptr(), zp.data_ptr(), _ptr(addend),
+                                      h1p.shape[0], h1p.shape[1], y.data_ptr(), _ptr(z_out), self._s()), "gmu_fwd")
+
+    def gmu_bwd(self, features, a1, a2, h1p, h2p, zp, dy, dh1, dh2, dz, da1, da2):
+        self._ck(self.lib.bpm_gmu_bwd(_dt(h1p), int(features), _ptr(a1), _ptr(a2), h1p.data_ptr(), h2p.data_ptr(), zp.data_ptr(), dy.data_ptr(),
+                                      h1p.shape[0], h1p.shape[1], dh1.data_ptr(), dh2.data_ptr(), dz.data_ptr(), _ptr(da1), _ptr(da2),
+                                      self._s()), "gmu_bwd")
+
+    def add(self, a, b, y):
+        self._ck(self.lib.bpm_add(_dt(a), a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), self._s()), "add")
+
+    def axpy_f32(self, src, dst, accumulate=True):
+        self._ck(self.lib.bpm_axpy_f32(src.data_ptr(), _dt(src), dst.data_ptr(), src.numel(), int(accumulate), self._s()), "axpy_f32")
+
+    def cast_drop(self, x, y, drop=None):
+        self._ck(self.lib.bpm_cast_drop(x.data_ptr(), y.data_ptr(), _dt(y), x.shape[0], x.shape[1], _drop(drop), self._s()), "cast_drop")
+
+    def pool_fwd(self, x, B, T, out, col_off):
+        self._ck(self.lib.bpm_pool_fwd(x.data_ptr(), _dt(x), B, T, x.shape[1], out.data_ptr(), out.stride(0), col_off, self._s()), "pool_fwd")
+
+    def pool_bwd(self, dout, col_off, B, T, dx):
+        self._ck(self.lib.bpm_pool_bwd(dout.data_ptr(), dout.stride(0), col_off, B, T, dx.shape[1], dx.data_ptr(), self._s()), "pool_bwd")
+
+    def tsgate_fwd(self, hpre, zpre, n_in, B, Dp, fused, z_out=None):
+        self._ck(self.lib.bpm_tsgate_fwd(hpre.data_ptr(), zpre.data_ptr(), n_in, B, Dp, fused.data_ptr(), _ptr(z_out), self._s()), "tsgate_fwd")
+
+    def tsgate_bwd(self, hpre, zpre, dfused, n_in, B, Dp, dhpre, dzpre):
+        self._ck(self.lib.bpm_tsgate_bwd(hpre.data_ptr(), zpre.data_ptr(), dfused.data_ptr(), n_in, B, Dp, dhpre.data_ptr(), dzpre.data_ptr(),
+                                         self._s()), "tsgate_bwd")
+
+    def bce_fwd_bwd(self, logits, targets, pos_weight, B, Cc, grad_scale, loss, dlogits):
+        self._ck(self.lib.bpm_bce_fwd_bwd(logits.data_ptr(), logits.stride(0), targets.data_ptr(), _ptr(pos_weight), B, Cc, float(grad_scale),
+                                          loss.data_ptr(), dlogits.data_ptr(), self._s()), "bce_fwd_bwd")
+
+    def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t):
+        self._ck(self.lib.bpm_adam_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), float(lr), float(beta1),
+                                        float(beta2), float(eps), float(grad_scale), step_t.data_ptr(), self._s()), "adam_step")
+
+    def zero_(self, t):
+        """memset on the current stream (cudaMemsetAsync through torch; capturable)."""
+        t.zero_()

@@ -1,0 +1,166 @@
+/* bpmult_b200 -- C ABI of the B200-native BPMulT fusion trunk (sm_100a).
+ *
+ * The reference (Damorgal/Biprojection-Multimodal-Transformer) has no FFI / plugin interface: its hot path is
+ * reached through the Python nn.Module API (bpmult/models/__init__.py:12-14 get_model -> train.py:311-321
+ * model_forward).  This header is therefore the boundary a maintainer binds instead of the ATen calls the
+ * reference makes on that path; each entry point names the reference op (file:line under /root/reference/bpmult)
+ * it replaces.  INTEGRATION.md shows the ctypes stub that wires these into the reference's modules.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  All pointers are DEVICE pointers unless stated otherwise.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls never allocate, never synchronise and are capturable in
+ *    CUDA graphs.  Every function returns 0 on success or a negative BPM_E* code; bpm_last_error() (host, per
+ *    thread) describes the failure.  There is NO CPU fallback: a missing GPU / wrong arch is an error.
+ *  - dtype codes: BPM_F32 = 0, BPM_BF16 = 1 ("storage type T" below).  Accumulation is always fp32.
+ *  - Internal activation layout ("rows"): batch-major rows r = b*T + t, row pitch Dp = round_up(D, 64) elements,
+ *    pad columns are ZERO.  Per-head tensors (q, k, v, attention output) use pitch H*dhp, dhp = round_up(dh, 32)
+ *    (16 for dh <= 16), head h at columns [h*dhp, h*dhp + dh), pad columns zero.
+ *  - Dropout: counter-based Philox4x32-10.  keep(e) <=> philox(key = seed, ctr = (e/4, site))[e%4] >= p*2^32, kept
+ *    values scaled by 1/(1-p).  `e` is the element index in the padded row-major tensor the mask applies to
+ *    (for attention: ((b*H + h)*T + i)*S + j).  `seed_ptr` (device, may be NULL) overrides `seed` when non-NULL so a
+ *    captured graph can be replayed with a new seed.  Backward kernels regenerate masks from (seed, site).
+ */
+#ifndef BPMULT_B200_H
+#define BPMULT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPM_F32 0
+#define BPM_BF16 1
+
+#define BPM_OK 0
+#define BPM_EINVAL (-1)      /* bad argument / unsupported shape or alignment */
+#define BPM_ELAUNCH (-2)     /* CUDA launch / driver error */
+#define BPM_ENOGPU (-3)      /* no sm_100 device */
+
+typedef struct {
+  uint64_t seed;             /* used when seed_ptr == NULL */
+  const uint64_t* seed_ptr;  /* device pointer to the seed (graph-replay safe), or NULL */
+  uint64_t site;             /* unique id of the dropout site (selects the Philox stream) */
+  float p;                   /* drop probability; 0 disables */
+} bpm_dropout_t;
+
+int bpm_version(void);
+const char* bpm_last_error(void);
+/* 1 when device `dev` is compute capability 10.x */
+int bpm_device_ok(int dev);
+
+/* ---- weight staging ------------------------------------------------------------------------------------------
+ * Reference parameters stay fp32 in reference layout (state_dict names of SURVEY 8b); kernels consume zero-padded
+ * copies in storage type T.  Optional head remap: row r = h*dh + j -> h*dhp + j (row_dh > 0), same for columns.
+ * Replaces nothing in the reference (layout glue); the inverse accumulates padded fp32 gradients back. */
+int bpm_pack_matrix(const float* src, int rows, int cols, int ld_src, void* dst, int rows_p, int cols_p, int dst_dtype,
+                    int row_dh, int row_dhp, int col_dh, int col_dhp, void* stream);
+int bpm_unpack_matrix(const float* src_p, int rows_p, int cols_p, float* dst, int rows, int cols, int ld_dst,
+                      int row_dh, int row_dhp, int col_dh, int col_dhp, int accumulate, float scale, void* stream);
+
+/* ---- input staging: models/mmtr.py:741-761 (transpose, embed dropout on text, zero-pad time to n_vec) ----------
+ * src fp32 element (b, t, c) at src[b*sb + t*st + c*sc]; dst T rows b*Tp + t, pitch Cp, zero for t >= T or c >= C. */
+int bpm_stage_rows(const float* src, int B, int T, int C, int64_t sb, int64_t st, int64_t sc, void* dst, int Tp, int Cp,
+                   int dst_dtype, bpm_dropout_t drop, void* stream);
+/* inverse gather for input gradients: dsrc(b,t,c) (+)= mask*g[b*Tp+t, c] */
+int bpm_unstage_rows(const float* g, int B, int T, int C, int Tp, int Cp, float* dsrc, int64_t sb, int64_t st, int64_t sc,
+                     int accumulate, bpm_dropout_t drop, void* stream);
+
+/* ---- embed: models/transformer.py:66-79 + models/position_embedding.py:8-76 -----------------------------------
+ * y[r, c] = dropout(scale * x[r, c] + pe[pos(r), c]);  pos = t+1 if x[r, 0] != 0 else 0;  pe is fp32 [T+1, Dp]
+ * (row 0 zero).  x is T [B*T, Dp]; y has dtype y_dtype.  bwd: dx[r, c] (+)= scale * mask * dy[r, c] (fp32). */
+int bpm_embed_fwd(const void* x, int x_dtype, const float* pe, int B, int T, int D, int Dp, float scale, void* y, int y_dtype,
+                  bpm_dropout_t drop, void* stream);
+int bpm_embed_bwd(const float* dy, int rows, int D, int Dp, float scale, float* dx, int accumulate, bpm_dropout_t drop,
+                  void* stream);
+
+/* ---- LayerNorm: models/transformer.py:197-202,227-229 (nn.LayerNorm, eps 1e-5, statistics over the D real columns)
+ * fwd writes zeros to pad columns and saves mean / rstd (fp32 [rows]).
+ * bwd: dx (fp32) = [accumulate ? dx : 0] + LN'(dy);  dgamma / dbeta (fp32 [Dp]) are accumulated atomically. */
+int bpm_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, int rows, int D, int Dp, float eps,
+                      void* y, int y_dtype, float* mean, float* rstd, void* stream);
+int bpm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                      const float* gamma, int rows, int D, int Dp, float* dx, int accumulate, float* dgamma, float* dbeta,
+                      void* stream);
+
+/* ---- GEMM with fused epilogue: F.linear (multihead_attention.py:152-158), fc1/fc2 (transformer.py:186-190),
+ *      out_proj (multihead_attention.py:130), Conv1d k=1 (mmtr.py:748-750), GMU linears (mmtr.py:190-194) ---------
+ * C[M,N] = epi( op(A)[M,K] * op(B)[K,N] ).  ta = 0: A stored [M,K] (pitch lda); ta = 1: A stored [K,M].
+ * tb = 0: B stored [N,K] (nn.Linear weight layout); tb = 1: B stored [K,N].
+ * epi(v)(m,n): v = (v + bias[n]) * alpha; relu if act==1; dropout; if gate: v = gate[m,n] > 0 ? v*gate_scale : 0;
+ *              v += residual[m,n]; accumulate ? C += v : C = v.
+ * bf16 inputs run on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> tcgen05.ld epilogue) and need
+ * 16-byte aligned pointers and pitches; fp32 inputs run an FFMA kernel (exact-fp32 "precision mode"). */
+typedef struct {
+  int ab_dtype, ta, tb, M, N, K;
+  const void* A; int lda;
+  const void* B; int ldb;
+  void* C; int ldc; int c_dtype;
+  const float* bias; float alpha; int act;
+  bpm_dropout_t drop;
+  const void* gate; int ldg; int gate_dtype; float gate_scale;
+  const void* residual; int ldr; int res_dtype;
+  int accumulate;            /* C must be fp32; split-K partial sums are added atomically */
+  int split_k;               /* 0 = auto */
+} bpm_gemm_t;
+int bpm_gemm(const bpm_gemm_t* g, void* stream);
+
+/* column sums for bias gradients: out[n] (+)= sum_m X[m, n]  (fp32 atomics) */
+int bpm_colsum(const void* X, int dtype, int M, int N, int ld, float* out, void* stream);
+
+/* ---- crossmodal attention: models/multihead_attention.py:95-127 + mask models/transformer.py:209-216 ----------
+ * q [B,T,H*dhp] (already scaled by dh^-0.5), k, v [B,S,H*dhp] in T; out [B,T,H*dhp]; lse fp32 [B,H,T].
+ * mask_off >= 0: key j visible to query i iff j <= i + mask_off (reference: mask_off = |S - T|); mask_off < 0: no mask.
+ * key_pad (uint8 [B,S], 1 = padded key, may be NULL): superset feature, default off (the reference has none).
+ * bwd writes dq * dq_scale, dk, dv (T) and needs delta workspace fp32 [B,H,T]. */
+typedef struct {
+  int dtype, B, T, S, H, dh, dhp, mask_off;
+  const uint8_t* key_pad;
+  bpm_dropout_t drop;
+} bpm_attn_t;
+int bpm_xattn_fwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, void* stream);
+int bpm_xattn_bwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout,
+                  const float* lse, float* delta, void* dq, float dq_scale, void* dk, void* dv, void* stream);
+/* head-averaged probabilities (multihead_attention.py:133-135), only on request: w fp32 [B,T,S] */
+int bpm_xattn_weights(const bpm_attn_t* a, const void* q, const void* k, const float* lse, float* w, void* stream);
+
+/* ---- sequence GMU: models/mmtr.py:179-195 (GatedMultimodalLayerFeatures), :161-177 (GatedMultimodalLayer) ------
+ * pre-activations come from bpm_gemm; this fuses tanh / sigmoid / gating (+ optional addend, mmtr.py:806).
+ * features = 1: y = z*h1*a1 + (1-z)*h2*a2 (+ add);  features = 0: y = z*h1 + (1-z)*h2.
+ * bwd: dh1pre, dh2pre, dzpre (T) and the direct input grads da1 / da2 (fp32, accumulated). */
+int bpm_gmu_fwd(int dtype, int features, const void* a1, const void* a2, const void* h1pre, const void* h2pre,
+                const void* zpre, const void* addend, int rows, int Dp, void* y, void* z_out, void* stream);
+int bpm_gmu_bwd(int dtype, int features, const void* a1, const void* a2, const void* h1pre, const void* h2pre,
+                const void* zpre, const float* dy, int rows, int Dp, void* dh1pre, void* dh2pre, void* dzpre,
+                float* da1, float* da2, void* stream);
+
+/* ---- elementwise helpers ------------------------------------------------------------------------------------- */
+/* y = a + b (T), mmtr.py:799-800 */
+int bpm_add(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream);
+/* dst(fp32) (+)= src (T or fp32) */
+int bpm_axpy_f32(const void* src, int src_dtype, float* dst, int64_t n, int accumulate, void* stream);
+/* y (T) = dropmask * x (fp32): fp32 gradient -> GEMM operand, regenerating a residual-dropout mask */
+int bpm_cast_drop(const float* x, void* y, int y_dtype, int rows, int cols, bpm_dropout_t drop, void* stream);
+/* pooling mmtr.py:808: out[b, col_off + c] = x[b*T + 0, c] + x[b*T + T-1, c] (fp32 out, pitch ld_out); bwd scatters */
+int bpm_pool_fwd(const void* x, int dtype, int B, int T, int Dp, float* out, int ld_out, int col_off, void* stream);
+int bpm_pool_bwd(const float* dout, int ld_out, int col_off, int B, int T, int Dp, float* dx, void* stream);
+
+/* ---- final GMU (TextShifting3/4Layer, mmtr.py:197-247): fused = sum_i sigmoid(zpre_i) * tanh(hpre_i) -----------
+ * hpre, zpre: fp32 [n_in][B, Dp] contiguous blocks; z_out fp32 [B, n_in*Dp] (gates, mmtr.py:863-866) */
+int bpm_tsgate_fwd(const float* hpre, const float* zpre, int n_in, int B, int Dp, float* fused, float* z_out, void* stream);
+int bpm_tsgate_bwd(const float* hpre, const float* zpre, const float* dfused, int n_in, int B, int Dp, float* dhpre,
+                   float* dzpre, void* stream);
+
+/* ---- loss: train.py:99-106,333 nn.BCEWithLogitsLoss(pos_weight), mean over (B, C) -----------------------------
+ * loss (fp32 scalar, overwritten) and dlogits = dloss/dlogits * grad_scale (fp32 [B, ldl]) in one launch. */
+int bpm_bce_fwd_bwd(const float* logits, int ldl, const float* targets, const float* pos_weight, int B, int C,
+                    float grad_scale, float* loss, float* dlogits, void* stream);
+
+/* ---- optimiser: train.py:123-125 optim.Adam (default betas / eps, no weight decay) ----------------------------
+ * step_ptr: device int64 step counter (already incremented); grad_scale multiplies the gradient (1/world, 1/accum). */
+int bpm_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float grad_scale, const int64_t* step_ptr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

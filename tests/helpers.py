@@ -1,0 +1,51 @@
+"""Shared test helpers: drive the product engines on reference-layout tensors."""
+import os
+
+import torch
+
+from bpmult_b200.engine import EncoderEngine, round_up
+from oracle import functional as Fn
+from oracle import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_gold(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def to_dev(sd, dev):
+    return {k: v.to(dev) for k, v in sd.items()}
+
+
+def run_encoder_engine(ops, sd, x, k, g, H, L, mask, biproj, self_only, dtype=torch.float32, p=None, training=True, seed=0):
+    """x (T,B,D), k (S,B,D) time-major fp32 CPU tensors; g upstream gradient (T,B,D).
+    Returns out (T,B,D), dx, dk, param grads (reference layout) as CPU fp32."""
+    dev = ops.device
+    T, B, D = x.shape
+    S = k.shape[0] if k is not None else None
+    p = p or {}
+    eng = EncoderEngine(ops, D, H, L, attn_mask=mask, biprojection=biproj, dtype=dtype, uid=3, **p)
+    params = to_dev(sd, dev)
+    eng.pack(params)
+    Dp = eng.d.Dp
+    xq = ops.empty((B * T, Dp), dtype)
+    ops.stage_rows(x.to(dev).permute(1, 0, 2), xq, T)
+    xk = None
+    if not self_only:
+        xk = ops.empty((B * S, Dp), dtype)
+        ops.stage_rows(k.to(dev).permute(1, 0, 2), xk, S)
+    out = eng.forward(xq, B, T, src_k=xk, S=S, training=training, seed=seed)
+    out_tbd = out.float().view(B, T, Dp)[:, :, :D].permute(1, 0, 2).cpu()
+    # backward
+    eng.zero_grads()
+    dout = ops.empty((B * T, Dp), torch.float32)
+    ops.stage_rows(g.to(dev).permute(1, 0, 2), dout, T)
+    dq = ops.zeros((B * T, Dp), torch.float32)
+    dk = ops.zeros((B * S, Dp), torch.float32) if not self_only else None
+    eng.backward(dout, dq, dk)
+    grads = {n: torch.zeros(s, device=dev) for n, s in eng.param_shapes().items()}
+    eng.unpack_grads(grads)
+    dx = dq.view(B, T, Dp)[:, :, :D].permute(1, 0, 2).cpu()
+    dkk = dk.view(B, S, Dp)[:, :, :D].permute(1, 0, 2).cpu() if dk is not None else None
+    return out_tbd, dx, dkk, {n: v.cpu() for n, v in grads.items()}, eng
