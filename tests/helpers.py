@@ -49,3 +49,29 @@ def run_encoder_engine(ops, sd, x, k, g, H, L, mask, biproj, self_only, dtype=to
     dx = dq.view(B, T, Dp)[:, :, :D].permute(1, 0, 2).cpu()
     dkk = dk.view(B, S, Dp)[:, :, :D].permute(1, 0, 2).cpu() if dk is not None else None
     return out_tbd, dx, dkk, {n: v.cpu() for n, v in grads.items()}, eng
+
+
+def run_model_engine(ops, rec, dtype=torch.float32, full=True):
+    from argparse import Namespace
+    from bpmult_b200.model_engine import MMTrVatEngine
+    cfg = Namespace(**rec["cfg"])
+    B, T_l, T_a, T_v = rec["dims"]
+    sd = synth.make_state_dict(synth.mmtrvat_shapes(cfg), rec["seed"])
+    txt, img, audio, tgt = synth.mmtrvat_inputs(cfg, B, T_l, T_a, T_v)
+    eng = MMTrVatEngine(ops, cfg, dtype=dtype)
+    dev = ops.device
+    params = {k: v.to(dev) for k, v in sd.items()}
+    assert set(eng.param_shapes().keys()) | set(eng.unused_params()) >= set(sd.keys())
+    eng.pack(params)
+    logits, z = eng.forward(txt.to(dev), img.to(dev), audio.to(dev), training=True)
+    loss, dlogits = eng.loss(logits, tgt.to(dev), rec["pos_weight"].to(dev))
+    eng.zero_grads()
+    dtxt = torch.zeros_like(txt, device=dev)
+    eng.backward(dlogits, {"l": dtxt})
+    grads = {n: torch.zeros(s, device=dev) for n, s in eng.param_shapes().items()}
+    eng.unpack_grads(grads)
+    D, Dp, C = cfg.hidden_sz, eng.d.Dp, cfg.n_classes
+    zz = z.view(B, 3, Dp)[:, :, :D].reshape(B, 3 * D)
+    return logits[:, :C].cpu(), zz.cpu(), loss.cpu(), dtxt.cpu(), {n: v.cpu() for n, v in grads.items()}, eng
+
+

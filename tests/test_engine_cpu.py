@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from emu_ops import EmuOps
-from helpers import load_gold, run_encoder_engine
+from helpers import load_gold, run_encoder_engine, run_model_engine
 from oracle import functional as Fn
 from oracle import synth
 
@@ -34,3 +34,19 @@ def test_encoder_engine_fp32_matches_reference_golden(rec):
             f = grads[n].reshape(-1).double()
             assert abs(f.norm().item() - s["norm"]) <= 5e-5 * s["norm"] + 1e-9, n
             assert torch.allclose(f[s["idx"]].float(), s["val"], rtol=2e-3, atol=2e-5 * max(1e-6, s["norm"])), n
+
+
+def test_mmtrvat_engine_fp32_matches_reference_golden():
+    rec = load_gold("mmtrvat_tiny.pt")
+    logits, z, loss, dtxt, grads, eng = run_model_engine(EmuOps(), rec)
+    assert Fn.max_rel(logits, rec["logits"]) < 2e-5
+    assert Fn.max_rel(z, rec["z"]) < 2e-5
+    assert abs(loss.item() - rec["loss"].item()) < 1e-5
+    assert Fn.max_rel(dtxt, rec["dtxt"]) < 1e-4
+    assert sorted(eng.unused_params()) == sorted(rec["nograd"])
+    worst = 0.0
+    for n, ref in rec["pgrads"].items():
+        e = Fn.rel_l2(grads[n], ref)
+        worst = max(worst, e)
+        assert e < 2e-4, (n, e)
+    print("worst param-grad rel-l2", worst)

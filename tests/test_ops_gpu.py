@@ -1,0 +1,294 @@
+"""GPU parity tests, op level: every C-ABI kernel (called through bpmult_b200.ops.CudaOps) against the pure-torch statement
+of the same contract (tests/emu_ops.py), on seeded inputs, in fp32 and bf16 storage.
+Tolerances: fp32 paths 2e-5 (max-rel per tensor); bf16-storage paths 1e-2 (the stated bf16 bar), elementwise-exact where
+both sides round the same fp32 value to bf16 (<= 1 bf16 ulp)."""
+import pytest
+import torch
+
+from emu_ops import EmuOps
+from bpmult_b200.ops import Drop
+
+pytestmark = pytest.mark.gpu
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from bpmult_b200.ops import CudaOps
+    return CudaOps()
+
+
+def rnd(shape, seed, dtype=F32, scale=1.0):
+    return (torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale).to(dtype)
+
+
+def max_rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def tol(dtype):
+    return 2e-5 if dtype == F32 else 1e-2
+
+
+def both(ops, fn, ins, outs):
+    """run `fn(o, *tensors)` with EmuOps on CPU copies and CudaOps on device copies; returns (emu outs, cuda outs)"""
+    emu = EmuOps()
+    ci = [None if t is None else t.clone() for t in ins]
+    co = [None if t is None else t.clone() for t in outs]
+    fn(emu, *ci, *co)
+    gi = [None if t is None else t.clone().cuda() for t in ins]
+    go = [None if t is None else t.clone().cuda() for t in outs]
+    fn(ops, *gi, *go)
+    torch.cuda.synchronize()
+    return co, [None if t is None else t.cpu() for t in go]
+
+
+DROP = Drop(0.3, 1234567, None, 77)
+
+
+# ------------------------------------------------------------------------------------------------ dropout bit-exactness
+def test_philox_mask_matches_emulation(ops):
+    x = torch.ones(37, 64)
+    (e,), (c,) = both(ops, lambda o, x, y: o.cast_drop(x, y, DROP), [x], [torch.zeros(37, 64)])
+    assert torch.equal(e, c)
+    keep = (c != 0).float().mean().item()
+    assert abs(keep - 0.7) < 0.05
+    assert torch.allclose(c[c != 0], torch.tensor(1 / 0.7))
+
+
+# ------------------------------------------------------------------------------------------------ pack / stage / embed
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_pack_unpack(ops, dtype):
+    src = rnd((300, 300), 1)
+    (e,), (c,) = both(ops, lambda o, s, d: o.pack_matrix(s, d, row_map=(25, 32), col_map=(0, 0)), [src], [torch.zeros(384, 320, dtype=dtype)])
+    assert torch.equal(e, c)
+    (e,), (c,) = both(ops, lambda o, s, d: o.pack_matrix(s, d, col_map=(25, 32)), [src], [torch.zeros(320, 384, dtype=dtype)])
+    assert torch.equal(e, c)
+    g = rnd((384, 320), 2)
+    (e,), (c,) = both(ops, lambda o, s, d: o.unpack_matrix(s, d, row_map=(25, 32), accumulate=True, scale=0.5), [g], [rnd((300, 300), 3)])
+    assert torch.allclose(e, c, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_stage_embed(ops, dtype):
+    B, T, C, Tp, Cp = 3, 10, 35, 16, 64
+    src = rnd((T, B, C), 4).permute(1, 0, 2)          # time-major storage, batch-major view
+    (e,), (c,) = both(ops, lambda o, s, d: o.stage_rows(s, d, Tp, DROP), [src], [torch.zeros(B * Tp, Cp, dtype=dtype)])
+    assert torch.equal(e, c)
+    g = rnd((B * Tp, Cp), 5)
+    (e,), (c,) = both(ops, lambda o, g, d: o.unstage_rows(g, d, Tp, False, DROP), [g], [torch.zeros(B, T, C)])
+    assert torch.equal(e, c)
+    # embed
+    D, Dp, T = 45, 64, 12
+    from bpmult_b200.engine import sinusoid_table
+    pe = sinusoid_table(T + 1, D, Dp, "cpu")
+    x = torch.zeros(B * T, Dp)
+    x[:, :D] = rnd((B * T, D), 6)
+    x[5] = 0
+    x[7, 0] = 0
+    x = x.to(dtype)
+    for yd in (F32, dtype):
+        (e,), (c,) = both(ops, lambda o, x, pe, y: o.embed_fwd(x, pe, B, T, D, D ** 0.5, y, DROP), [x, pe], [torch.zeros(B * T, Dp, dtype=yd)])
+        assert max_rel(c, e) < (1e-6 if yd == F32 else 8e-3)
+        assert (c[:, D:] == 0).all()
+    dy = rnd((B * T, Dp), 7)
+    (e,), (c,) = both(ops, lambda o, dy, dx: o.embed_bwd(dy, D, D ** 0.5, dx, True, DROP), [dy], [rnd((B * T, Dp), 8)])
+    assert max_rel(c, e) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ layernorm
+@pytest.mark.parametrize("D,Dp", [(300, 320), (40, 64), (768, 768), (45, 64)])
+@pytest.mark.parametrize("xd,yd", [(F32, F32), (F32, BF16), (BF16, BF16)])
+def test_layernorm(ops, D, Dp, xd, yd):
+    rows = 77
+    x = torch.zeros(rows, Dp)
+    x[:, :D] = rnd((rows, D), 9) * 3 + 1
+    x = x.to(xd)
+    gam, bet = torch.zeros(Dp), torch.zeros(Dp)
+    gam[:D] = 1 + 0.1 * rnd((D,), 10)
+    bet[:D] = 0.1 * rnd((D,), 11)
+    outs = [torch.zeros(rows, Dp, dtype=yd), torch.zeros(rows), torch.zeros(rows)]
+    e, c = both(ops, lambda o, x, g, b, y, m, r: o.layernorm_fwd(x, g, b, D, y, m, r), [x, gam, bet], outs)
+    assert max_rel(c[0], e[0]) < tol(yd)
+    assert max_rel(c[1], e[1]) < 1e-5 and max_rel(c[2], e[2]) < 1e-5
+    assert (c[0][:, D:] == 0).all()
+    dy = torch.zeros(rows, Dp)
+    dy[:, :D] = rnd((rows, D), 12)
+    dy = dy.to(yd)
+    outs = [rnd((rows, Dp), 13), torch.zeros(Dp), torch.zeros(Dp)]
+    e2, c2 = both(ops, lambda o, dy, x, m, r, g, dx, dg, db: o.layernorm_bwd(dy, x, m, r, g, D, dx, True, dg, db),
+                  [dy, x, e[1], e[2], gam], outs)
+    for a, b in zip(c2, e2):
+        assert max_rel(a, b) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ GEMM (FFMA fp32 + tcgen05 bf16)
+GEMM_SHAPES = [(128, 320, 320), (256, 384, 320), (40, 320, 384), (200, 1216, 320), (300, 320, 1216), (128, 64, 64), (130, 48, 72), (1024, 320, 320)]
+
+
+def _gemm_case(ops, dtype, M, N, K, ta, tb, cdt=None, **epi):
+    cdt = cdt or dtype
+    A = rnd((K, M) if ta else (M, K), 20, dtype, 0.5)
+    B = rnd((K, N) if tb else (N, K), 21, dtype, 0.5)
+    ins = [A, B]
+    kw = {}
+    if epi.get("bias"):
+        ins.append(rnd((N,), 22)); kw["bias"] = 2
+    if epi.get("gate"):
+        ins.append(rnd((M, N), 23, dtype)); kw["gate"] = len(ins) - 1
+    if epi.get("residual") is not None:
+        ins.append(rnd((M, N), 24, epi["residual"])); kw["residual"] = len(ins) - 1
+    C0 = rnd((M, N), 25, cdt) if epi.get("accumulate") else torch.zeros(M, N, dtype=cdt)
+
+    def fn(o, *t):
+        tensors = list(t)
+        Cout = tensors[-1]
+        args = {k: tensors[v] for k, v in kw.items()}
+        o.gemm(tensors[0], tensors[1], Cout, M, N, K, ta=ta, tb=tb, alpha=epi.get("alpha", 1.0), act=epi.get("act", 0),
+               drop=epi.get("drop"), gate_scale=epi.get("gate_scale", 1.0), accumulate=epi.get("accumulate", False), **args)
+    (e,), (c,) = both(ops, fn, ins, [C0])
+    return max_rel(c, e)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain_nt(ops, dtype, M, N, K):
+    assert _gemm_case(ops, dtype, M, N, K, 0, 0, cdt=F32) < 5e-5   # bf16 inputs are exact on both sides => pure fp32-accumulate parity
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("ta,tb", [(0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(128, 320, 320), (384, 320, 1000), (200, 1216, 320), (320, 384, 136)])
+def test_gemm_transposed_operands(ops, dtype, ta, tb, M, N, K):
+    assert _gemm_case(ops, dtype, M, N, K, ta, tb, cdt=F32) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_gemm_epilogues(ops, dtype):
+    M, N, K = 200, 320, 384
+    t = tol(dtype)
+    assert _gemm_case(ops, dtype, M, N, K, 0, 0, bias=True, alpha=0.2) < t
+    assert _gemm_case(ops, dtype, M, N, K, 0, 0, bias=True, act=1, drop=DROP) < t
+    assert _gemm_case(ops, dtype, M, N, K, 0, 0, cdt=F32, bias=True, drop=DROP, residual=F32) < 2e-5
+    assert _gemm_case(ops, dtype, M, N, K, 0, 1, gate=True, gate_scale=1.25) < t
+    assert _gemm_case(ops, dtype, M, N, K, 0, 0, residual=dtype) < t
+    assert _gemm_case(ops, dtype, 384, 320, 4096, 1, 1, cdt=F32, accumulate=True) < 2e-5       # split-K wgrad shape
+
+
+def test_colsum(ops):
+    for dtype in (F32, BF16):
+        X = rnd((1000, 384), 30, dtype)
+        (e,), (c,) = both(ops, lambda o, X, out: o.colsum(X, 380, out), [X], [rnd((384,), 31)])
+        assert max_rel(c, e) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention
+ATTN_CASES = [  # B, T, S, H, dh, dhp, mask_off, p
+    (2, 12, 12, 4, 10, 32, 0, 0.0), (2, 6, 4, 4, 10, 32, 2, 0.0), (3, 4, 6, 4, 10, 32, 2, 0.0), (2, 9, 17, 4, 10, 32, -1, 0.0),
+    (2, 130, 200, 12, 25, 32, 70, 0.1), (1, 256, 256, 12, 25, 32, 0, 0.0), (1, 200, 512, 6, 128, 128, -1, 0.1), (2, 512, 512, 2, 25, 32, 0, 0.2),
+]
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_xattn_fwd_bwd(ops, dtype, case):
+    B, T, S, H, dh, dhp, off, p = case
+    HP = H * dhp
+
+    def mk(rows, seed, scale):
+        t = torch.zeros(rows, H, dhp)
+        t[:, :, :dh] = rnd((rows, H, dh), seed) * scale
+        return t.view(rows, HP).to(dtype)
+    q, k, v, do = mk(B * T, 40, dh ** -0.25), mk(B * S, 41, dh ** -0.25), mk(B * S, 42, 1.0), mk(B * T, 43, 1.0)
+    drop = Drop(p, 99, None, 5) if p > 0 else None
+    outs = [torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * H * T)]
+    e, c = both(ops, lambda o, q, k, v, out, lse: o.xattn_fwd(q, k, v, out, lse, B, T, S, H, dh, dhp, off, None, drop), [q, k, v], outs)
+    assert max_rel(c[0], e[0]) < tol(dtype)
+    assert max_rel(c[1], e[1]) < (1e-5 if dtype == F32 else 2e-3)
+    outs = [torch.zeros(B * H * T), torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype)]
+    e2, c2 = both(ops, lambda o, q, k, v, out, do, lse, dl, dq, dk, dv: o.xattn_bwd(q, k, v, out, do, lse, dl, dq, 0.2, dk, dv, B, T, S, H, dh, dhp, off, None, drop),
+                  [q, k, v, e[0], do, e[1]], outs)
+    t = 2e-5 if dtype == F32 else 1.5e-2
+    for a, b, nm in zip(c2, e2, ["delta", "dq", "dk", "dv"]):
+        assert max_rel(a, b) < t, nm
+    if dtype == F32:
+        (ew,), (cw,) = both(ops, lambda o, q, k, lse, w: o.xattn_weights(q, k, lse, w, B, T, S, H, dh, dhp, off, None, drop), [q, k, e[1]], [torch.zeros(B, T, S)])
+        assert max_rel(cw, ew) < 2e-5
+
+
+def test_xattn_key_padding_mask(ops):
+    B, T, S, H, dh, dhp = 2, 8, 10, 2, 16, 32
+    q, k, v = rnd((B * T, H * dhp), 50), rnd((B * S, H * dhp), 51), rnd((B * S, H * dhp), 52)
+    kp = torch.zeros(B, S, dtype=torch.uint8)
+    kp[0, 7:] = 1
+    kp[1, 3] = 1
+    e, c = both(ops, lambda o, q, k, v, kp, out, lse: o.xattn_fwd(q, k, v, out, lse, B, T, S, H, dh, dhp, -1, kp, None), [q, k, v, kp],
+                [torch.zeros(B * T, H * dhp), torch.zeros(B * H * T)])
+    assert max_rel(c[0], e[0]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ GMU / pooling / head pieces / loss / adam
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("features", [1, 0])
+def test_gmu_combine(ops, dtype, features):
+    rows, Dp = 50, 64
+    a1, a2, h1, h2, zp, ad = [rnd((rows, Dp), 60 + i, dtype) for i in range(6)]
+    e, c = both(ops, lambda o, a1, a2, h1, h2, zp, ad, y, z: o.gmu_fwd(features, a1, a2, h1, h2, zp, ad, y, z), [a1, a2, h1, h2, zp, ad],
+                [torch.zeros(rows, Dp, dtype=dtype), torch.zeros(rows, Dp, dtype=dtype)])
+    assert max_rel(c[0], e[0]) < tol(dtype) and max_rel(c[1], e[1]) < tol(dtype)
+    dy = rnd((rows, Dp), 70)
+    outs = [torch.zeros(rows, Dp, dtype=dtype) for _ in range(3)] + [rnd((rows, Dp), 71), rnd((rows, Dp), 72)]
+    e, c = both(ops, lambda o, a1, a2, h1, h2, zp, dy, d1, d2, dz, g1, g2: o.gmu_bwd(features, a1, a2, h1, h2, zp, dy, d1, d2, dz, g1, g2),
+                [a1, a2, h1, h2, zp, dy], outs)
+    for a, b in zip(c, e):
+        assert max_rel(a, b) < tol(dtype)
+
+
+def test_small_ops(ops):
+    B, T, Dp = 3, 7, 64
+    for dtype in (F32, BF16):
+        x = rnd((B * T, Dp), 80, dtype)
+        (e,), (c,) = both(ops, lambda o, x, out: o.pool_fwd(x, B, T, out, Dp), [x], [torch.zeros(B, 3 * Dp)])
+        assert max_rel(c, e) < 1e-6
+        a, b = rnd((40, 64), 81, dtype), rnd((40, 64), 82, dtype)
+        (e,), (c,) = both(ops, lambda o, a, b, y: o.add(a, b, y), [a, b], [torch.zeros(40, 64, dtype=dtype)])
+        assert torch.equal(e, c)
+        (e,), (c,) = both(ops, lambda o, a, d: o.axpy_f32(a, d, True), [a], [rnd((40, 64), 83)])
+        assert torch.equal(e, c)
+    dout = rnd((B, 3 * Dp), 84)
+    (e,), (c,) = both(ops, lambda o, d, dx: o.pool_bwd(d, Dp, B, T, dx), [dout], [rnd((B * T, Dp), 85)])
+    assert torch.equal(e, c)
+    n = 3
+    hp, zp = rnd((n, B, Dp), 86), rnd((n, B, Dp), 87)
+    e, c = both(ops, lambda o, h, z, f, zo: o.tsgate_fwd(h, z, n, B, Dp, f, zo), [hp, zp], [torch.zeros(B, Dp), torch.zeros(B, n * Dp)])
+    assert max_rel(c[0], e[0]) < 1e-5 and max_rel(c[1], e[1]) < 1e-5
+    df = rnd((B, Dp), 88)
+    e, c = both(ops, lambda o, h, z, d, dh, dz: o.tsgate_bwd(h, z, d, n, B, Dp, dh, dz), [hp, zp, df], [torch.zeros(n, B, Dp), torch.zeros(n, B, Dp)])
+    assert max_rel(c[0], e[0]) < 1e-5 and max_rel(c[1], e[1]) < 1e-5
+
+
+def test_bce_matches_golden_and_torch(ops):
+    from helpers import load_gold
+    g = load_gold("modules.pt")["bce"]
+    B, C = g["x"].shape
+    logits = torch.zeros(B, 8)
+    logits[:, :C] = g["x"]
+    loss, dl = torch.zeros(1).cuda(), torch.zeros(B, 8).cuda()
+    ops.bce_fwd_bwd(logits.cuda(), g["y"].cuda(), g["w"].cuda(), B, C, 1.0, loss, dl)
+    assert abs(loss.item() - g["loss"].item()) < 1e-6
+    assert max_rel(dl[:, :C], g["dx"]) < 1e-5
+
+
+def test_adam_matches_torch(ops):
+    p0, g = rnd((1000,), 90), rnd((1000,), 91)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p, m, v = p0.clone().cuda(), torch.zeros(1000).cuda(), torch.zeros(1000).cuda()
+    step = torch.zeros(1, dtype=torch.int64).cuda()
+    for i in range(3):
+        ref.grad = g * (i + 1)
+        opt.step()
+        step += 1
+        ops.adam_step(p, (g * (i + 1)).cuda(), m, v, 1e-3, 0.9, 0.999, 1e-8, 1.0, step)
+    assert max_rel(p, ref.detach()) < 1e-6
