@@ -39,19 +39,19 @@ def positional_embedding(x_in):
     position(t, b) = t + 1 if x_in[t, b, 0] != 0 else 0 (padding_idx = 0, left_pad = 0).  x_in is (T, B, D).
     Returns (T, B, D), detached."""
     T, B, D = x_in.shape
-    tab = sinusoid_table(T + 1, D, x_in.dtype)
+    tab = sinusoid_table(T + 1, D, x_in.dtype).to(x_in.device)
     ch0 = x_in[:, :, 0]
-    pos = torch.arange(1, T + 1).unsqueeze(1).expand(T, B)
+    pos = torch.arange(1, T + 1, device=x_in.device).unsqueeze(1).expand(T, B)
     pos = torch.where(ch0 != 0, pos, torch.zeros_like(pos))
     return tab[pos.reshape(-1)].view(T, B, D).detach()
 
 
 # ----------------------------------------------------------------------------- attention
-def future_mask(T, S, dtype):
+def future_mask(T, S, dtype, device="cpu"):
     """models/transformer.py:209-216: M[i, j] = -inf if j - i >= 1 + |S - T| else 0."""
-    i = torch.arange(T).unsqueeze(1)
-    j = torch.arange(S).unsqueeze(0)
-    m = torch.zeros(T, S, dtype=dtype)
+    i = torch.arange(T, device=device).unsqueeze(1)
+    j = torch.arange(S, device=device).unsqueeze(0)
+    m = torch.zeros(T, S, dtype=dtype, device=device)
     m[(j - i) >= 1 + abs(S - T)] = float("-inf")
     return m
 
@@ -89,7 +89,7 @@ def _ln(sd, pfx, x):
 def encoder_layer(sd, pfx, x, x_k, x_v, num_heads, attn_mask, biprojection=False):
     """models/transformer.py:141-195 (pre-norm: normalize_before = True, :132)."""
     T = x.shape[0]
-    mk = lambda S: future_mask(T, S, x.dtype) if attn_mask else None
+    mk = lambda S: future_mask(T, S, x.dtype, x.device) if attn_mask else None
     residual = x
     xn = _ln(sd, pfx + "layer_norms.0.", x)
     if x_k is None and x_v is None:                                        # :158-159 self-attention only
@@ -170,7 +170,7 @@ def _pad_time(x, n):
     """models/mmtr.py:722-732 transfm_2dim(dim=0)."""
     if x.shape[0] == n:
         return x
-    return torch.cat([x, torch.zeros(n - x.shape[0], x.shape[1], x.shape[2], dtype=x.dtype)], 0)
+    return torch.cat([x, torch.zeros(n - x.shape[0], x.shape[1], x.shape[2], dtype=x.dtype, device=x.device)], 0)
 
 
 def mmtrvat_forward(sd, cfg, txt, img, audio, n_vec=512, return_intermediates=False):
