@@ -7,13 +7,17 @@ kernels behind the C ABI in include/bpmult_b200.h (libbpmult_b200.so); there is 
 __version__ = "0.1.0"
 
 
+_PUBLIC = {
+    "modules": ["MultiprojectionMMTransformer3DGMUClf", "TransformerEncoder", "TransformerEncoderLayer", "MultiheadAttention",
+                "SinusoidalPositionalEmbedding", "GatedMultimodalLayer", "GatedMultimodalLayerFeatures", "TextShifting3Layer",
+                "TextShifting4Layer", "buffered_future_mask", "get_model", "MODELS", "manual_seed"],
+    "trainer": ["Trainer"],
+}
+
+
 def __getattr__(name):            # lazy: importing the package must not require a GPU or the built library
     import importlib
-    for mod in ("modules", "trainer"):
-        try:
-            m = importlib.import_module("." + mod, __name__)
-        except ModuleNotFoundError:
-            continue
-        if hasattr(m, name):
-            return getattr(m, name)
+    for mod, names in _PUBLIC.items():
+        if name in names:
+            return getattr(importlib.import_module("." + mod, __name__), name)
     raise AttributeError(name)

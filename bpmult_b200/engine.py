@@ -80,8 +80,10 @@ class EncoderEngine:
 
     # parameter table: name-suffix -> (kind, packer)
     def __init__(self, ops, D, H, L, attn_dropout=0.0, relu_dropout=0.0, res_dropout=0.0, embed_dropout=0.0, attn_mask=False,
-                 biprojection=False, dtype=torch.bfloat16, uid=0, shared=None):
+                 biprojection=False, dtype=torch.bfloat16, uid=0, shared=None, with_embed=True, with_final_ln=True):
         self.ops, self.d, self.L = ops, Dims(D, H), L
+        self.with_embed, self.with_final_ln = with_embed, with_final_ln        # False: run bare layers (standalone layer module)
+        self._mask_override = None
         self.p_attn, self.p_relu, self.p_res, self.p_embed = attn_dropout, relu_dropout, res_dropout, embed_dropout
         self.attn_mask, self.biproj, self.T_ = attn_mask, biprojection, dtype
         self.uid = uid
@@ -108,8 +110,9 @@ class EncoderEngine:
             for j in range(self.n_ln):
                 s[p + "layer_norms.%d.weight" % j] = (D,)
                 s[p + "layer_norms.%d.bias" % j] = (D,)
-        s["layer_norm.weight"] = (D,)
-        s["layer_norm.bias"] = (D,)
+        if self.with_final_ln:
+            s["layer_norm.weight"] = (D,)
+            s["layer_norm.bias"] = (D,)
         return s
 
     def _alloc_weights(self):
@@ -128,13 +131,6 @@ class EncoderEngine:
         self.Wf = dict(g=z((d.Dp,), f32), b=z((d.Dp,), f32))
         self.Gf = dict(g=z((d.Dp,), f32), b=z((d.Dp,), f32))
 
-    def _param_map(self, l):
-        """(reference name, packed tensor key, row_map, col_map, q-scale-on-unpack)"""
-        d = self.d
-        hm = (d.dh, d.dhp)
-        p = "layers.%d." % l
-        return p, hm
-
     def pack(self, params, pfx=""):
         """reference-layout fp32 parameters -> zero-padded kernel operands (run whenever the parameters changed)."""
         o, d = self.ops, self.d
@@ -142,12 +138,8 @@ class EncoderEngine:
         for l in range(self.L):
             p = "%slayers.%d." % (pfx, l)
             w = self.W[l]
-            ipw, ipb = params[p + "self_attn.in_proj_weight"], params[p + "self_attn.in_proj_bias"]
-            for j in range(3):          # rows [0:D] = Q, [D:2D] = K, [2D:3D] = V  (multihead_attention.py:137-158)
-                o.pack_matrix(ipw[j * d.D:(j + 1) * d.D], w["Wqkv"][j * d.HP:(j + 1) * d.HP], row_map=hm)
-                o.pack_matrix(ipb[j * d.D:(j + 1) * d.D].view(1, -1), w["bqkv"][j * d.HP:(j + 1) * d.HP].view(1, -1), col_map=hm)
-            o.pack_matrix(params[p + "self_attn.out_proj.weight"], w["Wo"], col_map=hm)
-            o.pack_matrix(params[p + "self_attn.out_proj.bias"].view(1, -1), w["bo"].view(1, -1))
+            self.pack_attention(l, params[p + "self_attn.in_proj_weight"], params[p + "self_attn.in_proj_bias"],
+                                params[p + "self_attn.out_proj.weight"], params[p + "self_attn.out_proj.bias"])
             o.pack_matrix(params[p + "fc1.weight"], w["W1"])
             o.pack_matrix(params[p + "fc1.bias"].view(1, -1), w["b1"].view(1, -1))
             o.pack_matrix(params[p + "fc2.weight"], w["W2"])
@@ -155,8 +147,31 @@ class EncoderEngine:
             for j in range(self.n_ln):
                 o.pack_matrix(params[p + "layer_norms.%d.weight" % j].view(1, -1), w["ln_g"][j].view(1, -1))
                 o.pack_matrix(params[p + "layer_norms.%d.bias" % j].view(1, -1), w["ln_b"][j].view(1, -1))
-        o.pack_matrix(params[pfx + "layer_norm.weight"].view(1, -1), self.Wf["g"].view(1, -1))
-        o.pack_matrix(params[pfx + "layer_norm.bias"].view(1, -1), self.Wf["b"].view(1, -1))
+        if self.with_final_ln:
+            o.pack_matrix(params[pfx + "layer_norm.weight"].view(1, -1), self.Wf["g"].view(1, -1))
+            o.pack_matrix(params[pfx + "layer_norm.bias"].view(1, -1), self.Wf["b"].view(1, -1))
+
+    def pack_attention(self, l, ipw, ipb, ow, ob):
+        o, d, w = self.ops, self.d, self.W[l]
+        hm = (d.dh, d.dhp)
+        for j in range(3):          # rows [0:D] = Q, [D:2D] = K, [2D:3D] = V  (multihead_attention.py:137-158)
+            o.pack_matrix(ipw[j * d.D:(j + 1) * d.D], w["Wqkv"][j * d.HP:(j + 1) * d.HP], row_map=hm)
+            o.pack_matrix(ipb[j * d.D:(j + 1) * d.D].view(1, -1), w["bqkv"][j * d.HP:(j + 1) * d.HP].view(1, -1), col_map=hm)
+        o.pack_matrix(ow, w["Wo"], col_map=hm)
+        o.pack_matrix(ob.view(1, -1), w["bo"].view(1, -1))
+
+    def unpack_attention_grads(self, l):
+        """fresh reference-layout gradient tensors (in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias) of layer l"""
+        o, d, g = self.ops, self.d, self.G[l]
+        hm = (d.dh, d.dhp)
+        ipw, ipb = o.zeros((3 * d.D, d.D), torch.float32), o.zeros((3 * d.D,), torch.float32)
+        ow, ob = o.zeros((d.D, d.D), torch.float32), o.zeros((d.D,), torch.float32)
+        for j in range(3):
+            o.unpack_matrix(g["Wqkv"][j * d.HP:(j + 1) * d.HP], ipw[j * d.D:(j + 1) * d.D], row_map=hm)
+            o.unpack_matrix(g["bqkv"][j * d.HP:(j + 1) * d.HP].view(1, -1), ipb[j * d.D:(j + 1) * d.D].view(1, -1), col_map=hm)
+        o.unpack_matrix(g["Wo"], ow, col_map=hm)
+        o.unpack_matrix(g["bo"].view(1, -1), ob.view(1, -1))
+        return ipw, ipb, ow, ob
 
     def zero_grads(self):
         for g in self.G:
@@ -187,8 +202,9 @@ class EncoderEngine:
             for j in range(self.n_ln):
                 o.unpack_matrix(g["ln_g"][j].view(1, -1), grads[p + "layer_norms.%d.weight" % j].view(1, -1), accumulate=accumulate)
                 o.unpack_matrix(g["ln_b"][j].view(1, -1), grads[p + "layer_norms.%d.bias" % j].view(1, -1), accumulate=accumulate)
-        o.unpack_matrix(self.Gf["g"].view(1, -1), grads[pfx + "layer_norm.weight"].view(1, -1), accumulate=accumulate)
-        o.unpack_matrix(self.Gf["b"].view(1, -1), grads[pfx + "layer_norm.bias"].view(1, -1), accumulate=accumulate)
+        if self.with_final_ln:
+            o.unpack_matrix(self.Gf["g"].view(1, -1), grads[pfx + "layer_norm.weight"].view(1, -1), accumulate=accumulate)
+            o.unpack_matrix(self.Gf["b"].view(1, -1), grads[pfx + "layer_norm.bias"].view(1, -1), accumulate=accumulate)
 
     # ---------------------------------------------------------------- helpers
     def _site(self, layer, idx):
@@ -201,10 +217,12 @@ class EncoderEngine:
 
     def _mask_off(self, T, S):
         # models/transformer.py:209-216: masked iff j - i >= 1 + |S - T|  <=>  visible iff j <= i + |S - T|
+        if self._mask_override is not None:
+            return self._mask_override
         return abs(S - T) if self.attn_mask else -1
 
     # ---------------------------------------------------------------- attention block (in-proj, attention, out-proj + residual)
-    def _attn_fwd(self, l, blk, q_in, k_in, v_in, B, T, S, x_res, x_out):
+    def _attn_fwd(self, l, blk, q_in, k_in, v_in, B, T, S, x_res, x_out, res_drop=True):
         o, d, A, w = self.ops, self.d, self.arena, self.W[l]
         M, Ms = B * T, B * S
         key = "L%d.%s." % (l, blk)
@@ -220,10 +238,11 @@ class EncoderEngine:
         o.gemm(v_in, Wv, v, Ms, d.HP, d.Dp, bias=bv)
         o.xattn_fwd(q, k, v, a, lse, B, T, S, d.H, d.dh, d.dhp, mask_off=self._mask_off(T, S), drop=self._drop(self.p_attn, l, 10 + (blk == "x")))
         # x_out = x_res + dropout(a Wo^T + bo)                                   (transformer.py:174-175)
-        o.gemm(a, w["Wo"], x_out, M, d.Dp, d.HP, bias=w["bo"], drop=self._drop(self.p_res, l, 20 + (blk == "x")), residual=x_res)
+        o.gemm(a, w["Wo"], x_out, M, d.Dp, d.HP, bias=w["bo"], drop=self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")),
+               residual=x_res)
         return dict(q=q, k=k, v=v, a=a, lse=lse, q_in=q_in, k_in=k_in, v_in=v_in, S=S)
 
-    def _attn_bwd(self, l, blk, sv, B, T, gx):
+    def _attn_bwd(self, l, blk, sv, B, T, gx, res_drop=True):
         """gx: fp32 [M, Dp] gradient wrt the block output x_out (= also flows to x_res unchanged).
         Returns (dq_in, dk_in, dv_in) in storage type (gradients wrt the projection inputs)."""
         o, d, w, g, Sh = self.ops, self.d, self.W[l], self.G[l], self.shared
@@ -233,7 +252,7 @@ class EncoderEngine:
         gWq, gWk, gWv = g["Wqkv"][:d.HP], g["Wqkv"][d.HP:2 * d.HP], g["Wqkv"][2 * d.HP:]
         gbq, gbk, gbv = g["bqkv"][:d.HP], g["bqkv"][d.HP:2 * d.HP], g["bqkv"][2 * d.HP:]
         go = Sh.get("go", (M, d.Dp), self.T_)
-        o.cast_drop(gx, go, self._drop(self.p_res, l, 20 + (blk == "x")))                       # grad wrt out_proj output
+        o.cast_drop(gx, go, self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")))   # grad wrt out_proj output
         o.colsum(go, d.Dp, g["bo"])
         o.gemm(go, sv["a"], g["Wo"], d.Dp, d.HP, M, ta=1, tb=1, accumulate=True)               # dWo = go^T a
         da = Sh.get("da", (M, d.HP), self.T_)
@@ -318,10 +337,17 @@ class EncoderEngine:
         scale = math.sqrt(d.D)
         # x = dropout(sqrt(D) x_in + PE)                                         (transformer.py:66-69)
         xs = [A.get("x%d" % i, (M, d.Dp), torch.float32) for i in range(2 * self.L + 1 + (self.L if self.biproj and self.cross else 0))]
-        o.embed_fwd(src_q, self.pe, B, T, d.D, scale, xs[0], self._drop(self.p_embed, -1, 1))
         xk = xv = None
         self.kv_shared = False
-        if self.cross:
+        if not self.with_embed:                                                  # bare layers: inputs are used as they are
+            o.axpy_f32(src_q, xs[0], False)
+            if self.cross:
+                xk = src_k
+                self.kv_shared = src_v is None or src_v is src_k
+                xv = xk if self.kv_shared else src_v
+        else:
+            o.embed_fwd(src_q, self.pe, B, T, d.D, scale, xs[0], self._drop(self.p_embed, -1, 1))
+        if self.cross and self.with_embed:
             xk = A.get("xk", (Ms, d.Dp), self.T_)
             o.embed_fwd(src_k, self.pe, B, S, d.D, scale, xk, self._drop(self.p_embed, -1, 2))
             # x_k and x_v are the same tensor unless embed dropout draws two masks (transformer.py:78-79)
@@ -371,6 +397,9 @@ class EncoderEngine:
             x = x2
             self.saved.append(sv)
         out = A.get("out", (M, d.Dp), self.T_)
+        if not self.with_final_ln:
+            o.cast_drop(x, out, None)
+            return out
         mean = A.get("f.mean", (M,), torch.float32)
         rstd = A.get("f.rstd", (M,), torch.float32)
         o.layernorm_fwd(x, self.Wf["g"], self.Wf["b"], d.D, out, mean, rstd)    # :90-91
@@ -386,7 +415,10 @@ class EncoderEngine:
         M = B * T
         Ms = B * S if self.cross else 0
         gx = Sh.get("gx", (M, d.Dp), torch.float32)
-        o.layernorm_bwd(dout, self.final["x"], self.final["mean"], self.final["rstd"], self.Wf["g"], d.D, gx, False, self.Gf["g"], self.Gf["b"])
+        if self.with_final_ln:
+            o.layernorm_bwd(dout, self.final["x"], self.final["mean"], self.final["rstd"], self.Wf["g"], d.D, gx, False, self.Gf["g"], self.Gf["b"])
+        else:
+            o.axpy_f32(dout, gx, False)
         gxk = gxv = None
         if self.cross:
             gxk = Sh.get("gxk", (Ms, d.Dp), torch.float32)
@@ -416,6 +448,15 @@ class EncoderEngine:
                 self._ln_bwd(l, sv["ln_k"], dk_in, gxk)
                 self._ln_bwd(l, sv["ln_v"], dv_in, gxv)
         scale = math.sqrt(d.D)
+        if not self.with_embed:
+            if d_src_q is not None:
+                o.axpy_f32(gx, d_src_q, True)
+            if self.cross:
+                if d_src_k is not None:
+                    o.axpy_f32(gxk, d_src_k, True)
+                if not self.kv_shared:
+                    o.axpy_f32(gxv, d_src_v if d_src_v is not None else d_src_k, True)
+            return
         if d_src_q is not None:
             o.embed_bwd(gx, d.D, scale, d_src_q, True, self._drop(self.p_embed, -1, 1))
         if self.cross:
@@ -553,6 +594,21 @@ class HeadEngine:
         """expects self.cat (fp32 [B, n_in*Dp]) filled by pool_fwd / direct inputs.  Returns logits [B, Cp] (first C valid)."""
         o, A, Dp, n, W = self.ops, self.arena, self.Dp, self.n_in, self.W
         self.B, self.training, self.seed, self.seed_ptr = B, training, seed, seed_ptr
+        fused, z = self.gate_forward(B)
+        h1 = A.get("h1", (B, Dp), torch.float32)
+        y = A.get("y", (B, Dp), torch.float32)
+        logits = A.get("logits", (B, self.Cp), torch.float32)
+        drop = Drop(self.p_out, seed, seed_ptr, (self.uid << 20) | 1) if (training and self.p_out > 0) else None
+        o.gemm(fused, W["p1"], h1, B, Dp, Dp, bias=W["p1b"], act=1, drop=drop)
+        o.gemm(h1, W["p2"], y, B, Dp, Dp, bias=W["p2b"], residual=fused)
+        o.gemm(y, W["out"], logits, B, self.Cp, Dp, bias=W["outb"])
+        self.sv.update(fused=fused, h1=h1, y=y, z=z)
+        return logits, z
+
+    def gate_forward(self, B):
+        """TextShiftingN on self.cat_buf(B): returns (fused [B, Dp], z [B, n*Dp])"""
+        o, A, Dp, n, W = self.ops, self.arena, self.Dp, self.n_in, self.W
+        self.B = B
         cat = self.cat_buf(B)
         hpre = A.get("hpre", (n, B, Dp), torch.float32)
         zpre = A.get("zpre", (n, B, Dp), torch.float32)
@@ -562,15 +618,8 @@ class HeadEngine:
         fused = A.get("fused", (B, Dp), torch.float32)
         z = A.get("z", (B, n * Dp), torch.float32)
         o.tsgate_fwd(hpre, zpre, n, B, Dp, fused, z)
-        h1 = A.get("h1", (B, Dp), torch.float32)
-        y = A.get("y", (B, Dp), torch.float32)
-        logits = A.get("logits", (B, self.Cp), torch.float32)
-        drop = Drop(self.p_out, seed, seed_ptr, (self.uid << 20) | 1) if (training and self.p_out > 0) else None
-        o.gemm(fused, W["p1"], h1, B, Dp, Dp, bias=W["p1b"], act=1, drop=drop)
-        o.gemm(h1, W["p2"], y, B, Dp, Dp, bias=W["p2b"], residual=fused)
-        o.gemm(y, W["out"], logits, B, self.Cp, Dp, bias=W["outb"])
-        self.sv = dict(cat=cat, hpre=hpre, zpre=zpre, fused=fused, h1=h1, y=y, z=z)
-        return logits, z
+        self.sv = dict(cat=cat, hpre=hpre, zpre=zpre, fused=fused, z=z)
+        return fused, z
 
     def cat_buf(self, B):
         return self.arena.get("cat", (B, self.n_in * self.Dp), torch.float32)
@@ -598,6 +647,10 @@ class HeadEngine:
         o.gemm(dh1, sv["fused"], G["p1"], Dp, Dp, B, ta=1, tb=1, accumulate=True)
         dfused = A.get("dfused", (B, Dp), torch.float32)
         o.gemm(dh1, W["p1"], dfused, B, Dp, Dp, tb=1, residual=dy)            # + residual branch (last_hs_proj += last_hs)
+        return self.gate_backward(dfused)
+
+    def gate_backward(self, dfused):
+        o, A, Dp, n, W, G, sv, B = self.ops, self.arena, self.Dp, self.n_in, self.W, self.G, self.sv, self.B
         dhpre = A.get("dhpre", (n, B, Dp), torch.float32)
         dzpre = A.get("dzpre", (n, B, Dp), torch.float32)
         o.tsgate_bwd(sv["hpre"], sv["zpre"], dfused, n, B, Dp, dhpre, dzpre)

@@ -216,6 +216,15 @@ def main():
     torch.save(run_mmtrvat(ref, synth.tiny_cfg(), 2, 10, 30, 25, 77, True), os.path.join(OUT, "mmtrvat_tiny.pt"))
     cfg = synth.tiny_cfg(orig_d_l=96, orig_d_v=35, orig_d_a=74, hidden_sz=96, num_heads=4, layers=1)
     torch.save(run_mmtrvat(ref, cfg, 2, 50, 60, 40, 78, False), os.path.join(OUT, "mmtrvat_d96.pt"))
+    # state_dict contract: key names + shapes of the reference model, and its init under the default seed
+    import json
+    from oracle.ref_shim import mmtrvat_args
+    torch.manual_seed(1234)
+    m = ref.mmtr.MultiprojectionMMTransformer3DGMUClf(synth.tiny_cfg())
+    sdm = m.state_dict()
+    keys = {k: list(v.shape) for k, v in sdm.items()}
+    fp = {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in sdm.items() if not k.endswith("_float_tensor")}
+    json.dump(dict(keys=keys, init_fingerprint_seed1234=fp), open(os.path.join(OUT, "mmtrvat_state_dict.json"), "w"), indent=0)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 
