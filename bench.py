@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/s of BPMulT `mmtrvat` on CMU-MOSEI-shaped synthetic data (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host cores (CPU)
+
+A "step" = forward + BCEWithLogits + backward + gradient all-reduce (N > 1) + Adam on one batch of 64 samples per GPU
+(cfg 2: text 50x768, audio 500x74, vision 500x35, all zero-padded to 512 steps by the model; D=300, H=12, L=8; README
+dropouts).  `value` times K steps with the batch already resident in HBM; `e2e` times K steps through the public
+`Trainer.step()` with HOST tensors (pinned staging + H2D every step, D2H of the loss every step).  Timing: CUDA events,
+barrier + synchronize on both sides, max over ranks.  Prints ONE JSON line on rank 0."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from argparse import Namespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def cfg2_args(layers=8, hidden=300, heads=12):
+    return Namespace(model="mmtrvat", orig_d_l=768, orig_d_v=35, orig_d_a=74, orig_d_p=4096, hidden_sz=hidden, num_heads=heads, layers=layers,
+                     vonly=True, lonly=True, aonly=True, attn_mask=True, hybrid=False, n_classes=6,
+                     attn_dropout=0.1, attn_dropout_v=0.0, attn_dropout_a=0.0, relu_dropout=0.1, res_dropout=0.1,
+                     out_dropout=0.0, embed_dropout=0.25, bert_model="none")          # README.md:43 + train.py:86-92 defaults
+
+
+def synth_batch(args, B, seed, T_l=50, T_a=500, T_v=500):
+    g = torch.Generator().manual_seed(seed)
+    txt = torch.randn(B, T_l, args.orig_d_l, generator=g)
+    img = torch.randn(B, T_v, args.orig_d_v, generator=g)
+    audio = torch.randn(B, T_a, args.orig_d_a, generator=g)
+    tgt = (torch.rand(B, args.n_classes, generator=g) < 0.3).float()
+    return txt, img, audio, tgt
+
+
+def flops_per_sample_train(D=300, L=8, T=512, S=512):
+    """SURVEY 8d algorithmic FLOPs (unpadded dims, dense attention): fwd = 12 encoders * L * (D^2 (20T + 4S) + 4 T S D) + seq-GMU; x3"""
+    layer = D * D * (20 * T + 4 * S) + 4 * T * S * D
+    gmu = 6 * 2 * T * D * (4 * D)
+    return 3 * (12 * L * layer + gmu)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        clk = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": clk[len(clk) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(clk)}
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_step_fn(args, B, threads):
+    """fwd + BCE + bwd of the reference algorithm on the host: the shimmed reference itself when /root/reference (or
+    baseline/_ref) exists, else the oracle port (oracle/functional.py).  Returns (callable, kind)."""
+    from oracle import functional as Fn
+    from oracle import synth
+    from oracle.ref_shim import load_reference
+    torch.set_num_threads(threads)
+    a = Namespace(**vars(args))
+    txt, img, audio, tgt = synth_batch(a, B, 2024)
+    ref = load_reference()
+    if ref is not None:
+        torch.manual_seed(1234)
+        model = ref.mmtr.MultiprojectionMMTransformer3DGMUClf(a)
+        model.train()
+        crit = torch.nn.BCEWithLogitsLoss()
+
+        def step():
+            model.zero_grad()
+            loss = crit(model(txt, None, None, img, audio), tgt)
+            loss.backward()
+            return float(loss)
+        return step, "reference"
+    for k in ("attn_dropout", "attn_dropout_v", "attn_dropout_a", "relu_dropout", "res_dropout", "out_dropout", "embed_dropout"):
+        setattr(a, k, 0.0)                                   # the port is the dropout-free restatement (cheaper than the reference)
+    sd = {k: v.requires_grad_() for k, v in synth.make_state_dict(synth.mmtrvat_shapes(a), 1234).items()}
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        logits, _ = Fn.mmtrvat_forward(sd, a, txt, img, audio)
+        loss = Fn.bce_with_logits(logits, tgt)
+        loss.backward()
+        return float(loss)
+    return step, "port"
+
+
+def run_reference(opt):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    args = cfg2_args()
+    threads = os.cpu_count() or 1
+    B = 1
+    step, kind = cpu_step_fn(args, B, threads)
+    for _ in range(opt.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(opt.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = B * opt.steps / dt
+    sample = "B=%d per step of the cfg-2 workload (fwd+BCE+bwd, fp32, %s)" % (B, "unmodified reference modules, shimmed" if kind == "reference" else "oracle port, dropout-free")
+    print(json.dumps({"impl": "reference", "metric": "train samples/s", "value": v, "unit": "samples/s", "n_gpus": opt.gpus, "steps": opt.steps,
+                      "warmup": opt.warmup, "ms_per_step": 1e3 * dt / opt.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": workload_config(args, B, 1),
+                      "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
+                      "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, B, world):
+    return {"workload": "BPMulT mmtrvat train step, synthetic CMU-MOSEI-unaligned shape (BASELINE configs[1])", "batch_per_gpu": B,
+            "global_batch": B * world, "text": "50x768", "audio": "500x74", "vision": "500x35", "padded_len": 512, "hidden": args.hidden_sz,
+            "heads": args.num_heads, "layers": args.layers, "classes": args.n_classes, "parallelism": "dp%d" % world,
+            "dropout": "README (embed .25, attn .1/0/0, relu .1, res .1)", "optimizer": "Adam lr 1e-3",
+            "l2": "working set per step >> 126 MB L2 (tens of GB of activations): no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ isolated-kernel rooflines
+def time_kernel(fn, n_rot, iters=20, warm=3):
+    """CUDA-event timing on the launching stream; `fn(i)` launches the kernel on buffer set i % n_rot (rotating sets keep every
+    iteration's operands out of L2)."""
+    for i in range(warm):
+        fn(i % n_rot)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % n_rot)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / iters
+
+
+def kernel_rooflines(ops, args, B, peaks):
+    from bpmult_b200.engine import Dims
+    from bpmult_b200.ops import Drop
+    d = Dims(args.hidden_sz, args.num_heads)
+    T = 512
+    M = B * T
+    bf, f32 = torch.bfloat16, torch.float32
+    dev = ops.device
+    R = 4
+    out = {}
+    # fc1 GEMM (largest GEMM of the layer): [M, Dp] x [FP, Dp]^T, relu + dropout epilogue
+    A = [torch.randn(M, d.Dp, device=dev).to(bf) for _ in range(R)]
+    W = torch.randn(d.FP, d.Dp, device=dev).to(bf)
+    bias = torch.zeros(d.FP, device=dev)
+    Cs = [torch.empty(M, d.FP, device=dev, dtype=bf) for _ in range(R)]
+    t = time_kernel(lambda i: ops.gemm(A[i], W, Cs[i], M, d.FP, d.Dp, bias=bias, act=1, drop=Drop(0.1, 1, None, 3)), R)
+    fl = 2.0 * M * args.hidden_sz * 4 * args.hidden_sz
+    out["gemm_fc1"] = {"bound": "tensor", "achieved": fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / peaks["bf16_tflops"],
+                       "us": t * 1e6, "traffic": None, "note": "algorithmic 2*M*D*4D, M=%d D=%d (executed on padded 320x1216)" % (M, args.hidden_sz)}
+    del A, Cs
+    # attention forward + backward
+    q = [torch.randn(M, d.HP, device=dev).to(bf) * 0.3 for _ in range(R)]
+    k = [torch.randn(M, d.HP, device=dev).to(bf) * 0.3 for _ in range(R)]
+    v = [torch.randn(M, d.HP, device=dev).to(bf) for _ in range(R)]
+    o = torch.empty(M, d.HP, device=dev, dtype=bf)
+    lse = torch.empty(B * d.H * T, device=dev)
+    t = time_kernel(lambda i: ops.xattn_fwd(q[i], k[i], v[i], o, lse, B, T, T, d.H, d.dh, d.dhp, mask_off=0), R, iters=5, warm=2)
+    rho = (T + 1) / (2.0 * T)
+    fl = 4.0 * B * d.H * T * T * d.dh * rho
+    out["xattn_fwd"] = {"bound": "tensor", "achieved": fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / peaks["bf16_tflops"],
+                        "us": t * 1e6, "traffic": None, "note": "algorithmic 4*B*H*T*S*dh*rho, rho=(T+1)/2T causal, dh=25 (stored 32)"}
+    do = torch.randn(M, d.HP, device=dev).to(bf)
+    dq, dk, dv = [torch.empty(M, d.HP, device=dev, dtype=bf) for _ in range(3)]
+    delta = torch.empty(B * d.H * T, device=dev)
+    ops.xattn_fwd(q[0], k[0], v[0], o, lse, B, T, T, d.H, d.dh, d.dhp, mask_off=0)
+    t = time_kernel(lambda i: ops.xattn_bwd(q[0], k[0], v[0], o, do, lse, delta, dq, d.scaling, dk, dv, B, T, T, d.H, d.dh, d.dhp, mask_off=0), 1, iters=3, warm=1)
+    out["xattn_bwd"] = {"bound": "tensor", "achieved": 2.5 * fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                        "frac": 2.5 * fl / t / 1e12 / peaks["bf16_tflops"], "us": t * 1e6, "traffic": None, "note": "2.5x forward FLOPs"}
+    del q, k, v
+    # LayerNorm forward (fp32 residual stream in, bf16 out)
+    xs = [torch.randn(M, d.Dp, device=dev) for _ in range(R)]
+    ys = [torch.empty(M, d.Dp, device=dev, dtype=bf) for _ in range(R)]
+    gam, bet = torch.ones(d.Dp, device=dev), torch.zeros(d.Dp, device=dev)
+    mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    t = time_kernel(lambda i: ops.layernorm_fwd(xs[i], gam, bet, d.D, ys[i], mean, rstd), R)
+    by = M * d.D * (4 + 2)
+    out["layernorm_fwd"] = {"bound": "hbm", "achieved": by / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / t / 1e9 / peaks["hbm_gbs"],
+                            "us": t * 1e6, "traffic": None, "note": "algorithmic rows*D*(4+2) B, rows=%d D=%d" % (M, d.D)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(opt):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from bpmult_b200 import MultiprojectionMMTransformer3DGMUClf, Trainer
+    args = cfg2_args(layers=opt.layers)
+    B = opt.batch
+    torch.manual_seed(1234)                                   # reference default seed (train.py:61)
+    model = MultiprojectionMMTransformer3DGMUClf(args, precision=opt.precision).to(dev)
+    model.train()
+    tr = Trainer(model, lr=1e-3, seed=1234)
+    host = synth_batch(args, B, 2024 + rank)
+    devb = [t.to(dev) for t in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
+
+    for _ in range(max(opt.warmup, 3)):                       # >= 3 warm-up steps (2 eager + graph capture + replay)
+        tr.step_device(*devb)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(lambda: tr.step_device(*devb), opt.steps)
+    loss_dev = float(tr.loss_dev[0])
+    # e2e: public API with host tensors, H2D + D2H inside the timed region
+    tr.step(*host)
+    ms_e2e = timed(lambda: tr.step(*host), opt.steps)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * B * opt.steps / (ms * 1e-3)
+    e2e = world * B * opt.steps / (ms_e2e * 1e-3)
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks = {"hbm_gbs": pk["hbm_gbs"], "bf16_tflops": pk["bf16_tflops"], "bf16_tflops_sustained": pk["bf16_tflops_sustained"], "src": "measured"}
+    except Exception:
+        pass
+    line = {"metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": opt.steps, "warmup": max(opt.warmup, 3),
+            "ms_per_step": ms / opt.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if opt.precision == "bf16" else "f32", "data": "synthetic", "config": workload_config(args, B, world),
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": tr.bytes_in(), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / opt.steps},
+            "gpu_launches": int(getattr(tr, "launches_per_step", 0)) * opt.steps, "launches_per_step": int(getattr(tr, "launches_per_step", 0)),
+            "cuda_graph": bool(tr.use_graph), "loss": loss_dev, "params": tr.n_params,
+            "clocks": sampler.summary() if sampler else None}
+    fl = flops_per_sample_train(args.hidden_sz, args.layers) * B
+    line["step_tflops_algorithmic"] = fl / (ms / opt.steps * 1e-3) / 1e12
+    line["step_frac_of_bf16_sustained_peak"] = line["step_tflops_algorithmic"] / peaks["bf16_tflops_sustained"]
+    line["peaks"] = peaks
+    if not opt.no_kernels:
+        ks = kernel_rooflines(tr.ops, args, B, peaks)
+        n_attn = 12 * args.layers
+        share = {"xattn_fwd": n_attn * ks["xattn_fwd"]["us"], "xattn_bwd": n_attn * ks["xattn_bwd"]["us"],
+                 "gemm_fc1": n_attn * ks["gemm_fc1"]["us"], "layernorm_fwd": n_attn * 4 * ks["layernorm_fwd"]["us"]}
+        step_us = ms / opt.steps * 1e3
+        for k_, v_ in share.items():
+            ks[k_]["share_of_step_est"] = v_ / step_us
+        dom = max(("xattn_bwd", "xattn_fwd", "gemm_fc1"), key=lambda k_: share[k_])
+        line["roofline"] = dict(ks[dom], kernel=dom)
+        line["kernels"] = ks
+    if world == 1 and not opt.no_cpu:
+        threads = os.cpu_count() or 1
+        step, kind = cpu_step_fn(cfg2_args(), 1, threads)
+        step()
+        t0 = time.perf_counter()
+        n = 2
+        for _ in range(n):
+            step()
+        dt = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "samples/s", "cores": threads, "kind": kind,
+                                "sample": "1 warm-up + %d timed steps of B=1 of the same cfg-2 workload (fwd+BCE+bwd, fp32)" % n}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step (cfg 2: 64)")
+    ap.add_argument("--layers", type=int, default=8)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-kernels", action="store_true", help="skip the isolated-kernel roofline timings")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    opt = ap.parse_args()
+    if opt.impl == "reference":
+        return run_reference(opt)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if opt.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(opt.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(opt)
+
+
+if __name__ == "__main__":
+    main()

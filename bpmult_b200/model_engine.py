@@ -152,7 +152,7 @@ class MMTrVatEngine:
         return self.head.loss(logits, targets, pos_weight, grad_scale)
 
     # ---------------------------------------------------------------- backward
-    def backward(self, dlogits, d_inputs=None):
+    def backward(self, dlogits, d_inputs=None, on_done=None):
         """dlogits fp32 [B, Cp].  Parameter gradients accumulate in the padded buffers (see unpack_grads).
         d_inputs: optional dict m -> fp32 tensor shaped like the input features, overwritten with input gradients."""
         o, d, A, nv, B = self.ops, self.d, self.arena, self.n_vec, self.B
@@ -177,9 +177,15 @@ class MMTrVatEngine:
             o.axpy_f32(da1, dh[u], True)
             o.axpy_f32(da2, dh[w], True)
             self.enc[qn].backward(da2, dP[m], dh[w])
+            if on_done:
+                on_done(qn)
             self.enc[pn].backward(da1, dP[m], dh[u])
+            if on_done:
+                on_done(pn)
         for n, (qm, km) in reversed(list(WAVE1.items())):
             self.enc[n].backward(dh[n], dP[qm], dP[km])
+            if on_done:
+                on_done(n)
         for m in "lav":
             if self.Wproj[m] is not None:
                 g = self.shared.get("dPc", (M, d.Dp), self.T_)
@@ -191,6 +197,14 @@ class MMTrVatEngine:
                     self._unstage(m, dX, d_inputs[m])
             elif d_inputs is not None and m in d_inputs:
                 self._unstage(m, dP[m], d_inputs[m])
+
+    def backward_order(self):
+        """encoder names in the order their gradients complete during backward (bucket launch order)"""
+        order = []
+        for m in reversed(HEAD_ORDER):
+            u, w, pn, qn = TARGETS[m]
+            order += [qn, pn]
+        return order + list(reversed(list(WAVE1.keys())))
 
     def _unstage(self, m, g, dst):
         drop = Drop(self.args.embed_dropout, self.seed, self.seed_ptr, 7) if (m == "l" and self.training and self.args.embed_dropout > 0) else None

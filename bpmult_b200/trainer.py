@@ -1,0 +1,181 @@
+"""Graph-captured, data-parallel training step for the drop-in model (train.py:341-448 semantics: forward, BCEWithLogits,
+backward, Adam; gradient accumulation = 1).
+
+  * one process per GPU; gradients live in ONE flat fp32 buffer laid out in the order the encoders finish their backward
+    (wave-2 first), so each encoder's bucket is all-reduced (NCCL, side stream) as soon as its last wgrad has landed, while the
+    remaining backward keeps the SMs busy; parameters that never receive a gradient (transfm_*, an unused proj_*) are left out.
+  * parameters are re-pointed into one flat fp32 buffer as well => a single fused Adam launch (bpm_adam_step).
+  * the whole step (H2D of the batch from pinned memory, weight staging, forward, loss, backward, all-reduces, Adam, D2H of
+    the loss) is captured once into a CUDA graph and replayed: shapes are static by construction (everything is padded to 512
+    time steps) and the dropout seed lives in device memory."""
+import os
+
+import torch
+import torch.distributed as dist
+
+from .modules import MultiprojectionMMTransformer3DGMUClf
+
+
+class Trainer:
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, pos_weight=None, seed=1234, use_graph=None):
+        assert isinstance(model, MultiprojectionMMTransformer3DGMUClf)
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.eng = model.engine(self.device)
+        self.ops = self.eng.ops
+        if use_graph is None:
+            use_graph = os.environ.get("BPM_NO_GRAPH", "0") != "1"
+        self.use_graph = use_graph
+        self.pos_weight = None if pos_weight is None else pos_weight.to(self.device, torch.float32)
+        self._flatten()
+        dev = self.device
+        self.seed_t = torch.tensor([seed + 7919 * self.rank], dtype=torch.int64, device=dev)     # per-rank Philox seed
+        self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.comm = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.graph, self.static, self.shapes = None, None, None
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.steps_done = 0
+
+    # ---------------------------------------------------------------- flat parameter / gradient buffers
+    def _flatten(self):
+        eng, model = self.eng, self.model
+        pmap = dict(model.trunk_named_parameters())
+        used = [n for n in eng.param_shapes() if n not in set(eng.unused_params())]
+        order = []
+        self.buckets = []                                   # (name, start, end) in flat-buffer elements
+        off = 0
+        for enc in eng.backward_order():
+            names = [n for n in used if n.startswith("trans_%s." % enc)]
+            n_el = sum(pmap[n].numel() for n in names)
+            self.buckets.append((enc, off, off + n_el))
+            order += names
+            off += n_el
+        misc = [n for n in used if not n.startswith("trans_")]
+        self.buckets.append(("misc", off, off + sum(pmap[n].numel() for n in misc)))
+        order += misc
+        total = sum(pmap[n].numel() for n in order)
+        dev = self.device
+        self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params, self.grads = {}, {}
+        off = 0
+        for n in order:
+            p = pmap[n]
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            p.grad = self.flat_g[off:off + k].view_as(p)
+            self.params[n], self.grads[n] = p.data, p.grad
+            off += k
+        for n in eng.unused_params():                       # packed too (never read by a kernel), keeps pack() uniform
+            if n in pmap:
+                self.params[n] = pmap[n].data
+        self.n_params = total
+
+    # ---------------------------------------------------------------- one step (enqueue only)
+    def _enqueue(self, txt, img, audio, tgt):
+        eng, o = self.eng, self.ops
+        self.step_t += 1
+        self.seed_t += 1
+        eng.pack(self.params)
+        logits, _ = eng.forward(txt, img, audio, training=True, seed=0, seed_ptr=self.seed_t)
+        loss, dlogits = eng.loss(logits, tgt, self.pos_weight, 1.0)
+        eng.zero_grads()
+        cur = torch.cuda.current_stream(self.device)
+        bucket_of = {b[0]: b for b in self.buckets}
+
+        def reduce_bucket(name):
+            if self.world == 1:
+                return
+            _, s, e = bucket_of[name]
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                dist.all_reduce(self.flat_g[s:e])
+
+        def on_done(enc):
+            eng.enc[enc].unpack_grads(self.grads, "trans_%s." % enc)
+            reduce_bucket(enc)
+        eng.backward(dlogits, None, on_done)
+        for m, g in eng.gmu.items():
+            g.unpack_grads(self.grads, "gmu_%s." % m)
+        eng.head.unpack_grads(self.grads)
+        for m in "lav":
+            if eng.Gproj[m] is not None:
+                gw = self.grads["proj_%s.weight" % m]
+                o.unpack_matrix(eng.Gproj[m], gw.view(gw.shape[0], gw.shape[1]))
+        reduce_bucket("misc")
+        if self.world > 1:
+            cur.wait_stream(self.comm)
+        o.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world, self.step_t)
+        return loss
+
+    # ---------------------------------------------------------------- public API
+    def _ensure_static(self, txt, img, audio, tgt):
+        shapes = tuple(tuple(t.shape) for t in (txt, img, audio, tgt))
+        if self.shapes != shapes:
+            dev = self.device
+            self.static = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
+            self.pinned = [torch.zeros(s, dtype=torch.float32).pin_memory() for s in shapes]
+            self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.shapes, self.graph = shapes, None
+            self.warm = 0
+
+    def step_device(self, txt, img, audio, tgt):
+        """inputs already resident on the device (fp32).  Returns the device loss tensor (no sync)."""
+        self._ensure_static(txt, img, audio, tgt)
+        for s, t in zip(self.static, (txt, img, audio, tgt)):
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t, non_blocking=True)
+        self._run()
+        return self.loss_dev
+
+    def step(self, txt, img, audio, tgt):
+        """end-to-end step from HOST tensors: pinned staging -> H2D -> step -> D2H of the loss.  Returns a python float."""
+        self._ensure_static(txt, img, audio, tgt)
+        for pbuf, s, t in zip(self.pinned, self.static, (txt, img, audio, tgt)):
+            pbuf.copy_(t)
+            s.copy_(pbuf, non_blocking=True)
+        self._run()
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self.loss_host[0])
+
+    def _run(self):
+        if not self.use_graph:
+            self.loss_dev.copy_(self._enqueue(*self.static))
+            self.steps_done += 1
+            return
+        if self.graph is None:
+            if self.warm < 2:                               # eager warm-up steps (allocate every arena buffer, NCCL init)
+                self.loss_dev.copy_(self._enqueue(*self.static))
+                self.warm += 1
+                self.steps_done += 1
+                return
+            torch.cuda.synchronize(self.device)
+            self.ops.launches = 0
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self.loss_dev.copy_(self._enqueue(*self.static))
+                self.graph = g
+                self.launches_per_step = self.ops.launches
+            except Exception as e:                         # e.g. a collective that cannot be captured on this stack
+                if self.rank == 0:
+                    print("bpmult_b200.Trainer: CUDA-graph capture failed (%s); running eagerly" % str(e).splitlines()[0])
+                self.use_graph = False
+                torch.cuda.synchronize(self.device)
+                self.loss_dev.copy_(self._enqueue(*self.static))
+                self.steps_done += 1
+                return
+        self.graph.replay()
+        self.steps_done += 1
+
+    def bytes_in(self):
+        return sum(t.numel() * 4 for t in self.static)
