@@ -268,10 +268,314 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   return BPM_OK;
 }
 
+
+// =====================================================================================================================
+// Backward.  One CTA per (batch, head) for T <= 512: the dQ accumulators of all (<= 4) query tiles stay resident in TMEM for
+// the whole kernel and dK / dV of the current 128-key tile are accumulated in TMEM over the inner query-tile loop, so NO
+// atomics and no second pass are needed.  The score tile is computed TRANSPOSED (rows = keys, columns = queries):
+//     S^T  = K_j Q_i^T          dP^T = V_j dO_i^T                               (M128 N128 K32, both operands K-major)
+//     P^T  = exp2(S^T log2e - lse_q),   P~^T = P^T * dropmask,   dS^T = P^T * (dP^T * dropmask - delta_q)   [8 compute warps]
+//     dV_j += P~^T dO_i         dK_j += dS^T Q_i      (A = the bf16 tile just written to smem, K-major; B = dO_i / Q_i MN-major)
+//     dQ_i += dS K_j            (A = the SAME dS^T smem tile read as an MN-major operand; B = K_j MN-major)
+// No row reductions are needed in the backward (lse and delta are per query = per column), so the 128x128 tile is split
+// between two warps per TMEM lane quarter (64 columns each).  TMEM: S^T 128 + dP^T 128 + dK 32 + dV 32 + dQ 4x32 = 448 cols.
+// =====================================================================================================================
+#define AB_THREADS 320
+#define AB_MAXQT 4
+
+struct AttnBwdSmem {
+  static constexpr int KV = 0;                                  // 2 stages x (K 8 KB + V 8 KB)
+  static constexpr int QD = KV + 2 * 2 * 128 * 64;              // 2 stages x (Q 8 KB + dO 8 KB)
+  static constexpr int PT = QD + 2 * 2 * 128 * 64;              // 2 chunk tiles x 16 KB
+  static constexpr int DST = PT + 2 * 128 * 128;
+  static constexpr int LSE = DST + 2 * 128 * 128;               // 512 floats (pre-multiplied by log2e; +inf beyond T)
+  static constexpr int DEL = LSE + 512 * 4;
+  static constexpr int BAR = DEL + 512 * 4;
+  static constexpr int NBAR = 15;
+  static constexpr int TOTAL = BAR + 8 * NBAR + 16;
+};
+
+__global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta, int B, int T, int H) {
+  // delta[b, h, t] = sum_d dO * O   (one thread per (row, head): 2 x 64 B)
+  int64_t n = (int64_t)B * T * H;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    int h = (int)(idx % H);
+    int64_t row = idx / H;
+    int t = (int)(row % T), b = (int)(row / T);
+    const bf16* o = out + row * (H * AT_DH) + h * AT_DH;
+    const bf16* g = dout + row * (H * AT_DH) + h * AT_DH;
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < AT_DH / 8; u++) {
+      Vec8<bf16> a, c; a.load(o + u * 8); c.load(g + u * 8);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc = fmaf(a.v[j], c.v[j], acc);
+    }
+    delta[((int64_t)b * H + h) * T + t] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmdO, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
+                   bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + AttnBwdSmem::BAR;
+  auto kv_full = [&](int s) { return bar0 + 8u * s; };
+  auto kv_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto q_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto q_empty = [&](int s) { return bar0 + 8u * (6 + s); };
+  const uint32_t st_full = bar0 + 8u * 8, st_free = bar0 + 8u * 9, pt_full = bar0 + 8u * 10, pair_done = bar0 + 8u * 11;
+  const uint32_t dkv_full = bar0 + 8u * 12, dkv_free = bar0 + 8u * 13, dq_full = bar0 + 8u * 14;
+  const uint32_t tmem_ptr_addr = bar0 + 8u * AttnBwdSmem::NBAR;
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + AttnBwdSmem::BAR + 8 * AttnBwdSmem::NBAR);
+  float* lse_s = (float*)(base_gen + AttnBwdSmem::LSE);
+  float* del_s = (float*)(base_gen + AttnBwdSmem::DEL);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int nq = (T + 127) / 128, nkv = (S + 127) / 128;
+  // first query tile that can see key tile j (visible iff key <= q + off)
+  auto i_min_of = [&](int j) { int qlo = j * 128 - mask_off; return (mask_off < 0 || qlo <= 0) ? 0 : qlo / 128; };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    for (int s = 0; s < 2; s++) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
+    mbar_init(st_full, 1); mbar_init(st_free, 8); mbar_init(pt_full, 8); mbar_init(pair_done, 1);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, 8); mbar_init(dq_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, 512);
+  for (int t = threadIdx.x; t < 512; t += AB_THREADS) {
+    lse_s[t] = t < T ? lse[(int64_t)bh * T + t] * LOG2E_F : INFINITY;      // exp2(x - inf) = 0 for the padded query columns
+    del_s[t] = t < T ? delta[(int64_t)bh * T + t] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_gen;
+  const uint32_t tST = tmem, tDPT = tmem + 128, tDK = tmem + 256, tDV = tmem + 288, tDQ = tmem + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int pc = 0, jc = 0;
+      for (int j = 0; j < nkv; j++) {
+        int imin = i_min_of(j);
+        if (imin >= nq) continue;
+        int ks = jc & 1;
+        mbar_wait(kv_empty(ks), ((uint32_t)(jc >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(kv_full(ks), 2 * 128 * 64);
+        tma_load_3d(base + AttnBwdSmem::KV + ks * 16384, &tmK, kv_full(ks), h * AT_DH, j * 128, b);
+        tma_load_3d(base + AttnBwdSmem::KV + ks * 16384 + 8192, &tmV, kv_full(ks), h * AT_DH, j * 128, b);
+        jc++;
+        for (int i = imin; i < nq; i++, pc++) {
+          int qs = pc & 1;
+          mbar_wait(q_empty(qs), ((uint32_t)(pc >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(q_full(qs), 2 * 128 * 64);
+          tma_load_3d(base + AttnBwdSmem::QD + qs * 16384, &tmQ, q_full(qs), h * AT_DH, i * 128, b);
+          tma_load_3d(base + AttnBwdSmem::QD + qs * 16384 + 8192, &tmdO, q_full(qs), h * AT_DH, i * 128, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_st = umma_idesc_bf16(128, 128, 0, 0);      // S^T, dP^T
+      const uint32_t id_kv = umma_idesc_bf16(128, AT_DH, 0, 1);    // dV, dK : A K-major (smem tile), B MN-major
+      const uint32_t id_dq = umma_idesc_bf16(128, AT_DH, 1, 1);    // dQ     : A = dS^T read MN-major, B = K_j MN-major
+      int pc = 0, jc = 0;
+      for (int j = 0; j < nkv; j++) {
+        int imin = i_min_of(j);
+        if (imin >= nq) continue;
+        int ks = jc & 1;
+        mbar_wait(kv_full(ks), (uint32_t)(jc >> 1) & 1u);
+        const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384, va = ka + 8192;
+        for (int i = imin; i < nq; i++, pc++) {
+          int qs = pc & 1;
+          const uint32_t qa = base + AttnBwdSmem::QD + qs * 16384, ga = qa + 8192;
+          mbar_wait(q_full(qs), (uint32_t)(pc >> 1) & 1u);
+          mbar_wait(st_free, ((uint32_t)pc & 1u) ^ 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            umma_bf16(tST, umma_desc(ka + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(qa + k * 32, 16, 512, BPM_SWZ_64B), id_st, k > 0);
+            umma_bf16(tDPT, umma_desc(va + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(ga + k * 32, 16, 512, BPM_SWZ_64B), id_st, k > 0);
+          }
+          umma_commit(st_full);
+          mbar_wait(pt_full, (uint32_t)pc & 1u);
+          if (i == imin) mbar_wait(dkv_free, ((uint32_t)(jc) & 1u) ^ 1u);      // previous key tile's dK/dV drained from TMEM
+          tc_fence_after();
+          const uint32_t pa = base + AttnBwdSmem::PT, da = base + AttnBwdSmem::DST;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const uint32_t acc = (i > imin || k > 0) ? 1u : 0u;
+            const uint32_t aoff = (k >> 2) * 16384 + (k & 3) * 32;
+            umma_bf16(tDV, umma_desc(pa + aoff, 16, 1024, BPM_SWZ_128B), umma_desc(ga + k * 1024, 512, 512, BPM_SWZ_64B), id_kv, acc);
+            umma_bf16(tDK, umma_desc(da + aoff, 16, 1024, BPM_SWZ_128B), umma_desc(qa + k * 1024, 512, 512, BPM_SWZ_64B), id_kv, acc);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            umma_bf16(tDQ + 32 * i, umma_desc(da + k * 2048, 16384, 1024, BPM_SWZ_128B), umma_desc(ka + k * 1024, 512, 512, BPM_SWZ_64B), id_dq,
+                      (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(pair_done);
+          umma_commit(q_empty(qs));
+        }
+        umma_commit(dkv_full);
+        umma_commit(kv_empty(ks));
+        jc++;
+      }
+      umma_commit(dq_full);
+    }
+  } else {
+    // ===================== compute warps =====================
+    const int cw = warp - 2;
+    const int quarter = warp & 3, half = cw >> 2;
+    const int r = quarter * 32 + lane;                      // key row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    DropCtx dc = make_drop(drop);
+    const int HP = H * AT_DH;
+    int pc = 0, jc = 0;
+    for (int j = 0; j < nkv; j++) {
+      const int key = j * 128 + r;
+      int imin = i_min_of(j);
+      if (imin >= nq) {                                     // no query sees this key tile: dK = dV = 0
+        if (key < S) {
+          bf16* dst = (half == 0 ? dk : dv) + ((int64_t)b * S + key) * HP + h * AT_DH;
+#pragma unroll
+          for (int u = 0; u < AT_DH / 8; u++) *(uint4*)(dst + u * 8) = make_uint4(0, 0, 0, 0);
+        }
+        continue;
+      }
+      for (int i = imin; i < nq; i++, pc++) {
+        const int q0 = i * 128;
+        const bool diag = (mask_off >= 0) && (j * 128 + 127 > q0 + mask_off);
+        const int cmin = key - mask_off - q0;               // columns < cmin are masked for this key row (diag tiles only)
+        mbar_wait(st_full, (uint32_t)pc & 1u);
+        tc_fence_after();
+        uint32_t pw[2][16], dw[2][16];
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          const int c0 = half * 64 + ch * 32;
+          float sv[32], dpv[32];
+          tmem_ld32(tST + lane_off + c0, sv);
+          tmem_ld32(tDPT + lane_off + c0, dpv);
+          tmem_ld_wait();
+          if (ch == 1) {                                    // all of this warp's S^T / dP^T columns are in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(st_free);
+          }
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 l4 = *(const float4*)(lse_s + q0 + c0 + c);
+            const float4 d4 = *(const float4*)(del_s + q0 + c0 + c);
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int col = c0 + c + e;
+              float p = ex2f(fmaf(sv[c + e], LOG2E_F, -ls[e]));
+              if (key >= S || (diag && col < cmin)) p = 0.f;
+              float mult = 1.f;
+              if (dc.on) mult = drop_mult1(dc, ((uint64_t)bh * T + (uint64_t)min(q0 + col, T - 1)) * (uint64_t)S + (uint64_t)min(key, S - 1));
+              sv[c + e] = p * mult;                                     // P~^T
+              dpv[c + e] = p * fmaf(dpv[c + e], mult, -dl[e]);          // dS^T
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 16; c++) { pw[ch][c] = pack_bf16x2(sv[2 * c], sv[2 * c + 1]); dw[ch][c] = pack_bf16x2(dpv[2 * c], dpv[2 * c + 1]); }
+        }
+        // the previous pair's accumulate MMAs must have finished reading the P^T / dS^T tiles
+        mbar_wait(pair_done, ((uint32_t)pc & 1u) ^ 1u);
+        {
+          // this thread owns row r, columns [64*half, 64*half + 64) = chunk tile `half`, all 8 16-byte units
+          uint8_t* prow = base_gen + AttnBwdSmem::PT + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+          uint8_t* drow = base_gen + AttnBwdSmem::DST + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int ch = u >> 2, o4 = (u & 3) * 4;
+            *(uint4*)(prow + ((u ^ (r & 7)) << 4)) = make_uint4(pw[ch][o4], pw[ch][o4 + 1], pw[ch][o4 + 2], pw[ch][o4 + 3]);
+            *(uint4*)(drow + ((u ^ (r & 7)) << 4)) = make_uint4(dw[ch][o4], dw[ch][o4 + 1], dw[ch][o4 + 2], dw[ch][o4 + 3]);
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pt_full);
+      }
+      // ---- dK (half 0) / dV (half 1) of key tile j
+      mbar_wait(dkv_full, (uint32_t)jc & 1u);
+      tc_fence_after();
+      {
+        float acc[AT_DH];
+        tmem_ld32((half == 0 ? tDK : tDV) + lane_off, acc);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_free);
+        if (key < S) {
+          bf16* dst = (half == 0 ? dk : dv) + ((int64_t)b * S + key) * HP + h * AT_DH;
+#pragma unroll
+          for (int u = 0; u < AT_DH / 8; u++)
+            *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8], acc[u * 8 + 1]), pack_bf16x2(acc[u * 8 + 2], acc[u * 8 + 3]),
+                                                pack_bf16x2(acc[u * 8 + 4], acc[u * 8 + 5]), pack_bf16x2(acc[u * 8 + 6], acc[u * 8 + 7]));
+        }
+      }
+      jc++;
+    }
+    // ---- dQ of every query tile (tile i is drained by the warps of half i & 1)
+    mbar_wait(dq_full, 0);
+    tc_fence_after();
+    for (int i = half; i < nq; i += 2) {
+      float acc[AT_DH];
+      tmem_ld32(tDQ + 32 * i + lane_off, acc);
+      tmem_ld_wait();
+      const int qi = i * 128 + r;
+      if (qi < T) {
+        bf16* dst = dq + ((int64_t)b * T + qi) * HP + h * AT_DH;
+#pragma unroll
+        for (int u = 0; u < AT_DH / 8; u++)
+          *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8] * dq_scale, acc[u * 8 + 1] * dq_scale), pack_bf16x2(acc[u * 8 + 2] * dq_scale, acc[u * 8 + 3] * dq_scale),
+                                              pack_bf16x2(acc[u * 8 + 4] * dq_scale, acc[u * 8 + 5] * dq_scale), pack_bf16x2(acc[u * 8 + 6] * dq_scale, acc[u * 8 + 7] * dq_scale));
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 int bpm_xattn_bwd_simt(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                        float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t s);
+
 int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
-                     float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t s) {
-  // the tensor-core backward lands next; until then the fp32-math kernel (bf16 storage) serves this entry point
-  return bpm_xattn_bwd_simt(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, s);
+                     float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t stream) {
+  if (a->T > 128 * AB_MAXQT)      // dQ accumulators of all query tiles must fit in TMEM; longer targets use the fp32-math kernel
+    return bpm_xattn_bwd_simt(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, stream);
+  BPM_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) % 16 == 0,
+              "xattn_bwd: pointers must be 16-byte aligned");
+  const int HP = a->H * a->dhp;
+  {
+    int64_t n = (int64_t)a->B * a->T * a->H;
+    int grid = (int)((n + 255) / 256 < (int64_t)bpm_num_sms() * 8 ? (n + 255) / 256 : (int64_t)bpm_num_sms() * 8);
+    attn_delta_kernel<<<grid, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, a->B, a->T, a->H);
+    BPM_CHECK_LAUNCH("xattn_delta");
+  }
+  CUtensorMap tq, tk, tv, tg;
+  int rc;
+  if ((rc = make_qkv_map(&tq, q, a->B, a->T, HP, 128))) return rc;
+  if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, 128))) return rc;
+  if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, 128))) return rc;
+  if ((rc = make_qkv_map(&tg, dout, a->B, a->T, HP, 128))) return rc;
+  size_t smem = AttnBwdSmem::TOTAL + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { bpm_set_error("xattn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
+    attr_set = true;
+  }
+  attn_bwd_tc_kernel<<<a->B * a->H, AB_THREADS, smem, stream>>>(tq, tk, tv, tg, lse, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S,
+                                                                  a->H, a->mask_off, a->drop);
+  BPM_CHECK_LAUNCH("xattn_bwd_tc");
+  return BPM_OK;
 }
