@@ -145,15 +145,21 @@ def workload_config(args, B, world):
 
 # ------------------------------------------------------------------------------------------------ isolated-kernel rooflines
 def time_kernel(fn, n_rot, iters=20, warm=3):
-    """CUDA-event timing on the launching stream; `fn(i)` launches the kernel on buffer set i % n_rot (rotating sets keep every
-    iteration's operands out of L2)."""
+    """Average launch duration from CUDA events around a captured CUDA graph of `iters` launches (so the Python / ctypes launch
+    cost is not in the number).  `fn(i)` launches the kernel on buffer set i % n_rot: rotating operand sets larger than the
+    126 MB L2 keep every launch cold, like inside the training step."""
     for i in range(warm):
         fn(i % n_rot)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i % n_rot)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i % n_rot)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e-3 / iters
