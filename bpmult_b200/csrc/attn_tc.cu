@@ -45,7 +45,8 @@ struct AttnFwdSmem {
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   bf16* __restrict__ out, float* __restrict__ lse, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop) {
+                   bf16* __restrict__ out, float* __restrict__ lse, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
+                   uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -163,22 +164,40 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int c = 0; c < AT_BN; c++) sv[c] = (k0 + c <= row_lim) ? sv[c] : -INFINITY;
       }
-      float mx = sv[0];
+      // 4-way trees: a 64-long dependent FMNMX / FADD chain would leave the warp latency-bound
+      float mx4[4] = {sv[0], sv[1], sv[2], sv[3]};
 #pragma unroll
-      for (int c = 1; c < AT_BN; c++) mx = fmaxf(mx, sv[c]);
+      for (int c = 4; c < AT_BN; c += 4) {
+        mx4[0] = fmaxf(mx4[0], sv[c]); mx4[1] = fmaxf(mx4[1], sv[c + 1]); mx4[2] = fmaxf(mx4[2], sv[c + 2]); mx4[3] = fmaxf(mx4[3], sv[c + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m, mx * LOG2E_F);
       const float alpha = ex2f(m - m_new);
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < AT_BN; c++) { sv[c] = ex2f(fmaf(sv[c], LOG2E_F, -m_new)); rs += sv[c]; }
-      l = fmaf(l, alpha, rs);
+      for (int c = 0; c < AT_BN; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) { sv[c + e] = ex2f(fmaf(sv[c + e], LOG2E_F, -m_new)); rs4[e] += sv[c + e]; }
+      }
+      l = fmaf(l, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m = m_new;
       if (dc.on) {
-        // Philox words are shared by 4 consecutive element indices e = ebase + key
+        // keep decisions: one Philox call per 8 consecutive keys (element index e = ebase + key)
+        uint32_t kb[2] = {0u, 0u};
+        const uint64_t e0 = ebase + (uint64_t)k0;
+        if ((e0 & 7) == 0) {
 #pragma unroll
-        for (int c = 0; c < AT_BN; c++) {
-          uint64_t e = ebase + (uint64_t)(k0 + c);
-          sv[c] *= drop_mult1(dc, e);
+          for (int u = 0; u < AT_BN / 8; u++) kb[u >> 2] |= drop_keep8(dc, (e0 >> 3) + u) << ((u & 3) * 8);
+        } else {
+#pragma unroll
+          for (int c = 0; c < AT_BN; c++) kb[c >> 5] |= (drop_mult1(dc, e0 + c) != 0.f ? 1u : 0u) << (c & 31);
+        }
+#pragma unroll
+        for (int c = 0; c < AT_BN; c++) sv[c] = ((kb[c >> 5] >> (c & 31)) & 1u) ? sv[c] * dc.inv_keep : 0.f;
+        if (drop_bits != nullptr && qi < T) {
+          uint32_t* wrow = drop_bits + ((int64_t)bh * T + qi) * (int64_t)((S + 31) >> 5) + (k0 >> 5);
+          wrow[0] = kb[0];
+          if (k0 + 32 < S) wrow[1] = kb[1];
         }
       }
       // ---- P_j -> shared memory (bf16, K-major SWIZZLE_128B: 16-byte chunk u of row r lands at chunk u ^ (r & 7))
@@ -263,7 +282,7 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     attr_set = true;
   }
   dim3 grid(bpm_cdiv(a->T, AT_BM), a->B * a->H);
-  attn_fwd_tc_kernel<<<grid, AT_THREADS, smem, stream>>>(tq, tk, tv, (bf16*)out, lse, a->B, a->T, a->S, a->H, a->mask_off, a->drop);
+  attn_fwd_tc_kernel<<<grid, AT_THREADS, smem, stream>>>(tq, tk, tv, (bf16*)out, lse, a->B, a->T, a->S, a->H, a->mask_off, a->drop, a->drop_bits);
   BPM_CHECK_LAUNCH("xattn_fwd_tc");
   return BPM_OK;
 }
@@ -315,10 +334,11 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
   }
 }
 
-__global__ void __launch_bounds__(AB_THREADS, 1)
+__global__ void __maxnreg__(200)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmdO, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
-                   bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop) {
+                   bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
+                   const uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -384,27 +404,44 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t id_st = umma_idesc_bf16(128, 128, 0, 0);      // S^T, dP^T
       const uint32_t id_kv = umma_idesc_bf16(128, AT_DH, 0, 1);    // dV, dK : A K-major (smem tile), B MN-major
       const uint32_t id_dq = umma_idesc_bf16(128, AT_DH, 1, 1);    // dQ     : A = dS^T read MN-major, B = K_j MN-major
-      int pc = 0, jc = 0;
-      for (int j = 0; j < nkv; j++) {
-        int imin = i_min_of(j);
-        if (imin >= nq) continue;
-        int ks = jc & 1;
-        mbar_wait(kv_full(ks), (uint32_t)(jc >> 1) & 1u);
+      // pair iterator over (key tile j, query tile i); jc counts the non-empty key tiles (K/V ring index)
+      auto next_pair = [&](int& j, int& i, int& jc) {
+        i++;
+        if (i >= nq) {
+          do { j++; } while (j < nkv && i_min_of(j) >= nq);
+          if (j < nkv) { i = i_min_of(j); jc++; }
+        }
+      };
+      // S^T / dP^T of pair pc are issued one pair AHEAD of the accumulate MMAs, so the compute warps never wait for them
+      auto issue_st = [&](int j, int i, int pc, int jc) {
+        const int ks = jc & 1, qs = pc & 1;
+        if (i == i_min_of(j)) mbar_wait(kv_full(ks), (uint32_t)(jc >> 1) & 1u);
         const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384, va = ka + 8192;
-        for (int i = imin; i < nq; i++, pc++) {
-          int qs = pc & 1;
-          const uint32_t qa = base + AttnBwdSmem::QD + qs * 16384, ga = qa + 8192;
-          mbar_wait(q_full(qs), (uint32_t)(pc >> 1) & 1u);
-          mbar_wait(st_free, ((uint32_t)pc & 1u) ^ 1u);
-          tc_fence_after();
+        const uint32_t qa = base + AttnBwdSmem::QD + qs * 16384, ga = qa + 8192;
+        mbar_wait(q_full(qs), (uint32_t)(pc >> 1) & 1u);
+        mbar_wait(st_free, ((uint32_t)pc & 1u) ^ 1u);
+        tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            umma_bf16(tST, umma_desc(ka + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(qa + k * 32, 16, 512, BPM_SWZ_64B), id_st, k > 0);
-            umma_bf16(tDPT, umma_desc(va + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(ga + k * 32, 16, 512, BPM_SWZ_64B), id_st, k > 0);
-          }
-          umma_commit(st_full);
+        for (int k = 0; k < 2; k++) {
+          umma_bf16(tST, umma_desc(ka + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(qa + k * 32, 16, 512, BPM_SWZ_64B), id_st, k > 0);
+          umma_bf16(tDPT, umma_desc(va + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(ga + k * 32, 16, 512, BPM_SWZ_64B), id_st, k > 0);
+        }
+        umma_commit(st_full);
+      };
+      int j = 0, jc = 0;
+      while (j < nkv && i_min_of(j) >= nq) j++;
+      if (j < nkv) {
+        int i = i_min_of(j), pc = 0;
+        issue_st(j, i, 0, 0);
+        while (j < nkv) {
+          int nj = j, ni = i, njc = jc;
+          next_pair(nj, ni, njc);
+          if (nj < nkv) issue_st(nj, ni, pc + 1, njc);
+          const int ks = jc & 1, qs = pc & 1, imin = i_min_of(j);
+          const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384;
+          const uint32_t qa = base + AttnBwdSmem::QD + qs * 16384, ga = qa + 8192;
           mbar_wait(pt_full, (uint32_t)pc & 1u);
-          if (i == imin) mbar_wait(dkv_free, ((uint32_t)(jc) & 1u) ^ 1u);      // previous key tile's dK/dV drained from TMEM
+          if (i == imin) mbar_wait(dkv_free, ((uint32_t)jc & 1u) ^ 1u);        // previous key tile's dK/dV drained from TMEM
           tc_fence_after();
           const uint32_t pa = base + AttnBwdSmem::PT, da = base + AttnBwdSmem::DST;
 #pragma unroll
@@ -420,10 +457,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                       (j > 0 || k > 0) ? 1u : 0u);
           umma_commit(pair_done);
           umma_commit(q_empty(qs));
+          if (i == nq - 1) { umma_commit(dkv_full); umma_commit(kv_empty(ks)); }
+          j = nj; i = ni; jc = njc; pc++;
         }
-        umma_commit(dkv_full);
-        umma_commit(kv_empty(ks));
-        jc++;
       }
       umma_commit(dq_full);
     }
@@ -435,6 +471,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     DropCtx dc = make_drop(drop);
     const int HP = H * AT_DH;
+    const int W = (S + 31) >> 5;
+    uint8_t* const prow = base_gen + AttnBwdSmem::PT + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* const drow = base_gen + AttnBwdSmem::DST + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
     int pc = 0, jc = 0;
     for (int j = 0; j < nkv; j++) {
       const int key = j * 128 + r;
@@ -451,9 +490,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int q0 = i * 128;
         const bool diag = (mask_off >= 0) && (j * 128 + 127 > q0 + mask_off);
         const int cmin = key - mask_off - q0;               // columns < cmin are masked for this key row (diag tiles only)
+        // keep bits written by the forward: word (query, 32-key group); this lane fetches the words of 2 of its 64 columns
+        uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (dc.on && drop_bits != nullptr) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; h2++) {
+            const int qq = q0 + half * 64 + h2 * 32 + lane;
+            mw[h2] = (qq < T && j * 4 + quarter < W) ? drop_bits[((int64_t)bh * T + qq) * W + j * 4 + quarter] : 0u;
+          }
+        }
         mbar_wait(st_full, (uint32_t)pc & 1u);
         tc_fence_after();
-        uint32_t pw[2][16], dw[2][16];
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
           const int c0 = half * 64 + ch * 32;
@@ -477,25 +524,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               float p = ex2f(fmaf(sv[c + e], LOG2E_F, -ls[e]));
               if (key >= S || (diag && col < cmin)) p = 0.f;
               float mult = 1.f;
-              if (dc.on) mult = drop_mult1(dc, ((uint64_t)bh * T + (uint64_t)min(q0 + col, T - 1)) * (uint64_t)S + (uint64_t)min(key, S - 1));
+              if (dc.on) {
+                if (drop_bits != nullptr) {
+                  const uint32_t wq = __shfl_sync(0xffffffffu, mw[ch], c + e);
+                  mult = ((wq >> lane) & 1u) ? dc.inv_keep : 0.f;
+                } else {
+                  mult = drop_mult1(dc, ((uint64_t)bh * T + (uint64_t)min(q0 + col, T - 1)) * (uint64_t)S + (uint64_t)min(key, S - 1));
+                }
+              }
               sv[c + e] = p * mult;                                     // P~^T
               dpv[c + e] = p * fmaf(dpv[c + e], mult, -dl[e]);          // dS^T
             }
           }
+          // the previous pair's accumulate MMAs must have finished reading the P^T / dS^T tiles before they are overwritten
+          if (ch == 0) mbar_wait(pair_done, ((uint32_t)pc & 1u) ^ 1u);
+          // this thread owns row r, columns [64*half + 32*ch, +32) = chunk tile `half`, 16-byte units 4*ch .. 4*ch+3
 #pragma unroll
-          for (int c = 0; c < 16; c++) { pw[ch][c] = pack_bf16x2(sv[2 * c], sv[2 * c + 1]); dw[ch][c] = pack_bf16x2(dpv[2 * c], dpv[2 * c + 1]); }
-        }
-        // the previous pair's accumulate MMAs must have finished reading the P^T / dS^T tiles
-        mbar_wait(pair_done, ((uint32_t)pc & 1u) ^ 1u);
-        {
-          // this thread owns row r, columns [64*half, 64*half + 64) = chunk tile `half`, all 8 16-byte units
-          uint8_t* prow = base_gen + AttnBwdSmem::PT + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-          uint8_t* drow = base_gen + AttnBwdSmem::DST + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int ch = u >> 2, o4 = (u & 3) * 4;
-            *(uint4*)(prow + ((u ^ (r & 7)) << 4)) = make_uint4(pw[ch][o4], pw[ch][o4 + 1], pw[ch][o4 + 2], pw[ch][o4 + 3]);
-            *(uint4*)(drow + ((u ^ (r & 7)) << 4)) = make_uint4(dw[ch][o4], dw[ch][o4 + 1], dw[ch][o4 + 2], dw[ch][o4 + 3]);
+          for (int uu = 0; uu < 4; uu++) {
+            const int u = ch * 4 + uu;
+            *(uint4*)(prow + ((u ^ (r & 7)) << 4)) = make_uint4(pack_bf16x2(sv[uu * 8], sv[uu * 8 + 1]), pack_bf16x2(sv[uu * 8 + 2], sv[uu * 8 + 3]),
+                                                               pack_bf16x2(sv[uu * 8 + 4], sv[uu * 8 + 5]), pack_bf16x2(sv[uu * 8 + 6], sv[uu * 8 + 7]));
+            *(uint4*)(drow + ((u ^ (r & 7)) << 4)) = make_uint4(pack_bf16x2(dpv[uu * 8], dpv[uu * 8 + 1]), pack_bf16x2(dpv[uu * 8 + 2], dpv[uu * 8 + 3]),
+                                                               pack_bf16x2(dpv[uu * 8 + 4], dpv[uu * 8 + 5]), pack_bf16x2(dpv[uu * 8 + 6], dpv[uu * 8 + 7]));
           }
         }
         fence_async_smem();
@@ -575,7 +625,7 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     attr_set = true;
   }
   attn_bwd_tc_kernel<<<a->B * a->H, AB_THREADS, smem, stream>>>(tq, tk, tv, tg, lse, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S,
-                                                                  a->H, a->mask_off, a->drop);
+                                                                  a->H, a->mask_off, a->drop, a->drop_bits);
   BPM_CHECK_LAUNCH("xattn_bwd_tc");
   return BPM_OK;
 }

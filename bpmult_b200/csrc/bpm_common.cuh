@@ -77,10 +77,12 @@ template <> struct Vec8<bf16> {
 };
 
 // ---------------------------------------------------------------- Philox4x32-10 dropout
+// One Philox call yields 4 x 32 bit = 8 half-words = the keep decisions of 8 consecutive elements:
+//   element e uses call counter e >> 3, half-word e & 7 (word (e & 7) >> 1, low half first); keep <=> hw >= round(p * 65536).
 struct DropCtx {
   uint32_t k0, k1;      // key = seed
   uint32_t s0, s1;      // site (counter words 2,3)
-  uint32_t thresh;      // drop if r < thresh
+  uint32_t thresh;      // drop if half-word < thresh (0 .. 65536)
   float inv_keep;
   bool on;
 };
@@ -91,8 +93,7 @@ __device__ __forceinline__ DropCtx make_drop(const bpm_dropout_t& d) {
   uint64_t seed = d.seed_ptr ? *d.seed_ptr : d.seed;
   c.k0 = (uint32_t)seed; c.k1 = (uint32_t)(seed >> 32);
   c.s0 = (uint32_t)d.site; c.s1 = (uint32_t)(d.site >> 32);
-  double t = (double)d.p * 4294967296.0;
-  c.thresh = d.p >= 1.f ? 0xFFFFFFFFu : (uint32_t)t;
+  c.thresh = d.p >= 1.f ? 65536u : (uint32_t)((double)d.p * 65536.0 + 0.5);
   c.inv_keep = d.p < 1.f ? 1.f / (1.f - d.p) : 0.f;
   return c;
 }
@@ -110,16 +111,25 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
-// random words for elements 4*q .. 4*q+3
-__device__ __forceinline__ uint4 drop_rand4(const DropCtx& c, uint64_t q) {
-  return philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), c.s0, c.s1, c.k0, c.k1);
+// random half-words for elements 8*g .. 8*g+7
+__device__ __forceinline__ uint4 drop_rand8(const DropCtx& c, uint64_t g) {
+  return philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), c.s0, c.s1, c.k0, c.k1);
+}
+// keep decisions of 8 consecutive elements as a bit mask (bit i = element 8*g + i is kept)
+__device__ __forceinline__ uint32_t drop_keep8(const DropCtx& c, uint64_t g) {
+  uint4 r = drop_rand8(c, g);
+  uint32_t m = 0;
+  m |= ((r.x & 0xFFFFu) >= c.thresh) ? 1u : 0u;   m |= ((r.x >> 16) >= c.thresh) ? 2u : 0u;
+  m |= ((r.y & 0xFFFFu) >= c.thresh) ? 4u : 0u;   m |= ((r.y >> 16) >= c.thresh) ? 8u : 0u;
+  m |= ((r.z & 0xFFFFu) >= c.thresh) ? 16u : 0u;  m |= ((r.z >> 16) >= c.thresh) ? 32u : 0u;
+  m |= ((r.w & 0xFFFFu) >= c.thresh) ? 64u : 0u;  m |= ((r.w >> 16) >= c.thresh) ? 128u : 0u;
+  return m;
 }
 // multiplier (0 or 1/(1-p)) for a single element index e
 __device__ __forceinline__ float drop_mult1(const DropCtx& c, uint64_t e) {
   if (!c.on) return 1.f;
-  uint4 r = drop_rand4(c, e >> 2);
-  uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-  return w >= c.thresh ? c.inv_keep : 0.f;
+  uint32_t m = drop_keep8(c, e >> 3);
+  return ((m >> (uint32_t)(e & 7)) & 1u) ? c.inv_keep : 0.f;
 }
 // multipliers for 8 consecutive elements starting at e (e % 8 == 0)
 __device__ __forceinline__ void drop_mult8(const DropCtx& c, uint64_t e, float* m) {
@@ -128,11 +138,9 @@ __device__ __forceinline__ void drop_mult8(const DropCtx& c, uint64_t e, float* 
     for (int i = 0; i < 8; i++) m[i] = 1.f;
     return;
   }
-  uint4 a = drop_rand4(c, e >> 2), b = drop_rand4(c, (e >> 2) + 1);
-  m[0] = a.x >= c.thresh ? c.inv_keep : 0.f; m[1] = a.y >= c.thresh ? c.inv_keep : 0.f;
-  m[2] = a.z >= c.thresh ? c.inv_keep : 0.f; m[3] = a.w >= c.thresh ? c.inv_keep : 0.f;
-  m[4] = b.x >= c.thresh ? c.inv_keep : 0.f; m[5] = b.y >= c.thresh ? c.inv_keep : 0.f;
-  m[6] = b.z >= c.thresh ? c.inv_keep : 0.f; m[7] = b.w >= c.thresh ? c.inv_keep : 0.f;
+  uint32_t k = drop_keep8(c, e >> 3);
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = ((k >> i) & 1u) ? c.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------- warp / block reductions

@@ -236,11 +236,13 @@ class EncoderEngine:
         o.gemm(k_in, Wk, k, Ms, d.HP, d.Dp, bias=bk)
         v = A.get(key + "v", (Ms, d.HP), self.T_)
         o.gemm(v_in, Wv, v, Ms, d.HP, d.Dp, bias=bv)
-        o.xattn_fwd(q, k, v, a, lse, B, T, S, d.H, d.dh, d.dhp, mask_off=self._mask_off(T, S), drop=self._drop(self.p_attn, l, 10 + (blk == "x")))
+        adrop = self._drop(self.p_attn, l, 10 + (blk == "x"))
+        bits = A.get(key + "bits", (B * d.H * T * ((S + 31) // 32),), torch.int32) if adrop is not None else None
+        o.xattn_fwd(q, k, v, a, lse, B, T, S, d.H, d.dh, d.dhp, mask_off=self._mask_off(T, S), drop=adrop, drop_bits=bits)
         # x_out = x_res + dropout(a Wo^T + bo)                                   (transformer.py:174-175)
         o.gemm(a, w["Wo"], x_out, M, d.Dp, d.HP, bias=w["bo"], drop=self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")),
                residual=x_res)
-        return dict(q=q, k=k, v=v, a=a, lse=lse, q_in=q_in, k_in=k_in, v_in=v_in, S=S)
+        return dict(q=q, k=k, v=v, a=a, lse=lse, q_in=q_in, k_in=k_in, v_in=v_in, S=S, bits=bits)
 
     def _attn_bwd(self, l, blk, sv, B, T, gx, res_drop=True):
         """gx: fp32 [M, Dp] gradient wrt the block output x_out (= also flows to x_res unchanged).
@@ -262,7 +264,7 @@ class EncoderEngine:
         dv = Sh.get("dv", (Ms, d.HP), self.T_)
         delta = Sh.get("delta", (B * d.H * T,), torch.float32)
         o.xattn_bwd(sv["q"], sv["k"], sv["v"], sv["a"], da, sv["lse"], delta, dq, d.scaling, dk, dv, B, T, S, d.H, d.dh, d.dhp,
-                    mask_off=self._mask_off(T, S), drop=self._drop(self.p_attn, l, 10 + (blk == "x")))
+                    mask_off=self._mask_off(T, S), drop=self._drop(self.p_attn, l, 10 + (blk == "x")), drop_bits=sv["bits"])
         # dq already carries the dh^-0.5 factor => it is the gradient wrt (x Wq^T + bq)
         o.colsum(dq, d.HP, gbq)
         o.colsum(dk, d.HP, gbk)

@@ -15,8 +15,8 @@
  *  - Internal activation layout ("rows"): batch-major rows r = b*T + t, row pitch Dp = round_up(D, 64) elements,
  *    pad columns are ZERO.  Per-head tensors (q, k, v, attention output) use pitch H*dhp, dhp = round_up(dh, 32)
  *    (16 for dh <= 16), head h at columns [h*dhp, h*dhp + dh), pad columns zero.
- *  - Dropout: counter-based Philox4x32-10.  keep(e) <=> philox(key = seed, ctr = (e/4, site))[e%4] >= p*2^32, kept
- *    values scaled by 1/(1-p).  `e` is the element index in the padded row-major tensor the mask applies to
+ *  - Dropout: counter-based Philox4x32-10, 16-bit decisions: one call (key = seed, counter = (e/8, site)) gives 8 half-words;
+ *    keep(e) <=> half-word (e%8) >= round(p * 65536) (low half of word (e%8)/2 first); kept values scaled by 1/(1-p).  `e` is the element index in the padded row-major tensor the mask applies to
  *    (for attention: ((b*H + h)*T + i)*S + j).  `seed_ptr` (device, may be NULL) overrides `seed` when non-NULL so a
  *    captured graph can be replayed with a new seed.  Backward kernels regenerate masks from (seed, site).
  */
@@ -116,6 +116,8 @@ typedef struct {
   int dtype, B, T, S, H, dh, dhp, mask_off;
   const uint8_t* key_pad;
   bpm_dropout_t drop;
+  uint32_t* drop_bits;  /* optional scratch [B*H, T, ceil(S/32)]: keep bits written by the forward (dropout on) and read by the
+                           backward instead of regenerating the Philox stream; NULL = regenerate */
 } bpm_attn_t;
 int bpm_xattn_fwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, void* stream);
 int bpm_xattn_bwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout,

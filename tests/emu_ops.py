@@ -23,22 +23,26 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def drop_mult(drop, idx):
-    """multiplier (0 or 1/(1-p)) for int64 element indices `idx` (any shape)"""
+    """multiplier (0 or 1/(1-p)) for int64 element indices `idx` (any shape): 16-bit decisions, 8 per Philox call"""
     if drop is None or drop.p <= 0:
         return torch.ones(idx.shape, dtype=torch.float32)
     seed = int(drop.seed_ptr.item()) if drop.seed_ptr is not None else int(drop.seed)
-    q = idx >> 2
+    seed &= 0xFFFFFFFFFFFFFFFF
+    q = idx >> 3
     c0, c1 = q & MASK32, (q >> 32) & MASK32
     c2 = torch.full_like(q, drop.site & MASK32)
     c3 = torch.full_like(q, (drop.site >> 32) & MASK32)
     k0 = torch.full_like(q, seed & MASK32)
     k1 = torch.full_like(q, (seed >> 32) & MASK32)
     r = philox4x32_10(c0, c1, c2, c3, k0, k1)
-    lane = idx & 3
-    w = torch.where(lane == 0, r[0], torch.where(lane == 1, r[1], torch.where(lane == 2, r[2], r[3])))
-    thresh = 0xFFFFFFFF if drop.p >= 1 else int(float(torch.tensor(drop.p, dtype=torch.float32).double()) * 4294967296.0)
+    lane = idx & 7
+    wi = lane >> 1
+    w = torch.where(wi == 0, r[0], torch.where(wi == 1, r[1], torch.where(wi == 2, r[2], r[3])))
+    hw = (w >> (16 * (lane & 1))) & 0xFFFF
+    p32 = float(torch.tensor(drop.p, dtype=torch.float32))
+    thresh = 65536 if p32 >= 1 else int(p32 * 65536.0 + 0.5)
     inv = torch.tensor(1.0, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(drop.p, dtype=torch.float32))
-    return torch.where(w >= thresh, inv, torch.zeros((), dtype=torch.float32))
+    return torch.where(hw >= thresh, inv, torch.zeros((), dtype=torch.float32))
 
 
 def _idx2d(rows, ld, cols):
@@ -185,7 +189,7 @@ class EmuOps:
         idx = torch.arange(B * H * T * S).view(B, H, T, S)
         return drop_mult(drop, idx)
 
-    def xattn_fwd(self, q, k, v, out, lse, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None):
+    def xattn_fwd(self, q, k, v, out, lse, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None, drop_bits=None):
         s = self._probs(q, k, B, T, S, H, dhp, mask_off, key_pad)
         L = torch.logsumexp(s, -1)
         p = torch.exp(s - L.unsqueeze(-1)) * self._attn_mult(B, T, S, H, drop)
@@ -194,7 +198,7 @@ class EmuOps:
         out.copy_(o.to(out.dtype))
         lse.copy_(L.reshape(-1))
 
-    def xattn_bwd(self, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None):
+    def xattn_bwd(self, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None, drop_bits=None):
         s = self._probs(q, k, B, T, S, H, dhp, mask_off, key_pad)
         p = torch.exp(s - lse.view(B, H, T, 1))
         mult = self._attn_mult(B, T, S, H, drop)

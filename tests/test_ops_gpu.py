@@ -202,16 +202,20 @@ def test_xattn_fwd_bwd(ops, dtype, case):
         return t.view(rows, HP).to(dtype)
     q, k, v, do = mk(B * T, 40, dh ** -0.25), mk(B * S, 41, dh ** -0.25), mk(B * S, 42, 1.0), mk(B * T, 43, 1.0)
     drop = Drop(p, 99, None, 5) if p > 0 else None
-    outs = [torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * H * T)]
-    e, c = both(ops, lambda o, q, k, v, out, lse: o.xattn_fwd(q, k, v, out, lse, B, T, S, H, dh, dhp, off, None, drop), [q, k, v], outs)
-    assert max_rel(c[0], e[0]) < tol(dtype)
-    assert max_rel(c[1], e[1]) < (1e-5 if dtype == F32 else 2e-3)
-    outs = [torch.zeros(B * H * T), torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype)]
-    e2, c2 = both(ops, lambda o, q, k, v, out, do, lse, dl, dq, dk, dv: o.xattn_bwd(q, k, v, out, do, lse, dl, dq, 0.2, dk, dv, B, T, S, H, dh, dhp, off, None, drop),
-                  [q, k, v, e[0], do, e[1]], outs)
-    t = 2e-5 if dtype == F32 else 1.5e-2
-    for a, b, nm in zip(c2, e2, ["delta", "dq", "dk", "dv"]):
-        assert max_rel(a, b) < t, nm
+    W = (S + 31) // 32
+    for use_bits in ([False, True] if p > 0 else [False]):
+        outs = [torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * H * T), torch.zeros(B * H * T * W, dtype=torch.int32)]
+        e, c = both(ops, lambda o, q, k, v, out, lse, bits: o.xattn_fwd(q, k, v, out, lse, B, T, S, H, dh, dhp, off, None, drop,
+                                                                         drop_bits=bits if use_bits else None), [q, k, v], outs)
+        assert max_rel(c[0], e[0]) < tol(dtype)
+        assert max_rel(c[1], e[1]) < (1e-5 if dtype == F32 else 2e-3)
+        outs = [torch.zeros(B * H * T), torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype)]
+        e2, c2 = both(ops, lambda o, q, k, v, out, do, lse, bits, dl, dq, dk, dv: o.xattn_bwd(q, k, v, out, do, lse, dl, dq, 0.2, dk, dv, B, T, S, H, dh, dhp, off,
+                                                                                             None, drop, drop_bits=bits if use_bits else None),
+                      [q, k, v, e[0], do, e[1], c[2]], outs)
+        t = 2e-5 if dtype == F32 else 1.5e-2
+        for a, b, nm in zip(c2, e2, ["delta", "dq", "dk", "dv"]):
+            assert max_rel(a, b) < t, (nm, use_bits)
     if dtype == F32:
         (ew,), (cw,) = both(ops, lambda o, q, k, lse, w: o.xattn_weights(q, k, lse, w, B, T, S, H, dh, dhp, off, None, drop), [q, k, e[1]], [torch.zeros(B, T, S)])
         assert max_rel(cw, ew) < 2e-5
