@@ -23,7 +23,7 @@ class Gemm(C.Structure):
                 ("drop", Dropout),
                 ("gate", C.c_void_p), ("ldg", C.c_int), ("gate_dtype", C.c_int), ("gate_scale", C.c_float),
                 ("residual", C.c_void_p), ("ldr", C.c_int), ("res_dtype", C.c_int),
-                ("accumulate", C.c_int), ("split_k", C.c_int)]
+                ("accumulate", C.c_int), ("split_k", C.c_int), ("colsum_out", C.c_void_p)]
 
 
 class Attn(C.Structure):

@@ -12,6 +12,7 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
 int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                      float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t s);
 int bpm_xattn_tc_supported(const bpm_attn_t* a);
+extern "C" int bpm_colsum(const void* X, int dtype, int M, int N, int ld, float* out, void* stream);
 
 // BPM_DEBUG_FFMA=1 routes bf16 problems through the FFMA kernels too (kernel bring-up / bisecting only).
 static int debug_ffma() {
@@ -25,7 +26,14 @@ extern "C" int bpm_gemm(const bpm_gemm_t* g, void* stream) {
   BPM_REQUIRE(g->ab_dtype == BPM_F32 || g->ab_dtype == BPM_BF16, "gemm: bad dtype");
   BPM_REQUIRE(!g->accumulate || g->c_dtype == BPM_F32, "gemm: accumulate needs fp32 C");
   // tiny-M problems (the [B, D] head) are >90% tile padding on a 128-row MMA: they stay on the FFMA kernel
-  if (g->ab_dtype == BPM_F32 || debug_ffma()) return bpm_gemm_simt(g, (cudaStream_t)stream);
+  BPM_REQUIRE(!g->colsum_out || g->ta == 1, "gemm: colsum_out needs ta = 1");
+  if (g->ab_dtype == BPM_F32 || debug_ffma()) {
+    if (g->colsum_out) {      // op(A) = A^T with A stored [K, M]: row sums of op(A) = column sums of the stored matrix
+      int rc = bpm_colsum(g->A, g->ab_dtype, g->K, g->M, g->lda, g->colsum_out, stream);
+      if (rc) return rc;
+    }
+    return bpm_gemm_simt(g, (cudaStream_t)stream);
+  }
   return bpm_gemm_tc(g, (cudaStream_t)stream);
 }
 

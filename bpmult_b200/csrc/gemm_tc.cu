@@ -1,51 +1,83 @@
 // bf16 GEMM on 5th-gen tensor cores (sm_100a): TMA (SWIZZLE_128B) -> shared memory ring -> tcgen05.mma (cta_group::1,
-// M = 128, N = BN <= 256, K = 16 per instruction) -> fp32 accumulator in TMEM -> tcgen05.ld -> fused epilogue.
+// M = 128, N = BN <= 256, K = 16 per instruction) -> fp32 accumulator in TMEM -> tcgen05.ld -> fused epilogue -> TMA store.
 //
-//  * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-//    warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
-//  * All four operand layouts without any transposed copies: K-major operands use the canonical SW128 K-major
-//    layout (SBO = 1024 B); "transposed" operands (dgrad's W, wgrad's dY^T and X) are loaded as 64-wide MN chunks
-//    and described to the MMA as MN-major (LBO = BK*128 B between chunks, SBO = 1024 B between 8-row k groups).
-//  * K = 300..1216 here, i.e. only 5..19 k-blocks per tile: the kernel is prologue/epilogue dominated, so it is sized
-//    for TWO co-resident CTAs per SM (<= 110 KB smem, <= 256 TMEM columns each): one CTA's epilogue overlaps the
-//    other's main loop.  wgrad (K = B*T rows) is split along K across blockIdx.z and accumulated with vector
-//    fp32 reductions (red.global.add.v4.f32).
+//  * Warp roles (192 threads): warp 0 = TMA producer (operands, then the epilogue's residual / gate tiles), warp 1 = TMEM
+//    allocator + single-thread MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4, one thread per row).
+//  * All four operand layouts without any transposed copies: K-major operands use the canonical SW128 K-major layout
+//    (SBO = 1024 B); "transposed" operands (dgrad's W, wgrad's dY^T and X) are loaded as 64-wide MN chunks and described to
+//    the MMA as MN-major (LBO = BK*128 B between chunks, SBO = 1024 B between 8-row k groups).
+//  * Epilogue: K is only 300..1216 here (5..19 k-blocks per tile), so the kernel lives or dies by its epilogue.  The
+//    accumulator is drained in 128-byte-wide column chunks; residual / relu-gate tiles arrive by TMA into shared memory
+//    (prefetched one chunk ahead), the bias sits in shared memory, results are staged in shared memory (swizzled, conflict
+//    free) and leave with ONE TMA store per chunk (or one TMA reduce-add for split-K wgrad) -- every global access is a
+//    full 128-byte line and M / N tails are clipped by the TMA unit.  The staging buffers alias the drained operand ring.
+//  * Two CTAs are co-resident per SM (<= 111 KB smem, <= 256 TMEM columns each): one CTA's epilogue overlaps the other's
+//    main loop.
+//  * wgrad (K = B*T rows) is split along K across blockIdx.z.  The bias gradient (column sums of dY) is fused into wgrad as
+//    one extra N=16 MMA per k-step against a tile of ones (dY^T * 1), so dY is never re-read for it.
 #include "gemm_epilogue.cuh"
 #include "tc_common.cuh"
 
 #define TC_BM 128
 #define TC_BK 64
 #define TC_THREADS 192
+#define TC_SLOT 16384          // one 128-row x 128-byte epilogue tile
 
 struct TcGemmParams {
   int M, N, K;
-  int BN;            // multiple of 16, <= 256
-  int a_mn, b_mn;    // 1: operand is MN-major in memory ("transposed")
+  int BN;                 // multiple of 32, <= 256
+  int a_mn, b_mn;         // 1: operand is MN-major in memory ("transposed")
   int stages;
   int a_bytes, b_bytes;   // per-stage bytes (multiples of 1024)
+  int ring_bytes;         // operand ring (>= the epilogue's slot needs)
   int kb_per_split;
   int tmem_cols;
-  int plain_acc;     // split-K accumulate with a pure (alpha-only) epilogue
-  uint32_t idesc;
+  uint32_t idesc, idesc_ones;
+  int elem;               // output / residual / gate element size (2 or 4)
+  int chunk_bytes;        // 128 or 64: bytes per row of one epilogue chunk
+  int n_chunks;
+  int has_res, has_gate, reduce_add;
+  float* colsum;          // fused bias gradient (wgrad only), or null
   EpiParams ep;
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m), "r"(smem_src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// byte offset of 16-byte unit u of row r inside a swizzled [128 rows x chunk_bytes] tile (TMA SWIZZLE_128B / SWIZZLE_64B)
+__device__ __forceinline__ uint32_t swz_off(int r, int u, int chunk_bytes) {
+  return chunk_bytes == 128 ? (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4))
+                            : (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((u ^ ((r >> 1) & 3)) << 4));
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmG, const TcGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B tiles
-  uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte alignment for SWIZZLE_128B tiles
+  uint8_t* const base_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  uint32_t bar_base = smem_base + p.stages * stage_bytes;      // full[stages], empty[stages], tmem_full, tmem_ptr
+  // layout: [operand ring | ones tile 2 KB | bias BN floats | barriers]
+  const uint32_t ones_addr = smem_base + p.ring_bytes;
+  float* const bias_s = (float*)(base_gen + p.ring_bytes + 2048);
+  const uint32_t bar_base = smem_base + p.ring_bytes + 2048 + 1024;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-  uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
-  uint32_t tmem_ptr_addr = bar_base + 8u * (2 * p.stages + 1);
-  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * 8;
+  auto in_full = [&](int s) { return bar_base + 8u * (9 + s); };
+  auto in_empty = [&](int s) { return bar_base + 8u * (11 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * 13;
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + p.ring_bytes + 2048 + 1024 + 8 * 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * p.BN, m0 = blockIdx.y * TC_BM;
@@ -53,92 +85,200 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
   const int num_kb = kb1 - kb0;
+  const bool do_colsum = p.colsum != nullptr && blockIdx.x == 0;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(in_full(s), 1); mbar_init(in_empty(s), 4); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    for (int c = t; c < p.BN; c += 128) bias_s[c] = (p.ep.bias && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.f;
+    if (do_colsum) {                                                      // 16 x 64 tile of bf16 ones (B operand of the colsum MMA)
+      uint32_t* o = (uint32_t*)(base_gen + p.ring_bytes);
+      for (int c = t; c < 512; c += 128) o[c] = 0x3F803F80u;
+      fence_async_smem();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  if (num_kb > 0) {
-    if (warp == 0) {
-      // ===================== TMA producer =====================
-      if (lane == 0) {
-        const int b_chunks = (p.BN + 63) / 64;
-        for (int i = 0; i < num_kb; i++) {
-          int s = i % p.stages;
-          uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
-          mbar_expect_tx(full_bar(s), (uint32_t)(p.a_bytes + p.b_bytes));
-          int k = (kb0 + i) * TC_BK;
-          if (!p.a_mn) tma_load_2d(sa, &tmA, full_bar(s), k, m0);                        // box {64 k, 128 m}
-          else { tma_load_2d(sa, &tmA, full_bar(s), m0, k); tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, k); }   // box {64 m, 64 k} x2
-          if (!p.b_mn) tma_load_2d(sb, &tmB, full_bar(s), k, n0);                        // box {64 k, BN n}
-          else
-            for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + 64 * c, k);        // box {64 n, 64 k}
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int b_chunks = (p.BN + 63) / 64;
+      for (int i = 0; i < num_kb; i++) {
+        int s = i % p.stages;
+        uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
+        mbar_expect_tx(full_bar(s), (uint32_t)(p.a_bytes + p.b_bytes));
+        int k = (kb0 + i) * TC_BK;
+        if (!p.a_mn) tma_load_2d(sa, &tmA, full_bar(s), k, m0);                        // box {64 k, 128 m}
+        else { tma_load_2d(sa, &tmA, full_bar(s), m0, k); tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, k); }   // box {64 m, 64 k} x2
+        if (!p.b_mn) tma_load_2d(sb, &tmB, full_bar(s), k, n0);                        // box {64 k, BN n}
+        else
+          for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + 64 * c, k);        // box {64 n, 64 k}
+      }
+      if (p.has_res || p.has_gate) {
+        // epilogue inputs: one [128 x chunk] tile per chunk into 2-deep slot rings that alias the (drained) operand ring
+        mbar_wait(tmem_full_bar, 0);
+        const int cw = p.chunk_bytes / p.elem;
+        const uint32_t tile_bytes = 128u * (uint32_t)p.chunk_bytes;
+        for (int c = 0; c < p.n_chunks; c++) {
+          int s = c & 1;
+          mbar_wait(in_empty(s), ((uint32_t)(c >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(in_full(s), tile_bytes * (uint32_t)(p.has_res + p.has_gate));
+          if (p.has_res) tma_load_2d(smem_base + (2 + s) * TC_SLOT, &tmR, in_full(s), n0 + c * cw, m0);
+          if (p.has_gate) tma_load_2d(smem_base + (4 + s) * TC_SLOT, &tmG, in_full(s), n0 + c * cw, m0);
         }
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer (one thread) =====================
-      if (lane == 0) {
-        for (int i = 0; i < num_kb; i++) {
-          int s = i % p.stages;
-          uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; i++) {
+        int s = i % p.stages;
+        uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; k++) {
-            // K-major: +32 B per 16-element k step inside the 128 B swizzle row; MN-major: +16 rows * 128 B
-            uint64_t da = p.a_mn ? umma_desc(sa + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sa + k * 32, 16, 1024, BPM_SWZ_128B);
-            uint64_t db = p.b_mn ? umma_desc(sb + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sb + k * 32, 16, 1024, BPM_SWZ_128B);
-            umma_bf16(tmem_base, da, db, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+        for (int k = 0; k < TC_BK / 16; k++) {
+          // K-major: +32 B per 16-element k step inside the 128 B swizzle row; MN-major: +16 rows * 128 B
+          uint64_t da = p.a_mn ? umma_desc(sa + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sa + k * 32, 16, 1024, BPM_SWZ_128B);
+          uint64_t db = p.b_mn ? umma_desc(sb + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sb + k * 32, 16, 1024, BPM_SWZ_128B);
+          umma_bf16(tmem_base, da, db, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if (do_colsum)      // column sums of dY: dY^T (this A tile) times a tile of ones -> 16 identical columns at TMEM col BN
+            umma_bf16(tmem_base + p.BN, da, umma_desc(ones_addr + k * 32, 16, 1024, BPM_SWZ_128B), p.idesc_ones, (i > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(tmem_full_bar);             // accumulator complete
+        umma_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
       }
-    } else {
-      // ===================== epilogue warps =====================
-      const int quarter = warp & 3;
-      const int row = m0 + quarter * 32 + lane;
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-      DropCtx dc = make_drop(p.ep.drop);
-      const bool vec_ok = (p.ep.ldc % 8 == 0) && (!p.ep.gate || p.ep.ldg % 8 == 0) && (!p.ep.residual || p.ep.ldr % 8 == 0);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        float v[32];
-        uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-        if (c0 + 32 <= p.BN) tmem_ld32(taddr, v);
-        else tmem_ld16(taddr, v);               // BN % 32 == 16 tail
-        tmem_ld_wait();
-        if (row < p.M) {
-          int ncols = min(32, p.BN - c0);
-          for (int j = 0; j < ncols; j += 8) {
-            int n = n0 + c0 + j;
-            if (n >= p.N) break;
-            if (vec_ok && n + 8 <= p.N) {
-              if (p.plain_acc) {
-                float* c = (float*)p.ep.C + (int64_t)row * p.ep.ldc + n;
-                red_add_v4(c, v[j] * p.ep.alpha, v[j + 1] * p.ep.alpha, v[j + 2] * p.ep.alpha, v[j + 3] * p.ep.alpha);
-                red_add_v4(c + 4, v[j + 4] * p.ep.alpha, v[j + 5] * p.ep.alpha, v[j + 6] * p.ep.alpha, v[j + 7] * p.ep.alpha);
-              } else {
-                epi_store8(p.ep, dc, row, n, v + j);
-              }
-            } else {
-              for (int jj = 0; jj < 8 && n + jj < p.N; jj++) epi_store1(p.ep, dc, row, n + jj, v[j + jj]);
+      umma_commit(tmem_full_bar);             // accumulator complete (and the whole operand ring is drained)
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int row = m0 + r;
+    const int et = threadIdx.x - 64;                                       // 0..127
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    DropCtx dc = make_drop(p.ep.drop);
+    const int cw = p.chunk_bytes / p.elem;                                  // columns per chunk: 16 / 32 / 64
+    const int upr = p.chunk_bytes / 16;                                     // 16-byte units per row
+    const int epu = 16 / p.elem;                                            // elements per unit (8 bf16 / 4 fp32)
+    if (num_kb > 0) {
+      for (int c = 0; c < p.n_chunks; c++) {
+        const int s = c & 1;
+        const int col0 = c * cw;
+        float v[64];
+        {
+          const uint32_t taddr = tmem_base + lane_off + (uint32_t)col0;
+          if (cw >= 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+          if (cw == 64) tmem_ld32(taddr + 32, v + 32);
+          tmem_ld_wait();
+        }
+        // ---- bias, alpha, relu, dropout
+#pragma unroll
+        for (int g8 = 0; g8 < 8; g8++) {
+          if (g8 * 8 < cw) {
+            float mlt[8];
+            const int n = n0 + col0 + g8 * 8;
+            drop_mult8(dc, (uint64_t)row * (uint64_t)p.ep.ldc + (uint64_t)n, mlt);
+            const float4 b0 = *(const float4*)(bias_s + col0 + g8 * 8), b1 = *(const float4*)(bias_s + col0 + g8 * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              float x = (v[g8 * 8 + e] + bb[e]) * p.ep.alpha;
+              if (p.ep.act == 1) x = fmaxf(x, 0.f);
+              v[g8 * 8 + e] = x * mlt[e];
             }
           }
         }
+        // ---- relu-backward gate and residual from the TMA-staged tiles
+        if (p.has_res || p.has_gate) {
+          mbar_wait(in_full(s), (uint32_t)(c >> 1) & 1u);
+          const uint8_t* rs = base_gen + (2 + s) * TC_SLOT;
+          const uint8_t* gs = base_gen + (4 + s) * TC_SLOT;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            if (u < upr) {
+              const uint32_t off = swz_off(r, u, p.chunk_bytes);
+              if (p.has_gate) {
+                const uint4 w = *(const uint4*)(gs + off);
+                if (p.elem == 2) {
+                  const __nv_bfloat162* h2 = (const __nv_bfloat162*)&w;
+#pragma unroll
+                  for (int e = 0; e < 4; e++) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    v[u * 8 + 2 * e] = f.x > 0.f ? v[u * 8 + 2 * e] * p.ep.gate_scale : 0.f;
+                    v[u * 8 + 2 * e + 1] = f.y > 0.f ? v[u * 8 + 2 * e + 1] * p.ep.gate_scale : 0.f;
+                  }
+                } else {
+                  const float* f = (const float*)&w;
+#pragma unroll
+                  for (int e = 0; e < 4; e++) v[u * 4 + e] = f[e] > 0.f ? v[u * 4 + e] * p.ep.gate_scale : 0.f;
+                }
+              }
+              if (p.has_res) {
+                const uint4 w = *(const uint4*)(rs + off);
+                if (p.elem == 2) {
+                  const __nv_bfloat162* h2 = (const __nv_bfloat162*)&w;
+#pragma unroll
+                  for (int e = 0; e < 4; e++) { const float2 f = __bfloat1622float2(h2[e]); v[u * 8 + 2 * e] += f.x; v[u * 8 + 2 * e + 1] += f.y; }
+                } else {
+                  const float* f = (const float*)&w;
+#pragma unroll
+                  for (int e = 0; e < 4; e++) v[u * 4 + e] += f[e];
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(in_empty(s));
+        }
+        // ---- stage the chunk (swizzled) and hand it to the TMA unit
+        if (et == 0) bulk_wait_read<1>();                                   // the store that last used this staging slot has read it
+        epi_bar();
+        uint8_t* st = base_gen + s * TC_SLOT;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (u < upr) {
+            uint4 w;
+            if (p.elem == 2) {
+              __nv_bfloat162* h2 = (__nv_bfloat162*)&w;
+#pragma unroll
+              for (int e = 0; e < 4; e++) h2[e] = __floats2bfloat162_rn(v[u * 8 + 2 * e], v[u * 8 + 2 * e + 1]);
+            } else {
+              w = make_uint4(__float_as_uint(v[u * 4]), __float_as_uint(v[u * 4 + 1]), __float_as_uint(v[u * 4 + 2]), __float_as_uint(v[u * 4 + 3]));
+            }
+            *(uint4*)(st + swz_off(r, u, p.chunk_bytes)) = w;
+          }
+        }
+        (void)epu;
+        fence_async_smem();
+        epi_bar();
+        if (et == 0) {
+          if (p.reduce_add) tma_reduce_add_2d(&tmC, smem_base + s * TC_SLOT, n0 + col0, m0);
+          else tma_store_2d(&tmC, smem_base + s * TC_SLOT, n0 + col0, m0);
+          bulk_commit();
+        }
       }
+      if (do_colsum) {
+        float cs[16];
+        tmem_ld16(tmem_base + lane_off + (uint32_t)p.BN, cs);
+        tmem_ld_wait();
+        if (row < p.M) atomicAdd(p.colsum + row, cs[0]);
+      }
+      if (et == 0) bulk_wait_read<0>();                                     // smem must outlive the last TMA store's read
     }
   }
   tc_fence_before();
@@ -161,14 +301,15 @@ bpm_encode_tiled_fn bpm_get_encode_tiled() {
   return fn;
 }
 
-int bpm_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                       CUtensorMapSwizzle swz) {
+static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int elem, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   bpm_encode_tiled_fn enc = bpm_get_encode_tiled();
   if (!enc) { bpm_set_error("cuTensorMapEncodeTiled entry point unavailable"); return BPM_ELAUNCH; }
   cuuint64_t gd[5]; cuuint64_t gs[5]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; i++) gs[i] = strides_bytes[i];
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+  (void)elem;
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     bpm_set_error("cuTensorMapEncodeTiled failed (%d): base %p rank %d dims %llu,%llu stride %llu box %u,%u", (int)r, base, rank,
@@ -178,10 +319,23 @@ int bpm_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
   return BPM_OK;
 }
 
-static int pick_bn(int N) {
-  // fewest tiles first, then least padding; BN multiple of 16 in [32, 256]
-  int tiles = bpm_cdiv(N, 256);
-  int bn = bpm_cdiv(bpm_cdiv(N, tiles), 16) * 16;
+int bpm_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                       CUtensorMapSwizzle swz) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rank, dims, strides_bytes, box, swz);
+}
+
+// [rows, cols] row-major tile map for the epilogue (C / residual / gate): box {chunk columns, 128 rows}
+static int make_epi_map(CUtensorMap* out, const void* base, int rows, int cols, int ld, int elem, int chunk_bytes) {
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows}, str[1] = {(uint64_t)ld * elem};
+  uint32_t box[2] = {(uint32_t)(chunk_bytes / elem), TC_BM};
+  return make_tmap(out, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, elem, base, 2, dims, str, box,
+                   chunk_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+static int pick_bn(int N, int max_bn) {
+  // fewest tiles first, then least padding; BN multiple of 32 in [32, max_bn]
+  int tiles = bpm_cdiv(N, max_bn);
+  int bn = bpm_cdiv(bpm_cdiv(N, tiles), 32) * 32;
   return bn < 32 ? 32 : bn;
 }
 
@@ -189,29 +343,46 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   BPM_REQUIRE(((uintptr_t)g->A % 16 == 0) && ((uintptr_t)g->B % 16 == 0) && g->lda % 8 == 0 && g->ldb % 8 == 0,
               "gemm(bf16): A/B must be 16-byte aligned with pitches multiple of 8 elements (lda %d ldb %d)", g->lda, g->ldb);
   BPM_REQUIRE(!g->accumulate || g->c_dtype == BPM_F32, "gemm: accumulate needs fp32 C");
+  const int elem = g->c_dtype == BPM_BF16 ? 2 : 4;
+  BPM_REQUIRE(((uintptr_t)g->C % 16 == 0) && ((int64_t)g->ldc * elem) % 16 == 0, "gemm(bf16): C must be 16-byte aligned with a 16-byte multiple pitch");
+  BPM_REQUIRE(!g->residual || (g->res_dtype == g->c_dtype && ((uintptr_t)g->residual % 16 == 0) && ((int64_t)g->ldr * elem) % 16 == 0),
+              "gemm(bf16): residual must have C's dtype and 16-byte alignment");
+  BPM_REQUIRE(!g->gate || (g->gate_dtype == g->c_dtype && ((uintptr_t)g->gate % 16 == 0) && ((int64_t)g->ldg * elem) % 16 == 0),
+              "gemm(bf16): gate must have C's dtype and 16-byte alignment");
+  BPM_REQUIRE(!g->colsum_out || g->ta == 1, "gemm: the fused column sum is defined for ta = 1 (wgrad) only");
+  const bool plain = !g->bias && g->act == 0 && g->drop.p == 0.f && !g->gate && !g->residual;
+  BPM_REQUIRE(!g->accumulate || plain, "gemm(bf16): accumulate supports the plain (alpha-only) epilogue");
   TcGemmParams p;
   p.M = g->M; p.N = g->N; p.K = g->K;
-  p.BN = pick_bn(g->N);
+  p.colsum = g->colsum_out;
+  p.BN = pick_bn(g->N, p.colsum ? 224 : 256);
   p.a_mn = g->ta ? 1 : 0;
   p.b_mn = g->tb ? 1 : 0;
   p.a_bytes = TC_BM * TC_BK * 2;
   p.b_bytes = p.b_mn ? bpm_cdiv(p.BN, 64) * 8192 : bpm_cdiv(p.BN * 128, 1024) * 1024;
   int stage_bytes = p.a_bytes + p.b_bytes;
-  p.stages = max(2, min(4, (108 * 1024) / stage_bytes));
-  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  p.stages = max(2, min(4, (104 * 1024) / stage_bytes));
+  p.has_res = g->residual ? 1 : 0;
+  p.has_gate = g->gate ? 1 : 0;
+  p.reduce_add = g->accumulate ? 1 : 0;
+  const int slots = p.has_gate ? 6 : (p.has_res ? 4 : 2);
+  p.ring_bytes = max(p.stages * stage_bytes, slots * TC_SLOT);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.BN + (p.colsum ? 16 : 0)) p.tmem_cols *= 2;
   p.idesc = umma_idesc_bf16(TC_BM, p.BN, p.a_mn, p.b_mn);
+  p.idesc_ones = umma_idesc_bf16(TC_BM, 16, p.a_mn, 0);
+  p.elem = elem;
+  p.chunk_bytes = (p.BN * elem) % 128 == 0 ? 128 : 64;
+  p.n_chunks = p.BN * elem / p.chunk_bytes;
   p.ep = make_epi(g);
   int num_kb = bpm_cdiv(g->K, TC_BK);
   int gx = bpm_cdiv(g->N, p.BN), gy = bpm_cdiv(g->M, TC_BM);
   int split = 1;
-  p.plain_acc = g->accumulate && !g->bias && g->act == 0 && g->drop.p == 0.f && !g->gate && !g->residual;
-  if (p.plain_acc) {
-    split = g->split_k > 0 ? g->split_k : max(1, min(num_kb / 4, (2 * bpm_num_sms()) / max(1, gx * gy)));
-  }
+  if (g->accumulate) split = g->split_k > 0 ? g->split_k : max(1, min(num_kb / 4, (2 * bpm_num_sms()) / max(1, gx * gy)));
   p.kb_per_split = bpm_cdiv(num_kb, split);
   split = bpm_cdiv(num_kb, p.kb_per_split);
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmR, tmG;
   {
     // A: ta == 0 -> stored [M, K]: dims {K, M}, box {64, 128}.  ta == 1 -> stored [K, M]: dims {M, K}, box {64, 64}
     uint64_t dims[2], str[1]; uint32_t box[2];
@@ -226,17 +397,21 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
     str[0] = (uint64_t)g->ldb * 2;
     rc = bpm_make_tmap_bf16(&tmB, g->B, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    if ((rc = make_epi_map(&tmC, g->C, g->M, g->N, g->ldc, elem, p.chunk_bytes))) return rc;
+    tmR = tmC; tmG = tmC;
+    if (g->residual && (rc = make_epi_map(&tmR, g->residual, g->M, g->N, g->ldr, elem, p.chunk_bytes))) return rc;
+    if (g->gate && (rc = make_epi_map(&tmG, g->gate, g->M, g->N, g->ldg, elem, p.chunk_bytes))) return rc;
   }
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(111 * 1024));
+  size_t smem = (size_t)p.ring_bytes + 2048 + 1024 + 8 * 16 + 1024;
+  BPM_REQUIRE(smem <= 112 * 1024, "gemm_tc: smem %zu too large", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024));
     if (e != cudaSuccess) { bpm_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
-    smem_set = 111 * 1024;
+    attr_set = true;
   }
-  BPM_REQUIRE(smem <= 111 * 1024, "gemm_tc: smem %zu too large", smem);
   dim3 grid(gx, gy, split);
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, tmG, p);
   BPM_CHECK_LAUNCH("gemm_tc");
   return BPM_OK;
 }

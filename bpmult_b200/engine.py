@@ -255,8 +255,7 @@ class EncoderEngine:
         gbq, gbk, gbv = g["bqkv"][:d.HP], g["bqkv"][d.HP:2 * d.HP], g["bqkv"][2 * d.HP:]
         go = Sh.get("go", (M, d.Dp), self.T_)
         o.cast_drop(gx, go, self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")))   # grad wrt out_proj output
-        o.colsum(go, d.Dp, g["bo"])
-        o.gemm(go, sv["a"], g["Wo"], d.Dp, d.HP, M, ta=1, tb=1, accumulate=True)               # dWo = go^T a
+        o.gemm(go, sv["a"], g["Wo"], d.Dp, d.HP, M, ta=1, tb=1, accumulate=True, colsum=g["bo"])   # dWo = go^T a, dbo = colsum(go)
         da = Sh.get("da", (M, d.HP), self.T_)
         o.gemm(go, w["Wo"], da, M, d.HP, d.Dp, tb=1)                                           # da = go Wo
         dq = Sh.get("dq", (M, d.HP), self.T_)
@@ -266,12 +265,9 @@ class EncoderEngine:
         o.xattn_bwd(sv["q"], sv["k"], sv["v"], sv["a"], da, sv["lse"], delta, dq, d.scaling, dk, dv, B, T, S, d.H, d.dh, d.dhp,
                     mask_off=self._mask_off(T, S), drop=self._drop(self.p_attn, l, 10 + (blk == "x")), drop_bits=sv["bits"])
         # dq already carries the dh^-0.5 factor => it is the gradient wrt (x Wq^T + bq)
-        o.colsum(dq, d.HP, gbq)
-        o.colsum(dk, d.HP, gbk)
-        o.colsum(dv, d.HP, gbv)
-        o.gemm(dq, sv["q_in"], gWq, d.HP, d.Dp, M, ta=1, tb=1, accumulate=True)
-        o.gemm(dk, sv["k_in"], gWk, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True)
-        o.gemm(dv, sv["v_in"], gWv, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True)
+        o.gemm(dq, sv["q_in"], gWq, d.HP, d.Dp, M, ta=1, tb=1, accumulate=True, colsum=gbq)
+        o.gemm(dk, sv["k_in"], gWk, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=gbk)
+        o.gemm(dv, sv["v_in"], gWv, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=gbv)
         dq_in = Sh.get("dq_in", (M, d.Dp), self.T_)
         dk_in = Sh.get("dk_in", (Ms, d.Dp), self.T_)
         dv_in = Sh.get("dv_in", (Ms, d.Dp), self.T_)
@@ -298,13 +294,11 @@ class EncoderEngine:
         o, d, w, g, Sh = self.ops, self.d, self.W[l], self.G[l], self.shared
         g2 = Sh.get("go", (M, d.Dp), self.T_)
         o.cast_drop(gx, g2, self._drop(self.p_res, l, 31))
-        o.colsum(g2, d.Dp, g["b2"])
-        o.gemm(g2, sv["h"], g["W2"], d.Dp, d.FP, M, ta=1, tb=1, accumulate=True)               # dW2 = g2^T h
+        o.gemm(g2, sv["h"], g["W2"], d.Dp, d.FP, M, ta=1, tb=1, accumulate=True, colsum=g["b2"])   # dW2 = g2^T h, db2 = colsum(g2)
         dh = Sh.get("dh", (M, d.FP), self.T_)
         keep = 1.0 / (1.0 - self.p_relu) if (self.training and self.p_relu > 0) else 1.0
         o.gemm(g2, w["W2"], dh, M, d.FP, d.Dp, tb=1, gate=sv["h"], gate_scale=keep)            # through dropout + relu
-        o.colsum(dh, d.FP, g["b1"])
-        o.gemm(dh, sv["hn"], g["W1"], d.FP, d.Dp, M, ta=1, tb=1, accumulate=True)              # dW1 = dh^T hn
+        o.gemm(dh, sv["hn"], g["W1"], d.FP, d.Dp, M, ta=1, tb=1, accumulate=True, colsum=g["b1"])  # dW1 = dh^T hn, db1 = colsum(dh)
         dhn = Sh.get("dq_in", (M, d.Dp), self.T_)
         o.gemm(dh, w["W1"], dhn, M, d.Dp, d.FP, tb=1)
         o.layernorm_bwd(dhn, sv["x_in"], sv["mean"], sv["rstd"], w["ln_g"][sv["ln"]], d.D, gx, True, g["ln_g"][sv["ln"]], g["ln_b"][sv["ln"]])

@@ -111,9 +111,10 @@ class CudaOps:
 
     # ------------------------------------------------------------------ gemm
     def gemm(self, A, B, Cout, M, N, K, ta=0, tb=0, bias=None, alpha=1.0, act=0, drop=None, gate=None, gate_scale=1.0, residual=None,
-             accumulate=False, split_k=0):
+             accumulate=False, split_k=0, colsum=None):
         assert A.dtype == B.dtype and A.stride(1) == 1 and B.stride(1) == 1 and Cout.stride(1) == 1
         g = Gemm()
+        g.colsum_out = _ptr(colsum)
         g.ab_dtype, g.ta, g.tb, g.M, g.N, g.K = _dt(A), int(ta), int(tb), M, N, K
         g.A, g.lda, g.B, g.ldb = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
         g.C, g.ldc, g.c_dtype = Cout.data_ptr(), Cout.stride(0), _dt(Cout)

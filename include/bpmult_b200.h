@@ -101,6 +101,8 @@ typedef struct {
   const void* residual; int ldr; int res_dtype;
   int accumulate;            /* C must be fp32; split-K partial sums are added atomically */
   int split_k;               /* 0 = auto */
+  float* colsum_out;         /* optional, ta = 1 only: colsum_out[m] += sum_k op(A)[m, k]  (= the bias gradient when this GEMM is a
+                                weight gradient dW = dY^T X); fused into the MMA main loop, dY is not re-read */
 } bpm_gemm_t;
 int bpm_gemm(const bpm_gemm_t* g, void* stream);
 

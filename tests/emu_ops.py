@@ -150,8 +150,11 @@ class EmuOps:
 
     # ------------------------------------------------------------------ gemm
     def gemm(self, A, B, Cout, M, N, K, ta=0, tb=0, bias=None, alpha=1.0, act=0, drop=None, gate=None, gate_scale=1.0, residual=None,
-             accumulate=False, split_k=0):
+             accumulate=False, split_k=0, colsum=None):
         a = (A[:K, :M].float().t() if ta else A[:M, :K].float())
+        if colsum is not None:
+            assert ta == 1
+            colsum[:M] += a.sum(1)
         b = (B[:K, :N].float() if tb else B[:N, :K].float().t())
         v = a @ b
         if bias is not None:

@@ -296,3 +296,25 @@ def test_adam_matches_torch(ops):
         step += 1
         ops.adam_step(p, (g * (i + 1)).cuda(), m, v, 1e-3, 0.9, 0.999, 1e-8, 1.0, step)
     assert max_rel(p, ref.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("M,N,K", [(384, 320, 4096), (320, 1216, 2000), (1216, 320, 1000)])
+def test_gemm_wgrad_with_fused_bias_grad(ops, dtype, M, N, K):
+    """dW = dY^T X (split-K, fp32 accumulate) with the column sums of dY (= bias gradient) fused into the same launch"""
+    A, Bm = rnd((K, M), 26, dtype, 0.5), rnd((K, N), 27, dtype, 0.5)
+    C0, cs0 = rnd((M, N), 28), rnd((M,), 29)
+    e, c = both(ops, lambda o, A, Bm, C, cs: o.gemm(A, Bm, C, M, N, K, ta=1, tb=1, accumulate=True, colsum=cs), [A, Bm], [C0, cs0])
+    assert max_rel(c[0], e[0]) < 2e-5
+    assert max_rel(c[1], e[1]) < 2e-5
+
+
+@pytest.mark.parametrize("cdt", [F32, BF16])
+def test_gemm_bf16_tails_are_clipped(ops, cdt):
+    """M, N tails: the TMA store must not touch memory outside C[:M, :N] (C is a view inside a larger poisoned buffer)"""
+    M, N, K = 200, 328, 320
+    A, Bm = rnd((M, K), 30, BF16, 0.5), rnd((N, K), 31, BF16, 0.5)
+    big = torch.full((256, 512), 7.0, dtype=cdt)
+    e, c = both(ops, lambda o, A, Bm, big: o.gemm(A, Bm, big[:M, :N], M, N, K), [A, Bm], [big])
+    assert max_rel(c[0][:M, :N], e[0][:M, :N]) < tol(cdt)
+    assert (c[0][M:] == 7.0).all() and (c[0][:, N:] == 7.0).all()
