@@ -334,7 +334,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
   }
 }
 
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmdO, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
                    bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,

@@ -28,15 +28,18 @@ class Trainer:
         self.ops = self.eng.ops
         if use_graph is None:
             use_graph = os.environ.get("BPM_NO_GRAPH", "0") != "1"
-        self.use_graph = use_graph
+        self.use_graph = use_graph and self.device.type == "cuda"
         self.pos_weight = None if pos_weight is None else pos_weight.to(self.device, torch.float32)
         self._flatten()
         dev = self.device
         self.seed_t = torch.tensor([seed + 7919 * self.rank], dtype=torch.int64, device=dev)     # per-rank Philox seed
         self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.comm = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.on_gpu = dev.type == "cuda"                     # (CPU only in the gloo host-logic tests, with the ops emulation)
+        self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.on_gpu) else None
         self.graph, self.static, self.shapes = None, None, None
-        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.loss_host = torch.zeros(1, dtype=torch.float32)
+        if self.device.type == "cuda":
+            self.loss_host = self.loss_host.pin_memory()
         self.steps_done = 0
 
     # ---------------------------------------------------------------- flat parameter / gradient buffers
@@ -86,13 +89,16 @@ class Trainer:
         logits, _ = eng.forward(txt, img, audio, training=True, seed=0, seed_ptr=self.seed_t)
         loss, dlogits = eng.loss(logits, tgt, self.pos_weight, 1.0)
         eng.zero_grads()
-        cur = torch.cuda.current_stream(self.device)
+        cur = torch.cuda.current_stream(self.device) if self.on_gpu else None
         bucket_of = {b[0]: b for b in self.buckets}
 
         def reduce_bucket(name):
             if self.world == 1:
                 return
             _, s, e = bucket_of[name]
+            if not self.on_gpu:
+                dist.all_reduce(self.flat_g[s:e])
+                return
             ev = torch.cuda.Event()
             ev.record(cur)
             with torch.cuda.stream(self.comm):
@@ -111,7 +117,7 @@ class Trainer:
                 gw = self.grads["proj_%s.weight" % m]
                 o.unpack_matrix(eng.Gproj[m], gw.view(gw.shape[0], gw.shape[1]))
         reduce_bucket("misc")
-        if self.world > 1:
+        if self.world > 1 and self.on_gpu:
             cur.wait_stream(self.comm)
         o.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world, self.step_t)
         return loss
@@ -122,7 +128,7 @@ class Trainer:
         if self.shapes != shapes:
             dev = self.device
             self.static = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
-            self.pinned = [torch.zeros(s, dtype=torch.float32).pin_memory() for s in shapes]
+            self.pinned = [torch.zeros(s, dtype=torch.float32).pin_memory() if self.on_gpu else torch.zeros(s) for s in shapes]
             self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
             self.shapes, self.graph = shapes, None
             self.warm = 0
@@ -144,7 +150,8 @@ class Trainer:
             s.copy_(pbuf, non_blocking=True)
         self._run()
         self.loss_host.copy_(self.loss_dev, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if self.on_gpu:
+            torch.cuda.current_stream(self.device).synchronize()
         return float(self.loss_host[0])
 
     def _run(self):
