@@ -39,6 +39,7 @@ SIGNATURES = {
     "bpm_device_ok": [_I],
     "bpm_pack_matrix": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpm_unpack_matrix": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "bpm_remap_batch": [_P, _I, _I, _P],
     "bpm_stage_rows": [_P, _I, _I, _I, _L, _L, _L, _P, _I, _I, _I, Dropout, _P],
     "bpm_unstage_rows": [_P, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, Dropout, _P],
     "bpm_embed_fwd": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _I, Dropout, _P],

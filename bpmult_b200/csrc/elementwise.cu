@@ -96,6 +96,45 @@ extern "C" int bpm_unpack_matrix(const float* src_p, int rows_p, int cols_p, flo
   return BPM_OK;
 }
 
+__global__ void remap_batch_kernel(const bpm_remap_desc_t* __restrict__ descs, int mode) {
+  const bpm_remap_desc_t d = descs[blockIdx.y];
+  if (mode == 0) {                                   // pack: one thread per destination (padded) element
+    int64_t n = (int64_t)d.rows_p * d.cols_p;
+    const float* src = (const float*)d.src;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      int rp = (int)(i / d.cols_p), cp = (int)(i % d.cols_p);
+      int r = rp, c = cp;
+      bool ok = true;
+      if (d.row_dh > 0) { int h = rp / d.row_dhp, j = rp % d.row_dhp; ok = ok && j < d.row_dh; r = h * d.row_dh + j; }
+      if (d.col_dh > 0) { int h = cp / d.col_dhp, j = cp % d.col_dhp; ok = ok && j < d.col_dh; c = h * d.col_dh + j; }
+      ok = ok && r < d.rows && c < d.cols;
+      float v = ok ? src[(int64_t)r * d.ld_src + c] : 0.f;
+      int64_t o = (int64_t)rp * d.ld_dst + cp;
+      if (d.dst_dtype == BPM_BF16) ((bf16*)d.dst)[o] = __float2bfloat16_rn(v);
+      else ((float*)d.dst)[o] = v;
+    }
+  } else {                                           // unpack: one thread per destination (reference-layout) element
+    int64_t n = (int64_t)d.rows * d.cols;
+    const float* src = (const float*)d.src;
+    float* dst = (float*)d.dst;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      int r = (int)(i / d.cols), c = (int)(i % d.cols);
+      int rp = remap_fwd(r, d.row_dh, d.row_dhp), cp = remap_fwd(c, d.col_dh, d.col_dhp);
+      float v = src[(int64_t)rp * d.ld_src + cp] * d.scale;
+      float* o = dst + (int64_t)r * d.ld_dst + c;
+      *o = d.accumulate ? *o + v : v;
+    }
+  }
+}
+
+extern "C" int bpm_remap_batch(const bpm_remap_desc_t* descs_dev, int n, int mode, void* stream) {
+  BPM_REQUIRE(descs_dev && n > 0 && (mode == 0 || mode == 1), "remap_batch: bad args");
+  dim3 grid(16, n);
+  remap_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, mode);
+  BPM_CHECK_LAUNCH("remap_batch");
+  return BPM_OK;
+}
+
 // ---------------------------------------------------------------- stage / unstage rows
 template <typename T>
 __global__ void stage_rows_kernel(const float* __restrict__ src, int B, int T_, int C, int64_t sb, int64_t st, int64_t sc, T* __restrict__ dst,

@@ -54,6 +54,25 @@ def sinusoid_table(num_pos, D, Dp, device):
     return out.to(device)
 
 
+def carve(ops, dtype, shapes):
+    """one flat zeroed buffer + a view per shape (128-element aligned starts): lets a whole group be cleared with ONE memset"""
+    offs, total = [], 0
+    for shp in shapes:
+        n = 1
+        for x in shp:
+            n *= x
+        offs.append(total)
+        total += round_up(n, 128)
+    flat = ops.zeros((total,), dtype)
+    views = []
+    for shp, o in zip(shapes, offs):
+        n = 1
+        for x in shp:
+            n *= x
+        views.append(flat[o:o + n].view(shp))
+    return flat, views
+
+
 class Arena:
     """Named, persistent device buffers (static addresses => the step can be captured in a CUDA graph)."""
 
@@ -119,22 +138,29 @@ class EncoderEngine:
         d, T_, f32 = self.d, self.T_, torch.float32
         z = self.ops.zeros
         self.W, self.G = [], []                     # packed weights / padded fp32 gradient accumulators per layer
+        gshapes = []
+        for _ in range(self.L):
+            gshapes += [(3 * d.HP, d.Dp), (3 * d.HP,), (d.Dp, d.HP), (d.Dp,), (d.FP, d.Dp), (d.FP,), (d.Dp, d.FP), (d.Dp,)] + [(d.Dp,)] * (2 * self.n_ln)
+        gshapes += [(d.Dp,), (d.Dp,)]
+        self.G_flat, gv = carve(self.ops, f32, gshapes)      # every gradient accumulator of this encoder: zeroed with one memset
+        it = iter(gv)
         for _ in range(self.L):
             w = dict(Wqkv=z((3 * d.HP, d.Dp), T_), bqkv=z((3 * d.HP,), f32), Wo=z((d.Dp, d.HP), T_), bo=z((d.Dp,), f32),
                      W1=z((d.FP, d.Dp), T_), b1=z((d.FP,), f32), W2=z((d.Dp, d.FP), T_), b2=z((d.Dp,), f32),
                      ln_g=[z((d.Dp,), f32) for _ in range(self.n_ln)], ln_b=[z((d.Dp,), f32) for _ in range(self.n_ln)])
-            g = dict(Wqkv=z((3 * d.HP, d.Dp), f32), bqkv=z((3 * d.HP,), f32), Wo=z((d.Dp, d.HP), f32), bo=z((d.Dp,), f32),
-                     W1=z((d.FP, d.Dp), f32), b1=z((d.FP,), f32), W2=z((d.Dp, d.FP), f32), b2=z((d.Dp,), f32),
-                     ln_g=[z((d.Dp,), f32) for _ in range(self.n_ln)], ln_b=[z((d.Dp,), f32) for _ in range(self.n_ln)])
+            g = dict(Wqkv=next(it), bqkv=next(it), Wo=next(it), bo=next(it), W1=next(it), b1=next(it), W2=next(it), b2=next(it))
+            g["ln_g"] = [next(it) for _ in range(self.n_ln)]
+            g["ln_b"] = [next(it) for _ in range(self.n_ln)]
             self.W.append(w)
             self.G.append(g)
         self.Wf = dict(g=z((d.Dp,), f32), b=z((d.Dp,), f32))
-        self.Gf = dict(g=z((d.Dp,), f32), b=z((d.Dp,), f32))
+        self.Gf = dict(g=next(it), b=next(it))
 
     def pack(self, params, pfx=""):
         """reference-layout fp32 parameters -> zero-padded kernel operands (run whenever the parameters changed)."""
         o, d = self.ops, self.d
         hm = (d.dh, d.dhp)
+        o.batch_begin("pack", ("enc", self.uid, pfx))
         for l in range(self.L):
             p = "%slayers.%d." % (pfx, l)
             w = self.W[l]
@@ -150,6 +176,7 @@ class EncoderEngine:
         if self.with_final_ln:
             o.pack_matrix(params[pfx + "layer_norm.weight"].view(1, -1), self.Wf["g"].view(1, -1))
             o.pack_matrix(params[pfx + "layer_norm.bias"].view(1, -1), self.Wf["b"].view(1, -1))
+        o.batch_end()
 
     def pack_attention(self, l, ipw, ipb, ow, ob):
         o, d, w = self.ops, self.d, self.W[l]
@@ -174,17 +201,13 @@ class EncoderEngine:
         return ipw, ipb, ow, ob
 
     def zero_grads(self):
-        for g in self.G:
-            for k, v in g.items():
-                for t in (v if isinstance(v, list) else [v]):
-                    self.ops.zero_(t)
-        self.ops.zero_(self.Gf["g"])
-        self.ops.zero_(self.Gf["b"])
+        self.ops.zero_(self.G_flat)
 
     def unpack_grads(self, grads, pfx="", accumulate=False):
         """padded fp32 gradient accumulators -> reference-layout gradient tensors `grads[name]`."""
         o, d = self.ops, self.d
         hm = (d.dh, d.dhp)
+        o.batch_begin("unpack", ("enc", self.uid, pfx))
         for l in range(self.L):
             p = "%slayers.%d." % (pfx, l)
             g = self.G[l]
@@ -205,6 +228,7 @@ class EncoderEngine:
         if self.with_final_ln:
             o.unpack_matrix(self.Gf["g"].view(1, -1), grads[pfx + "layer_norm.weight"].view(1, -1), accumulate=accumulate)
             o.unpack_matrix(self.Gf["b"].view(1, -1), grads[pfx + "layer_norm.bias"].view(1, -1), accumulate=accumulate)
+        o.batch_end()
 
     # ---------------------------------------------------------------- helpers
     def _site(self, layer, idx):

@@ -71,6 +71,7 @@ class MMTrVatEngine:
 
     def pack(self, params):
         o = self.ops
+        o.batch_begin("pack", "model")                        # ONE launch for all ~1400 parameter tensors
         for n in ENC_NAMES:
             self.enc[n].pack(params, "trans_%s." % n)
         for m, g in self.gmu.items():
@@ -80,6 +81,7 @@ class MMTrVatEngine:
             if self.Wproj[m] is not None:
                 w = params["proj_%s.weight" % m]
                 o.pack_matrix(w.view(w.shape[0], w.shape[1]), self.Wproj[m])
+        o.batch_end()
 
     def zero_grads(self):
         for e in self.enc.values():
@@ -92,6 +94,7 @@ class MMTrVatEngine:
                 self.ops.zero_(self.Gproj[m])
 
     def unpack_grads(self, grads, accumulate=False):
+        self.ops.batch_begin("unpack", "model")
         for n in ENC_NAMES:
             self.enc[n].unpack_grads(grads, "trans_%s." % n, accumulate)
         for m, g in self.gmu.items():
@@ -101,6 +104,7 @@ class MMTrVatEngine:
             if self.Gproj[m] is not None:
                 gw = grads["proj_%s.weight" % m]
                 self.ops.unpack_matrix(self.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=accumulate)
+        self.ops.batch_end()
 
     # ---------------------------------------------------------------- forward
     def forward(self, txt, img, audio, training=True, seed=0, seed_ptr=None):

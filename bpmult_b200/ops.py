@@ -45,6 +45,39 @@ class CudaOps:
         if not self.lib.bpm_device_ok(self.device.index or 0):
             raise _lib.BpmError("bpmult_b200: device %s is not sm_100 (B200)" % self.device)
         self.launches = 0
+        self._depth = 0
+        self._batch = None          # (mode, key, [descriptor tuples]) while pack / unpack calls are being collected
+        self._tables = {}           # (mode, key) -> (signature, device table)
+
+    # ------------------------------------------------------------------ batched pack / unpack (one launch per table)
+    def batch_begin(self, mode, key):
+        if self._batch is not None:                 # nested (e.g. an encoder inside the model-level batch): join the outer one
+            self._depth += 1
+            return
+        self._batch, self._depth = (mode, key, []), 0
+
+    def batch_end(self):
+        import numpy as np
+        if self._depth > 0:
+            self._depth -= 1
+            return
+        mode, key, items = self._batch
+        self._batch = None
+        if not items:
+            return
+        sig = tuple(items)
+        ent = self._tables.get((mode, key))
+        if ent is None or ent[0] != sig:
+            dt = np.dtype([("src", "u8"), ("dst", "u8")] + [(n, "i4") for n in ("rows", "cols", "ld_src", "ld_dst", "rows_p", "cols_p", "row_dh",
+                          "row_dhp", "col_dh", "col_dhp", "dst_dtype", "accumulate")] + [("scale", "f4"), ("pad", "i4")], align=True)
+            assert dt.itemsize == 72
+            arr = np.zeros(len(items), dtype=dt)
+            for i, it in enumerate(items):
+                arr[i] = it + (0,)
+            tab = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
+            ent = (sig, tab)
+            self._tables[(mode, key)] = ent
+        self._ck(self.lib.bpm_remap_batch(ent[1].data_ptr(), len(items), 0 if mode == "pack" else 1, self._s()), "remap_batch")
 
     # ------------------------------------------------------------------ helpers
     def _s(self):
@@ -63,12 +96,22 @@ class CudaOps:
 
     # ------------------------------------------------------------------ weight staging
     def pack_matrix(self, src, dst, row_map=(0, 0), col_map=(0, 0)):
-        assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1 and dst.is_contiguous()
+        assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1 and dst.stride(-1) == 1
+        if self._batch is not None and self._batch[0] == "pack":
+            self._batch[2].append((src.data_ptr(), dst.data_ptr(), src.shape[0], src.shape[1], src.stride(0), dst.stride(0), dst.shape[0],
+                                   dst.shape[1], row_map[0], row_map[1], col_map[0], col_map[1], _dt(dst), 0, 1.0))
+            return
+        assert dst.is_contiguous()
         self._ck(self.lib.bpm_pack_matrix(src.data_ptr(), src.shape[0], src.shape[1], src.stride(0), dst.data_ptr(), dst.shape[0],
                                           dst.shape[1], _dt(dst), row_map[0], row_map[1], col_map[0], col_map[1], self._s()), "pack_matrix")
 
     def unpack_matrix(self, src_p, dst, row_map=(0, 0), col_map=(0, 0), accumulate=False, scale=1.0):
         assert src_p.dtype == torch.float32 and dst.dtype == torch.float32 and dst.dim() == 2 and dst.stride(1) == 1
+        if self._batch is not None and self._batch[0] == "unpack":
+            self._batch[2].append((src_p.data_ptr(), dst.data_ptr(), dst.shape[0], dst.shape[1], src_p.stride(0), dst.stride(0), src_p.shape[0],
+                                   src_p.shape[1], row_map[0], row_map[1], col_map[0], col_map[1], 0, int(accumulate), float(scale)))
+            return
+        assert src_p.is_contiguous()
         self._ck(self.lib.bpm_unpack_matrix(src_p.data_ptr(), src_p.shape[0], src_p.shape[1], dst.data_ptr(), dst.shape[0], dst.shape[1],
                                             dst.stride(0), row_map[0], row_map[1], col_map[0], col_map[1], int(accumulate), float(scale),
                                             self._s()), "unpack_matrix")

@@ -109,6 +109,7 @@ class Trainer:
             eng.enc[enc].unpack_grads(self.grads, "trans_%s." % enc)
             reduce_bucket(enc)
         eng.backward(dlogits, None, on_done)
+        o.batch_begin("unpack", "misc")
         for m, g in eng.gmu.items():
             g.unpack_grads(self.grads, "gmu_%s." % m)
         eng.head.unpack_grads(self.grads)
@@ -116,6 +117,7 @@ class Trainer:
             if eng.Gproj[m] is not None:
                 gw = self.grads["proj_%s.weight" % m]
                 o.unpack_matrix(eng.Gproj[m], gw.view(gw.shape[0], gw.shape[1]))
+        o.batch_end()
         reduce_bucket("misc")
         if self.world > 1 and self.on_gpu:
             cur.wait_stream(self.comm)

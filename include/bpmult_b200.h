@@ -57,6 +57,16 @@ int bpm_pack_matrix(const float* src, int rows, int cols, int ld_src, void* dst,
 int bpm_unpack_matrix(const float* src_p, int rows_p, int cols_p, float* dst, int rows, int cols, int ld_dst,
                       int row_dh, int row_dhp, int col_dh, int col_dhp, int accumulate, float scale, void* stream);
 
+/* batched form: one launch for a table of remaps held in DEVICE memory (e.g. all ~115 parameters of an encoder).
+ * mode 0 = pack (src fp32 reference layout -> dst padded, dtype dst_dtype), mode 1 = unpack (src padded fp32 -> dst fp32 reference
+ * layout, (+)= scale * src). */
+typedef struct {
+  const void* src; void* dst;
+  int32_t rows, cols, ld_src, ld_dst, rows_p, cols_p, row_dh, row_dhp, col_dh, col_dhp, dst_dtype, accumulate;
+  float scale; int32_t pad_;
+} bpm_remap_desc_t;
+int bpm_remap_batch(const bpm_remap_desc_t* descs_dev, int n, int mode, void* stream);
+
 /* ---- input staging: models/mmtr.py:741-761 (transpose, embed dropout on text, zero-pad time to n_vec) ----------
  * src fp32 element (b, t, c) at src[b*sb + t*st + c*sc]; dst T rows b*Tp + t, pitch Cp, zero for t >= T or c >= C. */
 int bpm_stage_rows(const float* src, int B, int T, int C, int64_t sb, int64_t st, int64_t sc, void* dst, int Tp, int Cp,

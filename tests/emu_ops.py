@@ -70,6 +70,12 @@ class EmuOps:
     def zero_(self, t):
         t.zero_()
 
+    def batch_begin(self, mode, key):
+        pass
+
+    def batch_end(self):
+        pass
+
     # ------------------------------------------------------------------ weight staging
     def pack_matrix(self, src, dst, row_map=(0, 0), col_map=(0, 0)):
         dst.zero_()
