@@ -31,6 +31,7 @@ struct TcGemmParams {
   int a_bytes, b_bytes;   // per-stage bytes (multiples of 1024)
   int ring_bytes;         // operand ring (>= the epilogue's slot needs)
   int kb_per_split;
+  int gx, gy, split;
   int tmem_cols;
   uint32_t idesc, idesc_ones;
   int elem;               // output / residual / gate element size (2 or 4)
@@ -60,49 +61,49 @@ __device__ __forceinline__ uint32_t swz_off(int r, int u, int chunk_bytes) {
                             : (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((u ^ ((r >> 1) & 3)) << 4));
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n-tile fastest, so the CTAs that
+// run together share A tiles through L2).  Two TMEM accumulators alternate between tiles: the MMA warp starts tile t+1 while the
+// epilogue warps drain tile t, and the TMA producer simply keeps the operand ring full across tile boundaries.
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmG, const TcGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* const base_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  // layout: [operand ring | ones tile 2 KB | bias BN floats | barriers]
-  const uint32_t ones_addr = smem_base + p.ring_bytes;
-  float* const bias_s = (float*)(base_gen + p.ring_bytes + 2048);
-  const uint32_t bar_base = smem_base + p.ring_bytes + 2048 + 1024;
+  // layout: [operand ring | epilogue slots (out x2, res x2, gate x2) | ones tile 2 KB | bias 1 KB | barriers]
+  const int slot_base = p.ring_bytes;
+  const int n_slots = 2 + 2 * p.has_res + 2 * p.has_gate;
+  const int misc = slot_base + n_slots * TC_SLOT;
+  const uint32_t ones_addr = smem_base + misc;
+  float* const bias_s = (float*)(base_gen + misc + 2048);
+  const uint32_t bar_base = smem_base + misc + 2048 + 1024;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * 8;
-  auto in_full = [&](int s) { return bar_base + 8u * (9 + s); };
-  auto in_empty = [&](int s) { return bar_base + 8u * (11 + s); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * 13;
-  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + p.ring_bytes + 2048 + 1024 + 8 * 13);
+  auto tmem_full = [&](int a) { return bar_base + 8u * (8 + a); };
+  auto tmem_empty = [&](int a) { return bar_base + 8u * (10 + a); };
+  auto in_full = [&](int s) { return bar_base + 8u * (12 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * 14;
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + misc + 2048 + 1024 + 8 * 14);
+  const int out_slot = slot_base, res_slot = slot_base + 2 * TC_SLOT, gate_slot = slot_base + (2 + 2 * p.has_res) * TC_SLOT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * p.BN, m0 = blockIdx.y * TC_BM;
   const int num_kb_total = (p.K + TC_BK - 1) / TC_BK;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-  const int num_kb = kb1 - kb0;
-  const bool do_colsum = p.colsum != nullptr && blockIdx.x == 0;
+  const int tiles_mn = p.gx * p.gy;
+  const int total_tiles = tiles_mn * p.split;
+  const int acc_stride = p.tmem_cols >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(in_full(s), 1); mbar_init(in_empty(s), 4); }
+    for (int a = 0; a < 2; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); mbar_init(in_full(a), 1); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
-  if (warp >= 2) {
-    const int t = threadIdx.x - 64;
-    for (int c = t; c < p.BN; c += 128) bias_s[c] = (p.ep.bias && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.f;
-    if (do_colsum) {                                                      // 16 x 64 tile of bf16 ones (B operand of the colsum MMA)
-      uint32_t* o = (uint32_t*)(base_gen + p.ring_bytes);
-      for (int c = t; c < 512; c += 128) o[c] = 0x3F803F80u;
-      fence_async_smem();
-    }
+  if (warp >= 2 && p.colsum != nullptr) {                                   // 16 x 64 tile of bf16 ones (B operand of the colsum MMA)
+    uint32_t* o = (uint32_t*)(base_gen + misc);
+    for (int c = threadIdx.x - 64; c < 512; c += 128) o[c] = 0x3F803F80u;
+    fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -113,78 +114,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       const int b_chunks = (p.BN + 63) / 64;
-      for (int i = 0; i < num_kb; i++) {
-        int s = i % p.stages;
-        uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
-        mbar_expect_tx(full_bar(s), (uint32_t)(p.a_bytes + p.b_bytes));
-        int k = (kb0 + i) * TC_BK;
-        if (!p.a_mn) tma_load_2d(sa, &tmA, full_bar(s), k, m0);                        // box {64 k, 128 m}
-        else { tma_load_2d(sa, &tmA, full_bar(s), m0, k); tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, k); }   // box {64 m, 64 k} x2
-        if (!p.b_mn) tma_load_2d(sb, &tmB, full_bar(s), k, n0);                        // box {64 k, BN n}
-        else
-          for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + 64 * c, k);        // box {64 n, 64 k}
-      }
-      if (p.has_res || p.has_gate) {
-        // epilogue inputs: one [128 x chunk] tile per chunk into 2-deep slot rings that alias the (drained) operand ring
-        mbar_wait(tmem_full_bar, 0);
-        const int cw = p.chunk_bytes / p.elem;
-        const uint32_t tile_bytes = 128u * (uint32_t)p.chunk_bytes;
-        for (int c = 0; c < p.n_chunks; c++) {
-          int s = c & 1;
-          mbar_wait(in_empty(s), ((uint32_t)(c >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(in_full(s), tile_bytes * (uint32_t)(p.has_res + p.has_gate));
-          if (p.has_res) tma_load_2d(smem_base + (2 + s) * TC_SLOT, &tmR, in_full(s), n0 + c * cw, m0);
-          if (p.has_gate) tma_load_2d(smem_base + (4 + s) * TC_SLOT, &tmG, in_full(s), n0 + c * cw, m0);
+      int it = 0;                                                          // running k-block counter (ring position)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM, z = t / tiles_mn;
+        const int kb0 = z * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          int s = it % p.stages;
+          uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
+          mbar_expect_tx(full_bar(s), (uint32_t)(p.a_bytes + p.b_bytes));
+          int k = kb * TC_BK;
+          if (!p.a_mn) tma_load_2d(sa, &tmA, full_bar(s), k, m0);                        // box {64 k, 128 m}
+          else { tma_load_2d(sa, &tmA, full_bar(s), m0, k); tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, k); }   // box {64 m, 64 k} x2
+          if (!p.b_mn) tma_load_2d(sb, &tmB, full_bar(s), k, n0);                        // box {64 k, BN n}
+          else
+            for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + 64 * c, k);        // box {64 n, 64 k}
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      for (int i = 0; i < num_kb; i++) {
-        int s = i % p.stages;
-        uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-        mbar_wait(full_bar(s), ph);
+      int it = 0, tc = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tc++) {
+        const int z = t / tiles_mn;
+        const int kb0 = z * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        const bool do_colsum = p.colsum != nullptr && (t % p.gx) == 0;
+        const int a = tc & 1;
+        const uint32_t acc = tmem_base + (uint32_t)(a * acc_stride);
+        mbar_wait(tmem_empty(a), ((uint32_t)(tc >> 1) & 1u) ^ 1u);           // the epilogue has drained this accumulator
         tc_fence_after();
-        uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          int s = it % p.stages;
+          uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; k++) {
-          // K-major: +32 B per 16-element k step inside the 128 B swizzle row; MN-major: +16 rows * 128 B
-          uint64_t da = p.a_mn ? umma_desc(sa + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sa + k * 32, 16, 1024, BPM_SWZ_128B);
-          uint64_t db = p.b_mn ? umma_desc(sb + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sb + k * 32, 16, 1024, BPM_SWZ_128B);
-          umma_bf16(tmem_base, da, db, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
-          if (do_colsum)      // column sums of dY: dY^T (this A tile) times a tile of ones -> 16 identical columns at TMEM col BN
-            umma_bf16(tmem_base + p.BN, da, umma_desc(ones_addr + k * 32, 16, 1024, BPM_SWZ_128B), p.idesc_ones, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; k++) {
+            // K-major: +32 B per 16-element k step inside the 128 B swizzle row; MN-major: +16 rows * 128 B
+            uint64_t da = p.a_mn ? umma_desc(sa + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sa + k * 32, 16, 1024, BPM_SWZ_128B);
+            uint64_t db = p.b_mn ? umma_desc(sb + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sb + k * 32, 16, 1024, BPM_SWZ_128B);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            umma_bf16(acc, da, db, p.idesc, accum);
+            if (do_colsum)    // column sums of dY: dY^T (this A tile) times a tile of ones -> 16 identical columns behind the accumulator
+              umma_bf16(acc + p.BN, da, umma_desc(ones_addr + k * 32, 16, 1024, BPM_SWZ_128B), p.idesc_ones, accum);
+          }
+          umma_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
         }
-        umma_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+        umma_commit(tmem_full(a));              // accumulator complete
       }
-      umma_commit(tmem_full_bar);             // accumulator complete (and the whole operand ring is drained)
     }
   } else {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const int row = m0 + r;
     const int et = threadIdx.x - 64;                                       // 0..127
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     DropCtx dc = make_drop(p.ep.drop);
     const int cw = p.chunk_bytes / p.elem;                                  // columns per chunk: 16 / 32 / 64
     const int upr = p.chunk_bytes / 16;                                     // 16-byte units per row
-    const int epu = 16 / p.elem;                                            // elements per unit (8 bf16 / 4 fp32)
-    if (num_kb > 0) {
-      for (int c = 0; c < p.n_chunks; c++) {
-        const int s = c & 1;
+    const bool has_in = p.has_res || p.has_gate;
+    const uint32_t in_bytes = 128u * (uint32_t)p.chunk_bytes * (uint32_t)(p.has_res + p.has_gate);
+    // residual / gate tiles are fetched by TMA one chunk AHEAD (running chunk counter cc, 2 slots), also across tile boundaries
+    auto issue_in = [&](int t, int c, int cc) {
+      const int s = cc & 1;
+      const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM;
+      mbar_expect_tx(in_full(s), in_bytes);
+      if (p.has_res) tma_load_2d(smem_base + res_slot + s * TC_SLOT, &tmR, in_full(s), n0 + c * cw, m0);
+      if (p.has_gate) tma_load_2d(smem_base + gate_slot + s * TC_SLOT, &tmG, in_full(s), n0 + c * cw, m0);
+    };
+    int cc = 0, tc = 0;
+    if (has_in && et == 0 && (int)blockIdx.x < total_tiles) issue_in(blockIdx.x, 0, 0);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tc++) {
+      const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM;
+      const int row = m0 + r;
+      const int a = tc & 1;
+      const uint32_t acc = tmem_base + (uint32_t)(a * acc_stride) + lane_off;
+      const bool do_colsum = p.colsum != nullptr && (t % p.gx) == 0;
+      epi_bar();                                                            // previous tile's readers of bias_s are done
+      for (int c = et; c < p.BN; c += 128) bias_s[c] = (p.ep.bias && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.f;
+      epi_bar();
+      mbar_wait(tmem_full(a), (uint32_t)(tc >> 1) & 1u);
+      tc_fence_after();
+      for (int c = 0; c < p.n_chunks; c++, cc++) {
+        const int s = cc & 1;
         const int col0 = c * cw;
         float v[64];
         {
-          const uint32_t taddr = tmem_base + lane_off + (uint32_t)col0;
-          if (cw >= 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-          if (cw == 64) tmem_ld32(taddr + 32, v + 32);
+          if (cw >= 32) tmem_ld32(acc + (uint32_t)col0, v); else tmem_ld16(acc + (uint32_t)col0, v);
+          if (cw == 64) tmem_ld32(acc + (uint32_t)col0 + 32, v + 32);
           tmem_ld_wait();
+        }
+        if (c == p.n_chunks - 1) {
+          float cs[16];
+          if (do_colsum) {
+            tmem_ld16(acc + (uint32_t)p.BN, cs);
+            tmem_ld_wait();
+          }
+          tc_fence_before();                                                // this tile's accumulator is now entirely in registers
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(a));
+          if (do_colsum && row < p.M) atomicAdd(p.colsum + row, cs[0]);
         }
         // ---- bias, alpha, relu, dropout
 #pragma unroll
@@ -204,10 +236,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         // ---- relu-backward gate and residual from the TMA-staged tiles
-        if (p.has_res || p.has_gate) {
-          mbar_wait(in_full(s), (uint32_t)(c >> 1) & 1u);
-          const uint8_t* rs = base_gen + (2 + s) * TC_SLOT;
-          const uint8_t* gs = base_gen + (4 + s) * TC_SLOT;
+        if (has_in) {
+          mbar_wait(in_full(s), (uint32_t)(cc >> 1) & 1u);
+          const uint8_t* rs = base_gen + res_slot + s * TC_SLOT;
+          const uint8_t* gs = base_gen + gate_slot + s * TC_SLOT;
 #pragma unroll
           for (int u = 0; u < 8; u++) {
             if (u < upr) {
@@ -242,13 +274,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(in_empty(s));
         }
         // ---- stage the chunk (swizzled) and hand it to the TMA unit
         if (et == 0) bulk_wait_read<1>();                                   // the store that last used this staging slot has read it
-        epi_bar();
-        uint8_t* st = base_gen + s * TC_SLOT;
+        epi_bar();                                                          // (also: every thread has finished reading in-slot s^1's predecessor)
+        if (has_in && et == 0) {                                            // prefetch the next chunk's residual / gate tile
+          int nt = t, nc = c + 1;
+          if (nc == p.n_chunks) { nt = t + gridDim.x; nc = 0; }
+          if (nt < total_tiles) issue_in(nt, nc, cc + 1);
+        }
+        uint8_t* st = base_gen + out_slot + s * TC_SLOT;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           if (u < upr) {
@@ -263,23 +298,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *(uint4*)(st + swz_off(r, u, p.chunk_bytes)) = w;
           }
         }
-        (void)epu;
         fence_async_smem();
         epi_bar();
         if (et == 0) {
-          if (p.reduce_add) tma_reduce_add_2d(&tmC, smem_base + s * TC_SLOT, n0 + col0, m0);
-          else tma_store_2d(&tmC, smem_base + s * TC_SLOT, n0 + col0, m0);
+          if (p.reduce_add) tma_reduce_add_2d(&tmC, smem_base + out_slot + s * TC_SLOT, n0 + col0, m0);
+          else tma_store_2d(&tmC, smem_base + out_slot + s * TC_SLOT, n0 + col0, m0);
           bulk_commit();
         }
       }
-      if (do_colsum) {
-        float cs[16];
-        tmem_ld16(tmem_base + lane_off + (uint32_t)p.BN, cs);
-        tmem_ld_wait();
-        if (row < p.M) atomicAdd(p.colsum + row, cs[0]);
-      }
-      if (et == 0) bulk_wait_read<0>();                                     // smem must outlive the last TMA store's read
     }
+    if (et == 0) bulk_wait_read<0>();                                       // smem must outlive the last TMA store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -355,20 +383,22 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   TcGemmParams p;
   p.M = g->M; p.N = g->N; p.K = g->K;
   p.colsum = g->colsum_out;
-  p.BN = pick_bn(g->N, p.colsum ? 224 : 256);
+  p.BN = pick_bn(g->N, p.colsum ? 224 : 256);      // 2 x (224 + 16) TMEM columns still fit in 512
   p.a_mn = g->ta ? 1 : 0;
   p.b_mn = g->tb ? 1 : 0;
   p.a_bytes = TC_BM * TC_BK * 2;
   p.b_bytes = p.b_mn ? bpm_cdiv(p.BN, 64) * 8192 : bpm_cdiv(p.BN * 128, 1024) * 1024;
   int stage_bytes = p.a_bytes + p.b_bytes;
-  p.stages = max(2, min(4, (104 * 1024) / stage_bytes));
   p.has_res = g->residual ? 1 : 0;
   p.has_gate = g->gate ? 1 : 0;
   p.reduce_add = g->accumulate ? 1 : 0;
-  const int slots = p.has_gate ? 6 : (p.has_res ? 4 : 2);
-  p.ring_bytes = max(p.stages * stage_bytes, slots * TC_SLOT);
-  p.tmem_cols = 32;
-  while (p.tmem_cols < p.BN + (p.colsum ? 16 : 0)) p.tmem_cols *= 2;
+  const int slots = 2 + 2 * p.has_res + 2 * p.has_gate;
+  const int fixed = slots * TC_SLOT + 2048 + 1024 + 8 * 16 + 1024;         // epilogue slots, ones tile, bias, barriers, alignment slack
+  p.stages = max(2, min(4, (227 * 1024 - fixed) / stage_bytes));
+  p.ring_bytes = p.stages * stage_bytes;
+  // two accumulators (one per in-flight tile); each BN (+16 for the fused column sum) columns wide
+  p.tmem_cols = 64;
+  while (p.tmem_cols < 2 * (p.BN + (p.colsum ? 16 : 0))) p.tmem_cols *= 2;
   p.idesc = umma_idesc_bf16(TC_BM, p.BN, p.a_mn, p.b_mn);
   p.idesc_ones = umma_idesc_bf16(TC_BM, 16, p.a_mn, 0);
   p.elem = elem;
@@ -381,6 +411,7 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   if (g->accumulate) split = g->split_k > 0 ? g->split_k : max(1, min(num_kb / 4, (2 * bpm_num_sms()) / max(1, gx * gy)));
   p.kb_per_split = bpm_cdiv(num_kb, split);
   split = bpm_cdiv(num_kb, p.kb_per_split);
+  p.gx = gx; p.gy = gy; p.split = split;
 
   CUtensorMap tmA, tmB, tmC, tmR, tmG;
   {
@@ -402,16 +433,17 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
     if (g->residual && (rc = make_epi_map(&tmR, g->residual, g->M, g->N, g->ldr, elem, p.chunk_bytes))) return rc;
     if (g->gate && (rc = make_epi_map(&tmG, g->gate, g->M, g->N, g->ldg, elem, p.chunk_bytes))) return rc;
   }
-  size_t smem = (size_t)p.ring_bytes + 2048 + 1024 + 8 * 16 + 1024;
-  BPM_REQUIRE(smem <= 112 * 1024, "gemm_tc: smem %zu too large", smem);
+  size_t smem = (size_t)p.ring_bytes + fixed;
+  BPM_REQUIRE(smem <= 227 * 1024 && p.tmem_cols <= 512, "gemm_tc: smem %zu / tmem %d too large", smem, p.tmem_cols);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { bpm_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
     attr_set = true;
   }
-  dim3 grid(gx, gy, split);
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, tmG, p);
+  int total_tiles = gx * gy * split;
+  int ctas = min(total_tiles, bpm_num_sms());
+  gemm_tc_kernel<<<ctas, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, tmG, p);
   BPM_CHECK_LAUNCH("gemm_tc");
   return BPM_OK;
 }

@@ -6,6 +6,8 @@
 
 #define LN_WARPS 4
 
+// Pad columns of x, gamma and beta are ZERO by contract (include/bpmult_b200.h), so the statistics need no per-element mask:
+//   sum over Dp == sum over D,  sum (x - mean)^2 over D == sum over Dp - (Dp - D) * mean^2,  and y_pad = (0 - mean) * rstd * 0 + 0 = 0.
 template <typename TI, typename TO, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                int rows, int D, int Dp, float eps, TO* __restrict__ y, float* __restrict__ mean_out,
@@ -13,6 +15,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TI* __restr
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int nvec = Dp >> 3;
   float invD = 1.f / (float)D;
+  float npad = (float)(Dp - D);
+  Vec8<float> g[NV], b[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    int c = lane + 32 * i;
+    if (c < nvec) { g[i].load(gamma + c * 8); b[i].load(beta + c * 8); }
+  }
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const TI* xr = x + (int64_t)row * Dp;
     Vec8<TI> v[NV];
@@ -22,8 +31,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TI* __restr
       int c = lane + 32 * i;
       if (c < nvec) {
         v[i].load(xr + c * 8);
-#pragma unroll
-        for (int j = 0; j < 8; j++) s += (c * 8 + j < D) ? v[i].v[j] : 0.f;
+        s += ((v[i].v[0] + v[i].v[1]) + (v[i].v[2] + v[i].v[3])) + ((v[i].v[4] + v[i].v[5]) + (v[i].v[6] + v[i].v[7]));
       }
     }
     float mean = warp_sum(s) * invD;
@@ -33,20 +41,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TI* __restr
       int c = lane + 32 * i;
       if (c < nvec) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) { float d = (c * 8 + j < D) ? v[i].v[j] - mean : 0.f; q += d * d; }
+        for (int j = 0; j < 8; j++) { float d = v[i].v[j] - mean; v[i].v[j] = d; q = fmaf(d, d, q); }
       }
     }
-    float rstd = rsqrtf(warp_sum(q) * invD + eps);
+    float rstd = rsqrtf((warp_sum(q) - npad * mean * mean) * invD + eps);
     if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
     TO* yr = y + (int64_t)row * Dp;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
       int c = lane + 32 * i;
       if (c < nvec) {
-        Vec8<float> g, b; g.load(gamma + c * 8); b.load(beta + c * 8);
         Vec8<TO> o;
 #pragma unroll
-        for (int j = 0; j < 8; j++) o.v[j] = (c * 8 + j < D) ? (v[i].v[j] - mean) * rstd * g.v[j] + b.v[j] : 0.f;
+        for (int j = 0; j < 8; j++) o.v[j] = fmaf(v[i].v[j] * rstd, g[i].v[j], b[i].v[j]);
         o.store(yr + c * 8);
       }
     }
@@ -85,15 +92,16 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
       if (c < nvec) {
         g[i].load(gr + c * 8);
         xv[i].load(xr + c * 8);
+        // dy pads are zero (they come from GEMMs against zero-padded weights) and gamma pads are zero, so only x-hat needs care:
+        // x-hat_pad = -mean * rstd is finite and always multiplied by a zero gradient.
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          bool ok = c * 8 + j < D;
-          float xh = ok ? (xv[i].v[j] - mean) * rstd : 0.f;
-          float gy = ok ? g[i].v[j] : 0.f;
+          float xh = (xv[i].v[j] - mean) * rstd;
+          float gy = g[i].v[j];
           float gh = gy * gm[i].v[j];
           xv[i].v[j] = xh; g[i].v[j] = gh;
-          s1 += gh; s2 += gh * xh;
-          ag[i][j] += gy * xh; ab[i][j] += gy;
+          s1 += gh; s2 = fmaf(gh, xh, s2);
+          ag[i][j] = fmaf(gy, xh, ag[i][j]); ab[i][j] += gy;
         }
       }
     }
@@ -110,8 +118,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
 #pragma unroll
           for (int j = 0; j < 8; j++) o.v[j] = 0.f;
         }
+        if (c * 8 + 8 <= D) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) o.v[j] += (c * 8 + j < D) ? rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2) : 0.f;
+          for (int j = 0; j < 8; j++) o.v[j] += rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2);
+        } else {                                              // the chunk that straddles D (and pure pad chunks): keep pads at zero
+#pragma unroll
+          for (int j = 0; j < 8; j++) o.v[j] += (c * 8 + j < D) ? rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2) : 0.f;
+        }
         o.store(dr + c * 8);
       }
     }
