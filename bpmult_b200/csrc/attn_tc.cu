@@ -304,8 +304,9 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
 
 struct AttnBwdSmem {
   static constexpr int KV = 0;                                  // 2 stages x (K 8 KB + V 8 KB)
-  static constexpr int QD = KV + 2 * 2 * 128 * 64;              // 2 stages x (Q 8 KB + dO 8 KB)
-  static constexpr int PT = QD + 2 * 2 * 128 * 64;              // 2 chunk tiles x 16 KB
+  static constexpr int QD_STAGE = 2 * 128 * 64 + 2048;          // Q 8 KB + dO 8 KB + dropout keep bits (128 queries x 4 words)
+  static constexpr int QD = KV + 2 * 2 * 128 * 64;              // 2 stages
+  static constexpr int PT = QD + 2 * QD_STAGE;                  // 2 chunk tiles x 16 KB
   static constexpr int DST = PT + 2 * 128 * 128;
   static constexpr int LSE = DST + 2 * 128 * 128;               // 512 floats (pre-multiplied by log2e; +inf beyond T)
   static constexpr int DEL = LSE + 512 * 4;
@@ -336,7 +337,8 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const __grid_constant__ CUtensorMap tmdO, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
+                   const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmBits, const int bits_tma,
+                   const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
                    bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
                    const uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
@@ -393,9 +395,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int i = imin; i < nq; i++, pc++) {
           int qs = pc & 1;
           mbar_wait(q_empty(qs), ((uint32_t)(pc >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(q_full(qs), 2 * 128 * 64);
-          tma_load_3d(base + AttnBwdSmem::QD + qs * 16384, &tmQ, q_full(qs), h * AT_DH, i * 128, b);
-          tma_load_3d(base + AttnBwdSmem::QD + qs * 16384 + 8192, &tmdO, q_full(qs), h * AT_DH, i * 128, b);
+          mbar_expect_tx(q_full(qs), 2 * 128 * 64 + (bits_tma ? 2048 : 0));
+          tma_load_3d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, &tmQ, q_full(qs), h * AT_DH, i * 128, b);
+          tma_load_3d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 8192, &tmdO, q_full(qs), h * AT_DH, i * 128, b);
+          if (bits_tma) tma_load_2d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 16384, &tmBits, q_full(qs), j * 4, bh * T + i * 128);
         }
       }
     }
@@ -417,7 +420,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int ks = jc & 1, qs = pc & 1;
         if (i == i_min_of(j)) mbar_wait(kv_full(ks), (uint32_t)(jc >> 1) & 1u);
         const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384, va = ka + 8192;
-        const uint32_t qa = base + AttnBwdSmem::QD + qs * 16384, ga = qa + 8192;
+        const uint32_t qa = base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, ga = qa + 8192;
         mbar_wait(q_full(qs), (uint32_t)(pc >> 1) & 1u);
         mbar_wait(st_free, ((uint32_t)pc & 1u) ^ 1u);
         tc_fence_after();
@@ -439,7 +442,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (nj < nkv) issue_st(nj, ni, pc + 1, njc);
           const int ks = jc & 1, qs = pc & 1, imin = i_min_of(j);
           const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384;
-          const uint32_t qa = base + AttnBwdSmem::QD + qs * 16384, ga = qa + 8192;
+          const uint32_t qa = base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, ga = qa + 8192;
           mbar_wait(pt_full, (uint32_t)pc & 1u);
           if (i == imin) mbar_wait(dkv_free, ((uint32_t)jc & 1u) ^ 1u);        // previous key tile's dK/dV drained from TMEM
           tc_fence_after();
@@ -490,16 +493,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int q0 = i * 128;
         const bool diag = (mask_off >= 0) && (j * 128 + 127 > q0 + mask_off);
         const int cmin = key - mask_off - q0;               // columns < cmin are masked for this key row (diag tiles only)
-        // keep bits written by the forward: word (query, 32-key group); this lane fetches the words of 2 of its 64 columns
+        // keep bits written by the forward: word (query, 32-key group).  Fast path: the TMA producer staged the 128 x 4-word tile of
+        // this pair next to Q / dO (one broadcast LDS per column); otherwise each lane fetches the words of 2 of its 64 columns.
+        const uint32_t* bits_s = (const uint32_t*)(base_gen + AttnBwdSmem::QD + (pc & 1) * AttnBwdSmem::QD_STAGE + 16384) + quarter;
         uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (dc.on && drop_bits != nullptr) {
+        if (dc.on && drop_bits != nullptr && !bits_tma) {
 #pragma unroll
           for (int h2 = 0; h2 < 2; h2++) {
             const int qq = q0 + half * 64 + h2 * 32 + lane;
             mw[h2] = (qq < T && j * 4 + quarter < W) ? drop_bits[((int64_t)bh * T + qq) * W + j * 4 + quarter] : 0u;
           }
         }
-        mbar_wait(st_full, (uint32_t)pc & 1u);
+        mbar_wait(st_full, (uint32_t)pc & 1u);        // (S^T was computed from this pair's Q stage, so its keep-bit tile has landed too)
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
@@ -525,7 +530,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               if (key >= S || (diag && col < cmin)) p = 0.f;
               float mult = 1.f;
               if (dc.on) {
-                if (drop_bits != nullptr) {
+                if (bits_tma) {
+                  mult = ((bits_s[col * 4] >> lane) & 1u) ? dc.inv_keep : 0.f;
+                } else if (drop_bits != nullptr) {
                   const uint32_t wq = __shfl_sync(0xffffffffu, mw[ch], c + e);
                   mult = ((wq >> lane) & 1u) ? dc.inv_keep : 0.f;
                 } else {
@@ -617,6 +624,18 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, 128))) return rc;
   if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, 128))) return rc;
   if ((rc = make_qkv_map(&tg, dout, a->B, a->T, HP, 128))) return rc;
+  // dropout keep bits as a [B*H*T, W] uint32 tensor, box {4 words, 128 queries}; needs a 16-byte pitch (S % 128 == 0)
+  CUtensorMap tb = tq;
+  const int W = (a->S + 31) / 32;
+  const int bits_tma = (a->drop.p > 0.f && a->drop_bits != nullptr && a->S % 128 == 0) ? 1 : 0;
+  if (bits_tma) {
+    bpm_encode_tiled_fn enc = bpm_get_encode_tiled();
+    cuuint64_t gd[2] = {(cuuint64_t)W, (cuuint64_t)a->B * a->H * a->T}, gs[1] = {(cuuint64_t)W * 4};
+    cuuint32_t bx[2] = {4, 128}, es[2] = {1, 1};
+    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)a->drop_bits, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BPM_REQUIRE(r == CUDA_SUCCESS, "xattn_bwd: tensor map for the dropout bits failed (%d)", (int)r);
+  }
   size_t smem = AttnBwdSmem::TOTAL + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -624,7 +643,7 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     if (e != cudaSuccess) { bpm_set_error("xattn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
     attr_set = true;
   }
-  attn_bwd_tc_kernel<<<a->B * a->H, AB_THREADS, smem, stream>>>(tq, tk, tv, tg, lse, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S,
+  attn_bwd_tc_kernel<<<a->B * a->H, AB_THREADS, smem, stream>>>(tq, tk, tv, tg, tb, bits_tma, lse, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S,
                                                                   a->H, a->mask_off, a->drop, a->drop_bits);
   BPM_CHECK_LAUNCH("xattn_bwd_tc");
   return BPM_OK;

@@ -65,9 +65,9 @@ class CudaOps:
         self._batch = None
         if not items:
             return
-        sig = tuple(items)
-        ent = self._tables.get((mode, key))
-        if ent is None or ent[0] != sig:
+        sig = (mode,) + tuple(items)
+        tab = self._tables.get(sig)                 # keyed by the full descriptor list: alternating engines never rebuild (and never
+        if tab is None:                             # trigger a host->device copy inside a CUDA-graph capture)
             dt = np.dtype([("src", "u8"), ("dst", "u8")] + [(n, "i4") for n in ("rows", "cols", "ld_src", "ld_dst", "rows_p", "cols_p", "row_dh",
                           "row_dhp", "col_dh", "col_dhp", "dst_dtype", "accumulate")] + [("scale", "f4"), ("pad", "i4")], align=True)
             assert dt.itemsize == 72
@@ -75,8 +75,10 @@ class CudaOps:
             for i, it in enumerate(items):
                 arr[i] = it + (0,)
             tab = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
-            ent = (sig, tab)
-            self._tables[(mode, key)] = ent
+            if len(self._tables) > 256:
+                self._tables.clear()
+            self._tables[sig] = tab
+        ent = (sig, tab)
         self._ck(self.lib.bpm_remap_batch(ent[1].data_ptr(), len(items), 0 if mode == "pack" else 1, self._s()), "remap_batch")
 
     # ------------------------------------------------------------------ helpers

@@ -15,10 +15,11 @@
  *  - Internal activation layout ("rows"): batch-major rows r = b*T + t, row pitch Dp = round_up(D, 64) elements,
  *    pad columns are ZERO.  Per-head tensors (q, k, v, attention output) use pitch H*dhp, dhp = round_up(dh, 32)
  *    (16 for dh <= 16), head h at columns [h*dhp, h*dhp + dh), pad columns zero.
- *  - Dropout: counter-based Philox4x32-10, 16-bit decisions: one call (key = seed, counter = (e/8, site)) gives 8 half-words;
- *    keep(e) <=> half-word (e%8) >= round(p * 65536) (low half of word (e%8)/2 first); kept values scaled by 1/(1-p).  `e` is the element index in the padded row-major tensor the mask applies to
- *    (for attention: ((b*H + h)*T + i)*S + j).  `seed_ptr` (device, may be NULL) overrides `seed` when non-NULL so a
- *    captured graph can be replayed with a new seed.  Backward kernels regenerate masks from (seed, site).
+ *  - Dropout: counter-based and stateless.  Element e of the padded row-major tensor a mask applies to (for attention:
+ *    ((b*H + h)*T + i)*S + j) takes 16 bits of a 2-round 32-bit avalanche hash of its pair counter e/2, keyed by (seed, site):
+ *    keep(e) <=> half-word >= round(p * 65536); kept values are scaled by 1/(1-p) (exact definition: csrc/bpm_common.cuh).
+ *    `seed_ptr` (device, may be NULL) overrides `seed` when non-NULL so a captured graph can be replayed with a new seed.
+ *    Backward kernels regenerate masks from (seed, site); nothing is stored except the optional attention keep bits.
  */
 #ifndef BPMULT_B200_H
 #define BPMULT_B200_H

@@ -5,40 +5,37 @@ hand-derived backward, dropout-site bookkeeping) can be checked against the orac
 that GPU kernel tests have a second, op-level statement of each contract.  The product never imports this file."""
 import torch
 
-M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
 MASK32 = 0xFFFFFFFF
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """vectorised over int64 tensors holding uint32 values; mirrors csrc/bpm_common.cuh"""
-    for _ in range(10):
-        p0 = M0 * c0
-        p1 = M1 * c2
-        hi0, lo0 = (p0 >> 32) & MASK32, p0 & MASK32
-        hi1, lo1 = (p1 >> 32) & MASK32, p1 & MASK32
-        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
-        k0 = (k0 + W0) & MASK32
-        k1 = (k1 + W1) & MASK32
-    return c0, c1, c2, c3
+def mix32(x):
+    """vectorised over int64 tensors holding uint32 values; mirrors mix32() in csrc/bpm_common.cuh"""
+    x = x ^ (x >> 16)
+    x = (x * 0x7feb352d) & MASK32
+    x = x ^ (x >> 15)
+    x = (x * 0x846ca68b) & MASK32
+    x = x ^ (x >> 16)
+    return x
+
+
+def _mix_int(x):
+    return int(mix32(torch.tensor([x & MASK32], dtype=torch.int64))[0])
 
 
 def drop_mult(drop, idx):
-    """multiplier (0 or 1/(1-p)) for int64 element indices `idx` (any shape): 16-bit decisions, 8 per Philox call"""
+    """multiplier (0 or 1/(1-p)) for int64 element indices `idx` (any shape): 16-bit decisions from a 32-bit avalanche hash of the
+    element-pair counter (see csrc/bpm_common.cuh)"""
     if drop is None or drop.p <= 0:
         return torch.ones(idx.shape, dtype=torch.float32)
     seed = int(drop.seed_ptr.item()) if drop.seed_ptr is not None else int(drop.seed)
     seed &= 0xFFFFFFFFFFFFFFFF
-    q = idx >> 3
-    c0, c1 = q & MASK32, (q >> 32) & MASK32
-    c2 = torch.full_like(q, drop.site & MASK32)
-    c3 = torch.full_like(q, (drop.site >> 32) & MASK32)
-    k0 = torch.full_like(q, seed & MASK32)
-    k1 = torch.full_like(q, (seed >> 32) & MASK32)
-    r = philox4x32_10(c0, c1, c2, c3, k0, k1)
-    lane = idx & 7
-    wi = lane >> 1
-    w = torch.where(wi == 0, r[0], torch.where(wi == 1, r[1], torch.where(wi == 2, r[2], r[3])))
-    hw = (w >> (16 * (lane & 1))) & 0xFFFF
+    site = int(drop.site)
+    k0 = _mix_int((seed & MASK32) ^ _mix_int((site & MASK32) + 0x9E3779B9))
+    k1 = _mix_int(((seed >> 32) & MASK32) ^ _mix_int(((site >> 32) & MASK32) + 0x85EBCA6B) ^ 0xC2B2AE35)
+    pair = idx >> 1
+    lo, hi = pair & MASK32, (pair >> 32) & MASK32
+    r = mix32(lo ^ k0 ^ mix32((hi + k1) & MASK32))
+    hw = torch.where((idx & 1) == 1, r >> 16, r & 0xFFFF)
     p32 = float(torch.tensor(drop.p, dtype=torch.float32))
     thresh = 65536 if p32 >= 1 else int(p32 * 65536.0 + 0.5)
     inv = torch.tensor(1.0, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(drop.p, dtype=torch.float32))
