@@ -37,6 +37,7 @@ SIGNATURES = {
     "bpm_version": [],
     "bpm_last_error": [],
     "bpm_device_ok": [_I],
+    "bpm_debug_set": [_I, _I],
     "bpm_pack_matrix": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpm_unpack_matrix": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "bpm_remap_batch": [_P, _I, _I, _P],

@@ -14,6 +14,11 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
 int bpm_xattn_tc_supported(const bpm_attn_t* a);
 extern "C" int bpm_colsum(const void* X, int dtype, int M, int N, int ld, float* out, void* stream);
 
+// diagnostic knobs for kernel bring-up / profiling (scripts/ only; the product never sets them): slot 0 = GEMM, 1 = attention
+static int g_dbg[4] = {0, 0, 0, 0};
+int bpm_debug_get(int slot) { return g_dbg[slot & 3]; }
+extern "C" int bpm_debug_set(int slot, int value) { g_dbg[slot & 3] = value; return BPM_OK; }
+
 // BPM_DEBUG_FFMA=1 routes bf16 problems through the FFMA kernels too (kernel bring-up / bisecting only).
 static int debug_ffma() {
   static int v = -1;

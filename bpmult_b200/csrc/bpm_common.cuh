@@ -29,6 +29,7 @@ void bpm_set_error(const char* fmt, ...);
 
 static inline int bpm_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 int bpm_num_sms();
+int bpm_debug_get(int slot);   // diagnostic knobs (api.cu)
 
 // ---------------------------------------------------------------- dtype helpers
 template <typename T> __device__ __forceinline__ float to_f(T v);
@@ -79,15 +80,18 @@ template <> struct Vec8<bf16> {
 // ---------------------------------------------------------------- counter-based dropout RNG
 // Dropout needs one cheap, reproducible decision per element, regenerated identically in the backward pass -- not a
 // cryptographic stream.  Philox4x32-10 costs ~15 instructions per element and made every GEMM epilogue with dropout RNG-bound
-// (profiles/r01: fc1 100 us vs 19 us roofline), so decisions come from a 2-round 32-bit integer avalanche hash ("lowbias32"
-// constants) of the element-pair counter:
-//   pair counter c = e >> 1;  h = mix(c_lo ^ key0 ^ mix(c_hi + key1));  element e uses the low (e even) / high (e odd) 16 bits;
-//   keep <=> half-word >= round(p * 65536);  kept values are scaled by 1/(1-p).   key0 / key1 are derived from (seed, site).
+// (profiles/r01: fc1 100 us vs 19 us roofline), so decisions come from a multiply-xorshift-multiply hash of the element-pair
+// counter (4 integer instructions per 32 random bits):
+//   pair counter c = e >> 1;   x = lo32(c) * 0x7feb352d + (k0 ^ hi32(c) * 0x85ebca77);   x ^= x >> 16;   x = x * 0x846ca68b + k1
+//   element e uses the low (e even) / high (e odd) 16 bits;  keep <=> half-word >= round(p * 65536);  kept values are scaled by 1/(1-p).
+//   k0 / k1 are derived from (seed, site) with a full avalanche mix once per kernel.
 struct DropCtx {
   uint32_t k0, k1;      // stream key (seed, site)
   uint32_t thresh;      // drop if half-word < thresh (0 .. 65536)
+  uint32_t t16;         // thresh << 16 (saturated): "x >= t16" tests the high half-word, "(x << 16) >= t16" the low one
   float inv_keep;
   bool on;
+  bool all;             // p >= 1: everything is dropped
 };
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -104,24 +108,29 @@ __device__ __forceinline__ DropCtx make_drop(const bpm_dropout_t& d) {
   c.k0 = mix32((uint32_t)seed ^ mix32((uint32_t)d.site + 0x9E3779B9u));
   c.k1 = mix32((uint32_t)(seed >> 32) ^ mix32((uint32_t)(d.site >> 32) + 0x85EBCA6Bu) ^ 0xC2B2AE35u);
   c.thresh = d.p >= 1.f ? 65536u : (uint32_t)((double)d.p * 65536.0 + 0.5);
+  c.all = c.thresh >= 65536u;
+  c.t16 = c.all ? 0xFFFFFFFFu : (c.thresh << 16);
   c.inv_keep = d.p < 1.f ? 1.f / (1.f - d.p) : 0.f;
   return c;
 }
 
 // 32 random bits for the element pair (2c, 2c+1)
 __device__ __forceinline__ uint32_t drop_rand_pair(const DropCtx& c, uint64_t pair) {
-  return mix32((uint32_t)pair ^ c.k0 ^ mix32((uint32_t)(pair >> 32) + c.k1));
+  uint32_t x = (uint32_t)pair * 0x7feb352du + (c.k0 ^ ((uint32_t)(pair >> 32) * 0x85ebca77u));
+  x ^= x >> 16;
+  return x * 0x846ca68bu + c.k1;
 }
+// keep decisions of the pair's two elements from its 32 random bits
+__device__ __forceinline__ bool drop_keep_lo(const DropCtx& c, uint32_t x) { return (x << 16) >= c.t16 && !c.all; }
+__device__ __forceinline__ bool drop_keep_hi(const DropCtx& c, uint32_t x) { return x >= c.t16 && !c.all; }
 // keep decisions of 8 consecutive elements 8*g .. 8*g+7 as a bit mask (bit i = element 8*g + i is kept)
 __device__ __forceinline__ uint32_t drop_keep8(const DropCtx& c, uint64_t g) {
-  const uint32_t hi = mix32((uint32_t)((g << 2) >> 32) + c.k1) ^ c.k0;    // the 4 pairs of a group share the high counter word
-  const uint32_t lo = (uint32_t)(g << 2);
   uint32_t m = 0;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const uint32_t r = mix32((lo + i) ^ hi);
-    m |= ((r & 0xFFFFu) >= c.thresh ? 1u : 0u) << (2 * i);
-    m |= ((r >> 16) >= c.thresh ? 1u : 0u) << (2 * i + 1);
+    const uint32_t r = drop_rand_pair(c, (g << 2) + i);
+    m |= (drop_keep_lo(c, r) ? 1u : 0u) << (2 * i);
+    m |= (drop_keep_hi(c, r) ? 1u : 0u) << (2 * i + 1);
   }
   return m;
 }
@@ -129,8 +138,7 @@ __device__ __forceinline__ uint32_t drop_keep8(const DropCtx& c, uint64_t g) {
 __device__ __forceinline__ float drop_mult1(const DropCtx& c, uint64_t e) {
   if (!c.on) return 1.f;
   const uint32_t r = drop_rand_pair(c, e >> 1);
-  const uint32_t hw = (e & 1) ? (r >> 16) : (r & 0xFFFFu);
-  return hw >= c.thresh ? c.inv_keep : 0.f;
+  return ((e & 1) ? drop_keep_hi(c, r) : drop_keep_lo(c, r)) ? c.inv_keep : 0.f;
 }
 // multipliers for 8 consecutive elements starting at e (e % 8 == 0)
 __device__ __forceinline__ void drop_mult8(const DropCtx& c, uint64_t e, float* m) {
@@ -139,9 +147,12 @@ __device__ __forceinline__ void drop_mult8(const DropCtx& c, uint64_t e, float* 
     for (int i = 0; i < 8; i++) m[i] = 1.f;
     return;
   }
-  const uint32_t k = drop_keep8(c, e >> 3);
 #pragma unroll
-  for (int i = 0; i < 8; i++) m[i] = ((k >> i) & 1u) ? c.inv_keep : 0.f;
+  for (int i = 0; i < 4; i++) {
+    const uint32_t r = drop_rand_pair(c, (e >> 1) + i);
+    m[2 * i] = drop_keep_lo(c, r) ? c.inv_keep : 0.f;
+    m[2 * i + 1] = drop_keep_hi(c, r) ? c.inv_keep : 0.f;
+  }
 }
 
 // ---------------------------------------------------------------- warp / block reductions

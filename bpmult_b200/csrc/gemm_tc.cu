@@ -1,27 +1,33 @@
 // bf16 GEMM on 5th-gen tensor cores (sm_100a): TMA (SWIZZLE_128B) -> shared memory ring -> tcgen05.mma (cta_group::1,
 // M = 128, N = BN <= 256, K = 16 per instruction) -> fp32 accumulator in TMEM -> tcgen05.ld -> fused epilogue -> TMA store.
 //
-//  * Warp roles (192 threads): warp 0 = TMA producer (operands, then the epilogue's residual / gate tiles), warp 1 = TMEM
-//    allocator + single-thread MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4, one thread per row).
+//  * Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so the CTAs that run
+//    together share A tiles through L2).  Two TMEM accumulators alternate between tiles: the MMA warp starts tile t+1 while
+//    the epilogue warps drain tile t; the TMA producer keeps the operand ring full across tile boundaries.
+//  * Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer (descriptors are
+//    formed once and advanced by adds: the issuing thread is latency-bound, every instruction in its loop counts),
+//    warps 2..9 = epilogue.  K is only 320..1216 here (5..19 k-blocks per tile), so the kernel lives or dies by its epilogue:
+//    each epilogue warp owns the 32 accumulator rows of its TMEM lane quarter (warp % 4) and every second 128-byte column
+//    chunk, and runs its OWN pipeline with no CTA-wide barrier: tcgen05.ld -> math -> swizzled staging buffer (conflict-free
+//    16-byte stores) -> one TMA store (or TMA reduce-add for split-K wgrad) of a {chunk, 32 rows} box.  Two warps per
+//    scheduler hide each other's TMEM / shared-memory latency.
+//  * A residual (or relu-backward gate) tile is fetched by the same warp with a TMA load INTO its staging buffer two chunks
+//    ahead, combined in place, and stored from there: every global access of the epilogue is a full 128-byte line and
+//    M / N tails are clipped by the TMA unit.
 //  * All four operand layouts without any transposed copies: K-major operands use the canonical SW128 K-major layout
 //    (SBO = 1024 B); "transposed" operands (dgrad's W, wgrad's dY^T and X) are loaded as 64-wide MN chunks and described to
 //    the MMA as MN-major (LBO = BK*128 B between chunks, SBO = 1024 B between 8-row k groups).
-//  * Epilogue: K is only 300..1216 here (5..19 k-blocks per tile), so the kernel lives or dies by its epilogue.  The
-//    accumulator is drained in 128-byte-wide column chunks; residual / relu-gate tiles arrive by TMA into shared memory
-//    (prefetched one chunk ahead), the bias sits in shared memory, results are staged in shared memory (swizzled, conflict
-//    free) and leave with ONE TMA store per chunk (or one TMA reduce-add for split-K wgrad) -- every global access is a
-//    full 128-byte line and M / N tails are clipped by the TMA unit.  The staging buffers alias the drained operand ring.
-//  * Two CTAs are co-resident per SM (<= 111 KB smem, <= 256 TMEM columns each): one CTA's epilogue overlaps the other's
-//    main loop.
-//  * wgrad (K = B*T rows) is split along K across blockIdx.z.  The bias gradient (column sums of dY) is fused into wgrad as
-//    one extra N=16 MMA per k-step against a tile of ones (dY^T * 1), so dY is never re-read for it.
+//  * wgrad (K = B*T rows) is split along K across tiles.  The bias gradient (column sums of dY) is fused into wgrad as one
+//    extra N=16 MMA per k-step against a tile of ones (dY^T * 1), so dY is never re-read for it.
 #include "gemm_epilogue.cuh"
 #include "tc_common.cuh"
 
 #define TC_BM 128
 #define TC_BK 64
-#define TC_THREADS 192
-#define TC_SLOT 16384          // one 128-row x 128-byte epilogue tile
+#define TC_EPI_WARPS 8
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS)
+#define TC_MAX_STAGES 6
+#define TC_MAX_NB 4
 
 struct TcGemmParams {
   int M, N, K;
@@ -29,17 +35,19 @@ struct TcGemmParams {
   int a_mn, b_mn;         // 1: operand is MN-major in memory ("transposed")
   int stages;
   int a_bytes, b_bytes;   // per-stage bytes (multiples of 1024)
-  int ring_bytes;         // operand ring (>= the epilogue's slot needs)
+  int ring_bytes;
   int kb_per_split;
   int gx, gy, split;
   int tmem_cols;
   uint32_t idesc, idesc_ones;
-  int elem;               // output / residual / gate element size (2 or 4)
-  int chunk_bytes;        // 128 or 64: bytes per row of one epilogue chunk
-  int n_chunks;
-  int has_res, has_gate, reduce_add;
+  int n_chunks;           // column chunks per tile
+  int nb;                 // staging buffers per epilogue warp (2..4)
+  int in_mode;            // 0 none, 1 residual (added), 2 gate (relu-backward mask from a saved activation)
+  int reduce_add;
   float* colsum;          // fused bias gradient (wgrad only), or null
-  EpiParams ep;
+  int dbg;                // diagnostic knobs (bpm_debug_set slot 0): 1 no TMA loads, 2 no MMAs, 4 no epilogue math, 8 no staging/store, 16 no tcgen05.ld
+  const float* bias; float alpha; int act; float gate_scale; int ldc;
+  bpm_dropout_t drop;
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
@@ -53,39 +61,43 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// byte offset of 16-byte unit u of row r inside a swizzled [128 rows x chunk_bytes] tile (TMA SWIZZLE_128B / SWIZZLE_64B)
-__device__ __forceinline__ uint32_t swz_off(int r, int u, int chunk_bytes) {
-  return chunk_bytes == 128 ? (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4))
-                            : (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((u ^ ((r >> 1) & 3)) << 4));
+__device__ __forceinline__ void bulk_wait_read_n(int n) {
+  if (n <= 0) bulk_wait_read<0>();
+  else if (n == 1) bulk_wait_read<1>();
+  else if (n == 2) bulk_wait_read<2>();
+  else bulk_wait_read<3>();
 }
 
-// Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  (n-tile fastest, so the CTAs that
-// run together share A tiles through L2).  Two TMEM accumulators alternate between tiles: the MMA warp starts tile t+1 while the
-// epilogue warps drain tile t, and the TMA producer simply keeps the operand ring full across tile boundaries.
+// byte offset of 16-byte unit u of row r inside a swizzled [32 rows x CB] box (TMA SWIZZLE_128B / SWIZZLE_64B)
+template <int CB> __device__ __forceinline__ uint32_t swz_off(int r, int u) {
+  return CB == 128 ? (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)) : (uint32_t)(r * 64 + ((u ^ ((r >> 1) & 3)) << 4));
+}
+
+// ELEM: bytes per output element (2 = bf16, 4 = fp32); CB: bytes per row of one epilogue chunk (128, or 64 when BN * ELEM is not
+// a multiple of 128).  CW = CB / ELEM accumulator columns per chunk.
+template <int ELEM, int CB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmG, const TcGemmParams p) {
+               const __grid_constant__ CUtensorMap tmI, const TcGemmParams p) {
+  constexpr int CW = CB / ELEM;
+  constexpr int EB = 32 * CB;                                             // bytes of one staging buffer ({CW cols, 32 rows} box)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* const base_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  // layout: [operand ring | epilogue slots (out x2, res x2, gate x2) | ones tile 2 KB | bias 1 KB | barriers]
-  const int slot_base = p.ring_bytes;
-  const int n_slots = 2 + 2 * p.has_res + 2 * p.has_gate;
-  const int misc = slot_base + n_slots * TC_SLOT;
+  // layout: [operand ring | staging buffers: 8 warps x nb x EB | ones tile 2 KB | barriers]
+  const int ebuf_base = p.ring_bytes;
+  const int misc = ebuf_base + TC_EPI_WARPS * p.nb * EB;
   const uint32_t ones_addr = smem_base + misc;
-  float* const bias_s = (float*)(base_gen + misc + 2048);
-  const uint32_t bar_base = smem_base + misc + 2048 + 1024;
+  const uint32_t bar_base = smem_base + misc + 2048;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
-  auto tmem_full = [&](int a) { return bar_base + 8u * (8 + a); };
-  auto tmem_empty = [&](int a) { return bar_base + 8u * (10 + a); };
-  auto in_full = [&](int s) { return bar_base + 8u * (12 + s); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * 14;
-  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + misc + 2048 + 1024 + 8 * 14);
-  const int out_slot = slot_base, res_slot = slot_base + 2 * TC_SLOT, gate_slot = slot_base + (2 + 2 * p.has_res) * TC_SLOT;
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  auto tmem_full = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
+  auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+  auto in_full = [&](int w, int b) { return bar_base + 8u * (2 * TC_MAX_STAGES + 4 + w * TC_MAX_NB + b); };
+  constexpr int NBARS = 2 * TC_MAX_STAGES + 4 + TC_EPI_WARPS * TC_MAX_NB;
+  const uint32_t tmem_ptr_addr = bar_base + 8u * NBARS;
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + misc + 2048 + 8 * NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb_total = (p.K + TC_BK - 1) / TC_BK;
@@ -95,14 +107,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
+    if (p.in_mode) tma_prefetch_desc(&tmI);
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); mbar_init(in_full(a), 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), TC_EPI_WARPS); }
+    for (int w = 0; w < TC_EPI_WARPS; w++)
+      for (int b = 0; b < p.nb; b++) mbar_init(in_full(w, b), 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
   if (warp >= 2 && p.colsum != nullptr) {                                   // 16 x 64 tile of bf16 ones (B operand of the colsum MMA)
     uint32_t* o = (uint32_t*)(base_gen + misc);
-    for (int c = threadIdx.x - 64; c < 512; c += 128) o[c] = 0x3F803F80u;
+    for (int c = threadIdx.x - 64; c < 512; c += 32 * TC_EPI_WARPS) o[c] = 0x3F803F80u;
     fence_async_smem();
   }
   tc_fence_before();
@@ -114,29 +129,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       const int b_chunks = (p.BN + 63) / 64;
-      int it = 0;                                                          // running k-block counter (ring position)
+      const uint32_t tx = (uint32_t)stage_bytes;
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM, z = t / tiles_mn;
         const int kb0 = z * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; kb++, it++) {
-          int s = it % p.stages;
-          uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(empty_bar(s), ph ^ 1u);
-          uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
-          mbar_expect_tx(full_bar(s), (uint32_t)(p.a_bytes + p.b_bytes));
-          int k = kb * TC_BK;
-          if (!p.a_mn) tma_load_2d(sa, &tmA, full_bar(s), k, m0);                        // box {64 k, 128 m}
-          else { tma_load_2d(sa, &tmA, full_bar(s), m0, k); tma_load_2d(sa + 8192, &tmA, full_bar(s), m0 + 64, k); }   // box {64 m, 64 k} x2
-          if (!p.b_mn) tma_load_2d(sb, &tmB, full_bar(s), k, n0);                        // box {64 k, BN n}
-          else
-            for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + 64 * c, k);        // box {64 n, 64 k}
+          const uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
+          const uint32_t fb = full_bar(s);
+          if (p.dbg & 1) {
+            mbar_arrive(fb);
+          } else {
+            mbar_expect_tx(fb, tx);
+            const int k = kb * TC_BK;
+            if (!p.a_mn) tma_load_2d(sa, &tmA, fb, k, m0);                                  // box {64 k, 128 m}
+            else { tma_load_2d(sa, &tmA, fb, m0, k); tma_load_2d(sa + 8192, &tmA, fb, m0 + 64, k); }   // box {64 m, 64 k} x2
+            if (!p.b_mn) tma_load_2d(sb, &tmB, fb, k, n0);                                  // box {64 k, BN n}
+            else
+              for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, fb, n0 + 64 * c, k);   // box {64 n, 64 k}
+          }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      int it = 0, tc = 0;
+      // descriptor templates: K-major SW128 (LBO 16, SBO 1024; +32 B per k16 step) or MN-major (LBO BK*128, SBO 1024; +2048 B per step)
+      const uint64_t da_t = p.a_mn ? umma_desc(0, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(0, 16, 1024, BPM_SWZ_128B);
+      const uint64_t db_t = p.b_mn ? umma_desc(0, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(0, 16, 1024, BPM_SWZ_128B);
+      const uint64_t da_k = p.a_mn ? (2048 >> 4) : (32 >> 4), db_k = p.b_mn ? (2048 >> 4) : (32 >> 4);
+      const uint64_t d_ones = umma_desc(ones_addr, 16, 1024, BPM_SWZ_128B);
+      const bool no_mma = (p.dbg & 2) != 0;
+      int s = 0, tc = 0;
+      uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tc++) {
         const int z = t / tiles_mn;
         const int kb0 = z * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
@@ -145,169 +173,217 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t acc = tmem_base + (uint32_t)(a * acc_stride);
         mbar_wait(tmem_empty(a), ((uint32_t)(tc >> 1) & 1u) ^ 1u);           // the epilogue has drained this accumulator
         tc_fence_after();
-        for (int kb = kb0; kb < kb1; kb++, it++) {
-          int s = it % p.stages;
-          uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        uint32_t accum = 0;
+        for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
+          const uint32_t sa = smem_base + s * stage_bytes;
+          uint64_t da = da_t | (uint64_t)((sa & 0x3FFFFu) >> 4), db = db_t | (uint64_t)(((sa + p.a_bytes) & 0x3FFFFu) >> 4);
+          if (!no_mma) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; k++) {
-            // K-major: +32 B per 16-element k step inside the 128 B swizzle row; MN-major: +16 rows * 128 B
-            uint64_t da = p.a_mn ? umma_desc(sa + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sa + k * 32, 16, 1024, BPM_SWZ_128B);
-            uint64_t db = p.b_mn ? umma_desc(sb + k * 2048, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(sb + k * 32, 16, 1024, BPM_SWZ_128B);
-            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
-            umma_bf16(acc, da, db, p.idesc, accum);
-            if (do_colsum)    // column sums of dY: dY^T (this A tile) times a tile of ones -> 16 identical columns behind the accumulator
-              umma_bf16(acc + p.BN, da, umma_desc(ones_addr + k * 32, 16, 1024, BPM_SWZ_128B), p.idesc_ones, accum);
+            for (int k = 0; k < TC_BK / 16; k++) {
+              umma_bf16(acc, da, db, p.idesc, accum);
+              // column sums of dY: dY^T (this A tile) times a tile of ones -> 16 identical columns behind the accumulator
+              if (do_colsum) umma_bf16(acc + p.BN, da, d_ones + 2 * k, p.idesc_ones, accum);
+              accum = 1;
+              da += da_k; db += db_k;
+            }
           }
           umma_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         umma_commit(tmem_full(a));              // accumulator complete
       }
     }
   } else {
     // ===================== epilogue warps =====================
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;                                       // 0..127
+    const int ew = warp - 2;                                               // 0..7
+    const int quarter = warp & 3;                                          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                                              // takes chunks half, half + 2, ...
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    DropCtx dc = make_drop(p.ep.drop);
-    const int cw = p.chunk_bytes / p.elem;                                  // columns per chunk: 16 / 32 / 64
-    const int upr = p.chunk_bytes / 16;                                     // 16-byte units per row
-    const bool has_in = p.has_res || p.has_gate;
-    const uint32_t in_bytes = 128u * (uint32_t)p.chunk_bytes * (uint32_t)(p.has_res + p.has_gate);
-    // residual / gate tiles are fetched by TMA one chunk AHEAD (running chunk counter cc, 2 slots), also across tile boundaries
-    auto issue_in = [&](int t, int c, int cc) {
-      const int s = cc & 1;
-      const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM;
-      mbar_expect_tx(in_full(s), in_bytes);
-      if (p.has_res) tma_load_2d(smem_base + res_slot + s * TC_SLOT, &tmR, in_full(s), n0 + c * cw, m0);
-      if (p.has_gate) tma_load_2d(smem_base + gate_slot + s * TC_SLOT, &tmG, in_full(s), n0 + c * cw, m0);
+    const DropCtx dc = make_drop(p.drop);
+    const float alpha = dc.on ? p.alpha * dc.inv_keep : p.alpha;
+    const int nb = p.nb;
+    const int dist = nb - 1;                                               // residual / gate prefetch distance (chunks)
+    uint8_t* const ebuf_gen = base_gen + ebuf_base + ew * nb * EB;
+    const uint32_t ebuf_s = smem_base + ebuf_base + ew * nb * EB;
+    const bool skip_ld = (p.dbg & 16) != 0, skip_math = (p.dbg & 4) != 0, skip_store = (p.dbg & 8) != 0;
+
+    // this warp's chunk sequence over its tiles: (t, c) with c = half, half+2, ... while the chunk starts inside N
+    auto chunk_ok = [&](int t, int c) { return c < p.n_chunks && (t % p.gx) * p.BN + c * CW < p.N; };
+    auto advance = [&](int& t, int& c) {
+      c += 2;
+      while (t < total_tiles && !chunk_ok(t, c)) { t += gridDim.x; c = half; }
     };
-    int cc = 0, tc = 0;
-    if (has_in && et == 0 && (int)blockIdx.x < total_tiles) issue_in(blockIdx.x, 0, 0);
+    auto issue_in = [&](int t, int c, int idx) {                           // lane 0 only
+      const int b = idx % nb;
+      const int n = (t % p.gx) * p.BN + c * CW, m = ((t / p.gx) % p.gy) * TC_BM + quarter * 32;
+      mbar_expect_tx(in_full(ew, b), (uint32_t)EB);
+      tma_load_2d(ebuf_s + b * EB, &tmI, in_full(ew, b), n, m);
+    };
+    int pt = blockIdx.x, pc = half - 2, issued = 0;                        // prefetch cursor
+    if (p.in_mode) {
+      advance(pt, pc);
+      for (int i = 0; i < dist && pt < total_tiles; i++) {
+        if (lane == 0) issue_in(pt, pc, issued);
+        issued++;
+        advance(pt, pc);
+      }
+    }
+
+    int done = 0, tc = 0;                                                  // chunks processed by this warp; tiles seen
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tc++) {
-      const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM;
-      const int row = m0 + r;
+      const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM + quarter * 32;
+      const int row = m0 + lane;
       const int a = tc & 1;
       const uint32_t acc = tmem_base + (uint32_t)(a * acc_stride) + lane_off;
-      const bool do_colsum = p.colsum != nullptr && (t % p.gx) == 0;
-      epi_bar();                                                            // previous tile's readers of bias_s are done
-      for (int c = et; c < p.BN; c += 128) bias_s[c] = (p.ep.bias && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.f;
-      epi_bar();
+      const bool do_colsum = p.colsum != nullptr && n0 == 0 && half == 0;
+      int last_c = -1;
+      for (int c = half; chunk_ok(t, c); c += 2) last_c = c;
       mbar_wait(tmem_full(a), (uint32_t)(tc >> 1) & 1u);
       tc_fence_after();
-      for (int c = 0; c < p.n_chunks; c++, cc++) {
-        const int s = cc & 1;
-        const int col0 = c * cw;
-        float v[64];
-        {
-          if (cw >= 32) tmem_ld32(acc + (uint32_t)col0, v); else tmem_ld16(acc + (uint32_t)col0, v);
-          if (cw == 64) tmem_ld32(acc + (uint32_t)col0 + 32, v + 32);
+      if (last_c < 0) {                                                    // nothing for this warp in this tile
+        if (do_colsum) {
+          float cs[16];
+          tmem_ld16(acc + (uint32_t)p.BN, cs);
+          tmem_ld_wait();
+          if (row < p.M) atomicAdd(p.colsum + row, cs[0]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(a));
+        continue;
+      }
+      for (int c = half; c <= last_c; c += 2, done++) {
+        const int b = done % nb;
+        const int col0 = c * CW, n = n0 + col0;
+        float v[CW];
+        if (!skip_ld) {
+          if constexpr (CW == 64) { tmem_ld32(acc + (uint32_t)col0, v); tmem_ld32(acc + (uint32_t)col0 + 32, v + 32); }
+          else if constexpr (CW == 32) tmem_ld32(acc + (uint32_t)col0, v);
+          else tmem_ld16(acc + (uint32_t)col0, v);
           tmem_ld_wait();
         }
-        if (c == p.n_chunks - 1) {
-          float cs[16];
+        if (c == last_c) {
+          float cs0 = 0.f;
           if (do_colsum) {
+            float cs[16];
             tmem_ld16(acc + (uint32_t)p.BN, cs);
             tmem_ld_wait();
+            cs0 = cs[0];
           }
-          tc_fence_before();                                                // this tile's accumulator is now entirely in registers
+          tc_fence_before();                                                // this warp's part of the accumulator is in registers
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(a));
-          if (do_colsum && row < p.M) atomicAdd(p.colsum + row, cs[0]);
+          if (do_colsum && row < p.M) atomicAdd(p.colsum + row, cs0);
         }
         // ---- bias, alpha, relu, dropout
+        if (!skip_math) {
+          if (p.bias != nullptr) {
 #pragma unroll
-        for (int g8 = 0; g8 < 8; g8++) {
-          if (g8 * 8 < cw) {
-            float mlt[8];
-            const int n = n0 + col0 + g8 * 8;
-            drop_mult8(dc, (uint64_t)row * (uint64_t)p.ep.ldc + (uint64_t)n, mlt);
-            const float4 b0 = *(const float4*)(bias_s + col0 + g8 * 8), b1 = *(const float4*)(bias_s + col0 + g8 * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-              float x = (v[g8 * 8 + e] + bb[e]) * p.ep.alpha;
-              if (p.ep.act == 1) x = fmaxf(x, 0.f);
-              v[g8 * 8 + e] = x * mlt[e];
+            for (int g4 = 0; g4 < CW / 4; g4++) {
+              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (n + g4 * 4 + 4 <= p.N) bb = __ldg((const float4*)(p.bias + n + g4 * 4));
+              v[g4 * 4] += bb.x; v[g4 * 4 + 1] += bb.y; v[g4 * 4 + 2] += bb.z; v[g4 * 4 + 3] += bb.w;
             }
           }
-        }
-        // ---- relu-backward gate and residual from the TMA-staged tiles
-        if (has_in) {
-          mbar_wait(in_full(s), (uint32_t)(cc >> 1) & 1u);
-          const uint8_t* rs = base_gen + res_slot + s * TC_SLOT;
-          const uint8_t* gs = base_gen + gate_slot + s * TC_SLOT;
+          if (alpha != 1.f) {          // (the dropout scale 1/(1-p) is folded into alpha: relu is positively homogeneous)
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            if (u < upr) {
-              const uint32_t off = swz_off(r, u, p.chunk_bytes);
-              if (p.has_gate) {
-                const uint4 w = *(const uint4*)(gs + off);
-                if (p.elem == 2) {
-                  const __nv_bfloat162* h2 = (const __nv_bfloat162*)&w;
-#pragma unroll
-                  for (int e = 0; e < 4; e++) {
-                    const float2 f = __bfloat1622float2(h2[e]);
-                    v[u * 8 + 2 * e] = f.x > 0.f ? v[u * 8 + 2 * e] * p.ep.gate_scale : 0.f;
-                    v[u * 8 + 2 * e + 1] = f.y > 0.f ? v[u * 8 + 2 * e + 1] * p.ep.gate_scale : 0.f;
-                  }
-                } else {
-                  const float* f = (const float*)&w;
-#pragma unroll
-                  for (int e = 0; e < 4; e++) v[u * 4 + e] = f[e] > 0.f ? v[u * 4 + e] * p.ep.gate_scale : 0.f;
-                }
-              }
-              if (p.has_res) {
-                const uint4 w = *(const uint4*)(rs + off);
-                if (p.elem == 2) {
-                  const __nv_bfloat162* h2 = (const __nv_bfloat162*)&w;
-#pragma unroll
-                  for (int e = 0; e < 4; e++) { const float2 f = __bfloat1622float2(h2[e]); v[u * 8 + 2 * e] += f.x; v[u * 8 + 2 * e + 1] += f.y; }
-                } else {
-                  const float* f = (const float*)&w;
-#pragma unroll
-                  for (int e = 0; e < 4; e++) v[u * 4 + e] += f[e];
-                }
-              }
-            }
+            for (int e = 0; e < CW; e++) v[e] *= alpha;
           }
-        }
-        // ---- stage the chunk (swizzled) and hand it to the TMA unit
-        if (et == 0) bulk_wait_read<1>();                                   // the store that last used this staging slot has read it
-        epi_bar();                                                          // (also: every thread has finished reading in-slot s^1's predecessor)
-        if (has_in && et == 0) {                                            // prefetch the next chunk's residual / gate tile
-          int nt = t, nc = c + 1;
-          if (nc == p.n_chunks) { nt = t + gridDim.x; nc = 0; }
-          if (nt < total_tiles) issue_in(nt, nc, cc + 1);
-        }
-        uint8_t* st = base_gen + out_slot + s * TC_SLOT;
+          if (p.act == 1) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          if (u < upr) {
-            uint4 w;
-            if (p.elem == 2) {
-              __nv_bfloat162* h2 = (__nv_bfloat162*)&w;
+            for (int e = 0; e < CW; e++) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (dc.on) {
+            const uint64_t pair0 = ((uint64_t)row * (uint64_t)p.ldc + (uint64_t)n) >> 1;
+            const uint32_t lo0 = (uint32_t)pair0;
+            if (lo0 + (uint32_t)(CW / 2) >= lo0) {                           // no carry into the high counter word inside this chunk
+              const uint32_t hk = dc.k0 ^ ((uint32_t)(pair0 >> 32) * 0x85ebca77u);
 #pragma unroll
-              for (int e = 0; e < 4; e++) h2[e] = __floats2bfloat162_rn(v[u * 8 + 2 * e], v[u * 8 + 2 * e + 1]);
+              for (int j = 0; j < CW / 2; j++) {
+                uint32_t x = (lo0 + (uint32_t)j) * 0x7feb352du + hk;
+                x ^= x >> 16;
+                x = x * 0x846ca68bu + dc.k1;
+                v[2 * j] = drop_keep_lo(dc, x) ? v[2 * j] : 0.f;
+                v[2 * j + 1] = drop_keep_hi(dc, x) ? v[2 * j + 1] : 0.f;
+              }
             } else {
-              w = make_uint4(__float_as_uint(v[u * 4]), __float_as_uint(v[u * 4 + 1]), __float_as_uint(v[u * 4 + 2]), __float_as_uint(v[u * 4 + 3]));
+#pragma unroll
+              for (int j = 0; j < CW / 2; j++) {
+                const uint32_t x = drop_rand_pair(dc, pair0 + j);
+                v[2 * j] = drop_keep_lo(dc, x) ? v[2 * j] : 0.f;
+                v[2 * j + 1] = drop_keep_hi(dc, x) ? v[2 * j + 1] : 0.f;
+              }
             }
-            *(uint4*)(st + swz_off(r, u, p.chunk_bytes)) = w;
           }
+        }
+        if (skip_store) continue;
+        uint8_t* const st = ebuf_gen + b * EB;
+        if (p.in_mode) {
+          // ---- relu-backward gate or residual from the tile the TMA unit placed in this warp's staging buffer
+          mbar_wait(in_full(ew, b), (uint32_t)(done / nb) & 1u);
+#pragma unroll
+          for (int u = 0; u < CB / 16; u++) {
+            const uint4 w = *(const uint4*)(st + swz_off<CB>(lane, u));
+            if constexpr (ELEM == 2) {
+              const __nv_bfloat162* h2 = (const __nv_bfloat162*)&w;
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                if (p.in_mode == 2) {
+                  v[u * 8 + 2 * e] = f.x > 0.f ? v[u * 8 + 2 * e] * p.gate_scale : 0.f;
+                  v[u * 8 + 2 * e + 1] = f.y > 0.f ? v[u * 8 + 2 * e + 1] * p.gate_scale : 0.f;
+                } else {
+                  v[u * 8 + 2 * e] += f.x;
+                  v[u * 8 + 2 * e + 1] += f.y;
+                }
+              }
+            } else {
+              const float* f = (const float*)&w;
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                if (p.in_mode == 2) v[u * 4 + e] = f[e] > 0.f ? v[u * 4 + e] * p.gate_scale : 0.f;
+                else v[u * 4 + e] += f[e];
+              }
+            }
+          }
+          // the buffer of chunk done + dist is the one chunk done - 1 was stored from: once the TMA unit has read it, refill it
+          if (pt < total_tiles) {
+            if (lane == 0) {
+              bulk_wait_read<0>();
+              issue_in(pt, pc, issued);
+            }
+            issued++;
+            advance(pt, pc);
+          }
+        } else {
+          if (lane == 0) bulk_wait_read_n(nb - 1);                          // the store that last used this buffer has read it
+          __syncwarp();
+        }
+        // ---- stage the chunk (swizzled, in place over the residual / gate tile) and hand it to the TMA unit
+#pragma unroll
+        for (int u = 0; u < CB / 16; u++) {
+          uint4 w;
+          if constexpr (ELEM == 2) {
+            __nv_bfloat162* h2 = (__nv_bfloat162*)&w;
+#pragma unroll
+            for (int e = 0; e < 4; e++) h2[e] = __floats2bfloat162_rn(v[u * 8 + 2 * e], v[u * 8 + 2 * e + 1]);
+          } else {
+            w = make_uint4(__float_as_uint(v[u * 4]), __float_as_uint(v[u * 4 + 1]), __float_as_uint(v[u * 4 + 2]), __float_as_uint(v[u * 4 + 3]));
+          }
+          *(uint4*)(st + swz_off<CB>(lane, u)) = w;
         }
         fence_async_smem();
-        epi_bar();
-        if (et == 0) {
-          if (p.reduce_add) tma_reduce_add_2d(&tmC, smem_base + out_slot + s * TC_SLOT, n0 + col0, m0);
-          else tma_store_2d(&tmC, smem_base + out_slot + s * TC_SLOT, n0 + col0, m0);
+        __syncwarp();
+        if (lane == 0) {
+          if (p.reduce_add) tma_reduce_add_2d(&tmC, ebuf_s + b * EB, n, m0);
+          else tma_store_2d(&tmC, ebuf_s + b * EB, n, m0);
           bulk_commit();
         }
       }
     }
-    if (et == 0) bulk_wait_read<0>();                                       // smem must outlive the last TMA store's read
+    if (lane == 0) bulk_wait_read<0>();                                     // smem must outlive the last TMA store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -329,14 +405,13 @@ bpm_encode_tiled_fn bpm_get_encode_tiled() {
   return fn;
 }
 
-static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int elem, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, CUtensorMapSwizzle swz) {
   bpm_encode_tiled_fn enc = bpm_get_encode_tiled();
   if (!enc) { bpm_set_error("cuTensorMapEncodeTiled entry point unavailable"); return BPM_ELAUNCH; }
   cuuint64_t gd[5]; cuuint64_t gs[5]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; i++) gs[i] = strides_bytes[i];
-  (void)elem;
   CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -349,14 +424,14 @@ static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int elem, const v
 
 int bpm_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                        CUtensorMapSwizzle swz) {
-  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rank, dims, strides_bytes, box, swz);
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz);
 }
 
-// [rows, cols] row-major tile map for the epilogue (C / residual / gate): box {chunk columns, 128 rows}
+// [rows, cols] row-major map for the epilogue (C / residual / gate): box {chunk columns, 32 rows}
 static int make_epi_map(CUtensorMap* out, const void* base, int rows, int cols, int ld, int elem, int chunk_bytes) {
   uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows}, str[1] = {(uint64_t)ld * elem};
-  uint32_t box[2] = {(uint32_t)(chunk_bytes / elem), TC_BM};
-  return make_tmap(out, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, elem, base, 2, dims, str, box,
+  uint32_t box[2] = {(uint32_t)(chunk_bytes / elem), 32};
+  return make_tmap(out, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 2, dims, str, box,
                    chunk_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
@@ -365,6 +440,20 @@ static int pick_bn(int N, int max_bn) {
   int tiles = bpm_cdiv(N, max_bn);
   int bn = bpm_cdiv(bpm_cdiv(N, tiles), 32) * 32;
   return bn < 32 ? 32 : bn;
+}
+
+template <int ELEM, int CB>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmI, const TcGemmParams& p, int ctas,
+                     size_t smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ELEM, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) { bpm_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
+    attr_set = true;
+  }
+  gemm_tc_kernel<ELEM, CB><<<ctas, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, tmI, p);
+  BPM_CHECK_LAUNCH("gemm_tc");
+  return BPM_OK;
 }
 
 int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
@@ -377,34 +466,44 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
               "gemm(bf16): residual must have C's dtype and 16-byte alignment");
   BPM_REQUIRE(!g->gate || (g->gate_dtype == g->c_dtype && ((uintptr_t)g->gate % 16 == 0) && ((int64_t)g->ldg * elem) % 16 == 0),
               "gemm(bf16): gate must have C's dtype and 16-byte alignment");
+  BPM_REQUIRE(!(g->gate && g->residual), "gemm(bf16): gate and residual cannot be combined in one epilogue");
   BPM_REQUIRE(!g->colsum_out || g->ta == 1, "gemm: the fused column sum is defined for ta = 1 (wgrad) only");
+  BPM_REQUIRE(!g->bias || (g->N % 4 == 0 && (uintptr_t)g->bias % 16 == 0), "gemm(bf16): bias needs N %% 4 == 0 and 16-byte alignment");
+  BPM_REQUIRE(g->drop.p <= 0.f || g->ldc % 8 == 0, "gemm(bf16): dropout needs ldc %% 8 == 0");
   const bool plain = !g->bias && g->act == 0 && g->drop.p == 0.f && !g->gate && !g->residual;
   BPM_REQUIRE(!g->accumulate || plain, "gemm(bf16): accumulate supports the plain (alpha-only) epilogue");
   TcGemmParams p;
   p.M = g->M; p.N = g->N; p.K = g->K;
   p.colsum = g->colsum_out;
-  p.BN = pick_bn(g->N, p.colsum ? 224 : 256);      // 2 x (224 + 16) TMEM columns still fit in 512
+  p.dbg = bpm_debug_get(0);
+  int max_bn = p.colsum ? 224 : 256;               // 2 x (224 + 16) TMEM columns still fit in 512
+  if (bpm_debug_get(2) >= 32) max_bn = min(max_bn, bpm_debug_get(2));
+  p.BN = pick_bn(g->N, max_bn);
   p.a_mn = g->ta ? 1 : 0;
   p.b_mn = g->tb ? 1 : 0;
   p.a_bytes = TC_BM * TC_BK * 2;
   p.b_bytes = p.b_mn ? bpm_cdiv(p.BN, 64) * 8192 : bpm_cdiv(p.BN * 128, 1024) * 1024;
-  int stage_bytes = p.a_bytes + p.b_bytes;
-  p.has_res = g->residual ? 1 : 0;
-  p.has_gate = g->gate ? 1 : 0;
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  p.in_mode = g->residual ? 1 : (g->gate ? 2 : 0);
   p.reduce_add = g->accumulate ? 1 : 0;
-  const int slots = 2 + 2 * p.has_res + 2 * p.has_gate;
-  const int fixed = slots * TC_SLOT + 2048 + 1024 + 8 * 16 + 1024;         // epilogue slots, ones tile, bias, barriers, alignment slack
-  p.stages = max(2, min(4, (227 * 1024 - fixed) / stage_bytes));
+  const int cb = (p.BN * elem) % 128 == 0 ? 128 : 64;
+  p.n_chunks = p.BN * elem / cb;
+  const int eb = 32 * cb;
+  const int fixed = 2048 + 8 * (2 * TC_MAX_STAGES + 4 + TC_EPI_WARPS * TC_MAX_NB) + 16 + 1024;      // ones tile, barriers, alignment slack
+  const int budget = 227 * 1024 - fixed;
+  // staging buffers per epilogue warp: with a residual / gate tile prefetched through them 3 (two chunks ahead) when the operand
+  // ring still gets 3 stages, else 2
+  p.nb = 2;
+  if (p.in_mode && (budget - TC_EPI_WARPS * 3 * eb) / stage_bytes >= 3) p.nb = 3;
+  if (bpm_debug_get(3) >= 2 && bpm_debug_get(3) <= TC_MAX_NB) p.nb = bpm_debug_get(3);
+  p.stages = max(2, min(TC_MAX_STAGES, (budget - TC_EPI_WARPS * p.nb * eb) / stage_bytes));
   p.ring_bytes = p.stages * stage_bytes;
   // two accumulators (one per in-flight tile); each BN (+16 for the fused column sum) columns wide
   p.tmem_cols = 64;
   while (p.tmem_cols < 2 * (p.BN + (p.colsum ? 16 : 0))) p.tmem_cols *= 2;
   p.idesc = umma_idesc_bf16(TC_BM, p.BN, p.a_mn, p.b_mn);
   p.idesc_ones = umma_idesc_bf16(TC_BM, 16, p.a_mn, 0);
-  p.elem = elem;
-  p.chunk_bytes = (p.BN * elem) % 128 == 0 ? 128 : 64;
-  p.n_chunks = p.BN * elem / p.chunk_bytes;
-  p.ep = make_epi(g);
+  p.bias = g->bias; p.alpha = g->alpha; p.act = g->act; p.gate_scale = g->gate_scale; p.ldc = g->ldc; p.drop = g->drop;
   int num_kb = bpm_cdiv(g->K, TC_BK);
   int gx = bpm_cdiv(g->N, p.BN), gy = bpm_cdiv(g->M, TC_BM);
   int split = 1;
@@ -413,7 +512,7 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   split = bpm_cdiv(num_kb, p.kb_per_split);
   p.gx = gx; p.gy = gy; p.split = split;
 
-  CUtensorMap tmA, tmB, tmC, tmR, tmG;
+  CUtensorMap tmA, tmB, tmC, tmI;
   {
     // A: ta == 0 -> stored [M, K]: dims {K, M}, box {64, 128}.  ta == 1 -> stored [K, M]: dims {M, K}, box {64, 64}
     uint64_t dims[2], str[1]; uint32_t box[2];
@@ -428,22 +527,16 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
     str[0] = (uint64_t)g->ldb * 2;
     rc = bpm_make_tmap_bf16(&tmB, g->B, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    if ((rc = make_epi_map(&tmC, g->C, g->M, g->N, g->ldc, elem, p.chunk_bytes))) return rc;
-    tmR = tmC; tmG = tmC;
-    if (g->residual && (rc = make_epi_map(&tmR, g->residual, g->M, g->N, g->ldr, elem, p.chunk_bytes))) return rc;
-    if (g->gate && (rc = make_epi_map(&tmG, g->gate, g->M, g->N, g->ldg, elem, p.chunk_bytes))) return rc;
+    if ((rc = make_epi_map(&tmC, g->C, g->M, g->N, g->ldc, elem, cb))) return rc;
+    tmI = tmC;
+    if (g->residual && (rc = make_epi_map(&tmI, g->residual, g->M, g->N, g->ldr, elem, cb))) return rc;
+    if (g->gate && (rc = make_epi_map(&tmI, g->gate, g->M, g->N, g->ldg, elem, cb))) return rc;
   }
-  size_t smem = (size_t)p.ring_bytes + fixed;
+  size_t smem = (size_t)p.ring_bytes + TC_EPI_WARPS * p.nb * eb + fixed;
   BPM_REQUIRE(smem <= 227 * 1024 && p.tmem_cols <= 512, "gemm_tc: smem %zu / tmem %d too large", smem, p.tmem_cols);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e != cudaSuccess) { bpm_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
-    attr_set = true;
-  }
   int total_tiles = gx * gy * split;
   int ctas = min(total_tiles, bpm_num_sms());
-  gemm_tc_kernel<<<ctas, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, tmG, p);
-  BPM_CHECK_LAUNCH("gemm_tc");
-  return BPM_OK;
+  if (elem == 4) return launch_tc<4, 128>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+  if (cb == 128) return launch_tc<2, 128>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+  return launch_tc<2, 64>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
 }

@@ -16,7 +16,7 @@
  *    pad columns are ZERO.  Per-head tensors (q, k, v, attention output) use pitch H*dhp, dhp = round_up(dh, 32)
  *    (16 for dh <= 16), head h at columns [h*dhp, h*dhp + dh), pad columns zero.
  *  - Dropout: counter-based and stateless.  Element e of the padded row-major tensor a mask applies to (for attention:
- *    ((b*H + h)*T + i)*S + j) takes 16 bits of a 2-round 32-bit avalanche hash of its pair counter e/2, keyed by (seed, site):
+ *    ((b*H + h)*T + i)*S + j) takes 16 bits of a multiply-xorshift-multiply hash of its pair counter e/2, keyed by (seed, site):
  *    keep(e) <=> half-word >= round(p * 65536); kept values are scaled by 1/(1-p) (exact definition: csrc/bpm_common.cuh).
  *    `seed_ptr` (device, may be NULL) overrides `seed` when non-NULL so a captured graph can be replayed with a new seed.
  *    Backward kernels regenerate masks from (seed, site); nothing is stored except the optional attention keep bits.
@@ -48,6 +48,8 @@ int bpm_version(void);
 const char* bpm_last_error(void);
 /* 1 when device `dev` is compute capability 10.x */
 int bpm_device_ok(int dev);
+/* diagnostic knobs for profiling scripts (slot 0: GEMM stage bypass bits, 1: attention); the product never sets them */
+int bpm_debug_set(int slot, int value);
 
 /* ---- weight staging ------------------------------------------------------------------------------------------
  * Reference parameters stay fp32 in reference layout (state_dict names of SURVEY 8b); kernels consume zero-padded

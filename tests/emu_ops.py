@@ -23,8 +23,8 @@ def _mix_int(x):
 
 
 def drop_mult(drop, idx):
-    """multiplier (0 or 1/(1-p)) for int64 element indices `idx` (any shape): 16-bit decisions from a 32-bit avalanche hash of the
-    element-pair counter (see csrc/bpm_common.cuh)"""
+    """multiplier (0 or 1/(1-p)) for int64 element indices `idx` (any shape): 16-bit decisions from a multiply-xorshift-multiply
+    hash of the element-pair counter (see csrc/bpm_common.cuh)"""
     if drop is None or drop.p <= 0:
         return torch.ones(idx.shape, dtype=torch.float32)
     seed = int(drop.seed_ptr.item()) if drop.seed_ptr is not None else int(drop.seed)
@@ -34,7 +34,9 @@ def drop_mult(drop, idx):
     k1 = _mix_int(((seed >> 32) & MASK32) ^ _mix_int(((site >> 32) & MASK32) + 0x85EBCA6B) ^ 0xC2B2AE35)
     pair = idx >> 1
     lo, hi = pair & MASK32, (pair >> 32) & MASK32
-    r = mix32(lo ^ k0 ^ mix32((hi + k1) & MASK32))
+    x = (lo * 0x7feb352d + (k0 ^ ((hi * 0x85ebca77) & MASK32))) & MASK32
+    x = x ^ (x >> 16)
+    r = (x * 0x846ca68b + k1) & MASK32
     hw = torch.where((idx & 1) == 1, r >> 16, r & 0xFFFF)
     p32 = float(torch.tensor(drop.p, dtype=torch.float32))
     thresh = 65536 if p32 >= 1 else int(p32 * 65536.0 + 0.5)
