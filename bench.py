@@ -198,7 +198,7 @@ def kernel_rooflines(ops, args, B, peaks):
                         "us": t * 1e6, "traffic": None, "note": "algorithmic 4*B*H*T*S*dh*rho, rho=(T+1)/2T causal, dh=25 (stored 32)"}
     do = torch.randn(M, d.HP, device=dev).to(bf)
     dq, dk, dv = [torch.empty(M, d.HP, device=dev, dtype=bf) for _ in range(3)]
-    delta = torch.empty(B * d.H * T, device=dev)
+    delta = torch.empty(2 * B * d.H * T, device=dev)
     ops.xattn_fwd(q[0], k[0], v[0], o, lse, B, T, T, d.H, d.dh, d.dhp, mask_off=0)
     t = time_kernel(lambda i: ops.xattn_bwd(q[0], k[0], v[0], o, do, lse, delta, dq, d.scaling, dk, dv, B, T, T, d.H, d.dh, d.dhp, mask_off=0), 1, iters=3, warm=1)
     out["xattn_bwd"] = {"bound": "tensor", "achieved": 2.5 * fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

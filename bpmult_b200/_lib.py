@@ -38,6 +38,7 @@ SIGNATURES = {
     "bpm_last_error": [],
     "bpm_device_ok": [_I],
     "bpm_debug_set": [_I, _I],
+    "bpm_debug_set_ptr": [_P],
     "bpm_pack_matrix": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpm_unpack_matrix": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "bpm_remap_batch": [_P, _I, _I, _P],

@@ -18,6 +18,9 @@ extern "C" int bpm_colsum(const void* X, int dtype, int M, int N, int ld, float*
 static int g_dbg[4] = {0, 0, 0, 0};
 int bpm_debug_get(int slot) { return g_dbg[slot & 3]; }
 extern "C" int bpm_debug_set(int slot, int value) { g_dbg[slot & 3] = value; return BPM_OK; }
+static void* g_dbg_ptr = nullptr;
+void* bpm_debug_get_ptr() { return g_dbg_ptr; }
+extern "C" int bpm_debug_set_ptr(void* p) { g_dbg_ptr = p; return BPM_OK; }
 
 // BPM_DEBUG_FFMA=1 routes bf16 problems through the FFMA kernels too (kernel bring-up / bisecting only).
 static int debug_ffma() {

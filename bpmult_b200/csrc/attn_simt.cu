@@ -82,8 +82,11 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attn_bwd_dq_simt(bpm_attn_t a, 
   }
   dl = warp_sum(dl);
   __syncwarp();
-  if (lane == 0) delta[(int64_t)bh * a.T + i] = dl;
   float L = lse[(int64_t)bh * a.T + i];
+  if (lane == 0) {
+    delta[(int64_t)bh * a.T + i] = dl;
+    delta[(int64_t)a.B * a.H * a.T + (int64_t)bh * a.T + i] = L * 1.4426950408889634f;      // second half of the workspace: lse * log2e
+  }
   int jmax = a.mask_off >= 0 ? min(a.S - 1, i + a.mask_off) : a.S - 1;
   const T* kb = k + (int64_t)b * a.S * pitch + h * a.dhp;
   const T* vb = v + (int64_t)b * a.S * pitch + h * a.dhp;

@@ -289,34 +289,54 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
 
 
 // =====================================================================================================================
-// Backward.  One CTA per (batch, head) for T <= 512: the dQ accumulators of all (<= 4) query tiles stay resident in TMEM for
-// the whole kernel and dK / dV of the current 128-key tile are accumulated in TMEM over the inner query-tile loop, so NO
-// atomics and no second pass are needed.  The score tile is computed TRANSPOSED (rows = keys, columns = queries):
+// Backward.  Persistent: one CTA per SM walks (batch, head) pairs (T <= 512).  For one (b, h) the dQ accumulators of all (<= 4)
+// query tiles stay resident in TMEM and dK / dV of the current 128-key tile are accumulated in TMEM over the inner query-tile
+// loop, so NO atomics and no second pass are needed.  The score tile is computed TRANSPOSED (rows = keys, columns = queries):
 //     S^T  = K_j Q_i^T          dP^T = V_j dO_i^T                               (M128 N128 K32, both operands K-major)
-//     P^T  = exp2(S^T log2e - lse_q),   P~^T = P^T * dropmask,   dS^T = P^T * (dP^T * dropmask - delta_q)   [8 compute warps]
+//     P^T  = exp2(S^T log2e - lse_q log2e),   P~^T = P^T * dropmask,   dS^T = P^T * (dP^T * dropmask - delta_q)   [8 compute warps]
 //     dV_j += P~^T dO_i         dK_j += dS^T Q_i      (A = the bf16 tile just written to smem, K-major; B = dO_i / Q_i MN-major)
 //     dQ_i += dS K_j            (A = the SAME dS^T smem tile read as an MN-major operand; B = K_j MN-major)
 // No row reductions are needed in the backward (lse and delta are per query = per column), so the 128x128 tile is split
-// between two warps per TMEM lane quarter (64 columns each).  TMEM: S^T 128 + dP^T 128 + dK 32 + dV 32 + dQ 4x32 = 448 cols.
+// between two warps per TMEM lane quarter (64 columns each).
+//   warp 0    TMA producer: per (b,h) the lse*log2e / delta vectors (bulk copies), K/V tiles (2 stages), Q/dO(/keep-bit) tiles (4 stages)
+//   warp 1    issues S^T / dP^T (one thread);  warp 2 issues the accumulate MMAs dV, dK, dQ (one thread).  Two issuers, because a
+//             tcgen05.mma issue blocks while the tensor-core queue is full: each stream's barrier waits hide behind the other's
+//             MMAs.  Every shared-memory descriptor is formed once and advanced by adds.
+//   warps 3.. compute (AB_CW / 4 per TMEM lane quarter; 16-column sub-chunks).  P~^T goes back to TENSOR MEMORY as packed bf16 (tcgen05.st) and feeds dV as the A operand from TMEM:
+//             with N = dh = 32 an MMA whose A comes from shared memory is bound by the 4 KB A read (~80 clk), not by its math.
+//             dS^T is needed in both orientations (dK and dQ), so it is staged in shared memory (double-buffered).
+// TMEM: S^T 128 + dP^T 128 + P~^T 64 (bf16 pairs) + dK 32 + dV 32 + dQ 4x32 = 512 columns.
+// The pre-kernel computes delta = rowsum(dO * O) and lse * log2e into the [2, B, H, T] workspace.
 // =====================================================================================================================
-#define AB_THREADS 320
+#define AB_CW 8                           // compute warps: AB_CW/4 per TMEM lane quarter, 128/(AB_CW/4) query columns each
+#define AB_THREADS (96 + 32 * AB_CW)
 #define AB_MAXQT 4
+#define AB_QD_STAGES 4
+// optional per-role event trace of CTA 0 (bpm_debug_set_ptr; scripts/trace_attn.py): entry = (clock64 << 8) | event id
+#define AB_TRACE_N 4096
+#define TRACE(role, id)                                                                 \
+  do {                                                                                  \
+    if (trace != nullptr && blockIdx.x == 0 && tr_n < AB_TRACE_N) {                     \
+      trace[(role) * AB_TRACE_N + tr_n] = ((unsigned long long)clock64() << 8) | (id);  \
+      tr_n++;                                                                           \
+    }                                                                                   \
+  } while (0)
 
 struct AttnBwdSmem {
   static constexpr int KV = 0;                                  // 2 stages x (K 8 KB + V 8 KB)
   static constexpr int QD_STAGE = 2 * 128 * 64 + 2048;          // Q 8 KB + dO 8 KB + dropout keep bits (128 queries x 4 words)
-  static constexpr int QD = KV + 2 * 2 * 128 * 64;              // 2 stages
-  static constexpr int PT = QD + 2 * QD_STAGE;                  // 2 chunk tiles x 16 KB
-  static constexpr int DST = PT + 2 * 128 * 128;
-  static constexpr int LSE = DST + 2 * 128 * 128;               // 512 floats (pre-multiplied by log2e; +inf beyond T)
-  static constexpr int DEL = LSE + 512 * 4;
-  static constexpr int BAR = DEL + 512 * 4;
-  static constexpr int NBAR = 15;
+  static constexpr int QD = KV + 2 * 2 * 128 * 64;
+  static constexpr int DST = QD + AB_QD_STAGES * QD_STAGE;      // 2 buffers x (2 chunk tiles x 16 KB)
+  static constexpr int LD = DST + 2 * 2 * 128 * 128;            // 2 buffers x (512 floats lse*log2e (+inf beyond T) + 512 floats delta)
+  static constexpr int BAR = LD + 2 * 4096;
+  static constexpr int NBAR = 4 + 2 * AB_QD_STAGES + 16;
   static constexpr int TOTAL = BAR + 8 * NBAR + 16;
 };
+static_assert(AttnBwdSmem::DST % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
-__global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta, int B, int T, int H) {
-  // delta[b, h, t] = sum_d dO * O   (one thread per (row, head): 2 x 64 B)
+__global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ ws,
+                                  int B, int T, int H) {
+  // ws[0][b, h, t] = delta = sum_d dO * O   (one thread per (row, head): 2 x 64 B);   ws[1][b, h, t] = lse * log2e
   int64_t n = (int64_t)B * T * H;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
     int h = (int)(idx % H);
@@ -331,16 +351,59 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
 #pragma unroll
       for (int j = 0; j < 8; j++) acc = fmaf(a.v[j], c.v[j], acc);
     }
-    delta[((int64_t)b * H + h) * T + t] = acc;
+    const int64_t o_idx = ((int64_t)b * H + h) * T + t;
+    ws[o_idx] = acc;
+    ws[n + o_idx] = lse[o_idx] * LOG2E_F;
+  }
+}
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+
+// One NC-column chunk of a (128 keys x 128 queries) pair for key row `key`: sv (S^T) -> P~^T, dpv (dP^T) -> dS^T, in place.
+//   DROP: 0 no dropout, 1 keep bits staged in shared memory by TMA (word (query, 32-key group), bit = key lane),
+//         2 keep bits fetched from global memory into mw (one word per lane = query), 3 regenerate the decisions.
+//   MASKED: the tile touches the mask diagonal or the end of the key sequence.
+template <int DROP, bool MASKED, int NC>
+__device__ __forceinline__ void bwd_chunk_math(float* sv, float* dpv, const float* __restrict__ lse_c, const float* __restrict__ del_c, int c_lo, int cmin,
+                                               bool key_oob, bool diag, const DropCtx& dc, const uint32_t* __restrict__ bits_c, uint32_t mw, int lane,
+                                               uint64_t e_row, int q_lo, int T, int S) {
+#pragma unroll
+  for (int c = 0; c < NC; c += 4) {
+    const float4 l4 = *(const float4*)(lse_c + c);
+    const float4 d4 = *(const float4*)(del_c + c);
+    const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      float p = ex2f(fmaf(sv[c + e], LOG2E_F, -ls[e]));
+      if (MASKED) {
+        if (key_oob || (diag && c_lo + c + e < cmin)) p = 0.f;
+      }
+      if (DROP == 0) {
+        sv[c + e] = p;
+        dpv[c + e] = p * (dpv[c + e] - dl[e]);
+      } else {
+        float mult;
+        if (DROP == 1) mult = ((bits_c[(c + e) * 4] >> lane) & 1u) ? dc.inv_keep : 0.f;
+        else if (DROP == 2) mult = ((__shfl_sync(0xffffffffu, mw, c + e) >> lane) & 1u) ? dc.inv_keep : 0.f;
+        else mult = drop_mult1(dc, ((uint64_t)min(q_lo + c + e, T - 1)) * (uint64_t)S + e_row);
+        sv[c + e] = p * mult;                                     // P~^T
+        dpv[c + e] = p * fmaf(dpv[c + e], mult, -dl[e]);          // dS^T
+      }
+    }
   }
 }
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmBits, const int bits_tma,
-                   const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
-                   bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
-                   const uint32_t* __restrict__ drop_bits) {
+                   const float* __restrict__ ws, bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T,
+                   int S, int H, int mask_off, bpm_dropout_t drop, const uint32_t* __restrict__ drop_bits, const int dbg,
+                   unsigned long long* __restrict__ trace) {
+  int tr_n = 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -348,254 +411,380 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   auto kv_full = [&](int s) { return bar0 + 8u * s; };
   auto kv_empty = [&](int s) { return bar0 + 8u * (2 + s); };
   auto q_full = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto q_empty = [&](int s) { return bar0 + 8u * (6 + s); };
-  const uint32_t st_full = bar0 + 8u * 8, st_free = bar0 + 8u * 9, pt_full = bar0 + 8u * 10, pair_done = bar0 + 8u * 11;
-  const uint32_t dkv_full = bar0 + 8u * 12, dkv_free = bar0 + 8u * 13, dq_full = bar0 + 8u * 14;
+  auto q_empty = [&](int s) { return bar0 + 8u * (4 + AB_QD_STAGES + s); };
+  constexpr int B1 = 4 + 2 * AB_QD_STAGES;
+  const uint32_t st_full = bar0 + 8u * B1, st_free = bar0 + 8u * (B1 + 1);
+  const uint32_t pv_free = bar0 + 8u * (B1 + 2);                 // the dV MMAs have read P~^T from TMEM
+  const uint32_t dkv_full = bar0 + 8u * (B1 + 3);
+  auto pt_full = [&](int s) { return bar0 + 8u * (B1 + 4 + s); };   // P~^T (TMEM) and dS^T (smem buffer s) of a pair are written
+  auto ds_free = [&](int s) { return bar0 + 8u * (B1 + 6 + s); };   // the dK / dQ MMAs have read dS^T buffer s
+  const uint32_t dkv_free = bar0 + 8u * (B1 + 8);
+  const uint32_t dq_full = bar0 + 8u * (B1 + 9), dq_free = bar0 + 8u * (B1 + 10);
+  auto ld_full = [&](int s) { return bar0 + 8u * (B1 + 11 + s); };
+  auto ld_empty = [&](int s) { return bar0 + 8u * (B1 + 13 + s); };
+  static_assert(B1 + 15 <= AttnBwdSmem::NBAR, "barrier count");
   const uint32_t tmem_ptr_addr = bar0 + 8u * AttnBwdSmem::NBAR;
   volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + AttnBwdSmem::BAR + 8 * AttnBwdSmem::NBAR);
-  float* lse_s = (float*)(base_gen + AttnBwdSmem::LSE);
-  float* del_s = (float*)(base_gen + AttnBwdSmem::DEL);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int nbh = B * H;
+  const int64_t nrow = (int64_t)nbh * T;
   const int nq = (T + 127) / 128, nkv = (S + 127) / 128;
   // first query tile that can see key tile j (visible iff key <= q + off)
   auto i_min_of = [&](int j) { int qlo = j * 128 - mask_off; return (mask_off < 0 || qlo <= 0) ? 0 : qlo / 128; };
+  // pair iterator over (bh, key tile j, query tile i); jc counts the non-empty key tiles (K/V ring index)
+  struct Pair { int bh, j, i, jc; };
+  auto first_j = [&](int j) { while (j < nkv && i_min_of(j) >= nq) j++; return j; };
+  auto next_pair = [&](Pair& p) {
+    p.i++;
+    if (p.i >= nq) {
+      p.j = first_j(p.j + 1);
+      p.jc++;
+      if (p.j >= nkv) { p.bh += gridDim.x; p.j = first_j(0); }
+      p.i = i_min_of(p.j < nkv ? p.j : 0);
+    }
+  };
+  auto first_pair = [&]() { Pair p; p.bh = blockIdx.x; p.j = first_j(0); p.jc = 0; p.i = i_min_of(p.j < nkv ? p.j : 0); if (p.j >= nkv) p.bh = nbh; return p; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
-    for (int s = 0; s < 2; s++) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
-    mbar_init(st_full, 1); mbar_init(st_free, 8); mbar_init(pt_full, 8); mbar_init(pair_done, 1);
-    mbar_init(dkv_full, 1); mbar_init(dkv_free, 8); mbar_init(dq_full, 1);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1);
+      mbar_init(pt_full(s), AB_CW); mbar_init(ds_free(s), 1);
+      mbar_init(ld_full(s), 1); mbar_init(ld_empty(s), AB_CW);
+    }
+    for (int s = 0; s < AB_QD_STAGES; s++) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
+    mbar_init(st_full, 1); mbar_init(st_free, AB_CW); mbar_init(pv_free, 1);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, AB_CW);
+    mbar_init(dq_full, 1); mbar_init(dq_free, AB_CW);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, 512);
-  for (int t = threadIdx.x; t < 512; t += AB_THREADS) {
-    lse_s[t] = t < T ? lse[(int64_t)bh * T + t] * LOG2E_F : INFINITY;      // exp2(x - inf) = 0 for the padded query columns
-    del_s[t] = t < T ? delta[(int64_t)bh * T + t] : 0.f;
+  // query columns beyond T: lse = +inf (exp2(x - inf) = 0), delta = 0; the bulk copies only ever write the first T entries
+  for (int t = threadIdx.x; t < 2 * 1024; t += AB_THREADS) {
+    float* ld = (float*)(base_gen + AttnBwdSmem::LD);
+    ld[t] = ((t & 1023) < 512) ? INFINITY : 0.f;
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_gen;
-  const uint32_t tST = tmem, tDPT = tmem + 128, tDK = tmem + 256, tDV = tmem + 288, tDQ = tmem + 320;
+  const uint32_t tST = tmem, tDPT = tmem + 128, tPT = tmem + 256, tDK = tmem + 320, tDV = tmem + 352, tDQ = tmem + 384;
+  auto adr = [](uint32_t a) { return (uint64_t)((a & 0x3FFFFu) >> 4); };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int pc = 0, jc = 0;
-      for (int j = 0; j < nkv; j++) {
-        int imin = i_min_of(j);
-        if (imin >= nq) continue;
-        int ks = jc & 1;
-        mbar_wait(kv_empty(ks), ((uint32_t)(jc >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(kv_full(ks), 2 * 128 * 64);
-        tma_load_3d(base + AttnBwdSmem::KV + ks * 16384, &tmK, kv_full(ks), h * AT_DH, j * 128, b);
-        tma_load_3d(base + AttnBwdSmem::KV + ks * 16384 + 8192, &tmV, kv_full(ks), h * AT_DH, j * 128, b);
-        jc++;
-        for (int i = imin; i < nq; i++, pc++) {
-          int qs = pc & 1;
-          mbar_wait(q_empty(qs), ((uint32_t)(pc >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(q_full(qs), 2 * 128 * 64 + (bits_tma ? 2048 : 0));
-          tma_load_3d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, &tmQ, q_full(qs), h * AT_DH, i * 128, b);
-          tma_load_3d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 8192, &tmdO, q_full(qs), h * AT_DH, i * 128, b);
-          if (bits_tma) tma_load_2d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 16384, &tmBits, q_full(qs), j * 4, bh * T + i * 128);
+    {   // converged warp; one elected lane issues
+      int pc = 0, jc = 0, bc = 0;
+      for (int bh = blockIdx.x; bh < nbh; bh += gridDim.x, bc++) {
+        const int b = bh / H, h = bh % H;
+        {
+          const int s = bc & 1;
+          mbar_wait(ld_empty(s), ((uint32_t)(bc >> 1) & 1u) ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(ld_full(s), 2u * (uint32_t)T * 4u);
+            bulk_load_1d(base + AttnBwdSmem::LD + s * 4096, ws + nrow + (int64_t)bh * T, (uint32_t)T * 4u, ld_full(s));
+            bulk_load_1d(base + AttnBwdSmem::LD + s * 4096 + 2048, ws + (int64_t)bh * T, (uint32_t)T * 4u, ld_full(s));
+          }
+          __syncwarp();
+        }
+        for (int j = 0; j < nkv; j++) {
+          const int imin = i_min_of(j);
+          if (imin >= nq) continue;
+          const int ks = jc & 1;
+          mbar_wait(kv_empty(ks), ((uint32_t)(jc >> 1) & 1u) ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(kv_full(ks), 2 * 128 * 64);
+            tma_load_3d(base + AttnBwdSmem::KV + ks * 16384, &tmK, kv_full(ks), h * AT_DH, j * 128, b);
+            tma_load_3d(base + AttnBwdSmem::KV + ks * 16384 + 8192, &tmV, kv_full(ks), h * AT_DH, j * 128, b);
+          }
+          __syncwarp();
+          jc++;
+          for (int i = imin; i < nq; i++, pc++) {
+            const int qs = pc % AB_QD_STAGES;
+            mbar_wait(q_empty(qs), ((uint32_t)(pc / AB_QD_STAGES) & 1u) ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(q_full(qs), 2 * 128 * 64 + (bits_tma ? 2048 : 0));
+              tma_load_3d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, &tmQ, q_full(qs), h * AT_DH, i * 128, b);
+              tma_load_3d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 8192, &tmdO, q_full(qs), h * AT_DH, i * 128, b);
+              if (bits_tma) tma_load_2d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 16384, &tmBits, q_full(qs), j * 4, bh * T + i * 128);
+            }
+            __syncwarp();
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t id_st = umma_idesc_bf16(128, 128, 0, 0);      // S^T, dP^T
-      const uint32_t id_kv = umma_idesc_bf16(128, AT_DH, 0, 1);    // dV, dK : A K-major (smem tile), B MN-major
-      const uint32_t id_dq = umma_idesc_bf16(128, AT_DH, 1, 1);    // dQ     : A = dS^T read MN-major, B = K_j MN-major
-      // pair iterator over (key tile j, query tile i); jc counts the non-empty key tiles (K/V ring index)
-      auto next_pair = [&](int& j, int& i, int& jc) {
-        i++;
-        if (i >= nq) {
-          do { j++; } while (j < nkv && i_min_of(j) >= nq);
-          if (j < nkv) { i = i_min_of(j); jc++; }
-        }
-      };
-      // S^T / dP^T of pair pc are issued one pair AHEAD of the accumulate MMAs, so the compute warps never wait for them
-      auto issue_st = [&](int j, int i, int pc, int jc) {
-        const int ks = jc & 1, qs = pc & 1;
-        if (i == i_min_of(j)) mbar_wait(kv_full(ks), (uint32_t)(jc >> 1) & 1u);
+    // ===================== S^T = K_j Q_i^T and dP^T = V_j dO_i^T (one pair ahead of the compute warps) =====================
+    {   // converged warp; one elected lane issues
+      const uint32_t id_st = umma_idesc_bf16(128, 128, 0, 0);
+      const uint64_t d_k64 = umma_desc(0, 16, 512, BPM_SWZ_64B);          // K-major 64-byte rows; +32 B per k16
+      int pc = 0;
+      for (Pair p = first_pair(); p.bh < nbh; next_pair(p), pc++) {
+        const int ks = p.jc & 1, qs = pc % AB_QD_STAGES;
+        TRACE(1, 10);
+        if (p.i == i_min_of(p.j)) mbar_wait(kv_full(ks), (uint32_t)(p.jc >> 1) & 1u);
         const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384, va = ka + 8192;
         const uint32_t qa = base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, ga = qa + 8192;
-        mbar_wait(q_full(qs), (uint32_t)(pc >> 1) & 1u);
+        mbar_wait(q_full(qs), (uint32_t)(pc / AB_QD_STAGES) & 1u);
+        TRACE(1, 11);
         mbar_wait(st_free, ((uint32_t)pc & 1u) ^ 1u);
+        TRACE(1, 12);
         tc_fence_after();
+        const uint64_t dka = d_k64 | adr(ka), dva = d_k64 | adr(va), dqa = d_k64 | adr(qa), dga = d_k64 | adr(ga);
+        if (elect_one()) {
+          if (!(dbg & 8)) {
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-          umma_bf16(tST, umma_desc(ka + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(qa + k * 32, 16, 512, BPM_SWZ_64B), id_st, k > 0);
-          umma_bf16(tDPT, umma_desc(va + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(ga + k * 32, 16, 512, BPM_SWZ_64B), id_st, k > 0);
-        }
-        umma_commit(st_full);
-      };
-      int j = 0, jc = 0;
-      while (j < nkv && i_min_of(j) >= nq) j++;
-      if (j < nkv) {
-        int i = i_min_of(j), pc = 0;
-        issue_st(j, i, 0, 0);
-        while (j < nkv) {
-          int nj = j, ni = i, njc = jc;
-          next_pair(nj, ni, njc);
-          if (nj < nkv) issue_st(nj, ni, pc + 1, njc);
-          const int ks = jc & 1, qs = pc & 1, imin = i_min_of(j);
-          const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384;
-          const uint32_t qa = base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, ga = qa + 8192;
-          mbar_wait(pt_full, (uint32_t)pc & 1u);
-          if (i == imin) mbar_wait(dkv_free, ((uint32_t)jc & 1u) ^ 1u);        // previous key tile's dK/dV drained from TMEM
-          tc_fence_after();
-          const uint32_t pa = base + AttnBwdSmem::PT, da = base + AttnBwdSmem::DST;
+            for (int k = 0; k < 2; k++) umma_bf16(tST, dka + 2 * k, dqa + 2 * k, id_st, k > 0);
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const uint32_t acc = (i > imin || k > 0) ? 1u : 0u;
-            const uint32_t aoff = (k >> 2) * 16384 + (k & 3) * 32;
-            umma_bf16(tDV, umma_desc(pa + aoff, 16, 1024, BPM_SWZ_128B), umma_desc(ga + k * 1024, 512, 512, BPM_SWZ_64B), id_kv, acc);
-            umma_bf16(tDK, umma_desc(da + aoff, 16, 1024, BPM_SWZ_128B), umma_desc(qa + k * 1024, 512, 512, BPM_SWZ_64B), id_kv, acc);
+            for (int k = 0; k < 2; k++) umma_bf16(tDPT, dva + 2 * k, dga + 2 * k, id_st, k > 0);
           }
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-            umma_bf16(tDQ + 32 * i, umma_desc(da + k * 2048, 16384, 1024, BPM_SWZ_128B), umma_desc(ka + k * 1024, 512, 512, BPM_SWZ_64B), id_dq,
-                      (j > 0 || k > 0) ? 1u : 0u);
-          umma_commit(pair_done);
-          umma_commit(q_empty(qs));
-          if (i == nq - 1) { umma_commit(dkv_full); umma_commit(kv_empty(ks)); }
-          j = nj; i = ni; jc = njc; pc++;
+          umma_commit(st_full);
         }
+        __syncwarp();
+        TRACE(1, 13);
       }
-      umma_commit(dq_full);
+    }
+  } else if (warp == 2) {
+    // ===================== dV_j += P~^T dO_i (A from TMEM),  dK_j += dS^T Q_i,  dQ_i += dS K_j =====================
+    {   // converged warp; one elected lane issues
+      const uint32_t id_kv = umma_idesc_bf16(128, AT_DH, 0, 1);    // dV, dK : A K-major (TMEM / smem tile), B MN-major
+      const uint32_t id_dq = umma_idesc_bf16(128, AT_DH, 1, 1);    // dQ     : A = dS^T read MN-major, B = K_j MN-major
+      const uint64_t d_mn64 = umma_desc(0, 512, 512, BPM_SWZ_64B);        // Q / dO / K tiles as MN-major B operands; +1024 B per k16
+      const uint64_t d_k128 = umma_desc(0, 16, 1024, BPM_SWZ_128B);       // dS^T chunk tiles, K-major
+      const uint64_t d_mn128 = umma_desc(0, 16384, 1024, BPM_SWZ_128B);   // dS^T read MN-major (LBO = chunk tile pitch); +2048 B per k16
+      int pc = 0, bc = 0;
+      for (Pair cur = first_pair(); cur.bh < nbh; pc++) {
+        Pair nx = cur;
+        next_pair(nx);
+        const int ks = cur.jc & 1, qs = pc % AB_QD_STAGES, pb = pc & 1, imin = i_min_of(cur.j);
+        const bool first_of_bh = cur.j == first_j(0) && cur.i == imin;
+        const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384;
+        const uint32_t qa = base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, ga = qa + 8192;
+        const uint32_t da = base + AttnBwdSmem::DST + pb * 32768;
+        TRACE(2, 14);
+        mbar_wait(pt_full(pb), (uint32_t)(pc >> 1) & 1u);
+        if (cur.i == imin) mbar_wait(dkv_free, ((uint32_t)cur.jc & 1u) ^ 1u);                // dK / dV of the previous key tile have been drained
+        if (first_of_bh) mbar_wait(dq_free, ((uint32_t)bc & 1u) ^ 1u);                        // previous (b,h)'s dQ has been drained
+        tc_fence_after();
+        TRACE(2, 15);
+        const uint64_t dda = d_k128 | adr(da), ddm = d_mn128 | adr(da);
+        const uint64_t dgb = d_mn64 | adr(ga), dqb = d_mn64 | adr(qa), dkb = d_mn64 | adr(ka);
+        const uint32_t t_dq = tDQ + 32 * cur.i;
+        if (elect_one()) {
+          const uint32_t acc_kv = cur.i > imin ? 1u : 0u, acc_q = cur.j > 0 ? 1u : 0u;
+          if (!(dbg & 4)) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) umma_bf16_ts(tDV, tPT + 8 * k, dgb + 64 * k, id_kv, acc_kv | (uint32_t)k);
+          }
+          umma_commit(pv_free);
+          if (!(dbg & 4)) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              umma_bf16(tDK, dda + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4), dqb + 64 * k, id_kv, acc_kv | (uint32_t)k);
+#pragma unroll
+            for (int k = 0; k < 8; k++) umma_bf16(t_dq, ddm + 128 * k, dkb + 64 * k, id_dq, acc_q | (uint32_t)k);
+          }
+          umma_commit(ds_free(pb));
+          umma_commit(q_empty(qs));
+          if (cur.i == nq - 1) { umma_commit(dkv_full); umma_commit(kv_empty(ks)); }
+          if (nx.bh != cur.bh) umma_commit(dq_full);
+        }
+        __syncwarp();
+        if (nx.bh != cur.bh) bc++;
+        TRACE(2, 16);
+        cur = nx;
+      }
     }
   } else {
     // ===================== compute warps =====================
-    const int cw = warp - 2;
-    const int quarter = warp & 3, half = cw >> 2;
+    constexpr int NCG = AB_CW / 4;                          // column groups (warps per lane quarter)
+    constexpr int NCOL = 128 / NCG;                         // query columns per warp
+    const int cw = warp - 3;
+    const int quarter = warp & 3, colq = cw >> 2;          // TMEM lane quarter; column group [NCOL*colq, +NCOL) of the pair tile
     const int r = quarter * 32 + lane;                      // key row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    DropCtx dc = make_drop(drop);
+    const int c0 = colq * NCOL;
+    const DropCtx dc = make_drop(drop);
+    const int drop_mode = !dc.on ? 0 : (bits_tma ? 1 : (drop_bits != nullptr ? 2 : 3));
     const int HP = H * AT_DH;
     const int W = (S + 31) >> 5;
-    uint8_t* const prow = base_gen + AttnBwdSmem::PT + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-    uint8_t* const drow = base_gen + AttnBwdSmem::DST + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
-    int pc = 0, jc = 0;
-    for (int j = 0; j < nkv; j++) {
-      const int key = j * 128 + r;
-      int imin = i_min_of(j);
-      if (imin >= nq) {                                     // no query sees this key tile: dK = dV = 0
-        if (key < S) {
-          bf16* dst = (half == 0 ? dk : dv) + ((int64_t)b * S + key) * HP + h * AT_DH;
-#pragma unroll
-          for (int u = 0; u < AT_DH / 8; u++) *(uint4*)(dst + u * 8) = make_uint4(0, 0, 0, 0);
-        }
-        continue;
-      }
-      for (int i = imin; i < nq; i++, pc++) {
-        const int q0 = i * 128;
-        const bool diag = (mask_off >= 0) && (j * 128 + 127 > q0 + mask_off);
-        const int cmin = key - mask_off - q0;               // columns < cmin are masked for this key row (diag tiles only)
-        // keep bits written by the forward: word (query, 32-key group).  Fast path: the TMA producer staged the 128 x 4-word tile of
-        // this pair next to Q / dO (one broadcast LDS per column); otherwise each lane fetches the words of 2 of its 64 columns.
-        const uint32_t* bits_s = (const uint32_t*)(base_gen + AttnBwdSmem::QD + (pc & 1) * AttnBwdSmem::QD_STAGE + 16384) + quarter;
-        uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (dc.on && drop_bits != nullptr && !bits_tma) {
-#pragma unroll
-          for (int h2 = 0; h2 < 2; h2++) {
-            const int qq = q0 + half * 64 + h2 * 32 + lane;
-            mw[h2] = (qq < T && j * 4 + quarter < W) ? drop_bits[((int64_t)bh * T + qq) * W + j * 4 + quarter] : 0u;
-          }
-        }
-        mbar_wait(st_full, (uint32_t)pc & 1u);        // (S^T was computed from this pair's Q stage, so its keep-bit tile has landed too)
-        tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-          const int c0 = half * 64 + ch * 32;
-          float sv[32], dpv[32];
-          tmem_ld32(tST + lane_off + c0, sv);
-          tmem_ld32(tDPT + lane_off + c0, dpv);
-          tmem_ld_wait();
-          if (ch == 1) {                                    // all of this warp's S^T / dP^T columns are in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(st_free);
-          }
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const float4 l4 = *(const float4*)(lse_s + q0 + c0 + c);
-            const float4 d4 = *(const float4*)(del_s + q0 + c0 + c);
-            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int col = c0 + c + e;
-              float p = ex2f(fmaf(sv[c + e], LOG2E_F, -ls[e]));
-              if (key >= S || (diag && col < cmin)) p = 0.f;
-              float mult = 1.f;
-              if (dc.on) {
-                if (bits_tma) {
-                  mult = ((bits_s[col * 4] >> lane) & 1u) ? dc.inv_keep : 0.f;
-                } else if (drop_bits != nullptr) {
-                  const uint32_t wq = __shfl_sync(0xffffffffu, mw[ch], c + e);
-                  mult = ((wq >> lane) & 1u) ? dc.inv_keep : 0.f;
-                } else {
-                  mult = drop_mult1(dc, ((uint64_t)bh * T + (uint64_t)min(q0 + col, T - 1)) * (uint64_t)S + (uint64_t)min(key, S - 1));
-                }
-              }
-              sv[c + e] = p * mult;                                     // P~^T
-              dpv[c + e] = p * fmaf(dpv[c + e], mult, -dl[e]);          // dS^T
-            }
-          }
-          // the previous pair's accumulate MMAs must have finished reading the P^T / dS^T tiles before they are overwritten
-          if (ch == 0) mbar_wait(pair_done, ((uint32_t)pc & 1u) ^ 1u);
-          // this thread owns row r, columns [64*half + 32*ch, +32) = chunk tile `half`, 16-byte units 4*ch .. 4*ch+3
-#pragma unroll
-          for (int uu = 0; uu < 4; uu++) {
-            const int u = ch * 4 + uu;
-            *(uint4*)(prow + ((u ^ (r & 7)) << 4)) = make_uint4(pack_bf16x2(sv[uu * 8], sv[uu * 8 + 1]), pack_bf16x2(sv[uu * 8 + 2], sv[uu * 8 + 3]),
-                                                               pack_bf16x2(sv[uu * 8 + 4], sv[uu * 8 + 5]), pack_bf16x2(sv[uu * 8 + 6], sv[uu * 8 + 7]));
-            *(uint4*)(drow + ((u ^ (r & 7)) << 4)) = make_uint4(pack_bf16x2(dpv[uu * 8], dpv[uu * 8 + 1]), pack_bf16x2(dpv[uu * 8 + 2], dpv[uu * 8 + 3]),
-                                                               pack_bf16x2(dpv[uu * 8 + 4], dpv[uu * 8 + 5]), pack_bf16x2(dpv[uu * 8 + 6], dpv[uu * 8 + 7]));
-          }
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pt_full);
-      }
-      // ---- dK (half 0) / dV (half 1) of key tile j
-      mbar_wait(dkv_full, (uint32_t)jc & 1u);
+    // dS^T row r lives at (r >> 3) * 1024 + (r & 7) * 128 inside each 64-column chunk tile (16 KB), 16-byte unit u at u ^ (r & 7)
+    const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    int pc = 0, jc = 0, bc = 0;
+    // dK / dV of a finished key tile are drained while the NEXT pair is being computed (no stall on the last accumulate MMAs):
+    // the 32 dK and 32 dV columns are split evenly over the NCG warps of a lane quarter (first half of the groups dK, second half dV)
+    constexpr int DCOL = 64 / NCG;                          // accumulator columns per warp: 32 (NCG = 2) or 16 (NCG = 4)
+    const bool drain_dv = colq >= NCG / 2;
+    const int dcol0 = (colq % (NCG / 2)) * DCOL;
+    int pend_jc = -1, pend_b = 0, pend_h = 0, pend_key = 0;
+    // dQ of a finished (b,h) is drained after the first pair of the NEXT (b,h) has been computed, for the same reason
+    int pend_q_bc = -1, pend_q_b = 0, pend_q_h = 0;
+    auto drain_dq = [&]() {
+      mbar_wait(dq_full, (uint32_t)pend_q_bc & 1u);
       tc_fence_after();
-      {
+      for (int i = colq; i < nq; i += NCG) {                  // query tile i is drained by column group i % NCG
         float acc[AT_DH];
-        tmem_ld32((half == 0 ? tDK : tDV) + lane_off, acc);
+        tmem_ld32(tDQ + 32 * i + lane_off, acc);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dkv_free);
-        if (key < S) {
-          bf16* dst = (half == 0 ? dk : dv) + ((int64_t)b * S + key) * HP + h * AT_DH;
+        const int qi = i * 128 + r;
+        if (qi < T) {
+          bf16* dst = dq + ((int64_t)pend_q_b * T + qi) * HP + pend_q_h * AT_DH;
 #pragma unroll
           for (int u = 0; u < AT_DH / 8; u++)
-            *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8], acc[u * 8 + 1]), pack_bf16x2(acc[u * 8 + 2], acc[u * 8 + 3]),
-                                                pack_bf16x2(acc[u * 8 + 4], acc[u * 8 + 5]), pack_bf16x2(acc[u * 8 + 6], acc[u * 8 + 7]));
+            *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8] * dq_scale, acc[u * 8 + 1] * dq_scale), pack_bf16x2(acc[u * 8 + 2] * dq_scale, acc[u * 8 + 3] * dq_scale),
+                                                pack_bf16x2(acc[u * 8 + 4] * dq_scale, acc[u * 8 + 5] * dq_scale), pack_bf16x2(acc[u * 8 + 6] * dq_scale, acc[u * 8 + 7] * dq_scale));
         }
       }
-      jc++;
-    }
-    // ---- dQ of every query tile (tile i is drained by the warps of half i & 1)
-    mbar_wait(dq_full, 0);
-    tc_fence_after();
-    for (int i = half; i < nq; i += 2) {
-      float acc[AT_DH];
-      tmem_ld32(tDQ + 32 * i + lane_off, acc);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+      pend_q_bc = -1;
+    };
+    auto drain_dkv = [&]() {
+      mbar_wait(dkv_full, (uint32_t)pend_jc & 1u);
+      tc_fence_after();
+      float acc[DCOL];
+      if (DCOL == 32) tmem_ld32((drain_dv ? tDV : tDK) + lane_off, acc);
+      else tmem_ld16((drain_dv ? tDV : tDK) + (uint32_t)dcol0 + lane_off, acc);
       tmem_ld_wait();
-      const int qi = i * 128 + r;
-      if (qi < T) {
-        bf16* dst = dq + ((int64_t)b * T + qi) * HP + h * AT_DH;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dkv_free);
+      if (pend_key < S) {
+        bf16* dst = (drain_dv ? dv : dk) + ((int64_t)pend_b * S + pend_key) * HP + pend_h * AT_DH + dcol0;
 #pragma unroll
-        for (int u = 0; u < AT_DH / 8; u++)
-          *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8] * dq_scale, acc[u * 8 + 1] * dq_scale), pack_bf16x2(acc[u * 8 + 2] * dq_scale, acc[u * 8 + 3] * dq_scale),
-                                              pack_bf16x2(acc[u * 8 + 4] * dq_scale, acc[u * 8 + 5] * dq_scale), pack_bf16x2(acc[u * 8 + 6] * dq_scale, acc[u * 8 + 7] * dq_scale));
+        for (int u = 0; u < DCOL / 8; u++)
+          *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8], acc[u * 8 + 1]), pack_bf16x2(acc[u * 8 + 2], acc[u * 8 + 3]),
+                                              pack_bf16x2(acc[u * 8 + 4], acc[u * 8 + 5]), pack_bf16x2(acc[u * 8 + 6], acc[u * 8 + 7]));
       }
+      pend_jc = -1;
+    };
+    for (int bh = blockIdx.x; bh < nbh; bh += gridDim.x, bc++) {
+      const int b = bh / H, h = bh % H;
+      const float* lse_s = (const float*)(base_gen + AttnBwdSmem::LD + (bc & 1) * 4096);
+      const float* del_s = lse_s + 512;
+      mbar_wait(ld_full(bc & 1), (uint32_t)(bc >> 1) & 1u);
+      for (int j = 0; j < nkv; j++) {
+        const int key = j * 128 + r;
+        const int imin = i_min_of(j);
+        if (imin >= nq) {                                     // no query sees this key tile: dK = dV = 0
+          if (key < S) {
+            bf16* dst = (drain_dv ? dv : dk) + ((int64_t)b * S + key) * HP + h * AT_DH + dcol0;
+#pragma unroll
+            for (int u = 0; u < DCOL / 8; u++) *(uint4*)(dst + u * 8) = make_uint4(0, 0, 0, 0);
+          }
+          continue;
+        }
+        const bool key_oob = key >= S;
+        // element index of (query q, key) in the [B*H, T, S] probability tensor = (bh*T + q)*S + key
+        const uint64_t e_row = (uint64_t)bh * (uint64_t)T * (uint64_t)S + (uint64_t)min(key, S - 1);
+        for (int i = imin; i < nq; i++, pc++) {
+          const int q0 = i * 128;
+          const int pb = pc & 1, qs = pc % AB_QD_STAGES;
+          const bool diag = (mask_off >= 0) && (j * 128 + 127 > q0 + mask_off);
+          const bool masked = diag || (j * 128 + 127 >= S);
+          const int cmin = key - mask_off - q0;               // columns < cmin are masked for this key row (diag tiles only)
+          uint8_t* const dtile = base_gen + AttnBwdSmem::DST + pb * 32768 + row_off;
+          // keep bits written by the forward: word (query, 32-key group).  Fast path: the TMA producer staged the 128 x 4-word tile of
+          // this pair next to Q / dO (one broadcast LDS per column); otherwise each lane fetches the words of its columns (32 per word).
+          const uint32_t* bits_s = (const uint32_t*)(base_gen + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 16384) + quarter;
+          uint32_t mw[NCOL / 32];
+#pragma unroll
+          for (int g = 0; g < NCOL / 32; g++) {
+            mw[g] = 0xFFFFFFFFu;
+            if (drop_mode == 2) {
+              const int qq = q0 + c0 + g * 32 + lane;
+              mw[g] = (qq < T && j * 4 + quarter < W) ? drop_bits[((int64_t)bh * T + qq) * W + j * 4 + quarter] : 0u;
+            }
+          }
+          TRACE(3 + (colq & 1), 20);
+          mbar_wait(st_full, (uint32_t)pc & 1u);        // (S^T was computed from this pair's Q stage, so its keep-bit tile has landed too)
+          tc_fence_after();
+          TRACE(3 + (colq & 1), 21);
+#pragma unroll 1
+          for (int ch = 0; ch < NCOL / 32; ch++) {            // (not unrolled: the hot loop has to stay inside the instruction cache)
+          uint32_t pk[16];                                    // P~^T of 32 queries, packed bf16 pairs
+#pragma unroll
+          for (int s2 = 0; s2 < 2; s2++) {                    // 16-column sub-chunks keep the live register set small
+            const int sc = ch * 2 + s2;
+            const int cs = c0 + sc * 16;
+            float sv[16], dpv[16];
+            if (!(dbg & 16)) {
+              tmem_ld16(tST + lane_off + cs, sv);
+              tmem_ld16(tDPT + lane_off + cs, dpv);
+              tmem_ld_wait();
+            }
+            if (sc == NCOL / 16 - 1) {
+              tc_fence_before();                              // all of this warp's S^T / dP^T columns are in registers
+              __syncwarp();
+              if (lane == 0) mbar_arrive(st_free);
+            }
+            if (!(dbg & 1)) {
+              const float* lse_c = lse_s + q0 + cs;
+              const float* del_c = del_s + q0 + cs;
+              const uint32_t mwc = NCOL / 32 == 1 ? mw[0] : (ch == 0 ? mw[0] : mw[NCOL / 32 - 1]);
+              const uint32_t mws = s2 == 0 ? mwc : __shfl_down_sync(0xffffffffu, mwc, 16);   // lane l: word of query cs + l
+#define BWD_MATH(DROP)                                                                                                                        \
+  do {                                                                                                                                        \
+    if (masked) bwd_chunk_math<DROP, true, 16>(sv, dpv, lse_c, del_c, cs, cmin, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S); \
+    else bwd_chunk_math<DROP, false, 16>(sv, dpv, lse_c, del_c, cs, cmin, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S);       \
+  } while (0)
+              if (drop_mode == 0) BWD_MATH(0);
+              else if (drop_mode == 1) BWD_MATH(1);
+              else if (drop_mode == 2) BWD_MATH(2);
+              else BWD_MATH(3);
+#undef BWD_MATH
+            }
+            if (sc == 0) {
+              TRACE(3 + (colq & 1), 23);
+              // the dV MMAs of the previous pair have read P~^T.  Their commit also covers every earlier MMA of that issuer, i.e. the
+              // dK / dQ MMAs that read this dS^T buffer two pairs ago.
+              mbar_wait(pv_free, ((uint32_t)pc & 1u) ^ 1u);
+              tc_fence_after();
+              TRACE(3 + (colq & 1), 24);
+            }
+            if (!(dbg & 2)) {
+#pragma unroll
+              for (int u = 0; u < 8; u++) pk[s2 * 8 + u] = pack_bf16x2(sv[2 * u], sv[2 * u + 1]);
+              // P~^T: row r, queries [cs - 16, cs + 16) -> 16 packed columns of the dV A operand in TMEM
+              if (s2 == 1) tmem_st16(tPT + lane_off + (uint32_t)((cs - 16) >> 1), pk);
+              // dS^T: columns [cs, cs + 16) = chunk tile cs / 64, 16-byte units (cs % 64) / 8, +1
+#pragma unroll
+              for (int uu = 0; uu < 2; uu++) {
+                const int u = ((cs & 63) >> 3) + uu;
+                *(uint4*)(dtile + (cs >> 6) * 16384 + ((u ^ (r & 7)) << 4)) =
+                    make_uint4(pack_bf16x2(dpv[uu * 8], dpv[uu * 8 + 1]), pack_bf16x2(dpv[uu * 8 + 2], dpv[uu * 8 + 3]),
+                               pack_bf16x2(dpv[uu * 8 + 4], dpv[uu * 8 + 5]), pack_bf16x2(dpv[uu * 8 + 6], dpv[uu * 8 + 7]));
+              }
+            }
+          }
+          }
+          TRACE(3 + (colq & 1), 30);
+          if (pend_jc >= 0) drain_dkv();                      // previous key tile's dK / dV: its MMAs finished while this pair was computed
+          if (pend_q_bc >= 0) drain_dq();                     // previous (b,h)'s dQ
+          tmem_st_wait();
+          tc_fence_before();
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pt_full(pb));
+          TRACE(3 + (colq & 1), 31);
+        }
+        pend_jc = jc; pend_b = b; pend_h = h; pend_key = key;
+        jc++;
+      }
+      // ---- end of this (b,h): release the lse / delta buffer; the last key tile's dK / dV and dQ are drained one pair later
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ld_empty(bc & 1));
+      pend_q_bc = bc; pend_q_b = b; pend_q_h = h;
+      TRACE(3 + (colq & 1), 40);
     }
-    tc_fence_before();
+    if (pend_q_bc >= 0) {                                     // after the last (b,h): dq_full also covers the last key tile's dK / dV
+      mbar_wait(dq_full, (uint32_t)pend_q_bc & 1u);
+      tc_fence_after();
+      if (pend_jc >= 0) drain_dkv();
+      drain_dq();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -607,15 +796,16 @@ int bpm_xattn_bwd_simt(const bpm_attn_t* a, const void* q, const void* k, const 
 
 int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                      float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t stream) {
-  if (a->T > 128 * AB_MAXQT)      // dQ accumulators of all query tiles must fit in TMEM; longer targets use the fp32-math kernel
-    return bpm_xattn_bwd_simt(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, stream);
-  BPM_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) % 16 == 0,
-              "xattn_bwd: pointers must be 16-byte aligned");
+  // dQ accumulators of all query tiles must fit in TMEM and the per-(b,h) lse / delta vectors travel as 16-byte bulk copies;
+  // other shapes use the fp32-math kernel
+  if (a->T > 128 * AB_MAXQT || a->T % 4 != 0) return bpm_xattn_bwd_simt(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, stream);
+  BPM_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv |
+               (uintptr_t)delta) % 16 == 0, "xattn_bwd: pointers must be 16-byte aligned");
   const int HP = a->H * a->dhp;
   {
     int64_t n = (int64_t)a->B * a->T * a->H;
     int grid = (int)((n + 255) / 256 < (int64_t)bpm_num_sms() * 8 ? (n + 255) / 256 : (int64_t)bpm_num_sms() * 8);
-    attn_delta_kernel<<<grid, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, a->B, a->T, a->H);
+    attn_delta_kernel<<<grid, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, lse, delta, a->B, a->T, a->H);
     BPM_CHECK_LAUNCH("xattn_delta");
   }
   CUtensorMap tq, tk, tv, tg;
@@ -643,8 +833,9 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     if (e != cudaSuccess) { bpm_set_error("xattn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
     attr_set = true;
   }
-  attn_bwd_tc_kernel<<<a->B * a->H, AB_THREADS, smem, stream>>>(tq, tk, tv, tg, tb, bits_tma, lse, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S,
-                                                                  a->H, a->mask_off, a->drop, a->drop_bits);
+  const int ctas = min(a->B * a->H, bpm_num_sms());
+  attn_bwd_tc_kernel<<<ctas, AB_THREADS, smem, stream>>>(tq, tk, tv, tg, tb, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
+                                                         a->mask_off, a->drop, a->drop_bits, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr());
   BPM_CHECK_LAUNCH("xattn_bwd_tc");
   return BPM_OK;
 }

@@ -30,6 +30,7 @@ void bpm_set_error(const char* fmt, ...);
 static inline int bpm_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 int bpm_num_sms();
 int bpm_debug_get(int slot);   // diagnostic knobs (api.cu)
+void* bpm_debug_get_ptr();     // optional device buffer for kernel event traces
 
 // ---------------------------------------------------------------- dtype helpers
 template <typename T> __device__ __forceinline__ float to_f(T v);

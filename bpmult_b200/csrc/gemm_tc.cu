@@ -45,7 +45,7 @@ struct TcGemmParams {
   int in_mode;            // 0 none, 1 residual (added), 2 gate (relu-backward mask from a saved activation)
   int reduce_add;
   float* colsum;          // fused bias gradient (wgrad only), or null
-  int dbg;                // diagnostic knobs (bpm_debug_set slot 0): 1 no TMA loads, 2 no MMAs, 4 no epilogue math, 8 no staging/store, 16 no tcgen05.ld
+  int dbg;                // diagnostic knobs (bpm_debug_set slot 0): 1 no TMA loads, 2 no MMAs, 4 no epilogue math, 8 no staging/store, 16 no tcgen05.ld, 32 MMA issuer skips the full-barrier wait, 64 no empty-barrier traffic
   const float* bias; float alpha; int act; float gate_scale; int ldc;
   bpm_dropout_t drop;
 };
@@ -126,8 +126,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    {
       const int b_chunks = (p.BN + 63) / 64;
       const uint32_t tx = (uint32_t)stage_bytes;
       int s = 0;
@@ -136,27 +136,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM, z = t / tiles_mn;
         const int kb0 = z * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (!(p.dbg & 64)) mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
           const uint32_t fb = full_bar(s);
-          if (p.dbg & 1) {
-            mbar_arrive(fb);
-          } else {
-            mbar_expect_tx(fb, tx);
-            const int k = kb * TC_BK;
-            if (!p.a_mn) tma_load_2d(sa, &tmA, fb, k, m0);                                  // box {64 k, 128 m}
-            else { tma_load_2d(sa, &tmA, fb, m0, k); tma_load_2d(sa + 8192, &tmA, fb, m0 + 64, k); }   // box {64 m, 64 k} x2
-            if (!p.b_mn) tma_load_2d(sb, &tmB, fb, k, n0);                                  // box {64 k, BN n}
-            else
-              for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, fb, n0 + 64 * c, k);   // box {64 n, 64 k}
+          if (elect_one()) {
+            if (p.dbg & 1) {
+              mbar_arrive(fb);
+            } else {
+              mbar_expect_tx(fb, tx);
+              const int k = kb * TC_BK;
+              if (!p.a_mn) tma_load_2d(sa, &tmA, fb, k, m0);                                  // box {64 k, 128 m}
+              else { tma_load_2d(sa, &tmA, fb, m0, k); tma_load_2d(sa + 8192, &tmA, fb, m0 + 64, k); }   // box {64 m, 64 k} x2
+              if (!p.b_mn) tma_load_2d(sb, &tmB, fb, k, n0);                                  // box {64 k, BN n}
+              else
+                for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, fb, n0 + 64 * c, k);   // box {64 n, 64 k}
+            }
           }
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp; one elected lane issues each k-block's batch) =====================
+    {
       // descriptor templates: K-major SW128 (LBO 16, SBO 1024; +32 B per k16 step) or MN-major (LBO BK*128, SBO 1024; +2048 B per step)
       const uint64_t da_t = p.a_mn ? umma_desc(0, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(0, 16, 1024, BPM_SWZ_128B);
       const uint64_t db_t = p.b_mn ? umma_desc(0, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(0, 16, 1024, BPM_SWZ_128B);
@@ -175,24 +178,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         uint32_t accum = 0;
         for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
+          if (!(p.dbg & 32)) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+          }
           const uint32_t sa = smem_base + s * stage_bytes;
           uint64_t da = da_t | (uint64_t)((sa & 0x3FFFFu) >> 4), db = db_t | (uint64_t)(((sa + p.a_bytes) & 0x3FFFFu) >> 4);
-          if (!no_mma) {
+          if (elect_one()) {
+            if (!no_mma) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; k++) {
-              umma_bf16(acc, da, db, p.idesc, accum);
-              // column sums of dY: dY^T (this A tile) times a tile of ones -> 16 identical columns behind the accumulator
-              if (do_colsum) umma_bf16(acc + p.BN, da, d_ones + 2 * k, p.idesc_ones, accum);
-              accum = 1;
-              da += da_k; db += db_k;
+              for (int k = 0; k < TC_BK / 16; k++) {
+                umma_bf16(acc, da, db, p.idesc, accum | (uint32_t)k);
+                // column sums of dY: dY^T (this A tile) times a tile of ones -> 16 identical columns behind the accumulator
+                if (do_colsum) umma_bf16(acc + p.BN, da, d_ones + 2 * k, p.idesc_ones, accum | (uint32_t)k);
+                da += da_k; db += db_k;
+              }
             }
+            if (!(p.dbg & 64)) umma_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
           }
-          umma_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+          __syncwarp();
+          accum = 1;
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tmem_full(a));              // accumulator complete
+        if (elect_one()) umma_commit(tmem_full(a));              // accumulator complete
+        __syncwarp();
       }
     }
   } else {
@@ -215,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       c += 2;
       while (t < total_tiles && !chunk_ok(t, c)) { t += gridDim.x; c = half; }
     };
-    auto issue_in = [&](int t, int c, int idx) {                           // lane 0 only
+    auto issue_in = [&](int t, int c, int idx) {                           // elected lane only
       const int b = idx % nb;
       const int n = (t % p.gx) * p.BN + c * CW, m = ((t / p.gx) % p.gy) * TC_BM + quarter * 32;
       mbar_expect_tx(in_full(ew, b), (uint32_t)EB);
@@ -225,7 +234,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.in_mode) {
       advance(pt, pc);
       for (int i = 0; i < dist && pt < total_tiles; i++) {
-        if (lane == 0) issue_in(pt, pc, issued);
+        if (elect_one()) issue_in(pt, pc, issued);
+        __syncwarp();
         issued++;
         advance(pt, pc);
       }
@@ -350,15 +360,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           // the buffer of chunk done + dist is the one chunk done - 1 was stored from: once the TMA unit has read it, refill it
           if (pt < total_tiles) {
-            if (lane == 0) {
+            if (elect_one()) {
               bulk_wait_read<0>();
               issue_in(pt, pc, issued);
             }
+            __syncwarp();
             issued++;
             advance(pt, pc);
           }
         } else {
-          if (lane == 0) bulk_wait_read_n(nb - 1);                          // the store that last used this buffer has read it
+          if (elect_one()) bulk_wait_read_n(nb - 1);                        // the store that last used this buffer has read it
           __syncwarp();
         }
         // ---- stage the chunk (swizzled, in place over the residual / gate tile) and hand it to the TMA unit
@@ -376,14 +387,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           if (p.reduce_add) tma_reduce_add_2d(&tmC, ebuf_s + b * EB, n, m0);
           else tma_store_2d(&tmC, ebuf_s + b * EB, n, m0);
           bulk_commit();
         }
+        __syncwarp();
       }
     }
-    if (lane == 0) bulk_wait_read<0>();                                     // smem must outlive the last TMA store's read
+    if (elect_one()) bulk_wait_read<0>();                                   // smem must outlive the last TMA store's read
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -50,6 +50,8 @@ const char* bpm_last_error(void);
 int bpm_device_ok(int dev);
 /* diagnostic knobs for profiling scripts (slot 0: GEMM stage bypass bits, 1: attention); the product never sets them */
 int bpm_debug_set(int slot, int value);
+/* device buffer (uint64 [5][4096]) that receives a per-role event trace of CTA 0 of the attention backward kernel; NULL = off */
+int bpm_debug_set_ptr(void* p);
 
 /* ---- weight staging ------------------------------------------------------------------------------------------
  * Reference parameters stay fp32 in reference layout (state_dict names of SURVEY 8b); kernels consume zero-padded
@@ -126,7 +128,7 @@ int bpm_colsum(const void* X, int dtype, int M, int N, int ld, float* out, void*
  * q [B,T,H*dhp] (already scaled by dh^-0.5), k, v [B,S,H*dhp] in T; out [B,T,H*dhp]; lse fp32 [B,H,T].
  * mask_off >= 0: key j visible to query i iff j <= i + mask_off (reference: mask_off = |S - T|); mask_off < 0: no mask.
  * key_pad (uint8 [B,S], 1 = padded key, may be NULL): superset feature, default off (the reference has none).
- * bwd writes dq * dq_scale, dk, dv (T) and needs delta workspace fp32 [B,H,T]. */
+ * bwd writes dq * dq_scale, dk, dv (T) and needs a workspace `delta` fp32 [2,B,H,T]: on return [0] = rowsum(dO*O), [1] = lse*log2e. */
 typedef struct {
   int dtype, B, T, S, H, dh, dhp, mask_off;
   const uint8_t* key_pad;

@@ -28,7 +28,7 @@ if which in ("attn_fwd", "attn_bwd", "attn_fwd_drop", "attn_bwd_drop"):
     if "bwd" in which:
         do = torch.randn(M, d.HP, device=dev).to(bf)
         dq, dk, dv = [torch.empty(M, d.HP, device=dev, dtype=bf) for _ in range(3)]
-        delta = torch.empty(B * d.H * T, device=dev)
+        delta = torch.empty(2 * B * d.H * T, device=dev)
         for _ in range(iters):
             ops.xattn_bwd(q, k, v, o, do, lse, delta, dq, d.scaling, dk, dv, B, T, T, d.H, d.dh, d.dhp, mask_off=0, drop=drop, drop_bits=bits)
 elif which.startswith("gemm"):

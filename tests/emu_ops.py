@@ -221,7 +221,9 @@ class EmuOps:
         ds = p * (dpt * mult - dl)
         dq_ = ds @ kh * dq_scale
         dk_ = ds.transpose(-1, -2) @ qh
-        delta.copy_(dl.reshape(-1))
+        n = B * H * T
+        delta[:n].copy_(dl.reshape(-1))
+        delta[n:].copy_((lse.float() * 1.4426950408889634).reshape(-1))      # workspace [1]: lse * log2e
         dq.copy_(dq_.permute(0, 2, 1, 3).reshape(B * T, H * dhp).to(dq.dtype))
         dk.copy_(dk_.permute(0, 2, 1, 3).reshape(B * S, H * dhp).to(dk.dtype))
         dv.copy_(dv_.permute(0, 2, 1, 3).reshape(B * S, H * dhp).to(dv.dtype))

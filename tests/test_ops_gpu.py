@@ -209,7 +209,7 @@ def test_xattn_fwd_bwd(ops, dtype, case):
                                                                          drop_bits=bits if use_bits else None), [q, k, v], outs)
         assert max_rel(c[0], e[0]) < tol(dtype)
         assert max_rel(c[1], e[1]) < (1e-5 if dtype == F32 else 2e-3)
-        outs = [torch.zeros(B * H * T), torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype)]
+        outs = [torch.zeros(2 * B * H * T), torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype)]
         e2, c2 = both(ops, lambda o, q, k, v, out, do, lse, bits, dl, dq, dk, dv: o.xattn_bwd(q, k, v, out, do, lse, dl, dq, 0.2, dk, dv, B, T, S, H, dh, dhp, off,
                                                                                              None, drop, drop_bits=bits if use_bits else None),
                       [q, k, v, e[0], do, e[1], c[2]], outs)
