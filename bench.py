@@ -268,8 +268,10 @@ def run_ours(opt):
         sampler.stop_flag = True
         sampler.join(timeout=2)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        if world > 1:                                       # wait for rank 0 (kernel timings, JSON line), then leave without NCCL teardown
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
         return
     value = world * B * opt.steps / (ms * 1e-3)
     e2e = world * B * opt.steps / (ms_e2e * 1e-3)
@@ -313,8 +315,14 @@ def run_ours(opt):
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "samples/s", "cores": threads, "kind": kind,
                                 "sample": "1 warm-up + %d timed steps of B=1 of the same cfg-2 workload (fwd+BCE+bwd, fp32)" % n}
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroying a communicator whose collectives live inside a captured CUDA graph hung the
+        # 2-GPU run at exit (the measurement had already been printed).  Every rank has passed the final MAX all-reduce.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

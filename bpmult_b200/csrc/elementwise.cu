@@ -135,6 +135,78 @@ extern "C" int bpm_remap_batch(const bpm_remap_desc_t* descs_dev, int n, int mod
   return BPM_OK;
 }
 
+// ---------------------------------------------------------------- LayerNorm affine folded into a projection
+// The key / value inputs of a crossmodal encoder are the same tensor for all L layers (transformer.py:83-85); only the layer's
+// LayerNorm affine and in_proj differ.  x_hat = (x - mean) * rstd is computed once per encoder and each layer uses
+//     K = LN(x) Wk^T + bk = x_hat (Wk diag(gamma))^T + (bk + Wk beta).
+// fwd: Wp[map(i), j] = W[i, j] * gamma[j];   bp[map(i)] = bias[i] + sum_j W[i, j] * beta[j]        (one warp per reference row)
+template <typename T>
+__global__ void ln_fold_fwd_kernel(const float* __restrict__ W, int ldw, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int rows, int cols, int row_dh, int row_dhp, T* __restrict__ Wp, int ldp,
+                                   float* __restrict__ bp) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int ip = remap_fwd(warp, row_dh, row_dhp);
+  const float* w = W + (int64_t)warp * ldw;
+  float acc = 0.f;
+  for (int j = lane; j < cols; j += 32) {
+    const float v = w[j];
+    acc = fmaf(v, beta[j], acc);
+    Wp[(int64_t)ip * ldp + j] = from_f<T>(v * gamma[j]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) bp[ip] = bias[warp] + acc;
+}
+
+extern "C" int bpm_ln_fold_fwd(const float* W, int ldw, const float* bias, const float* gamma, const float* beta, int rows, int cols, int row_dh,
+                               int row_dhp, void* Wp, int wp_dtype, int ldp, float* bp, void* stream) {
+  BPM_REQUIRE(W && bias && gamma && beta && Wp && bp && rows > 0 && cols > 0 && ldp >= cols, "ln_fold_fwd: bad args");
+  const int blocks = bpm_cdiv((int64_t)rows * 32, 256);
+  if (wp_dtype == BPM_BF16)
+    ln_fold_fwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(W, ldw, bias, gamma, beta, rows, cols, row_dh, row_dhp, (bf16*)Wp, ldp, bp);
+  else
+    ln_fold_fwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(W, ldw, bias, gamma, beta, rows, cols, row_dh, row_dhp, (float*)Wp, ldp, bp);
+  BPM_CHECK_LAUNCH("ln_fold_fwd");
+  return BPM_OK;
+}
+
+// bwd: from the padded fp32 gradient accumulators gWf / gbf of (Wp, bp) to those of (W, bias) and the LayerNorm affine:
+//     gW[i', j] += gWf[i', j] * gamma[j] + gbf[i'] * beta[j];      gb[i'] += gbf[i']
+//     dgamma[j] += sum_i gWf[i', j] * W[i, j];                     dbeta[j] += sum_i gbf[i'] * W[i, j]
+#define LNF_ROWS 8
+__global__ void ln_fold_bwd_kernel(const float* __restrict__ W, int ldw, const float* __restrict__ gamma, const float* __restrict__ beta, int rows,
+                                   int cols, int row_dh, int row_dhp, const float* __restrict__ gWf, int ldf, const float* __restrict__ gbf,
+                                   float* __restrict__ gW, int ldg, float* __restrict__ gb, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int r0 = blockIdx.x * LNF_ROWS;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float g = gamma[j], b = beta[j];
+    float ag = 0.f, ab = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < LNF_ROWS; rr++) {
+      const int i = r0 + rr;
+      if (i < rows) {
+        const int ip = remap_fwd(i, row_dh, row_dhp);
+        const float w = W[(int64_t)i * ldw + j], gbv = gbf[ip], tv = gWf[(int64_t)ip * ldf + j];
+        ag = fmaf(tv, w, ag);
+        ab = fmaf(gbv, w, ab);
+        gW[(int64_t)ip * ldg + j] += fmaf(tv, g, gbv * b);
+        if (j == 0) gb[ip] += gbv;
+      }
+    }
+    atomicAdd(dgamma + j, ag);
+    atomicAdd(dbeta + j, ab);
+  }
+}
+
+extern "C" int bpm_ln_fold_bwd(const float* W, int ldw, const float* gamma, const float* beta, int rows, int cols, int row_dh, int row_dhp,
+                               const float* gWf, int ldf, const float* gbf, float* gW, int ldg, float* gb, float* dgamma, float* dbeta, void* stream) {
+  BPM_REQUIRE(W && gamma && beta && gWf && gbf && gW && gb && dgamma && dbeta && rows > 0 && cols > 0, "ln_fold_bwd: bad args");
+  ln_fold_bwd_kernel<<<bpm_cdiv(rows, LNF_ROWS), 256, 0, (cudaStream_t)stream>>>(W, ldw, gamma, beta, rows, cols, row_dh, row_dhp, gWf, ldf, gbf, gW, ldg,
+                                                                                gb, dgamma, dbeta);
+  BPM_CHECK_LAUNCH("ln_fold_bwd");
+  return BPM_OK;
+}
+
 // ---------------------------------------------------------------- stage / unstage rows
 template <typename T>
 __global__ void stage_rows_kernel(const float* __restrict__ src, int B, int T_, int C, int64_t sb, int64_t st, int64_t sc, T* __restrict__ dst,

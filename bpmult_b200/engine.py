@@ -96,6 +96,7 @@ class Arena:
 # ============================================================================================== encoder
 class EncoderEngine:
     """One TransformerEncoder (L layers + final LayerNorm).  `uid` separates its dropout streams."""
+    fold_kv = True          # hoist the K / V LayerNorm out of the layer loop (x_hat once per encoder, affine folded into in_proj; SURVEY 7.3)
 
     # parameter table: name-suffix -> (kind, packer)
     def __init__(self, ops, D, H, L, attn_dropout=0.0, relu_dropout=0.0, res_dropout=0.0, embed_dropout=0.0, attn_mask=False,
@@ -107,6 +108,7 @@ class EncoderEngine:
         self.attn_mask, self.biproj, self.T_ = attn_mask, biprojection, dtype
         self.uid = uid
         self.n_ln = 3 if biprojection else 2
+        self.kv_ln = 1 if biprojection else 0                     # which LayerNorm the crossmodal K / V inputs go through
         self.arena = Arena(ops)
         self.shared = shared if shared is not None else Arena(ops)     # scratch shared between encoders (backward temporaries)
         self.pe = None
@@ -141,6 +143,7 @@ class EncoderEngine:
         gshapes = []
         for _ in range(self.L):
             gshapes += [(3 * d.HP, d.Dp), (3 * d.HP,), (d.Dp, d.HP), (d.Dp,), (d.FP, d.Dp), (d.FP,), (d.Dp, d.FP), (d.Dp,)] + [(d.Dp,)] * (2 * self.n_ln)
+            gshapes += [(2 * d.HP, d.Dp), (2 * d.HP,)]                       # folded K / V projection (x_hat operands)
         gshapes += [(d.Dp,), (d.Dp,)]
         self.G_flat, gv = carve(self.ops, f32, gshapes)      # every gradient accumulator of this encoder: zeroed with one memset
         it = iter(gv)
@@ -151,10 +154,16 @@ class EncoderEngine:
             g = dict(Wqkv=next(it), bqkv=next(it), Wo=next(it), bo=next(it), W1=next(it), b1=next(it), W2=next(it), b2=next(it))
             g["ln_g"] = [next(it) for _ in range(self.n_ln)]
             g["ln_b"] = [next(it) for _ in range(self.n_ln)]
+            g["Wkv_f"], g["bkv_f"] = next(it), next(it)
+            w["Wkv_f"], w["bkv_f"] = z((2 * d.HP, d.Dp), T_), z((2 * d.HP,), f32)
             self.W.append(w)
             self.G.append(g)
         self.Wf = dict(g=z((d.Dp,), f32), b=z((d.Dp,), f32))
         self.Gf = dict(g=next(it), b=next(it))
+        # unit LayerNorm affine (x_hat of the K / V inputs) and a sink for its unused affine gradients
+        self.unit_g, self.unit_b, self.ln_sink = z((d.Dp,), f32), z((d.Dp,), f32), z((2, d.Dp), f32)
+        self.unit_g[:d.D] = 1.0
+        self.P = [None] * self.L                    # per layer: reference-layout (in_proj_weight, in_proj_bias, K/V LayerNorm gamma, beta)
 
     def pack(self, params, pfx=""):
         """reference-layout fp32 parameters -> zero-padded kernel operands (run whenever the parameters changed)."""
@@ -173,10 +182,16 @@ class EncoderEngine:
             for j in range(self.n_ln):
                 o.pack_matrix(params[p + "layer_norms.%d.weight" % j].view(1, -1), w["ln_g"][j].view(1, -1))
                 o.pack_matrix(params[p + "layer_norms.%d.bias" % j].view(1, -1), w["ln_b"][j].view(1, -1))
+            self.P[l] = (params[p + "self_attn.in_proj_weight"], params[p + "self_attn.in_proj_bias"],
+                         params[p + "layer_norms.%d.weight" % self.kv_ln], params[p + "layer_norms.%d.bias" % self.kv_ln])
         if self.with_final_ln:
             o.pack_matrix(params[pfx + "layer_norm.weight"].view(1, -1), self.Wf["g"].view(1, -1))
             o.pack_matrix(params[pfx + "layer_norm.bias"].view(1, -1), self.Wf["b"].view(1, -1))
         o.batch_end()
+        if self.fold_kv:
+            for l in range(self.L):                 # K' = W_k diag(gamma), b_k' = b_k + W_k beta  (and the same for V)
+                ipw, ipb, g_, b_ = self.P[l]
+                o.ln_fold_fwd(ipw[d.D:], ipb[d.D:], g_, b_, self.W[l]["Wkv_f"], self.W[l]["bkv_f"], row_map=hm)
 
     def pack_attention(self, l, ipw, ipb, ow, ob):
         o, d, w = self.ops, self.d, self.W[l]
@@ -246,7 +261,8 @@ class EncoderEngine:
         return abs(S - T) if self.attn_mask else -1
 
     # ---------------------------------------------------------------- attention block (in-proj, attention, out-proj + residual)
-    def _attn_fwd(self, l, blk, q_in, k_in, v_in, B, T, S, x_res, x_out, res_drop=True):
+    def _attn_fwd(self, l, blk, q_in, k_in, v_in, B, T, S, x_res, x_out, res_drop=True, folded=False):
+        """folded: k_in / v_in are the un-affined x_hat rows and the K / V projections carry the layer's LayerNorm affine"""
         o, d, A, w = self.ops, self.d, self.arena, self.W[l]
         M, Ms = B * T, B * S
         key = "L%d.%s." % (l, blk)
@@ -256,6 +272,8 @@ class EncoderEngine:
         lse = A.get(key + "lse", (B * d.H * T,), torch.float32)
         Wq, Wk, Wv = w["Wqkv"][:d.HP], w["Wqkv"][d.HP:2 * d.HP], w["Wqkv"][2 * d.HP:]
         bq, bk, bv = w["bqkv"][:d.HP], w["bqkv"][d.HP:2 * d.HP], w["bqkv"][2 * d.HP:]
+        if folded:
+            Wk, Wv, bk, bv = w["Wkv_f"][:d.HP], w["Wkv_f"][d.HP:], w["bkv_f"][:d.HP], w["bkv_f"][d.HP:]
         o.gemm(q_in, Wq, q, M, d.HP, d.Dp, bias=bq, alpha=d.scaling)          # q = (x Wq^T + bq) * dh^-0.5  (:86)
         o.gemm(k_in, Wk, k, Ms, d.HP, d.Dp, bias=bk)
         v = A.get(key + "v", (Ms, d.HP), self.T_)
@@ -266,17 +284,21 @@ class EncoderEngine:
         # x_out = x_res + dropout(a Wo^T + bo)                                   (transformer.py:174-175)
         o.gemm(a, w["Wo"], x_out, M, d.Dp, d.HP, bias=w["bo"], drop=self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")),
                residual=x_res)
-        return dict(q=q, k=k, v=v, a=a, lse=lse, q_in=q_in, k_in=k_in, v_in=v_in, S=S, bits=bits)
+        return dict(q=q, k=k, v=v, a=a, lse=lse, q_in=q_in, k_in=k_in, v_in=v_in, S=S, bits=bits, folded=folded)
 
-    def _attn_bwd(self, l, blk, sv, B, T, gx, res_drop=True):
+    def _attn_bwd(self, l, blk, sv, B, T, gx, res_drop=True, gnk=None, gnv=None):
         """gx: fp32 [M, Dp] gradient wrt the block output x_out (= also flows to x_res unchanged).
-        Returns (dq_in, dk_in, dv_in) in storage type (gradients wrt the projection inputs)."""
+        Returns (dq_in, dk_in, dv_in) in storage type (gradients wrt the projection inputs).  Folded K / V projections instead
+        accumulate their input gradients into the fp32 buffers gnk / gnv (gradient wrt x_hat) and return (dq_in, None, None)."""
         o, d, w, g, Sh = self.ops, self.d, self.W[l], self.G[l], self.shared
         S = sv["S"]
         M, Ms = B * T, B * S
         Wq, Wk, Wv = w["Wqkv"][:d.HP], w["Wqkv"][d.HP:2 * d.HP], w["Wqkv"][2 * d.HP:]
         gWq, gWk, gWv = g["Wqkv"][:d.HP], g["Wqkv"][d.HP:2 * d.HP], g["Wqkv"][2 * d.HP:]
         gbq, gbk, gbv = g["bqkv"][:d.HP], g["bqkv"][d.HP:2 * d.HP], g["bqkv"][2 * d.HP:]
+        if sv["folded"]:
+            Wk, Wv = w["Wkv_f"][:d.HP], w["Wkv_f"][d.HP:]
+            gWk, gWv, gbk, gbv = g["Wkv_f"][:d.HP], g["Wkv_f"][d.HP:], g["bkv_f"][:d.HP], g["bkv_f"][d.HP:]
         go = Sh.get("go", (M, d.Dp), self.T_)
         o.cast_drop(gx, go, self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")))   # grad wrt out_proj output
         o.gemm(go, sv["a"], g["Wo"], d.Dp, d.HP, M, ta=1, tb=1, accumulate=True, colsum=g["bo"])   # dWo = go^T a, dbo = colsum(go)
@@ -293,9 +315,13 @@ class EncoderEngine:
         o.gemm(dk, sv["k_in"], gWk, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=gbk)
         o.gemm(dv, sv["v_in"], gWv, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=gbv)
         dq_in = Sh.get("dq_in", (M, d.Dp), self.T_)
+        o.gemm(dq, Wq, dq_in, M, d.Dp, d.HP, tb=1)
+        if sv["folded"]:                                                        # d x_hat += dK W_k' (+ dV W_v'), fp32, across all layers
+            o.gemm(dk, Wk, gnk, Ms, d.Dp, d.HP, tb=1, residual=gnk)
+            o.gemm(dv, Wv, gnv, Ms, d.Dp, d.HP, tb=1, residual=gnv)
+            return dq_in, None, None
         dk_in = Sh.get("dk_in", (Ms, d.Dp), self.T_)
         dv_in = Sh.get("dv_in", (Ms, d.Dp), self.T_)
-        o.gemm(dq, Wq, dq_in, M, d.Dp, d.HP, tb=1)
         o.gemm(dk, Wk, dk_in, Ms, d.Dp, d.HP, tb=1)
         o.gemm(dv, Wv, dv_in, Ms, d.Dp, d.HP, tb=1)
         return dq_in, dk_in, dv_in
@@ -378,6 +404,18 @@ class EncoderEngine:
                 xv = A.get("xv", (Ms, d.Dp), self.T_)
                 o.embed_fwd(src_k if src_v is None else src_v, self.pe, B, S, d.D, scale, xv, self._drop(self.p_embed, -1, 3))
         self.saved = []
+        self.folded = self.cross and self.fold_kv
+        nk = nv = None
+        if self.folded:                                                          # x_hat of the K / V inputs, shared by all L layers
+            def xhat(key, src):
+                y = A.get(key + "y", (Ms, d.Dp), self.T_)
+                mean = A.get(key + "mean", (Ms,), torch.float32)
+                rstd = A.get(key + "rstd", (Ms,), torch.float32)
+                o.layernorm_fwd(src, self.unit_g, self.unit_b, d.D, y, mean, rstd)
+                return dict(y=y, mean=mean, rstd=rstd, x=src)
+            nk = xhat("nk.", xk)
+            nv = nk if self.kv_shared else xhat("nv.", xv)
+            self.nkv = (nk, nv)
         xi = 0
         x = xs[0]
         for l in range(self.L):
@@ -392,23 +430,29 @@ class EncoderEngine:
             elif self.biproj:                                                    # :160-169
                 x1 = xs[xi + 1]
                 sv["self"] = self._attn_fwd(l, "s", ln_q["y"], ln_q["y"], ln_q["y"], B, T, T, x, x1)
-                ln_k = self._ln_fwd("L%d.lnk." % l, xk, l, 1, Ms)
-                ln_v = ln_k if self.kv_shared else self._ln_fwd("L%d.lnv." % l, xv, l, 1, Ms)
-                sv["ln_k"], sv["ln_v"] = ln_k, ln_v
+                if self.folded:
+                    ln_k, ln_v = nk, nv
+                else:
+                    ln_k = self._ln_fwd("L%d.lnk." % l, xk, l, 1, Ms)
+                    ln_v = ln_k if self.kv_shared else self._ln_fwd("L%d.lnv." % l, xv, l, 1, Ms)
+                    sv["ln_k"], sv["ln_v"] = ln_k, ln_v
                 # the cross-attention query is the residual stream itself, NOT re-normalised (:169)
                 qc = A.get("L%d.qcast" % l, (M, d.Dp), self.T_)
                 o.cast_drop(x1, qc, None)
                 x2 = xs[xi + 2]
-                sv["cross"] = self._attn_fwd(l, "x", qc, ln_k["y"], ln_v["y"], B, T, S, x1, x2)
+                sv["cross"] = self._attn_fwd(l, "x", qc, ln_k["y"], ln_v["y"], B, T, S, x1, x2, folded=self.folded)
                 x1 = x2
                 xi += 2
                 ffn_ln = 2
             else:                                                                # :170-173
-                ln_k = self._ln_fwd("L%d.lnk." % l, xk, l, 0, Ms)
-                ln_v = ln_k if self.kv_shared else self._ln_fwd("L%d.lnv." % l, xv, l, 0, Ms)
-                sv["ln_k"], sv["ln_v"] = ln_k, ln_v
+                if self.folded:
+                    ln_k, ln_v = nk, nv
+                else:
+                    ln_k = self._ln_fwd("L%d.lnk." % l, xk, l, 0, Ms)
+                    ln_v = ln_k if self.kv_shared else self._ln_fwd("L%d.lnv." % l, xv, l, 0, Ms)
+                    sv["ln_k"], sv["ln_v"] = ln_k, ln_v
                 x1 = xs[xi + 1]
-                sv["cross"] = self._attn_fwd(l, "x", ln_q["y"], ln_k["y"], ln_v["y"], B, T, S, x, x1)
+                sv["cross"] = self._attn_fwd(l, "x", ln_q["y"], ln_k["y"], ln_v["y"], B, T, S, x, x1, folded=self.folded)
                 xi += 1
                 ffn_ln = 1
             x2 = xs[xi + 1]
@@ -439,7 +483,7 @@ class EncoderEngine:
             o.layernorm_bwd(dout, self.final["x"], self.final["mean"], self.final["rstd"], self.Wf["g"], d.D, gx, False, self.Gf["g"], self.Gf["b"])
         else:
             o.axpy_f32(dout, gx, False)
-        gxk = gxv = None
+        gxk = gxv = gnk = gnv = None
         if self.cross:
             gxk = Sh.get("gxk", (Ms, d.Dp), torch.float32)
             o.zero_(gxk)
@@ -447,6 +491,13 @@ class EncoderEngine:
             if not self.kv_shared:
                 gxv = Sh.get("gxv", (Ms, d.Dp), torch.float32)
                 o.zero_(gxv)
+            if self.folded:                         # gradients wrt x_hat accumulate over the layers; one LayerNorm backward at the end
+                gnk = Sh.get("gnk", (Ms, d.Dp), torch.float32)
+                o.zero_(gnk)
+                gnv = gnk
+                if not self.kv_shared:
+                    gnv = Sh.get("gnv", (Ms, d.Dp), torch.float32)
+                    o.zero_(gnv)
         for l in reversed(range(self.L)):
             sv = self.saved[l]
             self._ffn_bwd(l, sv["ffn"], M, gx)
@@ -455,18 +506,31 @@ class EncoderEngine:
                 for t in (dq_in, dk_in, dv_in):
                     self._ln_bwd(l, sv["ln_q"], t, gx)
             elif self.biproj:
-                dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx)
+                dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx, gnk=gnk, gnv=gnv)
                 o.axpy_f32(dq_in, gx, True)                                      # query path is the raw residual stream
-                self._ln_bwd(l, sv["ln_k"], dk_in, gxk)
-                self._ln_bwd(l, sv["ln_v"], dv_in, gxv)
+                if not self.folded:
+                    self._ln_bwd(l, sv["ln_k"], dk_in, gxk)
+                    self._ln_bwd(l, sv["ln_v"], dv_in, gxv)
                 dq_in, dk_in, dv_in = self._attn_bwd(l, "s", sv["self"], B, T, gx)
                 for t in (dq_in, dk_in, dv_in):
                     self._ln_bwd(l, sv["ln_q"], t, gx)
             else:
-                dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx)
+                dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx, gnk=gnk, gnv=gnv)
                 self._ln_bwd(l, sv["ln_q"], dq_in, gx)
-                self._ln_bwd(l, sv["ln_k"], dk_in, gxk)
-                self._ln_bwd(l, sv["ln_v"], dv_in, gxv)
+                if not self.folded:
+                    self._ln_bwd(l, sv["ln_k"], dk_in, gxk)
+                    self._ln_bwd(l, sv["ln_v"], dv_in, gxv)
+        if self.cross and self.folded:
+            nk, nv = self.nkv
+            hm = (d.dh, d.dhp)
+            o.layernorm_bwd(gnk, nk["x"], nk["mean"], nk["rstd"], self.unit_g, d.D, gxk, True, self.ln_sink[0], self.ln_sink[1])
+            if not self.kv_shared:
+                o.layernorm_bwd(gnv, nv["x"], nv["mean"], nv["rstd"], self.unit_g, d.D, gxv, True, self.ln_sink[0], self.ln_sink[1])
+            for l in range(self.L):                 # gradients of (W_k', b_k') -> W_k, b_k and the layer's LayerNorm affine
+                ipw, ipb, g_, b_ = self.P[l]
+                G = self.G[l]
+                o.ln_fold_bwd(ipw[d.D:], g_, b_, G["Wkv_f"], G["bkv_f"], G["Wqkv"][d.HP:], G["bqkv"][d.HP:], G["ln_g"][self.kv_ln],
+                              G["ln_b"][self.kv_ln], row_map=hm)
         scale = math.sqrt(d.D)
         if not self.with_embed:
             if d_src_q is not None:

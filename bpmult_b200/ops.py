@@ -154,6 +154,19 @@ class CudaOps:
                                             x.shape[0], D, x.shape[1], dx.data_ptr(), int(accumulate), dgamma.data_ptr(), dbeta.data_ptr(),
                                             self._s()), "layernorm_bwd")
 
+    def ln_fold_fwd(self, W, bias, gamma, beta, Wp, bp, row_map=(0, 0)):
+        """Wp[map(i), :cols] = W[i] * gamma;  bp[map(i)] = bias[i] + W[i] . beta   (W, bias, gamma, beta fp32 reference layout)"""
+        assert W.dtype == torch.float32 and W.stride(1) == 1 and Wp.stride(1) == 1 and bp.dtype == torch.float32
+        self._ck(self.lib.bpm_ln_fold_fwd(W.data_ptr(), W.stride(0), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), W.shape[0], W.shape[1],
+                                          row_map[0], row_map[1], Wp.data_ptr(), _dt(Wp), Wp.stride(0), bp.data_ptr(), self._s()), "ln_fold_fwd")
+
+    def ln_fold_bwd(self, W, gamma, beta, gWf, gbf, gW, gb, dgamma, dbeta, row_map=(0, 0)):
+        """gW += gWf * gamma + gbf (x) beta, gb += gbf (padded fp32 accumulators); dgamma / dbeta (fp32) accumulated"""
+        assert gW.dtype == torch.float32 and gW.stride(1) == 1 and gWf.dtype == torch.float32 and gWf.stride(1) == 1
+        self._ck(self.lib.bpm_ln_fold_bwd(W.data_ptr(), W.stride(0), gamma.data_ptr(), beta.data_ptr(), W.shape[0], W.shape[1], row_map[0],
+                                          row_map[1], gWf.data_ptr(), gWf.stride(0), gbf.data_ptr(), gW.data_ptr(), gW.stride(0), gb.data_ptr(),
+                                          dgamma.data_ptr(), dbeta.data_ptr(), self._s()), "ln_fold_bwd")
+
     # ------------------------------------------------------------------ gemm
     def gemm(self, A, B, Cout, M, N, K, ta=0, tb=0, bias=None, alpha=1.0, act=0, drop=None, gate=None, gate_scale=1.0, residual=None,
              accumulate=False, split_k=0, colsum=None):

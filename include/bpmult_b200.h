@@ -97,6 +97,19 @@ int bpm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, 
                       const float* gamma, int rows, int D, int Dp, float* dx, int accumulate, float* dgamma, float* dbeta,
                       void* stream);
 
+/* ---- LayerNorm affine folded into the K / V projection of a crossmodal layer ---------------------------------------
+ * transformer.py:83-85 feeds the same x_k / x_v to all L layers; only layer_norms[.] and in_proj differ.  x_hat is computed
+ * once per encoder (bpm_layernorm_fwd with a unit affine) and K = x_hat (W diag(gamma))^T + (bias + W beta).
+ * fwd: Wp[map(i), j] = W[i,j]*gamma[j] (dtype wp_dtype, pitch ldp), bp[map(i)] = bias[i] + sum_j W[i,j]*beta[j];
+ *      map = head remap of rows (row_dh -> row_dhp, 0 = identity); W, bias, gamma, beta are fp32 in reference layout.
+ * bwd: gWf / gbf are the padded fp32 gradient accumulators of (Wp, bp); gW += gWf*gamma + gbf (x) beta, gb += gbf (padded
+ *      accumulators of W / bias), dgamma[j] += sum_i gWf*W, dbeta[j] += sum_i gbf[i]*W[i,j]. */
+int bpm_ln_fold_fwd(const float* W, int ldw, const float* bias, const float* gamma, const float* beta, int rows, int cols,
+                    int row_dh, int row_dhp, void* Wp, int wp_dtype, int ldp, float* bp, void* stream);
+int bpm_ln_fold_bwd(const float* W, int ldw, const float* gamma, const float* beta, int rows, int cols, int row_dh, int row_dhp,
+                    const float* gWf, int ldf, const float* gbf, float* gW, int ldg, float* gb, float* dgamma, float* dbeta,
+                    void* stream);
+
 /* ---- GEMM with fused epilogue: F.linear (multihead_attention.py:152-158), fc1/fc2 (transformer.py:186-190),
  *      out_proj (multihead_attention.py:130), Conv1d k=1 (mmtr.py:748-750), GMU linears (mmtr.py:190-194) ---------
  * C[M,N] = epi( op(A)[M,K] * op(B)[K,N] ).  ta = 0: A stored [M,K] (pitch lda); ta = 1: A stored [K,M].

@@ -76,6 +76,21 @@ class EmuOps:
         pass
 
     # ------------------------------------------------------------------ weight staging
+    def ln_fold_fwd(self, W, bias, gamma, beta, Wp, bp, row_map=(0, 0)):
+        r = _remap(W.shape[0], *row_map)
+        Wp[r, :W.shape[1]] = (W * gamma.unsqueeze(0)).to(Wp.dtype)
+        bp[r] = bias + W @ beta
+
+    def ln_fold_bwd(self, W, gamma, beta, gWf, gbf, gW, gb, dgamma, dbeta, row_map=(0, 0)):
+        r = _remap(W.shape[0], *row_map)
+        c = W.shape[1]
+        t = gWf[r, :c]
+        g = gbf[r]
+        dgamma[:c] += (t * W).sum(0)
+        dbeta[:c] += (g.unsqueeze(1) * W).sum(0)
+        gW[r, :c] += t * gamma.unsqueeze(0) + g.unsqueeze(1) * beta.unsqueeze(0)
+        gb[r] += g
+
     def pack_matrix(self, src, dst, row_map=(0, 0), col_map=(0, 0)):
         dst.zero_()
         r, c = _remap(src.shape[0], *row_map), _remap(src.shape[1], *col_map)

@@ -71,6 +71,22 @@ def test_pack_unpack(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", [F32, BF16])
+def test_ln_fold(ops, dtype):
+    """LayerNorm affine folded into the K / V projection: packed operands and the gradient unfold"""
+    D, H, dh, dhp, Dp = 300, 12, 25, 32, 320
+    W, bias, gamma, beta = rnd((2 * D, D), 4, scale=0.05), rnd((2 * D,), 5), 1 + 0.1 * rnd((D,), 6), 0.1 * rnd((D,), 7)
+    e, c = both(ops, lambda o, W, b, g, bt, Wp, bp: o.ln_fold_fwd(W, b, g, bt, Wp, bp, row_map=(dh, dhp)), [W, bias, gamma, beta],
+                [torch.zeros(2 * H * dhp, Dp, dtype=dtype), torch.zeros(2 * H * dhp)])
+    assert max_rel(c[0], e[0]) < (1e-6 if dtype == F32 else 4e-3) and max_rel(c[1], e[1]) < 1e-5
+    gWf, gbf = rnd((2 * H * dhp, Dp), 8), rnd((2 * H * dhp,), 9)
+    outs = [rnd((3 * H * dhp, Dp), 10), rnd((3 * H * dhp,), 11), rnd((Dp,), 12), rnd((Dp,), 13)]
+    e, c = both(ops, lambda o, W, g, bt, gWf, gbf, gW, gb, dg, db: o.ln_fold_bwd(W, g, bt, gWf, gbf, gW[H * dhp:], gb[H * dhp:], dg, db,
+                                                                                 row_map=(dh, dhp)), [W, gamma, beta, gWf, gbf], outs)
+    for a, b in zip(c, e):
+        assert max_rel(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
 def test_stage_embed(ops, dtype):
     B, T, C, Tp, Cp = 3, 10, 35, 16, 64
     src = rnd((T, B, C), 4).permute(1, 0, 2)          # time-major storage, batch-major view
