@@ -48,6 +48,7 @@ SIGNATURES = {
     "bpm_embed_bwd": [_P, _I, _I, _I, _F, _P, _I, Dropout, _P],
     "bpm_layernorm_fwd": [_P, _I, _P, _P, _I, _I, _I, _F, _P, _I, _P, _P, _P],
     "bpm_layernorm_bwd": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P],
+    "bpm_layernorm_bwd_cast": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _I, Dropout, _P],
     "bpm_ln_fold_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
     "bpm_ln_fold_bwd": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P],
     "bpm_gemm": [C.POINTER(Gemm), _P],

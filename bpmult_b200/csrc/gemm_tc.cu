@@ -520,7 +520,22 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   int num_kb = bpm_cdiv(g->K, TC_BK);
   int gx = bpm_cdiv(g->N, p.BN), gy = bpm_cdiv(g->M, TC_BM);
   int split = 1;
-  if (g->accumulate) split = g->split_k > 0 ? g->split_k : max(1, min(num_kb / 4, (2 * bpm_num_sms()) / max(1, gx * gy)));
+  if (g->accumulate) {
+    if (g->split_k > 0) {
+      split = g->split_k;
+    } else {
+      // split K so that the persistent CTAs finish together: minimise (rounds of tiles per SM) x (k-blocks per tile + a few
+      // k-block times of per-tile epilogue), instead of leaving a half-empty last round
+      const int sms = bpm_num_sms(), tiles_mn = gx * gy;
+      int best_cost = 1 << 30;
+      for (int s_ = 1; s_ <= max(1, min(num_kb / 4, (4 * sms) / tiles_mn)); s_++) {
+        const int kbps = bpm_cdiv(num_kb, s_), real = bpm_cdiv(num_kb, kbps);
+        const int rounds = bpm_cdiv(tiles_mn * real, sms);
+        const int cost = rounds * (kbps + 3);
+        if (cost < best_cost) { best_cost = cost; split = real; }
+      }
+    }
+  }
   p.kb_per_split = bpm_cdiv(num_kb, split);
   split = bpm_cdiv(num_kb, p.kb_per_split);
   p.gx = gx; p.gy = gy; p.split = split;

@@ -61,11 +61,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TI* __restr
 }
 
 // backward: persistent grid, each warp walks rows; dgamma/dbeta partials stay in registers until the end.
+// Optional fused epilogue: cast_out (bf16 / fp32, pitch Dp) = dropmask * dx_new, i.e. the GEMM operand the NEXT backward block would
+// otherwise produce with a separate pass over dx (bpm_cast_drop); element index of the mask = row * Dp + column.
 template <typename TG, typename TX, int NV>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean_in,
+__global__ void __launch_bounds__(LN_WARPS * 32, 4) ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean_in,
                                                                const float* __restrict__ rstd_in, const float* __restrict__ gamma, int rows, int D,
                                                                int Dp, float* __restrict__ dx, int accumulate, float* __restrict__ dgamma,
-                                                               float* __restrict__ dbeta) {
+                                                               float* __restrict__ dbeta, void* __restrict__ cast_out, int cast_dtype,
+                                                               bpm_dropout_t cast_drop) {
   extern __shared__ float sm[];  // [LN_WARPS][2][Dp]
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int nvec = Dp >> 3;
@@ -79,19 +82,33 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
     for (int j = 0; j < 8; j++) { ag[i][j] = 0.f; ab[i][j] = 0.f; gm[i].v[j] = 0.f; }
     if (c < nvec) gm[i].load(gamma + c * 8);
   }
+  const DropCtx dc = make_drop(cast_drop);
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const TG* gr = dy + (int64_t)row * Dp;
     const TX* xr = x + (int64_t)row * Dp;
+    float* dr = dx + (int64_t)row * Dp;
     float mean = mean_in[row], rstd = rstd_in[row];
     Vec8<TG> g[NV];
     Vec8<TX> xv[NV];
+    Vec8<float> o[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; i++) {
+    for (int i = 0; i < NV; i++) {                          // every load of the row is issued before anything is consumed
       int c = lane + 32 * i;
       if (c < nvec) {
         g[i].load(gr + c * 8);
         xv[i].load(xr + c * 8);
+        if (accumulate) o[i].load(dr + c * 8);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[i].v[j] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
         // dy pads are zero (they come from GEMMs against zero-padded weights) and gamma pads are zero, so only x-hat needs care:
         // x-hat_pad = -mean * rstd is finite and always multiplied by a zero gradient.
 #pragma unroll
@@ -107,25 +124,33 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
     }
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
-    float* dr = dx + (int64_t)row * Dp;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
       int c = lane + 32 * i;
       if (c < nvec) {
-        Vec8<float> o;
-        if (accumulate) o.load(dr + c * 8);
-        else {
-#pragma unroll
-          for (int j = 0; j < 8; j++) o.v[j] = 0.f;
-        }
         if (c * 8 + 8 <= D) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) o.v[j] += rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2);
+          for (int j = 0; j < 8; j++) o[i].v[j] += rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2);
         } else {                                              // the chunk that straddles D (and pure pad chunks): keep pads at zero
 #pragma unroll
-          for (int j = 0; j < 8; j++) o.v[j] += (c * 8 + j < D) ? rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2) : 0.f;
+          for (int j = 0; j < 8; j++) o[i].v[j] += (c * 8 + j < D) ? rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2) : 0.f;
         }
-        o.store(dr + c * 8);
+        o[i].store(dr + c * 8);
+        if (cast_out != nullptr) {
+          float m[8];
+          drop_mult8(dc, (uint64_t)row * (uint64_t)Dp + (uint64_t)(c * 8), m);
+          if (cast_dtype == BPM_BF16) {
+            Vec8<bf16> t;
+#pragma unroll
+            for (int j = 0; j < 8; j++) t.v[j] = o[i].v[j] * m[j];
+            t.store((bf16*)cast_out + (int64_t)row * Dp + c * 8);
+          } else {
+            Vec8<float> t;
+#pragma unroll
+            for (int j = 0; j < 8; j++) t.v[j] = o[i].v[j] * m[j];
+            t.store((float*)cast_out + (int64_t)row * Dp + c * 8);
+          }
+        }
       }
     }
   }
@@ -184,12 +209,13 @@ extern "C" int bpm_layernorm_fwd(const void* x, int x_dtype, const float* gamma,
 
 template <typename TG, typename TX>
 static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, int rows, int D, int Dp, float* dx,
-                         int accumulate, float* dgamma, float* dbeta, cudaStream_t s) {
+                         int accumulate, float* dgamma, float* dbeta, void* cast_out, int cast_dtype, bpm_dropout_t cast_drop, cudaStream_t s) {
   int nv = bpm_cdiv(Dp / 8, 32);
   int grid = min(bpm_cdiv(rows, LN_WARPS), bpm_num_sms() * 4);
   size_t smem = (size_t)LN_WARPS * 2 * Dp * sizeof(float);
 #define LNB(NV) \
-  ln_bwd_kernel<TG, TX, NV><<<grid, LN_WARPS * 32, smem, s>>>((const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta)
+  ln_bwd_kernel<TG, TX, NV><<<grid, LN_WARPS * 32, smem, s>>>((const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, \
+                                                             cast_out, cast_dtype, cast_drop)
   switch (nv) {
     case 1: LNB(1); break;
     case 2: LNB(2); break;
@@ -201,17 +227,26 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
   return BPM_OK;
 }
 
-extern "C" int bpm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
-                                 int rows, int D, int Dp, float* dx, int accumulate, float* dgamma, float* dbeta, void* stream) {
+extern "C" int bpm_layernorm_bwd_cast(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                                      const float* gamma, int rows, int D, int Dp, float* dx, int accumulate, float* dgamma, float* dbeta,
+                                      void* cast_out, int cast_dtype, bpm_dropout_t cast_drop, void* stream) {
   BPM_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && rows > 0 && D > 0 && Dp >= D && Dp % 8 == 0, "layernorm_bwd: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
-  if (dy_dtype == BPM_F32 && x_dtype == BPM_F32) rc = ln_bwd_launch<float, float>(dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, s);
-  else if (dy_dtype == BPM_BF16 && x_dtype == BPM_F32) rc = ln_bwd_launch<bf16, float>(dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, s);
-  else if (dy_dtype == BPM_BF16 && x_dtype == BPM_BF16) rc = ln_bwd_launch<bf16, bf16>(dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, s);
-  else if (dy_dtype == BPM_F32 && x_dtype == BPM_BF16) rc = ln_bwd_launch<float, bf16>(dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, s);
+#define LNB_ARGS dy, x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, cast_out, cast_dtype, cast_drop, s
+  if (dy_dtype == BPM_F32 && x_dtype == BPM_F32) rc = ln_bwd_launch<float, float>(LNB_ARGS);
+  else if (dy_dtype == BPM_BF16 && x_dtype == BPM_F32) rc = ln_bwd_launch<bf16, float>(LNB_ARGS);
+  else if (dy_dtype == BPM_BF16 && x_dtype == BPM_BF16) rc = ln_bwd_launch<bf16, bf16>(LNB_ARGS);
+  else if (dy_dtype == BPM_F32 && x_dtype == BPM_BF16) rc = ln_bwd_launch<float, bf16>(LNB_ARGS);
   else BPM_REQUIRE(false, "layernorm_bwd: bad dtype");
+#undef LNB_ARGS
   if (rc) return rc;
   BPM_CHECK_LAUNCH("layernorm_bwd");
   return BPM_OK;
+}
+
+extern "C" int bpm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd, const float* gamma,
+                                 int rows, int D, int Dp, float* dx, int accumulate, float* dgamma, float* dbeta, void* stream) {
+  bpm_dropout_t none = {0, nullptr, 0, 0.f};
+  return bpm_layernorm_bwd_cast(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, nullptr, 0, none, stream);
 }

@@ -96,6 +96,8 @@ class Arena:
 # ============================================================================================== encoder
 class EncoderEngine:
     """One TransformerEncoder (L layers + final LayerNorm).  `uid` separates its dropout streams."""
+    _go_valid = False       # the shared "go" buffer already holds the next block's gradient operand (fused into a LayerNorm backward)
+    fuse_cast = True        # LayerNorm backward also writes the next block's (dropped, storage-type) gradient operand
     fold_kv = True          # hoist the K / V LayerNorm out of the layer loop (x_hat once per encoder, affine folded into in_proj; SURVEY 7.3)
 
     # parameter table: name-suffix -> (kind, packer)
@@ -300,7 +302,9 @@ class EncoderEngine:
             Wk, Wv = w["Wkv_f"][:d.HP], w["Wkv_f"][d.HP:]
             gWk, gWv, gbk, gbv = g["Wkv_f"][:d.HP], g["Wkv_f"][d.HP:], g["bkv_f"][:d.HP], g["bkv_f"][d.HP:]
         go = Sh.get("go", (M, d.Dp), self.T_)
-        o.cast_drop(gx, go, self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")))   # grad wrt out_proj output
+        if not self._go_valid:                                                  # (else: fused into the LayerNorm backward that last wrote gx)
+            o.cast_drop(gx, go, self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")))   # grad wrt out_proj output
+        self._go_valid = False
         o.gemm(go, sv["a"], g["Wo"], d.Dp, d.HP, M, ta=1, tb=1, accumulate=True, colsum=g["bo"])   # dWo = go^T a, dbo = colsum(go)
         da = Sh.get("da", (M, d.HP), self.T_)
         o.gemm(go, w["Wo"], da, M, d.HP, d.Dp, tb=1)                                           # da = go Wo
@@ -343,7 +347,9 @@ class EncoderEngine:
         """gx (fp32, in/out): on entry d/d x_out, on exit d/d x_in."""
         o, d, w, g, Sh = self.ops, self.d, self.W[l], self.G[l], self.shared
         g2 = Sh.get("go", (M, d.Dp), self.T_)
-        o.cast_drop(gx, g2, self._drop(self.p_res, l, 31))
+        if not self._go_valid:
+            o.cast_drop(gx, g2, self._drop(self.p_res, l, 31))
+        self._go_valid = False
         o.gemm(g2, sv["h"], g["W2"], d.Dp, d.FP, M, ta=1, tb=1, accumulate=True, colsum=g["b2"])   # dW2 = g2^T h, db2 = colsum(g2)
         dh = Sh.get("dh", (M, d.FP), self.T_)
         keep = 1.0 / (1.0 - self.p_relu) if (self.training and self.p_relu > 0) else 1.0
@@ -351,7 +357,12 @@ class EncoderEngine:
         o.gemm(dh, sv["hn"], g["W1"], d.FP, d.Dp, M, ta=1, tb=1, accumulate=True, colsum=g["b1"])  # dW1 = dh^T hn, db1 = colsum(dh)
         dhn = Sh.get("dq_in", (M, d.Dp), self.T_)
         o.gemm(dh, w["W1"], dhn, M, d.Dp, d.FP, tb=1)
-        o.layernorm_bwd(dhn, sv["x_in"], sv["mean"], sv["rstd"], w["ln_g"][sv["ln"]], d.D, gx, True, g["ln_g"][sv["ln"]], g["ln_b"][sv["ln"]])
+        # the attention block of this layer is next: its out_proj gradient operand (dropout site 20 / 21) leaves this kernel too
+        blk_x = getattr(self, "cross", False)
+        fuse = self.fuse_cast
+        o.layernorm_bwd(dhn, sv["x_in"], sv["mean"], sv["rstd"], w["ln_g"][sv["ln"]], d.D, gx, True, g["ln_g"][sv["ln"]], g["ln_b"][sv["ln"]],
+                        cast_out=g2 if fuse else None, cast_drop=self._drop(self.p_res, l, 20 + int(blk_x)) if fuse else None)
+        self._go_valid = fuse
 
     # ---------------------------------------------------------------- LN helper with saved stats
     def _ln_fwd(self, key, x, l, idx, rows):
@@ -362,10 +373,16 @@ class EncoderEngine:
         o.layernorm_fwd(x, w["ln_g"][idx], w["ln_b"][idx], d.D, y, mean, rstd)
         return dict(y=y, mean=mean, rstd=rstd, x=x, idx=idx)
 
-    def _ln_bwd(self, l, sv, dy, dx, accumulate=True):
+    def _ln_bwd(self, l, sv, dy, dx, accumulate=True, cast_next=False):
+        """cast_next: dx is now final for this layer -> also emit the FFN gradient operand of layer l-1 (dropout site 31)"""
         w, g = self.W[l], self.G[l]
+        cast_out = cast_drop = None
+        if cast_next and l > 0 and self.fuse_cast:
+            cast_out = self.shared.get("go", tuple(dx.shape), self.T_)
+            cast_drop = self._drop(self.p_res, l - 1, 31)
+            self._go_valid = True
         self.ops.layernorm_bwd(dy, sv["x"], sv["mean"], sv["rstd"], w["ln_g"][sv["idx"]], self.d.D, dx, accumulate, g["ln_g"][sv["idx"]],
-                               g["ln_b"][sv["idx"]])
+                               g["ln_b"][sv["idx"]], cast_out=cast_out, cast_drop=cast_drop)
 
     # ---------------------------------------------------------------- forward
     def forward(self, src_q, B, T, src_k=None, S=None, src_v=None, training=True, seed=0, seed_ptr=None):
@@ -498,13 +515,14 @@ class EncoderEngine:
                 if not self.kv_shared:
                     gnv = Sh.get("gnv", (Ms, d.Dp), torch.float32)
                     o.zero_(gnv)
+        self._go_valid = False
         for l in reversed(range(self.L)):
             sv = self.saved[l]
             self._ffn_bwd(l, sv["ffn"], M, gx)
             if not self.cross:
                 dq_in, dk_in, dv_in = self._attn_bwd(l, "s", sv["self"], B, T, gx)
                 for t in (dq_in, dk_in, dv_in):
-                    self._ln_bwd(l, sv["ln_q"], t, gx)
+                    self._ln_bwd(l, sv["ln_q"], t, gx, cast_next=t is dv_in)
             elif self.biproj:
                 dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx, gnk=gnk, gnv=gnv)
                 o.axpy_f32(dq_in, gx, True)                                      # query path is the raw residual stream
@@ -513,10 +531,10 @@ class EncoderEngine:
                     self._ln_bwd(l, sv["ln_v"], dv_in, gxv)
                 dq_in, dk_in, dv_in = self._attn_bwd(l, "s", sv["self"], B, T, gx)
                 for t in (dq_in, dk_in, dv_in):
-                    self._ln_bwd(l, sv["ln_q"], t, gx)
+                    self._ln_bwd(l, sv["ln_q"], t, gx, cast_next=t is dv_in)
             else:
                 dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx, gnk=gnk, gnv=gnv)
-                self._ln_bwd(l, sv["ln_q"], dq_in, gx)
+                self._ln_bwd(l, sv["ln_q"], dq_in, gx, cast_next=True)
                 if not self.folded:
                     self._ln_bwd(l, sv["ln_k"], dk_in, gxk)
                     self._ln_bwd(l, sv["ln_v"], dv_in, gxv)

@@ -148,11 +148,13 @@ class CudaOps:
         self._ck(self.lib.bpm_layernorm_fwd(x.data_ptr(), _dt(x), gamma.data_ptr(), beta.data_ptr(), x.shape[0], D, x.shape[1], float(eps),
                                             y.data_ptr(), _dt(y), mean.data_ptr(), rstd.data_ptr(), self._s()), "layernorm_fwd")
 
-    def layernorm_bwd(self, dy, x, mean, rstd, gamma, D, dx, accumulate, dgamma, dbeta):
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, D, dx, accumulate, dgamma, dbeta, cast_out=None, cast_drop=None):
+        """cast_out (optional, storage type): dropmask(cast_drop) * dx_new, fused (replaces a following cast_drop(dx, cast_out, cast_drop))"""
         assert dx.dtype == torch.float32
-        self._ck(self.lib.bpm_layernorm_bwd(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                            x.shape[0], D, x.shape[1], dx.data_ptr(), int(accumulate), dgamma.data_ptr(), dbeta.data_ptr(),
-                                            self._s()), "layernorm_bwd")
+        self._ck(self.lib.bpm_layernorm_bwd_cast(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                                 x.shape[0], D, x.shape[1], dx.data_ptr(), int(accumulate), dgamma.data_ptr(), dbeta.data_ptr(),
+                                                 _ptr(cast_out), _dt(cast_out) if cast_out is not None else 0, _drop(cast_drop), self._s()),
+                 "layernorm_bwd")
 
     def ln_fold_fwd(self, W, bias, gamma, beta, Wp, bp, row_map=(0, 0)):
         """Wp[map(i), :cols] = W[i] * gamma;  bp[map(i)] = bias[i] + W[i] . beta   (W, bias, gamma, beta fp32 reference layout)"""

@@ -96,6 +96,11 @@ int bpm_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const floa
 int bpm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                       const float* gamma, int rows, int D, int Dp, float* dx, int accumulate, float* dgamma, float* dbeta,
                       void* stream);
+/* same, and additionally cast_out (cast_dtype, pitch Dp, may be NULL) = dropmask(cast_drop) * dx_new: the GEMM operand of the next
+ * backward block (what bpm_cast_drop would produce from dx in a separate pass) */
+int bpm_layernorm_bwd_cast(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                           const float* gamma, int rows, int D, int Dp, float* dx, int accumulate, float* dgamma, float* dbeta,
+                           void* cast_out, int cast_dtype, bpm_dropout_t cast_drop, void* stream);
 
 /* ---- LayerNorm affine folded into the K / V projection of a crossmodal layer ---------------------------------------
  * transformer.py:83-85 feeds the same x_k / x_v to all L layers; only layer_norms[.] and in_proj differ.  x_hat is computed

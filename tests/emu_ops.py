@@ -61,6 +61,8 @@ class EmuOps:
         self.launches = 0
 
     def empty(self, shape, dtype):
+        if not dtype.is_floating_point:
+            return torch.zeros(shape, dtype=dtype)
         return torch.full(shape, float("nan"), dtype=dtype)          # poison: catches reads of unwritten buffers
 
     def zeros(self, shape, dtype):
@@ -153,7 +155,7 @@ class EmuOps:
         mean.copy_(mu)
         rstd.copy_(rs)
 
-    def layernorm_bwd(self, dy, x, mean, rstd, gamma, D, dx, accumulate, dgamma, dbeta):
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, D, dx, accumulate, dgamma, dbeta, cast_out=None, cast_drop=None):
         g = dy.float()[:, :D]
         xh = (x.float()[:, :D] - mean[:, None]) * rstd[:, None]
         gh = g * gamma[:D]
@@ -167,6 +169,8 @@ class EmuOps:
             dx.copy_(v)
         dgamma[:D] += (g * xh).sum(0)
         dbeta[:D] += g.sum(0)
+        if cast_out is not None:
+            self.cast_drop(dx, cast_out, cast_drop)
 
     # ------------------------------------------------------------------ gemm
     def gemm(self, A, B, Cout, M, N, K, ta=0, tb=0, bias=None, alpha=1.0, act=0, drop=None, gate=None, gate_scale=1.0, residual=None,

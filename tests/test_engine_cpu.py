@@ -50,3 +50,29 @@ def test_mmtrvat_engine_fp32_matches_reference_golden():
         worst = max(worst, e)
         assert e < 2e-4, (n, e)
     print("worst param-grad rel-l2", worst)
+
+
+@pytest.mark.parametrize("bi", [False, True])
+def test_fused_schedules_match_the_plain_ones_with_dropout_on(bi):
+    """The K/V LayerNorm hoist (fold_kv) and the cast fused into the LayerNorm backward (fuse_cast) are schedule changes only:
+    with every dropout site live they must reproduce the plain per-layer schedule (same masks, same gradients)."""
+    from emu_ops import EmuOps
+    from bpmult_b200.engine import EncoderEngine
+    from oracle import synth
+    torch.manual_seed(0)
+    T, S, B, D, H, L = 12, 9, 2, 40, 4, 2
+    shapes = EncoderEngine(EmuOps(), D, H, L, biprojection=bi).param_shapes()
+    sd = synth.make_state_dict(shapes, 7)
+    x, k, g = torch.randn(T, B, D), torch.randn(S, B, D), torch.randn(T, B, D)
+    p = dict(attn_dropout=0.1, relu_dropout=0.1, res_dropout=0.2, embed_dropout=0.25)
+    res = {}
+    try:
+        for fold, fuse in ((False, False), (True, True)):
+            EncoderEngine.fold_kv, EncoderEngine.fuse_cast = fold, fuse
+            res[fold] = run_encoder_engine(EmuOps(), sd, x, k, g, H, L, True, bi, False, p=p, training=True, seed=11)
+    finally:
+        EncoderEngine.fold_kv, EncoderEngine.fuse_cast = True, True
+    (o0, dx0, dk0, g0, _), (o1, dx1, dk1, g1, _) = res[False], res[True]
+    assert Fn.max_rel(o1, o0) < 1e-5 and Fn.rel_l2(dx1, dx0) < 1e-5 and Fn.rel_l2(dk1, dk0) < 1e-5
+    for n in g0:
+        assert Fn.rel_l2(g1[n], g0[n]) < 1e-5, n
