@@ -2,23 +2,25 @@
 // Reference semantics: models/multihead_attention.py:95-127 (scores, fp32 softmax, dropout, PV) with the mask of
 // models/transformer.py:209-216 evaluated from indices (key j visible to query i iff j <= i + mask_off).
 //
-// Forward, one CTA per (128-query tile, batch*head):
-//   warp 0      TMA producer: Q tile once, K/V tiles (64 keys) through a 3-stage ring          [SWIZZLE_64B boxes, 64-byte rows]
-//   warp 1      TMEM allocator + single-thread MMA issuer:  S_j = Q K_j^T  (M128 N64 K32)  and  O_j = P_j V_j  (M128 N32 K64)
-//   warps 2-5   softmax, one thread per query row (= TMEM lane): tcgen05.ld S_j -> online softmax in registers (exp2, running
-//               max / sum) -> Philox dropout -> P_j as bf16 into shared memory in the canonical K-major SWIZZLE_128B layout ->
-//               tcgen05.ld O_j (32 columns) and accumulate O in registers with the usual rescale.
-//   S is double-buffered in TMEM and P in shared memory, so the MMA of tile j+1 overlaps the softmax of tile j; two CTAs are
-//   co-resident per SM (192 TMEM columns, ~66 KB smem each).  With dh = 32 the kernel is bound by exponentials (128x64 ex2 per
-//   tile on the 16/clk/SM MUFU vs 64+64 MMA cycles), see DESIGN.md.
+// Forward.  Persistent: one CTA per SM, two independent GROUPS per CTA; each group walks its own list of (batch*head, 128-query
+// tile) items (heavy = late query tiles first, snake order over the groups) and owns its own warps, shared-memory rings and
+// 256 TMEM columns.  While one group's softmax warps wait for the tensor core, the other group's keep the MUFU / FMA pipes busy.
+//   per group:  1 TMA producer warp  (Q double-buffered, K/V tiles of 128 keys through a 3-stage ring; SWIZZLE_64B boxes)
+//               1 MMA issuer warp    S_j = Q K_j^T (M128 N128 K32)  and  O_j = P_j V_j (M128 N32 K128, A = P_j FROM TMEM)
+//               4 softmax warps      one thread per query row (= TMEM lane): tcgen05.ld S_j twice (row max, then exp2 / row sum),
+//                                    P_j back to TMEM as packed bf16 (tcgen05.st), O_{j-1} folded into registers with the rescale.
+//   Converged issuer warps + elect.sync, descriptors advanced by adds (see tc_common.cuh: elect_one).
+//   With dh = 32 the kernel is bound by exponentials (128x128 ex2 per tile on the 16/clk/SM MUFU = 1024 clk vs ~410 MMA clk).
 //   V is consumed directly from its [keys, dh] tile as an MN-major B operand (no transpose).  Fully masked KV tiles are skipped.
 #include "tc_common.cuh"
 
 #define AT_BM 128
-#define AT_BN 64
+#define AT_BN 128
 #define AT_DH 32
 #define AT_KV_STAGES 3
-#define AT_THREADS 192
+#define AF_GROUPS 2
+#define AF_GROUP_WARPS 6
+#define AF_THREADS (32 * AF_GROUPS * AF_GROUP_WARPS)
 #define LOG2E_F 1.4426950408889634f
 #define LN2_F 0.6931471805599453f
 
@@ -33,225 +35,283 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 struct AttnFwdSmem {
-  // offsets from the 1024-aligned base
-  static constexpr int Q = 0;                                   // 128 x 64 B
-  static constexpr int K = Q + AT_BM * 64;                      // stages x 64 x 64 B
+  // per group, offsets from the group's 1024-aligned base
+  static constexpr int Q = 0;                                   // 2 x (128 x 64 B)
+  static constexpr int K = Q + 2 * AT_BM * 64;                  // stages x 128 x 64 B
   static constexpr int V = K + AT_KV_STAGES * AT_BN * 64;
-  static constexpr int P = V + AT_KV_STAGES * AT_BN * 64;       // 2 x (128 rows x 128 B)
-  static constexpr int BAR = P + 2 * AT_BM * 128;
-  static constexpr int NBAR = 1 + 2 * AT_KV_STAGES + 2 + 2 + 2 + 2;
-  static constexpr int TOTAL = BAR + 8 * NBAR + 16;
+  static constexpr int GROUP = V + AT_KV_STAGES * AT_BN * 64;   // 64 KB
+  static constexpr int BAR = AF_GROUPS * GROUP;
+  static constexpr int NBAR_G = 4 + 2 * AT_KV_STAGES + 2 + 1 + 2;   // q_full[2], q_free[2], kv_full/empty, s_full, s_free, p_full, o_full[2]
+  static constexpr int TOTAL = BAR + 8 * AF_GROUPS * NBAR_G + 16;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// mask / dropout of one 32-column chunk of a score row (thread = query row qi, keys k0c .. k0c+31)
+template <bool MASKED>
+__device__ __forceinline__ void fwd_mask32(float* sv, int k0c, int row_lim) {
+  if (MASKED) {
+#pragma unroll
+    for (int c = 0; c < 32; c++) sv[c] = (k0c + c <= row_lim) ? sv[c] : -INFINITY;
+  }
+}
+
+__global__ void __launch_bounds__(AF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    bf16* __restrict__ out, float* __restrict__ lse, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
                    uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar0 = base + AttnFwdSmem::BAR;
-  const uint32_t q_full = bar0;
-  auto kv_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bar0 + 8u * (1 + AT_KV_STAGES + s); };
-  auto s_full = [&](int i) { return bar0 + 8u * (1 + 2 * AT_KV_STAGES + i); };
-  auto s_empty = [&](int i) { return bar0 + 8u * (3 + 2 * AT_KV_STAGES + i); };
-  auto p_full = [&](int i) { return bar0 + 8u * (5 + 2 * AT_KV_STAGES + i); };
-  auto o_full = [&](int i) { return bar0 + 8u * (7 + 2 * AT_KV_STAGES + i); };
-  const uint32_t tmem_ptr_addr = bar0 + 8u * AttnFwdSmem::NBAR;
-  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + AttnFwdSmem::BAR + 8 * AttnFwdSmem::NBAR);
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;          // heavy (late) query tiles first
-  const int q0 = qt * AT_BM;
-  const int bh = blockIdx.y, b = bh / H, h = bh % H;
-  // KV tiles this query tile can see
-  int jmax = S - 1;
-  if (mask_off >= 0) jmax = min(jmax, q0 + AT_BM - 1 + mask_off);
-  const int n_tiles = jmax / AT_BN + 1;
+  const int grp = warp / AF_GROUP_WARPS, gw = warp % AF_GROUP_WARPS;      // group, role inside the group (0 producer, 1 MMA, 2..5 softmax)
+  const uint32_t gbase = base + grp * AttnFwdSmem::GROUP;
+  const uint32_t bar0 = base + AttnFwdSmem::BAR + 8u * grp * AttnFwdSmem::NBAR_G;
+  auto q_full = [&](int s) { return bar0 + 8u * s; };
+  auto q_free = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto kv_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto kv_empty = [&](int s) { return bar0 + 8u * (4 + AT_KV_STAGES + s); };
+  const uint32_t s_full = bar0 + 8u * (4 + 2 * AT_KV_STAGES), s_free = s_full + 8u, p_full = s_full + 16u;
+  auto o_full = [&](int i) { return s_full + 24u + 8u * i; };
+  const uint32_t tmem_ptr_addr = base + AttnFwdSmem::BAR + 8u * AF_GROUPS * AttnFwdSmem::NBAR_G;
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + AttnFwdSmem::BAR + 8 * AF_GROUPS * AttnFwdSmem::NBAR_G);
 
-  if (warp == 0 && lane == 0) {
+  const int nbh = B * H, nq = (T + AT_BM - 1) / AT_BM;
+  const int n_items = nbh * nq;
+  const int G = AF_GROUPS * gridDim.x, gid = blockIdx.x * AF_GROUPS + grp;
+  // r-th item of this group: heavy (late) query tiles first, snake order over the groups so that the loads even out
+  auto item_of = [&](int r, int& bh, int& qt) {
+    const int idx = r * G + ((r & 1) ? (G - 1 - gid) : gid);
+    if (idx >= n_items) return false;
+    qt = nq - 1 - idx / nbh;
+    bh = idx % nbh;
+    return true;
+  };
+  auto tiles_of = [&](int qt) {
+    int jmax = S - 1;
+    if (mask_off >= 0) jmax = min(jmax, qt * AT_BM + AT_BM - 1 + mask_off);
+    return jmax / AT_BN + 1;
+  };
+
+  if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < AT_KV_STAGES; s++) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4); mbar_init(p_full(i), 4); mbar_init(o_full(i), 1); }
+    for (int g = 0; g < AF_GROUPS; g++) {
+      const uint32_t b0 = base + AttnFwdSmem::BAR + 8u * g * AttnFwdSmem::NBAR_G;
+      for (int s = 0; s < 2; s++) { mbar_init(b0 + 8u * s, 1); mbar_init(b0 + 8u * (2 + s), 1); }
+      for (int s = 0; s < AT_KV_STAGES; s++) { mbar_init(b0 + 8u * (4 + s), 1); mbar_init(b0 + 8u * (4 + AT_KV_STAGES + s), 1); }
+      const uint32_t sf = b0 + 8u * (4 + 2 * AT_KV_STAGES);
+      mbar_init(sf, 1); mbar_init(sf + 8u, 4); mbar_init(sf + 16u, 4); mbar_init(sf + 24u, 1); mbar_init(sf + 32u, 1);
+    }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_addr, 256);
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_gen;
-  const uint32_t tS[2] = {tmem + 0, tmem + 64};
-  const uint32_t tO[2] = {tmem + 128, tmem + 160};
+  const uint32_t tmem = *tmem_ptr_gen + (uint32_t)(grp * 256);
+  const uint32_t tS = tmem, tP = tmem + 128, tO0 = tmem + 192;            // S 128 | P 64 (bf16 pairs) | O 2 x 32
+  auto adr = [](uint32_t a) { return (uint64_t)((a & 0x3FFFFu) >> 4); };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, AT_BM * 64);
-      tma_load_3d(base + AttnFwdSmem::Q, &tmQ, q_full, h * AT_DH, q0, b);
-      for (int j = 0; j < n_tiles; j++) {
-        int s = j % AT_KV_STAGES;
-        mbar_wait(kv_empty(s), ((uint32_t)(j / AT_KV_STAGES) & 1u) ^ 1u);
-        mbar_expect_tx(kv_full(s), 2 * AT_BN * 64);
-        tma_load_3d(base + AttnFwdSmem::K + s * AT_BN * 64, &tmK, kv_full(s), h * AT_DH, j * AT_BN, b);
-        tma_load_3d(base + AttnFwdSmem::V + s * AT_BN * 64, &tmV, kv_full(s), h * AT_DH, j * AT_BN, b);
+  if (gw == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    int kc = 0;                                                          // running K/V tile counter (ring position)
+    for (int r = 0;; r++) {
+      int bh, qt;
+      if (!item_of(r, bh, qt)) break;
+      const int b = bh / H, h = bh % H, qs = r & 1;
+      mbar_wait(q_free(qs), ((uint32_t)(r >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(q_full(qs), AT_BM * 64);
+        tma_load_3d(gbase + AttnFwdSmem::Q + qs * AT_BM * 64, &tmQ, q_full(qs), h * AT_DH, qt * AT_BM, b);
+      }
+      __syncwarp();
+      const int nt = tiles_of(qt);
+      for (int j = 0; j < nt; j++, kc++) {
+        const int s = kc % AT_KV_STAGES;
+        mbar_wait(kv_empty(s), ((uint32_t)(kc / AT_KV_STAGES) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(kv_full(s), 2 * AT_BN * 64);
+          tma_load_3d(gbase + AttnFwdSmem::K + s * AT_BN * 64, &tmK, kv_full(s), h * AT_DH, j * AT_BN, b);
+          tma_load_3d(gbase + AttnFwdSmem::V + s * AT_BN * 64, &tmV, kv_full(s), h * AT_DH, j * AT_BN, b);
+        }
+        __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);       // S = Q K^T : both operands K-major
-      const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_DH, 0, 1);       // O = P V   : V is MN-major (dh contiguous)
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int j) {
-        int s = j % AT_KV_STAGES, i = j & 1;
-        mbar_wait(kv_full(s), (uint32_t)(j / AT_KV_STAGES) & 1u);
-        mbar_wait(s_empty(i), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+  } else if (gw == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+    const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);       // S = Q K^T : both operands K-major
+    const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_DH, 0, 1);       // O = P V   : A from TMEM, V is MN-major (dh contiguous)
+    const uint64_t d_k64 = umma_desc(0, 16, 512, BPM_SWZ_64B);          // K-major 64-byte rows; +32 B per k16
+    const uint64_t d_mn64 = umma_desc(0, 512, 512, BPM_SWZ_64B);        // V as MN-major B operand; +1024 B (16 keys) per k16
+    int kc = 0, tc = 0;                                                  // K/V ring position; running tile counter (S / P / O phases)
+    for (int r = 0;; r++) {
+      int bh, qt;
+      if (!item_of(r, bh, qt)) break;
+      const int qs = r & 1, nt = tiles_of(qt);
+      mbar_wait(q_full(qs), (uint32_t)(r >> 1) & 1u);
+      const uint64_t dq = d_k64 | adr(gbase + AttnFwdSmem::Q + qs * AT_BM * 64);
+      auto issue_s = [&](int kcj, int tcj, bool last) {
+        const int s = kcj % AT_KV_STAGES;
+        mbar_wait(kv_full(s), (uint32_t)(kcj / AT_KV_STAGES) & 1u);
+        mbar_wait(s_free, ((uint32_t)tcj & 1u) ^ 1u);                      // the softmax warps have read the previous S tile
         tc_fence_after();
-        uint32_t qa = base + AttnFwdSmem::Q, ka = base + AttnFwdSmem::K + s * AT_BN * 64;
+        if (elect_one()) {
+          const uint64_t dk = d_k64 | adr(gbase + AttnFwdSmem::K + s * AT_BN * 64);
 #pragma unroll
-        for (int k = 0; k < AT_DH / 16; k++)
-          umma_bf16(tS[i], umma_desc(qa + k * 32, 16, 512, BPM_SWZ_64B), umma_desc(ka + k * 32, 16, 512, BPM_SWZ_64B), idesc_s, k > 0);
-        umma_commit(s_full(i));
+          for (int k = 0; k < AT_DH / 16; k++) umma_bf16(tS, dq + 2 * k, dk + 2 * k, idesc_s, (uint32_t)k);
+          umma_commit(s_full);
+          if (last) umma_commit(q_free(qs));                               // this item's Q tile has been read for the last time
+        }
+        __syncwarp();
       };
-      auto issue_pv = [&](int j) {
-        int s = j % AT_KV_STAGES, i = j & 1;
-        mbar_wait(p_full(i), (uint32_t)(j >> 1) & 1u);
+      issue_s(kc, tc, nt == 1);
+      for (int j = 0; j < nt; j++, kc++, tc++) {
+        if (j + 1 < nt) issue_s(kc + 1, tc + 1, j + 2 == nt);
+        const int s = kc % AT_KV_STAGES;
+        mbar_wait(p_full, (uint32_t)tc & 1u);
         tc_fence_after();
-        uint32_t pa = base + AttnFwdSmem::P + i * AT_BM * 128, va = base + AttnFwdSmem::V + s * AT_BN * 64;
+        if (elect_one()) {
+          const uint64_t dv = d_mn64 | adr(gbase + AttnFwdSmem::V + s * AT_BN * 64);
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; k++)
-          umma_bf16(tO[i], umma_desc(pa + k * 32, 16, 1024, BPM_SWZ_128B), umma_desc(va + k * 16 * 64, 512, 512, BPM_SWZ_64B), idesc_o, k > 0);
-        umma_commit(o_full(i));        // O_j ready (and P buffer i reusable)
-        umma_commit(kv_empty(s));      // K/V stage s free
-      };
-      issue_s(0);
-      for (int j = 0; j < n_tiles; j++) {
-        if (j + 1 < n_tiles) issue_s(j + 1);
-        issue_pv(j);
+          for (int k = 0; k < AT_BN / 16; k++) umma_bf16_ts(tO0 + 32 * (tc & 1), tP + 8 * k, dv + 64 * k, idesc_o, (uint32_t)k);
+          umma_commit(o_full(tc & 1));      // O_j ready, P consumed
+          umma_commit(kv_empty(s));         // K/V stage free
+        }
+        __syncwarp();
       }
     }
   } else {
     // ===================== softmax warps: one thread per query row =====================
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const int qi = q0 + r;
+    const int quarter = warp & 3;                                          // TMEM lane quarter this warp may access
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    DropCtx dc = make_drop(drop);
-    const uint64_t ebase = ((uint64_t)bh * T + (uint64_t)min(qi, T - 1)) * (uint64_t)S;
-    float m = -INFINITY, l = 0.f;
-    float oacc[AT_DH];
+    const int rr = quarter * 32 + lane;
+    const DropCtx dc = make_drop(drop);
+    const int W = (S + 31) >> 5;
+    int tc = 0;
+    for (int r = 0;; r++) {
+      int bh, qt;
+      if (!item_of(r, bh, qt)) break;
+      const int b = bh / H, h = bh % H, q0 = qt * AT_BM, qi = q0 + rr, nt = tiles_of(qt);
+      const int row_lim = (mask_off >= 0) ? min(qi + mask_off, S - 1) : S - 1;     // last visible key of this row
+      const int tile_lim = (mask_off >= 0) ? min(q0 + mask_off, S - 1) : S - 1;     // keys <= tile_lim are visible to every row of the tile
+      const uint64_t ebase = ((uint64_t)bh * T + (uint64_t)min(qi, T - 1)) * (uint64_t)S;
+      float m = -INFINITY, l = 0.f;
+      float oacc[AT_DH];
 #pragma unroll
-    for (int d = 0; d < AT_DH; d++) oacc[d] = 0.f;
-    const int row_lim = (mask_off >= 0) ? min(qi + mask_off, S - 1) : S - 1;     // last visible key of this row
-    uint8_t* prow[2];
-    prow[0] = base_gen + AttnFwdSmem::P + (r >> 3) * 1024 + (r & 7) * 128;
-    prow[1] = prow[0] + AT_BM * 128;
-
-    for (int j = 0; j < n_tiles; j++) {
-      const int i = j & 1;
-      float sv[AT_BN];
-      mbar_wait(s_full(i), (uint32_t)(j >> 1) & 1u);
-      tc_fence_after();
-      tmem_ld32(tS[i] + lane_off, sv);
-      tmem_ld32(tS[i] + lane_off + 32, sv + 32);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(i));
-      // ---- online softmax (log2 domain)
-      const int k0 = j * AT_BN;
-      if (k0 + AT_BN - 1 > row_lim) {
-#pragma unroll
-        for (int c = 0; c < AT_BN; c++) sv[c] = (k0 + c <= row_lim) ? sv[c] : -INFINITY;
-      }
-      // 4-way trees: a 64-long dependent FMNMX / FADD chain would leave the warp latency-bound
-      float mx4[4] = {sv[0], sv[1], sv[2], sv[3]};
-#pragma unroll
-      for (int c = 4; c < AT_BN; c += 4) {
-        mx4[0] = fmaxf(mx4[0], sv[c]); mx4[1] = fmaxf(mx4[1], sv[c + 1]); mx4[2] = fmaxf(mx4[2], sv[c + 2]); mx4[3] = fmaxf(mx4[3], sv[c + 3]);
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m, mx * LOG2E_F);
-      const float alpha = ex2f(m - m_new);
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < AT_BN; c += 4) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) { sv[c + e] = ex2f(fmaf(sv[c + e], LOG2E_F, -m_new)); rs4[e] += sv[c + e]; }
-      }
-      l = fmaf(l, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      m = m_new;
-      if (dc.on) {
-        // keep decisions: one Philox call per 8 consecutive keys (element index e = ebase + key)
-        uint32_t kb[2] = {0u, 0u};
-        const uint64_t e0 = ebase + (uint64_t)k0;
-        if ((e0 & 7) == 0) {
-#pragma unroll
-          for (int u = 0; u < AT_BN / 8; u++) kb[u >> 2] |= drop_keep8(dc, (e0 >> 3) + u) << ((u & 3) * 8);
-        } else {
-#pragma unroll
-          for (int c = 0; c < AT_BN; c++) kb[c >> 5] |= (drop_mult1(dc, e0 + c) != 0.f ? 1u : 0u) << (c & 31);
-        }
-#pragma unroll
-        for (int c = 0; c < AT_BN; c++) sv[c] = ((kb[c >> 5] >> (c & 31)) & 1u) ? sv[c] * dc.inv_keep : 0.f;
-        if (drop_bits != nullptr && qi < T) {
-          uint32_t* wrow = drop_bits + ((int64_t)bh * T + qi) * (int64_t)((S + 31) >> 5) + (k0 >> 5);
-          wrow[0] = kb[0];
-          if (k0 + 32 < S) wrow[1] = kb[1];
-        }
-      }
-      // ---- P_j -> shared memory (bf16, K-major SWIZZLE_128B: 16-byte chunk u of row r lands at chunk u ^ (r & 7))
-      uint8_t* pr = prow[i];
-#pragma unroll
-      for (int u = 0; u < AT_BN / 8; u++) {
-        uint4 w;
-        w.x = pack_bf16x2(sv[u * 8 + 0], sv[u * 8 + 1]); w.y = pack_bf16x2(sv[u * 8 + 2], sv[u * 8 + 3]);
-        w.z = pack_bf16x2(sv[u * 8 + 4], sv[u * 8 + 5]); w.w = pack_bf16x2(sv[u * 8 + 6], sv[u * 8 + 7]);
-        *(uint4*)(pr + ((u ^ (r & 7)) << 4)) = w;
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(i));
-      // ---- fold the previous tile's P V into the register accumulator, then rescale to the new max
-      if (j > 0) {
-        const int ip = (j - 1) & 1;
-        float ov[AT_DH];
-        mbar_wait(o_full(ip), (uint32_t)((j - 1) >> 1) & 1u);
+      for (int d = 0; d < AT_DH; d++) oacc[d] = 0.f;
+      for (int j = 0; j < nt; j++, tc++) {
+        const int k0 = j * AT_BN;
+        const bool masked = k0 + AT_BN - 1 > tile_lim;
+        mbar_wait(s_full, (uint32_t)tc & 1u);
         tc_fence_after();
-        tmem_ld32(tO[ip] + lane_off, ov);
+        // ---- pass 1: row maximum
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < AT_BN; c += 32) {
+          float sv[32];
+          tmem_ld32(tS + lane_off + c, sv);
+          tmem_ld_wait();
+          if (masked) fwd_mask32<true>(sv, k0 + c, row_lim);
+          float m4[4] = {sv[0], sv[1], sv[2], sv[3]};
+#pragma unroll
+          for (int e = 4; e < 32; e += 4) {
+            m4[0] = fmaxf(m4[0], sv[e]); m4[1] = fmaxf(m4[1], sv[e + 1]); m4[2] = fmaxf(m4[2], sv[e + 2]); m4[3] = fmaxf(m4[3], sv[e + 3]);
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+        const float m_new = fmaxf(m, mx * LOG2E_F);
+        const float alpha = ex2f(m - m_new);
+        // P (single TMEM buffer) is free once the previous tile's PV has been issued AND completed; its result O_{j-1} is then ready too
+        if (tc > 0) { mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u); tc_fence_after(); }
+        // ---- pass 2: P = exp2(S log2e - m_new), row sum, dropout, packed bf16 back to TMEM
+        float rs = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < AT_BN; c += 32) {
+          float sv[32];
+          tmem_ld32(tS + lane_off + c, sv);
+          tmem_ld_wait();
+          if (c + 32 == AT_BN) {                                           // the S tile is in registers / consumed: the next Q K^T may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);
+          }
+          if (masked) fwd_mask32<true>(sv, k0 + c, row_lim);
+          float r4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) { sv[e + u] = ex2f(fmaf(sv[e + u], LOG2E_F, -m_new)); r4[u] += sv[e + u]; }
+          }
+          rs += (r4[0] + r4[1]) + (r4[2] + r4[3]);
+          if (dc.on) {
+            // keep decisions of keys k0+c .. k0+c+31 (element index e = ebase + key): one 32-bit word per (query, 32-key group).
+            // The 1/(1-p) scale is applied once to the output row (every kept probability of the row shares it).
+            uint32_t kb = 0u;
+            const uint64_t e0 = ebase + (uint64_t)(k0 + c);
+            if ((e0 & 1) == 0) {
+#pragma unroll
+              for (int u = 0; u < 16; u++) {
+                const uint32_t x = drop_rand_pair(dc, (e0 >> 1) + u);
+                const bool kl = drop_keep_lo(dc, x), kh = drop_keep_hi(dc, x);
+                sv[2 * u] = kl ? sv[2 * u] : 0.f;
+                sv[2 * u + 1] = kh ? sv[2 * u + 1] : 0.f;
+                kb |= (kl ? 1u : 0u) << (2 * u) | (kh ? 1u : 0u) << (2 * u + 1);
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 32; u++) {
+                const bool kp = drop_mult1(dc, e0 + u) != 0.f;
+                sv[u] = kp ? sv[u] : 0.f;
+                kb |= (kp ? 1u : 0u) << u;
+              }
+            }
+            if (drop_bits != nullptr && qi < T && k0 + c < S) drop_bits[((int64_t)bh * T + qi) * (int64_t)W + ((k0 + c) >> 5)] = kb;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int u = 0; u < 16; u++) pk[u] = pack_bf16x2(sv[2 * u], sv[2 * u + 1]);
+          tmem_st16(tP + lane_off + (uint32_t)(c >> 1), pk);
+        }
+        l = fmaf(l, alpha, rs);
+        m = m_new;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // ---- fold the previous tile's P V into the register accumulator, then rescale to the new max
+        if (j > 0) {
+          float ov[AT_DH];
+          tmem_ld32(tO0 + 32 * ((tc - 1) & 1) + lane_off, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < AT_DH; d++) oacc[d] = (oacc[d] + ov[d]) * alpha;
+        }
+      }
+      {
+        float ov[AT_DH];
+        mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u);
+        tc_fence_after();
+        tmem_ld32(tO0 + 32 * ((tc - 1) & 1) + lane_off, ov);
         tmem_ld_wait();
         tc_fence_before();
+        const float inv_l = (dc.on ? dc.inv_keep : 1.f) / l;
 #pragma unroll
-        for (int d = 0; d < AT_DH; d++) oacc[d] = (oacc[d] + ov[d]) * alpha;
+        for (int d = 0; d < AT_DH; d++) oacc[d] = (oacc[d] + ov[d]) * inv_l;
       }
-    }
-    {
-      const int ip = (n_tiles - 1) & 1;
-      float ov[AT_DH];
-      mbar_wait(o_full(ip), (uint32_t)((n_tiles - 1) >> 1) & 1u);
-      tc_fence_after();
-      tmem_ld32(tO[ip] + lane_off, ov);
-      tmem_ld_wait();
-      tc_fence_before();
-      const float inv_l = 1.f / l;
+      if (qi < T) {
+        bf16* orow = out + ((int64_t)b * T + qi) * (int64_t)(H * AT_DH) + h * AT_DH;
 #pragma unroll
-      for (int d = 0; d < AT_DH; d++) oacc[d] = (oacc[d] + ov[d]) * inv_l;
-    }
-    if (qi < T) {
-      bf16* orow = out + ((int64_t)b * T + qi) * (int64_t)(H * AT_DH) + h * AT_DH;
-#pragma unroll
-      for (int u = 0; u < AT_DH / 8; u++) {
-        uint4 w;
-        w.x = pack_bf16x2(oacc[u * 8 + 0], oacc[u * 8 + 1]); w.y = pack_bf16x2(oacc[u * 8 + 2], oacc[u * 8 + 3]);
-        w.z = pack_bf16x2(oacc[u * 8 + 4], oacc[u * 8 + 5]); w.w = pack_bf16x2(oacc[u * 8 + 6], oacc[u * 8 + 7]);
-        *(uint4*)(orow + u * 8) = w;
+        for (int u = 0; u < AT_DH / 8; u++) {
+          uint4 w;
+          w.x = pack_bf16x2(oacc[u * 8 + 0], oacc[u * 8 + 1]); w.y = pack_bf16x2(oacc[u * 8 + 2], oacc[u * 8 + 3]);
+          w.z = pack_bf16x2(oacc[u * 8 + 4], oacc[u * 8 + 5]); w.w = pack_bf16x2(oacc[u * 8 + 6], oacc[u * 8 + 7]);
+          *(uint4*)(orow + u * 8) = w;
+        }
+        lse[(int64_t)bh * T + qi] = (m + log2f(l)) * LN2_F;
       }
-      lse[(int64_t)bh * T + qi] = (m + log2f(l)) * LN2_F;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(*tmem_ptr_gen, 512);
 }
 
 // ---------------------------------------------------------------- host
@@ -281,8 +341,9 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     if (e != cudaSuccess) { bpm_set_error("xattn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
     attr_set = true;
   }
-  dim3 grid(bpm_cdiv(a->T, AT_BM), a->B * a->H);
-  attn_fwd_tc_kernel<<<grid, AT_THREADS, smem, stream>>>(tq, tk, tv, (bf16*)out, lse, a->B, a->T, a->S, a->H, a->mask_off, a->drop, a->drop_bits);
+  const int n_items = a->B * a->H * bpm_cdiv(a->T, AT_BM);
+  const int ctas = min(bpm_num_sms(), bpm_cdiv(n_items, AF_GROUPS));
+  attn_fwd_tc_kernel<<<ctas, AF_THREADS, smem, stream>>>(tq, tk, tv, (bf16*)out, lse, a->B, a->T, a->S, a->H, a->mask_off, a->drop, a->drop_bits);
   BPM_CHECK_LAUNCH("xattn_fwd_tc");
   return BPM_OK;
 }
