@@ -28,7 +28,8 @@ class Gemm(C.Structure):
 
 class Attn(C.Structure):
     _fields_ = [("dtype", C.c_int), ("B", C.c_int), ("T", C.c_int), ("S", C.c_int), ("H", C.c_int), ("dh", C.c_int),
-                ("dhp", C.c_int), ("mask_off", C.c_int), ("key_pad", C.c_void_p), ("drop", Dropout), ("drop_bits", C.c_void_p)]
+                ("dhp", C.c_int), ("mask_off", C.c_int), ("key_pad", C.c_void_p), ("drop", Dropout), ("drop_bits", C.c_void_p),
+                ("ld_kv", C.c_int), ("ld_dkv", C.c_int)]
 
 
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64

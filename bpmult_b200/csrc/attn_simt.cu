@@ -27,16 +27,16 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attn_fwd_simt(bpm_attn_t a, con
   if (i >= a.T) return;
   float* sc = sm + (size_t)warp * (a.S + a.dhp);
   float* qs = sc + a.S;
-  int pitch = a.H * a.dhp;
+  int pitch = a.H * a.dhp, pkv = a.ld_kv ? a.ld_kv : pitch;
   const T* qrow = q + ((int64_t)b * a.T + i) * pitch + h * a.dhp;
   for (int d = lane; d < a.dhp; d += 32) qs[d] = to_f<T>(qrow[d]);
   __syncwarp();
   int jmax = a.mask_off >= 0 ? min(a.S - 1, i + a.mask_off) : a.S - 1;
-  const T* kb = k + (int64_t)b * a.S * pitch + h * a.dhp;
-  const T* vb = v + (int64_t)b * a.S * pitch + h * a.dhp;
+  const T* kb = k + (int64_t)b * a.S * pkv + h * a.dhp;
+  const T* vb = v + (int64_t)b * a.S * pkv + h * a.dhp;
   float m = -INFINITY;
   for (int j = lane; j <= jmax; j += 32) {
-    float s = (a.key_pad && a.key_pad[(int64_t)b * a.S + j]) ? -INFINITY : dot_row<T>(qs, kb + (int64_t)j * pitch, a.dhp);
+    float s = (a.key_pad && a.key_pad[(int64_t)b * a.S + j]) ? -INFINITY : dot_row<T>(qs, kb + (int64_t)j * pkv, a.dhp);
     sc[j] = s;
     m = fmaxf(m, s);
   }
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attn_fwd_simt(bpm_attn_t a, con
   T* orow = out + ((int64_t)b * a.T + i) * pitch + h * a.dhp;
   for (int d = lane; d < a.dhp; d += 32) {
     float acc = 0.f;
-    for (int j = 0; j <= jmax; j++) acc = fmaf(sc[j], to_f<T>(vb[(int64_t)j * pitch + d]), acc);
+    for (int j = 0; j <= jmax; j++) acc = fmaf(sc[j], to_f<T>(vb[(int64_t)j * pkv + d]), acc);
     orow[d] = from_f<T>(acc);
   }
 }
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attn_bwd_dq_simt(bpm_attn_t a, 
   float* sc = sm + (size_t)warp * (a.S + 2 * a.dhp);
   float* qs = sc + a.S;
   float* gs = qs + a.dhp;
-  int pitch = a.H * a.dhp;
+  int pitch = a.H * a.dhp, pkv = a.ld_kv ? a.ld_kv : pitch;
   int64_t ro = ((int64_t)b * a.T + i) * pitch + h * a.dhp;
   float dl = 0.f;
   for (int d = lane; d < a.dhp; d += 32) {
@@ -88,16 +88,16 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attn_bwd_dq_simt(bpm_attn_t a, 
     delta[(int64_t)a.B * a.H * a.T + (int64_t)bh * a.T + i] = L * 1.4426950408889634f;      // second half of the workspace: lse * log2e
   }
   int jmax = a.mask_off >= 0 ? min(a.S - 1, i + a.mask_off) : a.S - 1;
-  const T* kb = k + (int64_t)b * a.S * pitch + h * a.dhp;
-  const T* vb = v + (int64_t)b * a.S * pitch + h * a.dhp;
+  const T* kb = k + (int64_t)b * a.S * pkv + h * a.dhp;
+  const T* vb = v + (int64_t)b * a.S * pkv + h * a.dhp;
   DropCtx dc = make_drop(a.drop);
   uint64_t ebase = ((uint64_t)bh * a.T + i) * (uint64_t)a.S;
   for (int j = lane; j <= jmax; j += 32) {
     float ds = 0.f;
     if (!(a.key_pad && a.key_pad[(int64_t)b * a.S + j])) {
-      float s = dot_row<T>(qs, kb + (int64_t)j * pitch, a.dhp);
+      float s = dot_row<T>(qs, kb + (int64_t)j * pkv, a.dhp);
       float p = expf(s - L);
-      float dpt = dot_row<T>(gs, vb + (int64_t)j * pitch, a.dhp);
+      float dpt = dot_row<T>(gs, vb + (int64_t)j * pkv, a.dhp);
       ds = p * (dpt * drop_mult1(dc, ebase + j) - dl);
     }
     sc[j] = ds;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attn_bwd_dq_simt(bpm_attn_t a, 
   __syncwarp();
   for (int d = lane; d < a.dhp; d += 32) {
     float acc = 0.f;
-    for (int j = 0; j <= jmax; j++) acc = fmaf(sc[j], to_f<T>(kb[(int64_t)j * pitch + d]), acc);
+    for (int j = 0; j <= jmax; j++) acc = fmaf(sc[j], to_f<T>(kb[(int64_t)j * pkv + d]), acc);
     dq[ro + d] = from_f<T>(acc * dq_scale);
   }
 }
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attn_bwd_dkv_simt(bpm_attn_t a,
   float* ds = pt + a.T;
   float* ks = ds + a.T;
   float* vs = ks + a.dhp;
-  int pitch = a.H * a.dhp;
-  int64_t ko = ((int64_t)b * a.S + j) * pitch + h * a.dhp;
+  int pitch = a.H * a.dhp, pkv = a.ld_kv ? a.ld_kv : pitch, pdkv = a.ld_dkv ? a.ld_dkv : pitch;
+  int64_t ko = ((int64_t)b * a.S + j) * pkv + h * a.dhp, kdo = ((int64_t)b * a.S + j) * pdkv + h * a.dhp;
   for (int d = lane; d < a.dhp; d += 32) { ks[d] = to_f<T>(k[ko + d]); vs[d] = to_f<T>(v[ko + d]); }
   __syncwarp();
   bool padded = a.key_pad && a.key_pad[(int64_t)b * a.S + j];
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attn_bwd_dkv_simt(bpm_attn_t a,
       av = fmaf(pt[i], to_f<T>(gb[(int64_t)i * pitch + d]), av);
       ak = fmaf(ds[i], to_f<T>(qb[(int64_t)i * pitch + d]), ak);
     }
-    dv[ko + d] = from_f<T>(av);
-    dk[ko + d] = from_f<T>(ak);
+    dv[kdo + d] = from_f<T>(av);
+    dk[kdo + d] = from_f<T>(ak);
   }
 }
 
@@ -167,7 +167,7 @@ __global__ void attn_weights_simt(bpm_attn_t a, const T* __restrict__ q, const T
     if (vis) {
       for (int h = 0; h < a.H; h++) {
         const T* qr = q + ((int64_t)b * a.T + i) * pitch + h * a.dhp;
-        const T* kr = k + ((int64_t)b * a.S + j) * pitch + h * a.dhp;
+        const T* kr = k + ((int64_t)b * a.S + j) * (a.ld_kv ? a.ld_kv : pitch) + h * a.dhp;
         float s = 0.f;
         for (int d = 0; d < a.dhp; d++) s = fmaf(to_f<T>(qr[d]), to_f<T>(kr[d]), s);
         int64_t bh = (int64_t)b * a.H + h;

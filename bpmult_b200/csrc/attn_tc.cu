@@ -315,9 +315,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ---------------------------------------------------------------- host
-static int make_qkv_map(CUtensorMap* m, const void* p, int B, int rows, int HP, int box_rows) {
+static int make_qkv_map(CUtensorMap* m, const void* p, int B, int rows, int HP, int box_rows, int pitch = 0) {
+  if (pitch == 0) pitch = HP;                         // row pitch in elements (k / v may be column slices of a wider buffer)
   uint64_t dims[3] = {(uint64_t)HP, (uint64_t)rows, (uint64_t)B};
-  uint64_t str[2] = {(uint64_t)HP * 2, (uint64_t)rows * HP * 2};
+  uint64_t str[2] = {(uint64_t)pitch * 2, (uint64_t)rows * pitch * 2};
   uint32_t box[3] = {AT_DH, (uint32_t)box_rows, 1};
   return bpm_make_tmap_bf16(m, p, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
@@ -332,8 +333,9 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_qkv_map(&tq, q, a->B, a->T, HP, AT_BM))) return rc;
-  if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, AT_BN))) return rc;
-  if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, AT_BN))) return rc;
+  BPM_REQUIRE(a->ld_kv % 8 == 0, "xattn_fwd: ld_kv must be a multiple of 8 elements");
+  if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, AT_BN, a->ld_kv))) return rc;
+  if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, AT_BN, a->ld_kv))) return rc;
   size_t smem = AttnFwdSmem::TOTAL + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmBits, const int bits_tma,
                    const float* __restrict__ ws, bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T,
-                   int S, int H, int mask_off, bpm_dropout_t drop, const uint32_t* __restrict__ drop_bits, const int dbg,
+                   int S, int H, int mask_off, bpm_dropout_t drop, const uint32_t* __restrict__ drop_bits, const int ld_dkv, const int dbg,
                    unsigned long long* __restrict__ trace) {
   int tr_n = 0;
   extern __shared__ uint8_t smem_raw[];
@@ -713,7 +715,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(dkv_free);
       if (pend_key < S) {
-        bf16* dst = (drain_dv ? dv : dk) + ((int64_t)pend_b * S + pend_key) * HP + pend_h * AT_DH + dcol0;
+        bf16* dst = (drain_dv ? dv : dk) + ((int64_t)pend_b * S + pend_key) * ld_dkv + pend_h * AT_DH + dcol0;
 #pragma unroll
         for (int u = 0; u < DCOL / 8; u++)
           *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8], acc[u * 8 + 1]), pack_bf16x2(acc[u * 8 + 2], acc[u * 8 + 3]),
@@ -731,7 +733,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int imin = i_min_of(j);
         if (imin >= nq) {                                     // no query sees this key tile: dK = dV = 0
           if (key < S) {
-            bf16* dst = (drain_dv ? dv : dk) + ((int64_t)b * S + key) * HP + h * AT_DH + dcol0;
+            bf16* dst = (drain_dv ? dv : dk) + ((int64_t)b * S + key) * ld_dkv + h * AT_DH + dcol0;
 #pragma unroll
             for (int u = 0; u < DCOL / 8; u++) *(uint4*)(dst + u * 8) = make_uint4(0, 0, 0, 0);
           }
@@ -872,8 +874,9 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   CUtensorMap tq, tk, tv, tg;
   int rc;
   if ((rc = make_qkv_map(&tq, q, a->B, a->T, HP, 128))) return rc;
-  if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, 128))) return rc;
-  if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, 128))) return rc;
+  BPM_REQUIRE(a->ld_kv % 8 == 0 && a->ld_dkv % 8 == 0, "xattn_bwd: ld_kv / ld_dkv must be multiples of 8 elements");
+  if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, 128, a->ld_kv))) return rc;
+  if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, 128, a->ld_kv))) return rc;
   if ((rc = make_qkv_map(&tg, dout, a->B, a->T, HP, 128))) return rc;
   // dropout keep bits as a [B*H*T, W] uint32 tensor, box {4 words, 128 queries}; needs a 16-byte pitch (S % 128 == 0)
   CUtensorMap tb = tq;
@@ -896,7 +899,7 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   }
   const int ctas = min(a->B * a->H, bpm_num_sms());
   attn_bwd_tc_kernel<<<ctas, AB_THREADS, smem, stream>>>(tq, tk, tv, tg, tb, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
-                                                         a->mask_off, a->drop, a->drop_bits, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr());
+                                                         a->mask_off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr());
   BPM_CHECK_LAUNCH("xattn_bwd_tc");
   return BPM_OK;
 }

@@ -145,8 +145,8 @@ class EncoderEngine:
         gshapes = []
         for _ in range(self.L):
             gshapes += [(3 * d.HP, d.Dp), (3 * d.HP,), (d.Dp, d.HP), (d.Dp,), (d.FP, d.Dp), (d.FP,), (d.Dp, d.FP), (d.Dp,)] + [(d.Dp,)] * (2 * self.n_ln)
-            gshapes += [(2 * d.HP, d.Dp), (2 * d.HP,)]                       # folded K / V projection (x_hat operands)
         gshapes += [(d.Dp,), (d.Dp,)]
+        gshapes += [(self.L * d.HP, d.Dp), (self.L * d.HP, d.Dp), (self.L * d.HP,), (self.L * d.HP,)]   # folded K / V projections of ALL layers
         self.G_flat, gv = carve(self.ops, f32, gshapes)      # every gradient accumulator of this encoder: zeroed with one memset
         it = iter(gv)
         for _ in range(self.L):
@@ -156,12 +156,13 @@ class EncoderEngine:
             g = dict(Wqkv=next(it), bqkv=next(it), Wo=next(it), bo=next(it), W1=next(it), b1=next(it), W2=next(it), b2=next(it))
             g["ln_g"] = [next(it) for _ in range(self.n_ln)]
             g["ln_b"] = [next(it) for _ in range(self.n_ln)]
-            g["Wkv_f"], g["bkv_f"] = next(it), next(it)
-            w["Wkv_f"], w["bkv_f"] = z((2 * d.HP, d.Dp), T_), z((2 * d.HP,), f32)
             self.W.append(w)
             self.G.append(g)
         self.Wf = dict(g=z((d.Dp,), f32), b=z((d.Dp,), f32))
         self.Gf = dict(g=next(it), b=next(it))
+        # folded K / V projections (x_hat operands) of all L layers, stacked: one GEMM per encoder produces every layer's K (V)
+        self.Gkv = dict(Wk=next(it), Wv=next(it), bk=next(it), bv=next(it))
+        self.Wkv = dict(Wk=z((self.L * d.HP, d.Dp), T_), Wv=z((self.L * d.HP, d.Dp), T_), bk=z((self.L * d.HP,), f32), bv=z((self.L * d.HP,), f32))
         # unit LayerNorm affine (x_hat of the K / V inputs) and a sink for its unused affine gradients
         self.unit_g, self.unit_b, self.ln_sink = z((d.Dp,), f32), z((d.Dp,), f32), z((2, d.Dp), f32)
         self.unit_g[:d.D] = 1.0
@@ -193,7 +194,9 @@ class EncoderEngine:
         if self.fold_kv:
             for l in range(self.L):                 # K' = W_k diag(gamma), b_k' = b_k + W_k beta  (and the same for V)
                 ipw, ipb, g_, b_ = self.P[l]
-                o.ln_fold_fwd(ipw[d.D:], ipb[d.D:], g_, b_, self.W[l]["Wkv_f"], self.W[l]["bkv_f"], row_map=hm)
+                r = slice(l * d.HP, (l + 1) * d.HP)
+                o.ln_fold_fwd(ipw[d.D:2 * d.D], ipb[d.D:2 * d.D], g_, b_, self.Wkv["Wk"][r], self.Wkv["bk"][r], row_map=hm)
+                o.ln_fold_fwd(ipw[2 * d.D:], ipb[2 * d.D:], g_, b_, self.Wkv["Wv"][r], self.Wkv["bv"][r], row_map=hm)
 
     def pack_attention(self, l, ipw, ipb, ow, ob):
         o, d, w = self.ops, self.d, self.W[l]
@@ -264,22 +267,23 @@ class EncoderEngine:
 
     # ---------------------------------------------------------------- attention block (in-proj, attention, out-proj + residual)
     def _attn_fwd(self, l, blk, q_in, k_in, v_in, B, T, S, x_res, x_out, res_drop=True, folded=False):
-        """folded: k_in / v_in are the un-affined x_hat rows and the K / V projections carry the layer's LayerNorm affine"""
+        """folded: k_in / v_in ARE this layer's K / V (column slices of the all-layers projections of x_hat, made once per encoder)"""
         o, d, A, w = self.ops, self.d, self.arena, self.W[l]
         M, Ms = B * T, B * S
         key = "L%d.%s." % (l, blk)
         q = A.get(key + "q", (M, d.HP), self.T_)
-        k = A.get(key + "k", (Ms, d.HP), self.T_)
         a = A.get(key + "a", (M, d.HP), self.T_)
         lse = A.get(key + "lse", (B * d.H * T,), torch.float32)
         Wq, Wk, Wv = w["Wqkv"][:d.HP], w["Wqkv"][d.HP:2 * d.HP], w["Wqkv"][2 * d.HP:]
         bq, bk, bv = w["bqkv"][:d.HP], w["bqkv"][d.HP:2 * d.HP], w["bqkv"][2 * d.HP:]
-        if folded:
-            Wk, Wv, bk, bv = w["Wkv_f"][:d.HP], w["Wkv_f"][d.HP:], w["bkv_f"][:d.HP], w["bkv_f"][d.HP:]
         o.gemm(q_in, Wq, q, M, d.HP, d.Dp, bias=bq, alpha=d.scaling)          # q = (x Wq^T + bq) * dh^-0.5  (:86)
-        o.gemm(k_in, Wk, k, Ms, d.HP, d.Dp, bias=bk)
-        v = A.get(key + "v", (Ms, d.HP), self.T_)
-        o.gemm(v_in, Wv, v, Ms, d.HP, d.Dp, bias=bv)
+        if folded:                                                              # this layer's columns of the all-layers K / V projections
+            k, v = k_in, v_in
+        else:
+            k = A.get(key + "k", (Ms, d.HP), self.T_)
+            o.gemm(k_in, Wk, k, Ms, d.HP, d.Dp, bias=bk)
+            v = A.get(key + "v", (Ms, d.HP), self.T_)
+            o.gemm(v_in, Wv, v, Ms, d.HP, d.Dp, bias=bv)
         adrop = self._drop(self.p_attn, l, 10 + (blk == "x"))
         bits = A.get(key + "bits", (B * d.H * T * ((S + 31) // 32),), torch.int32) if adrop is not None else None
         o.xattn_fwd(q, k, v, a, lse, B, T, S, d.H, d.dh, d.dhp, mask_off=self._mask_off(T, S), drop=adrop, drop_bits=bits)
@@ -288,19 +292,17 @@ class EncoderEngine:
                residual=x_res)
         return dict(q=q, k=k, v=v, a=a, lse=lse, q_in=q_in, k_in=k_in, v_in=v_in, S=S, bits=bits, folded=folded)
 
-    def _attn_bwd(self, l, blk, sv, B, T, gx, res_drop=True, gnk=None, gnv=None):
+    def _attn_bwd(self, l, blk, sv, B, T, gx, res_drop=True, dkv=None):
         """gx: fp32 [M, Dp] gradient wrt the block output x_out (= also flows to x_res unchanged).
-        Returns (dq_in, dk_in, dv_in) in storage type (gradients wrt the projection inputs).  Folded K / V projections instead
-        accumulate their input gradients into the fp32 buffers gnk / gnv (gradient wrt x_hat) and return (dq_in, None, None)."""
+        Returns (dq_in, dk_in, dv_in) in storage type (gradients wrt the projection inputs).  Folded K / V projections: dK / dV go
+        into dkv = (this layer's column slices of the all-layers dK / dV buffers) and (dq_in, None, None) is returned; their weight
+        and input gradients are taken for all layers at once at the end of the encoder backward."""
         o, d, w, g, Sh = self.ops, self.d, self.W[l], self.G[l], self.shared
         S = sv["S"]
         M, Ms = B * T, B * S
         Wq, Wk, Wv = w["Wqkv"][:d.HP], w["Wqkv"][d.HP:2 * d.HP], w["Wqkv"][2 * d.HP:]
         gWq, gWk, gWv = g["Wqkv"][:d.HP], g["Wqkv"][d.HP:2 * d.HP], g["Wqkv"][2 * d.HP:]
         gbq, gbk, gbv = g["bqkv"][:d.HP], g["bqkv"][d.HP:2 * d.HP], g["bqkv"][2 * d.HP:]
-        if sv["folded"]:
-            Wk, Wv = w["Wkv_f"][:d.HP], w["Wkv_f"][d.HP:]
-            gWk, gWv, gbk, gbv = g["Wkv_f"][:d.HP], g["Wkv_f"][d.HP:], g["bkv_f"][:d.HP], g["bkv_f"][d.HP:]
         go = Sh.get("go", (M, d.Dp), self.T_)
         if not self._go_valid:                                                  # (else: fused into the LayerNorm backward that last wrote gx)
             o.cast_drop(gx, go, self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")))   # grad wrt out_proj output
@@ -309,21 +311,22 @@ class EncoderEngine:
         da = Sh.get("da", (M, d.HP), self.T_)
         o.gemm(go, w["Wo"], da, M, d.HP, d.Dp, tb=1)                                           # da = go Wo
         dq = Sh.get("dq", (M, d.HP), self.T_)
-        dk = Sh.get("dk", (Ms, d.HP), self.T_)
-        dv = Sh.get("dv", (Ms, d.HP), self.T_)
+        if sv["folded"]:
+            dk, dv = dkv
+        else:
+            dk = Sh.get("dk", (Ms, d.HP), self.T_)
+            dv = Sh.get("dv", (Ms, d.HP), self.T_)
         delta = Sh.get("delta", (2 * B * d.H * T,), torch.float32)      # [0] rowsum(dO*O), [1] lse*log2e
         o.xattn_bwd(sv["q"], sv["k"], sv["v"], sv["a"], da, sv["lse"], delta, dq, d.scaling, dk, dv, B, T, S, d.H, d.dh, d.dhp,
                     mask_off=self._mask_off(T, S), drop=self._drop(self.p_attn, l, 10 + (blk == "x")), drop_bits=sv["bits"])
         # dq already carries the dh^-0.5 factor => it is the gradient wrt (x Wq^T + bq)
         o.gemm(dq, sv["q_in"], gWq, d.HP, d.Dp, M, ta=1, tb=1, accumulate=True, colsum=gbq)
-        o.gemm(dk, sv["k_in"], gWk, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=gbk)
-        o.gemm(dv, sv["v_in"], gWv, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=gbv)
         dq_in = Sh.get("dq_in", (M, d.Dp), self.T_)
         o.gemm(dq, Wq, dq_in, M, d.Dp, d.HP, tb=1)
-        if sv["folded"]:                                                        # d x_hat += dK W_k' (+ dV W_v'), fp32, across all layers
-            o.gemm(dk, Wk, gnk, Ms, d.Dp, d.HP, tb=1, residual=gnk)
-            o.gemm(dv, Wv, gnv, Ms, d.Dp, d.HP, tb=1, residual=gnv)
+        if sv["folded"]:
             return dq_in, None, None
+        o.gemm(dk, sv["k_in"], gWk, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=gbk)
+        o.gemm(dv, sv["v_in"], gWv, d.HP, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=gbv)
         dk_in = Sh.get("dk_in", (Ms, d.Dp), self.T_)
         dv_in = Sh.get("dv_in", (Ms, d.Dp), self.T_)
         o.gemm(dk, Wk, dk_in, Ms, d.Dp, d.HP, tb=1)
@@ -433,6 +436,12 @@ class EncoderEngine:
             nk = xhat("nk.", xk)
             nv = nk if self.kv_shared else xhat("nv.", xv)
             self.nkv = (nk, nv)
+            LH = self.L * d.HP                                                    # K / V of every layer with one GEMM each
+            K_all = A.get("K_all", (Ms, LH), self.T_)
+            V_all = A.get("V_all", (Ms, LH), self.T_)
+            o.gemm(nk["y"], self.Wkv["Wk"], K_all, Ms, LH, d.Dp, bias=self.Wkv["bk"])
+            o.gemm(nv["y"], self.Wkv["Wv"], V_all, Ms, LH, d.Dp, bias=self.Wkv["bv"])
+            kv_of = lambda l_: (K_all[:, l_ * d.HP:(l_ + 1) * d.HP], V_all[:, l_ * d.HP:(l_ + 1) * d.HP])
         xi = 0
         x = xs[0]
         for l in range(self.L):
@@ -448,28 +457,30 @@ class EncoderEngine:
                 x1 = xs[xi + 1]
                 sv["self"] = self._attn_fwd(l, "s", ln_q["y"], ln_q["y"], ln_q["y"], B, T, T, x, x1)
                 if self.folded:
-                    ln_k, ln_v = nk, nv
+                    k_op, v_op = kv_of(l)
                 else:
                     ln_k = self._ln_fwd("L%d.lnk." % l, xk, l, 1, Ms)
                     ln_v = ln_k if self.kv_shared else self._ln_fwd("L%d.lnv." % l, xv, l, 1, Ms)
                     sv["ln_k"], sv["ln_v"] = ln_k, ln_v
+                    k_op, v_op = ln_k["y"], ln_v["y"]
                 # the cross-attention query is the residual stream itself, NOT re-normalised (:169)
                 qc = A.get("L%d.qcast" % l, (M, d.Dp), self.T_)
                 o.cast_drop(x1, qc, None)
                 x2 = xs[xi + 2]
-                sv["cross"] = self._attn_fwd(l, "x", qc, ln_k["y"], ln_v["y"], B, T, S, x1, x2, folded=self.folded)
+                sv["cross"] = self._attn_fwd(l, "x", qc, k_op, v_op, B, T, S, x1, x2, folded=self.folded)
                 x1 = x2
                 xi += 2
                 ffn_ln = 2
             else:                                                                # :170-173
                 if self.folded:
-                    ln_k, ln_v = nk, nv
+                    k_op, v_op = kv_of(l)
                 else:
                     ln_k = self._ln_fwd("L%d.lnk." % l, xk, l, 0, Ms)
                     ln_v = ln_k if self.kv_shared else self._ln_fwd("L%d.lnv." % l, xv, l, 0, Ms)
                     sv["ln_k"], sv["ln_v"] = ln_k, ln_v
+                    k_op, v_op = ln_k["y"], ln_v["y"]
                 x1 = xs[xi + 1]
-                sv["cross"] = self._attn_fwd(l, "x", ln_q["y"], ln_k["y"], ln_v["y"], B, T, S, x, x1, folded=self.folded)
+                sv["cross"] = self._attn_fwd(l, "x", ln_q["y"], k_op, v_op, B, T, S, x, x1, folded=self.folded)
                 xi += 1
                 ffn_ln = 1
             x2 = xs[xi + 1]
@@ -508,13 +519,11 @@ class EncoderEngine:
             if not self.kv_shared:
                 gxv = Sh.get("gxv", (Ms, d.Dp), torch.float32)
                 o.zero_(gxv)
-            if self.folded:                         # gradients wrt x_hat accumulate over the layers; one LayerNorm backward at the end
-                gnk = Sh.get("gnk", (Ms, d.Dp), torch.float32)
-                o.zero_(gnk)
-                gnv = gnk
-                if not self.kv_shared:
-                    gnv = Sh.get("gnv", (Ms, d.Dp), torch.float32)
-                    o.zero_(gnv)
+            if self.folded:                         # every layer's dK / dV side by side: one wgrad and one dgrad GEMM per encoder and side
+                LH = self.L * d.HP
+                dK_all = Sh.get("dK_all", (Ms, LH), self.T_)
+                dV_all = Sh.get("dV_all", (Ms, LH), self.T_)
+                dkv_of = lambda l_: (dK_all[:, l_ * d.HP:(l_ + 1) * d.HP], dV_all[:, l_ * d.HP:(l_ + 1) * d.HP])
         self._go_valid = False
         for l in reversed(range(self.L)):
             sv = self.saved[l]
@@ -524,7 +533,7 @@ class EncoderEngine:
                 for t in (dq_in, dk_in, dv_in):
                     self._ln_bwd(l, sv["ln_q"], t, gx, cast_next=t is dv_in)
             elif self.biproj:
-                dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx, gnk=gnk, gnv=gnv)
+                dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx, dkv=dkv_of(l) if self.folded else None)
                 o.axpy_f32(dq_in, gx, True)                                      # query path is the raw residual stream
                 if not self.folded:
                     self._ln_bwd(l, sv["ln_k"], dk_in, gxk)
@@ -533,7 +542,7 @@ class EncoderEngine:
                 for t in (dq_in, dk_in, dv_in):
                     self._ln_bwd(l, sv["ln_q"], t, gx, cast_next=t is dv_in)
             else:
-                dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx, gnk=gnk, gnv=gnv)
+                dq_in, dk_in, dv_in = self._attn_bwd(l, "x", sv["cross"], B, T, gx, dkv=dkv_of(l) if self.folded else None)
                 self._ln_bwd(l, sv["ln_q"], dq_in, gx, cast_next=True)
                 if not self.folded:
                     self._ln_bwd(l, sv["ln_k"], dk_in, gxk)
@@ -541,14 +550,28 @@ class EncoderEngine:
         if self.cross and self.folded:
             nk, nv = self.nkv
             hm = (d.dh, d.dhp)
+            Wkv, Gkv = self.Wkv, self.Gkv
+            # weight / bias gradients of all layers' folded projections: dW_k'(all) = dK(all)^T x_hat, db_k'(all) = colsum dK(all)
+            o.gemm(dK_all, nk["y"], Gkv["Wk"], LH, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=Gkv["bk"])
+            o.gemm(dV_all, nv["y"], Gkv["Wv"], LH, d.Dp, Ms, ta=1, tb=1, accumulate=True, colsum=Gkv["bv"])
+            # d x_hat = dK(all) W_k'(all) (+ dV(all) W_v'(all) when K and V share their input), fp32; then ONE LayerNorm backward
+            gnk = Sh.get("gnk", (Ms, d.Dp), torch.float32)
+            o.gemm(dK_all, Wkv["Wk"], gnk, Ms, d.Dp, LH, tb=1)
+            if self.kv_shared:
+                o.gemm(dV_all, Wkv["Wv"], gnk, Ms, d.Dp, LH, tb=1, residual=gnk)
             o.layernorm_bwd(gnk, nk["x"], nk["mean"], nk["rstd"], self.unit_g, d.D, gxk, True, self.ln_sink[0], self.ln_sink[1])
             if not self.kv_shared:
+                gnv = Sh.get("gnv", (Ms, d.Dp), torch.float32)
+                o.gemm(dV_all, Wkv["Wv"], gnv, Ms, d.Dp, LH, tb=1)
                 o.layernorm_bwd(gnv, nv["x"], nv["mean"], nv["rstd"], self.unit_g, d.D, gxv, True, self.ln_sink[0], self.ln_sink[1])
             for l in range(self.L):                 # gradients of (W_k', b_k') -> W_k, b_k and the layer's LayerNorm affine
                 ipw, ipb, g_, b_ = self.P[l]
                 G = self.G[l]
-                o.ln_fold_bwd(ipw[d.D:], g_, b_, G["Wkv_f"], G["bkv_f"], G["Wqkv"][d.HP:], G["bqkv"][d.HP:], G["ln_g"][self.kv_ln],
-                              G["ln_b"][self.kv_ln], row_map=hm)
+                r = slice(l * d.HP, (l + 1) * d.HP)
+                o.ln_fold_bwd(ipw[d.D:2 * d.D], g_, b_, Gkv["Wk"][r], Gkv["bk"][r], G["Wqkv"][d.HP:2 * d.HP], G["bqkv"][d.HP:2 * d.HP],
+                              G["ln_g"][self.kv_ln], G["ln_b"][self.kv_ln], row_map=hm)
+                o.ln_fold_bwd(ipw[2 * d.D:], g_, b_, Gkv["Wv"][r], Gkv["bv"][r], G["Wqkv"][2 * d.HP:], G["bqkv"][2 * d.HP:],
+                              G["ln_g"][self.kv_ln], G["ln_b"][self.kv_ln], row_map=hm)
         scale = math.sqrt(d.D)
         if not self.with_embed:
             if d_src_q is not None:

@@ -189,26 +189,33 @@ class CudaOps:
         self._ck(self.lib.bpm_colsum(X.data_ptr(), _dt(X), X.shape[0], N, X.stride(0), out.data_ptr(), self._s()), "colsum")
 
     # ------------------------------------------------------------------ attention
-    def _attn(self, q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, drop_bits=None):
+    def _attn(self, q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, drop_bits=None, k=None, v=None, dk=None, dv=None):
         a = Attn()
         a.drop_bits = _ptr(drop_bits)
+        a.ld_kv = a.ld_dkv = 0
+        if k is not None:                           # k / v (and dk / dv) may be column slices of wider row-major buffers
+            assert k.stride(1) == 1 and (v is None or (v.stride(1) == 1 and v.stride(0) == k.stride(0)))
+            a.ld_kv = k.stride(0)
+        if dk is not None:
+            assert dk.stride(1) == 1 and dv.stride(1) == 1 and dv.stride(0) == dk.stride(0)
+            a.ld_dkv = dk.stride(0)
         a.dtype, a.B, a.T, a.S, a.H, a.dh, a.dhp, a.mask_off = _dt(q), B, T, S, H, dh, dhp, int(mask_off)
         a.key_pad = _ptr(key_pad)
         a.drop = _drop(drop)
         return a
 
     def xattn_fwd(self, q, k, v, out, lse, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None, drop_bits=None):
-        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, drop_bits)
+        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, drop_bits, k=k, v=v)
         self._ck(self.lib.bpm_xattn_fwd(C.byref(a), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), self._s()), "xattn_fwd")
 
     def xattn_bwd(self, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None,
                   drop_bits=None):
-        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, drop_bits)
+        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, drop_bits, k=k, v=v, dk=dk, dv=dv)
         self._ck(self.lib.bpm_xattn_bwd(C.byref(a), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                         delta.data_ptr(), dq.data_ptr(), float(dq_scale), dk.data_ptr(), dv.data_ptr(), self._s()), "xattn_bwd")
 
     def xattn_weights(self, q, k, lse, w, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None):
-        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop)
+        a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, k=k)
         self._ck(self.lib.bpm_xattn_weights(C.byref(a), q.data_ptr(), k.data_ptr(), lse.data_ptr(), w.data_ptr(), self._s()), "xattn_weights")
 
     # ------------------------------------------------------------------ GMU / elementwise

@@ -153,6 +153,8 @@ typedef struct {
   bpm_dropout_t drop;
   uint32_t* drop_bits;  /* optional scratch [B*H, T, ceil(S/32)]: keep bits written by the forward (dropout on) and read by the
                            backward instead of regenerating the Philox stream; NULL = regenerate */
+  int ld_kv;            /* row pitch (elements) of k and v; 0 = H*dhp.  Lets k / v be column slices of an all-layers projection */
+  int ld_dkv;           /* row pitch (elements) of dk and dv; 0 = H*dhp */
 } bpm_attn_t;
 int bpm_xattn_fwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, void* stream);
 int bpm_xattn_bwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout,

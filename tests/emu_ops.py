@@ -203,7 +203,7 @@ class EmuOps:
     # ------------------------------------------------------------------ attention
     def _probs(self, q, k, B, T, S, H, dhp, mask_off, key_pad):
         qh = q.float().view(B, T, H, dhp).permute(0, 2, 1, 3)
-        kh = k.float().view(B, S, H, dhp).permute(0, 2, 1, 3)
+        kh = k.float().reshape(B, S, H, dhp).permute(0, 2, 1, 3)
         s = qh @ kh.transpose(-1, -2)                                  # [B,H,T,S]
         if mask_off >= 0:
             i, j = torch.arange(T).view(T, 1), torch.arange(S).view(1, S)
@@ -220,7 +220,7 @@ class EmuOps:
         s = self._probs(q, k, B, T, S, H, dhp, mask_off, key_pad)
         L = torch.logsumexp(s, -1)
         p = torch.exp(s - L.unsqueeze(-1)) * self._attn_mult(B, T, S, H, drop)
-        vh = v.float().view(B, S, H, dhp).permute(0, 2, 1, 3)
+        vh = v.float().reshape(B, S, H, dhp).permute(0, 2, 1, 3)
         o = (p @ vh).permute(0, 2, 1, 3).reshape(B * T, H * dhp)
         out.copy_(o.to(out.dtype))
         lse.copy_(L.reshape(-1))
@@ -230,8 +230,8 @@ class EmuOps:
         p = torch.exp(s - lse.view(B, H, T, 1))
         mult = self._attn_mult(B, T, S, H, drop)
         qh = q.float().view(B, T, H, dhp).permute(0, 2, 1, 3)
-        kh = k.float().view(B, S, H, dhp).permute(0, 2, 1, 3)
-        vh = v.float().view(B, S, H, dhp).permute(0, 2, 1, 3)
+        kh = k.float().reshape(B, S, H, dhp).permute(0, 2, 1, 3)
+        vh = v.float().reshape(B, S, H, dhp).permute(0, 2, 1, 3)
         go = dout.float().view(B, T, H, dhp).permute(0, 2, 1, 3)
         oh = out.float().view(B, T, H, dhp).permute(0, 2, 1, 3)
         dl = (go * oh).sum(-1, keepdim=True)
