@@ -52,6 +52,7 @@ SIGNATURES = {
     "bpm_layernorm_bwd_cast": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _I, Dropout, _P],
     "bpm_ln_fold_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
     "bpm_ln_fold_bwd": [_P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P],
+    "bpm_ln_fold_batch": [_P, _I, _I, _I, _P],
     "bpm_gemm": [C.POINTER(Gemm), _P],
     "bpm_colsum": [_P, _I, _I, _I, _I, _P, _P],
     "bpm_xattn_fwd": [C.POINTER(Attn), _P, _P, _P, _P, _P, _P],

@@ -22,6 +22,12 @@ static void* g_dbg_ptr = nullptr;
 void* bpm_debug_get_ptr() { return g_dbg_ptr; }
 extern "C" int bpm_debug_set_ptr(void* p) { g_dbg_ptr = p; return BPM_OK; }
 
+int bpm_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BPM_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v;
+}
+
 // BPM_DEBUG_FFMA=1 routes bf16 problems through the FFMA kernels too (kernel bring-up / bisecting only).
 static int debug_ffma() {
   static int v = -1;

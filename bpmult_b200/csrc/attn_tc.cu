@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    bf16* __restrict__ out, float* __restrict__ lse, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
                    uint32_t* __restrict__ drop_bits) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -106,6 +107,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_ptr_gen + (uint32_t)(grp * 256);
   const uint32_t tS = tmem, tP = tmem + 128, tO0 = tmem + 192;            // S 128 | P 64 (bf16 pairs) | O 2 x 32
   auto adr = [](uint32_t a) { return (uint64_t)((a & 0x3FFFFu) >> 4); };
@@ -345,8 +347,9 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   }
   const int n_items = a->B * a->H * bpm_cdiv(a->T, AT_BM);
   const int ctas = min(bpm_num_sms(), bpm_cdiv(n_items, AF_GROUPS));
-  attn_fwd_tc_kernel<<<ctas, AF_THREADS, smem, stream>>>(tq, tk, tv, (bf16*)out, lse, a->B, a->T, a->S, a->H, a->mask_off, a->drop, a->drop_bits);
-  BPM_CHECK_LAUNCH("xattn_fwd_tc");
+  cudaError_t le = bpm_launch(attn_fwd_tc_kernel, dim3(ctas), dim3(AF_THREADS), smem, stream, tq, tk, tv, (bf16*)out, lse, a->B, a->T, a->S, a->H,
+                              a->mask_off, a->drop, a->drop_bits);
+  if (le != cudaSuccess) { bpm_set_error("xattn_fwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
 }
 
@@ -400,6 +403,8 @@ static_assert(AttnBwdSmem::DST % 1024 == 0, "swizzled tiles need 1024-byte align
 __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ ws,
                                   int B, int T, int H) {
   // ws[0][b, h, t] = delta = sum_d dO * O   (one thread per (row, head): 2 x 64 B);   ws[1][b, h, t] = lse * log2e
+  pdl_trigger();
+  pdl_wait();
   int64_t n = (int64_t)B * T * H;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
     int h = (int)(idx % H);
@@ -467,6 +472,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    int S, int H, int mask_off, bpm_dropout_t drop, const uint32_t* __restrict__ drop_bits, const int ld_dkv, const int dbg,
                    unsigned long long* __restrict__ trace) {
   int tr_n = 0;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -532,6 +538,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_ptr_gen;
   const uint32_t tST = tmem, tDPT = tmem + 128, tPT = tmem + 256, tDK = tmem + 320, tDV = tmem + 352, tDQ = tmem + 384;
   auto adr = [](uint32_t a) { return (uint64_t)((a & 0x3FFFFu) >> 4); };
@@ -868,8 +875,8 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   {
     int64_t n = (int64_t)a->B * a->T * a->H;
     int grid = (int)((n + 255) / 256 < (int64_t)bpm_num_sms() * 8 ? (n + 255) / 256 : (int64_t)bpm_num_sms() * 8);
-    attn_delta_kernel<<<grid, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, lse, delta, a->B, a->T, a->H);
-    BPM_CHECK_LAUNCH("xattn_delta");
+    cudaError_t le = bpm_launch(attn_delta_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)out, (const bf16*)dout, lse, delta, a->B, a->T, a->H);
+    if (le != cudaSuccess) { bpm_set_error("xattn_delta: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   }
   CUtensorMap tq, tk, tv, tg;
   int rc;
@@ -898,8 +905,8 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     attr_set = true;
   }
   const int ctas = min(a->B * a->H, bpm_num_sms());
-  attn_bwd_tc_kernel<<<ctas, AB_THREADS, smem, stream>>>(tq, tk, tv, tg, tb, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
+  cudaError_t le = bpm_launch(attn_bwd_tc_kernel, dim3(ctas), dim3(AB_THREADS), smem, stream, tq, tk, tv, tg, tb, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
                                                          a->mask_off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr());
-  BPM_CHECK_LAUNCH("xattn_bwd_tc");
+  if (le != cudaSuccess) { bpm_set_error("xattn_bwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
 }

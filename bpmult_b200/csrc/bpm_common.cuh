@@ -32,6 +32,28 @@ int bpm_num_sms();
 int bpm_debug_get(int slot);   // diagnostic knobs (api.cu)
 void* bpm_debug_get_ptr();     // optional device buffer for kernel event traces
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A training step is ~3000 short kernels, each of which fills the GPU and depends on its predecessor.  Launched with the
+// programmatic-stream-serialization attribute a kernel may START while its predecessor's last CTAs are still running: its CTAs take
+// the SMs the predecessor frees and run their prologue (barrier init, TMEM allocation, descriptor prefetch) there, then block in
+// pdl_wait() until the predecessor has completed and flushed its memory.  Every kernel calls pdl_trigger() first (lets ITS successor
+// be scheduled) and pdl_wait() before its first access to global memory.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+int bpm_pdl_enabled();          // 0 when BPM_NO_PDL=1 (api.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t bpm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = bpm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- dtype helpers
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }

@@ -207,6 +207,60 @@ extern "C" int bpm_ln_fold_bwd(const float* W, int ldw, const float* gamma, cons
   return BPM_OK;
 }
 
+// batched variants: one launch for a whole table of (layer, K or V) problems (blockIdx.y = table entry)
+template <typename T>
+__device__ __forceinline__ void ln_fold_fwd_body(const bpm_fold_desc_t& d, int blk) {
+  const int warp = (blk * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= d.rows) return;
+  const int ip = remap_fwd(warp, d.row_dh, d.row_dhp);
+  const float* w = d.W + (int64_t)warp * d.ldw;
+  T* Wp = (T*)d.Wp;
+  float acc = 0.f;
+  for (int j = lane; j < d.cols; j += 32) {
+    const float v = w[j];
+    acc = fmaf(v, d.beta[j], acc);
+    Wp[(int64_t)ip * d.ldp + j] = from_f<T>(v * d.gamma[j]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) d.bp[ip] = d.bias[warp] + acc;
+}
+__global__ void ln_fold_batch_kernel(const bpm_fold_desc_t* __restrict__ descs, int mode) {
+  const bpm_fold_desc_t d = descs[blockIdx.y];
+  if (mode == 0) {
+    if (d.wp_dtype == BPM_BF16) ln_fold_fwd_body<bf16>(d, blockIdx.x);
+    else ln_fold_fwd_body<float>(d, blockIdx.x);
+    return;
+  }
+  const int r0 = blockIdx.x * LNF_ROWS;
+  if (r0 >= d.rows) return;
+  for (int j = threadIdx.x; j < d.cols; j += blockDim.x) {
+    const float g = d.gamma[j], b = d.beta[j];
+    float ag = 0.f, ab = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < LNF_ROWS; rr++) {
+      const int i = r0 + rr;
+      if (i < d.rows) {
+        const int ip = remap_fwd(i, d.row_dh, d.row_dhp);
+        const float w = d.W[(int64_t)i * d.ldw + j], gbv = d.gbf[ip], tv = d.gWf[(int64_t)ip * d.ldf + j];
+        ag = fmaf(tv, w, ag);
+        ab = fmaf(gbv, w, ab);
+        d.gW[(int64_t)ip * d.ldg + j] += fmaf(tv, g, gbv * b);
+        if (j == 0) d.gb[ip] += gbv;
+      }
+    }
+    atomicAdd(d.dgamma + j, ag);
+    atomicAdd(d.dbeta + j, ab);
+  }
+}
+
+extern "C" int bpm_ln_fold_batch(const bpm_fold_desc_t* descs_dev, int n, int max_rows, int mode, void* stream) {
+  BPM_REQUIRE(descs_dev && n > 0 && max_rows > 0 && (mode == 0 || mode == 1), "ln_fold_batch: bad args");
+  dim3 grid(mode == 0 ? bpm_cdiv((int64_t)max_rows * 32, 256) : bpm_cdiv(max_rows, LNF_ROWS), n);
+  ln_fold_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, mode);
+  BPM_CHECK_LAUNCH("ln_fold_batch");
+  return BPM_OK;
+}
+
 // ---------------------------------------------------------------- stage / unstage rows
 template <typename T>
 __global__ void stage_rows_kernel(const float* __restrict__ src, int B, int T_, int C, int64_t sb, int64_t st, int64_t sc, T* __restrict__ dst,

@@ -99,6 +99,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_ptr_addr = bar_base + 8u * NBARS;
   volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(base_gen + misc + 2048 + 8 * NBARS);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb_total = (p.K + TC_BK - 1) / TC_BK;
   const int tiles_mn = p.gx * p.gy;
@@ -124,6 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();                                   // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
@@ -464,8 +466,8 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     if (e != cudaSuccess) { bpm_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
     attr_set = true;
   }
-  gemm_tc_kernel<ELEM, CB><<<ctas, TC_THREADS, smem, stream>>>(tmA, tmB, tmC, tmI, p);
-  BPM_CHECK_LAUNCH("gemm_tc");
+  cudaError_t le = bpm_launch(gemm_tc_kernel<ELEM, CB>, dim3(ctas), dim3(TC_THREADS), smem, stream, tmA, tmB, tmC, tmI, p);
+  if (le != cudaSuccess) { bpm_set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
 }
 

@@ -12,6 +12,8 @@ template <typename TI, typename TO, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                int rows, int D, int Dp, float eps, TO* __restrict__ y, float* __restrict__ mean_out,
                                                                float* __restrict__ rstd_out) {
+  pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int nvec = Dp >> 3;
   float invD = 1.f / (float)D;
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 4) ln_bwd_kernel(const TG* __re
                                                                float* __restrict__ dbeta, void* __restrict__ cast_out, int cast_dtype,
                                                                bpm_dropout_t cast_drop) {
   extern __shared__ float sm[];  // [LN_WARPS][2][Dp]
+  pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int nvec = Dp >> 3;
   float invD = 1.f / (float)D;
@@ -180,7 +184,7 @@ static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, i
                          cudaStream_t s) {
   int nv = bpm_cdiv(Dp / 8, 32);
   int grid = min(bpm_cdiv(rows, LN_WARPS), bpm_num_sms() * 16);
-#define LNF(NV) ln_fwd_kernel<TI, TO, NV><<<grid, LN_WARPS * 32, 0, s>>>((const TI*)x, gamma, beta, rows, D, Dp, eps, (TO*)y, mean, rstd)
+#define LNF(NV) (void)bpm_launch(ln_fwd_kernel<TI, TO, NV>, dim3(grid), dim3(LN_WARPS * 32), 0, s, (const TI*)x, gamma, beta, rows, D, Dp, eps, (TO*)y, mean, rstd)
   switch (nv) {
     case 1: LNF(1); break;
     case 2: LNF(2); break;
@@ -214,8 +218,8 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
   int grid = min(bpm_cdiv(rows, LN_WARPS), bpm_num_sms() * 4);
   size_t smem = (size_t)LN_WARPS * 2 * Dp * sizeof(float);
 #define LNB(NV) \
-  ln_bwd_kernel<TG, TX, NV><<<grid, LN_WARPS * 32, smem, s>>>((const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, Dp, dx, accumulate, dgamma, dbeta, \
-                                                             cast_out, cast_dtype, cast_drop)
+  (void)bpm_launch(ln_bwd_kernel<TG, TX, NV>, dim3(grid), dim3(LN_WARPS * 32), smem, s, (const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, Dp, dx, \
+                   accumulate, dgamma, dbeta, cast_out, cast_dtype, cast_drop)
   switch (nv) {
     case 1: LNB(1); break;
     case 2: LNB(2); break;

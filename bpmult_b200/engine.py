@@ -192,11 +192,13 @@ class EncoderEngine:
             o.pack_matrix(params[pfx + "layer_norm.bias"].view(1, -1), self.Wf["b"].view(1, -1))
         o.batch_end()
         if self.fold_kv:
+            o.fold_batch_begin("fwd")
             for l in range(self.L):                 # K' = W_k diag(gamma), b_k' = b_k + W_k beta  (and the same for V)
                 ipw, ipb, g_, b_ = self.P[l]
                 r = slice(l * d.HP, (l + 1) * d.HP)
                 o.ln_fold_fwd(ipw[d.D:2 * d.D], ipb[d.D:2 * d.D], g_, b_, self.Wkv["Wk"][r], self.Wkv["bk"][r], row_map=hm)
                 o.ln_fold_fwd(ipw[2 * d.D:], ipb[2 * d.D:], g_, b_, self.Wkv["Wv"][r], self.Wkv["bv"][r], row_map=hm)
+            o.fold_batch_end()
 
     def pack_attention(self, l, ipw, ipb, ow, ob):
         o, d, w = self.ops, self.d, self.W[l]
@@ -564,6 +566,7 @@ class EncoderEngine:
                 gnv = Sh.get("gnv", (Ms, d.Dp), torch.float32)
                 o.gemm(dV_all, Wkv["Wv"], gnv, Ms, d.Dp, LH, tb=1)
                 o.layernorm_bwd(gnv, nv["x"], nv["mean"], nv["rstd"], self.unit_g, d.D, gxv, True, self.ln_sink[0], self.ln_sink[1])
+            o.fold_batch_begin("bwd")
             for l in range(self.L):                 # gradients of (W_k', b_k') -> W_k, b_k and the layer's LayerNorm affine
                 ipw, ipb, g_, b_ = self.P[l]
                 G = self.G[l]
@@ -572,6 +575,7 @@ class EncoderEngine:
                               G["ln_g"][self.kv_ln], G["ln_b"][self.kv_ln], row_map=hm)
                 o.ln_fold_bwd(ipw[2 * d.D:], g_, b_, Gkv["Wv"][r], Gkv["bv"][r], G["Wqkv"][2 * d.HP:], G["bqkv"][2 * d.HP:],
                               G["ln_g"][self.kv_ln], G["ln_b"][self.kv_ln], row_map=hm)
+            o.fold_batch_end()
         scale = math.sqrt(d.D)
         if not self.with_embed:
             if d_src_q is not None:

@@ -156,15 +156,48 @@ class CudaOps:
                                                  _ptr(cast_out), _dt(cast_out) if cast_out is not None else 0, _drop(cast_drop), self._s()),
                  "layernorm_bwd")
 
+    def fold_batch_begin(self, mode):
+        """collect ln_fold_fwd / ln_fold_bwd calls and run them as ONE launch at fold_batch_end() (mode "fwd" | "bwd")"""
+        self._fold = (mode, [])
+
+    def fold_batch_end(self):
+        import numpy as np
+        mode, items = self._fold
+        self._fold = None
+        if not items:
+            return
+        sig = ("fold", mode) + tuple(items)
+        tab = self._tables.get(sig)
+        if tab is None:
+            dt = np.dtype([(n, "u8") for n in ("W", "bias", "gamma", "beta", "Wp", "bp", "gWf", "gbf", "gW", "gb", "dgamma", "dbeta")] +
+                          [(n, "i4") for n in ("rows", "cols", "ldw", "ldp", "ldf", "ldg", "row_dh", "row_dhp", "wp_dtype", "pad")], align=True)
+            assert dt.itemsize == 136
+            arr = np.zeros(len(items), dtype=dt)
+            for i, it in enumerate(items):
+                arr[i] = it
+            tab = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
+            self._tables[sig] = tab
+        self._ck(self.lib.bpm_ln_fold_batch(tab.data_ptr(), len(items), max(it[12] for it in items), 0 if mode == "fwd" else 1, self._s()),
+                 "ln_fold_batch")
+
     def ln_fold_fwd(self, W, bias, gamma, beta, Wp, bp, row_map=(0, 0)):
         """Wp[map(i), :cols] = W[i] * gamma;  bp[map(i)] = bias[i] + W[i] . beta   (W, bias, gamma, beta fp32 reference layout)"""
         assert W.dtype == torch.float32 and W.stride(1) == 1 and Wp.stride(1) == 1 and bp.dtype == torch.float32
+        if getattr(self, "_fold", None) is not None:
+            self._fold[1].append((W.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), Wp.data_ptr(), bp.data_ptr(), 0, 0, 0, 0, 0, 0,
+                                  W.shape[0], W.shape[1], W.stride(0), Wp.stride(0), 0, 0, row_map[0], row_map[1], _dt(Wp), 0))
+            return
         self._ck(self.lib.bpm_ln_fold_fwd(W.data_ptr(), W.stride(0), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), W.shape[0], W.shape[1],
                                           row_map[0], row_map[1], Wp.data_ptr(), _dt(Wp), Wp.stride(0), bp.data_ptr(), self._s()), "ln_fold_fwd")
 
     def ln_fold_bwd(self, W, gamma, beta, gWf, gbf, gW, gb, dgamma, dbeta, row_map=(0, 0)):
         """gW += gWf * gamma + gbf (x) beta, gb += gbf (padded fp32 accumulators); dgamma / dbeta (fp32) accumulated"""
         assert gW.dtype == torch.float32 and gW.stride(1) == 1 and gWf.dtype == torch.float32 and gWf.stride(1) == 1
+        if getattr(self, "_fold", None) is not None:
+            self._fold[1].append((W.data_ptr(), 0, gamma.data_ptr(), beta.data_ptr(), 0, 0, gWf.data_ptr(), gbf.data_ptr(), gW.data_ptr(), gb.data_ptr(),
+                                  dgamma.data_ptr(), dbeta.data_ptr(), W.shape[0], W.shape[1], W.stride(0), 0, gWf.stride(0), gW.stride(0), row_map[0],
+                                  row_map[1], 0, 0))
+            return
         self._ck(self.lib.bpm_ln_fold_bwd(W.data_ptr(), W.stride(0), gamma.data_ptr(), beta.data_ptr(), W.shape[0], W.shape[1], row_map[0],
                                           row_map[1], gWf.data_ptr(), gWf.stride(0), gbf.data_ptr(), gW.data_ptr(), gW.stride(0), gb.data_ptr(),
                                           dgamma.data_ptr(), dbeta.data_ptr(), self._s()), "ln_fold_bwd")

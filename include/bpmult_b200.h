@@ -115,6 +115,15 @@ int bpm_ln_fold_bwd(const float* W, int ldw, const float* gamma, const float* be
                     const float* gWf, int ldf, const float* gbf, float* gW, int ldg, float* gb, float* dgamma, float* dbeta,
                     void* stream);
 
+/* batched form: a device table of problems (mode 0 = fwd uses W, bias, gamma, beta -> Wp, bp; mode 1 = bwd uses W, gamma, beta, gWf, gbf
+ * -> gW, gb, dgamma, dbeta), one launch; max_rows = largest `rows` in the table */
+typedef struct {
+  const float* W; const float* bias; const float* gamma; const float* beta; void* Wp; float* bp;
+  const float* gWf; const float* gbf; float* gW; float* gb; float* dgamma; float* dbeta;
+  int32_t rows, cols, ldw, ldp, ldf, ldg, row_dh, row_dhp, wp_dtype, pad_;
+} bpm_fold_desc_t;
+int bpm_ln_fold_batch(const bpm_fold_desc_t* descs_dev, int n, int max_rows, int mode, void* stream);
+
 /* ---- GEMM with fused epilogue: F.linear (multihead_attention.py:152-158), fc1/fc2 (transformer.py:186-190),
  *      out_proj (multihead_attention.py:130), Conv1d k=1 (mmtr.py:748-750), GMU linears (mmtr.py:190-194) ---------
  * C[M,N] = epi( op(A)[M,K] * op(B)[K,N] ).  ta = 0: A stored [M,K] (pitch lda); ta = 1: A stored [K,M].

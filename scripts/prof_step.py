@@ -1,0 +1,41 @@
+"""Per-kernel time breakdown of one training step with torch.profiler (CUPTI kernel durations, no replay / serialisation):
+a cheap complement to the ncu launch list (scripts/gpu_profile.sh)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+os.environ["BPM_NO_GRAPH"] = "1"
+import bench  # noqa: E402
+from bpmult_b200 import MultiprojectionMMTransformer3DGMUClf  # noqa: E402
+from bpmult_b200 import Trainer  # noqa: E402
+
+torch.manual_seed(0)
+args = bench.cfg2_args()
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+dev = torch.device("cuda", 0)
+model = MultiprojectionMMTransformer3DGMUClf(args, precision="bf16").to(dev)
+model.train()
+tr = Trainer(model, lr=1e-3)
+g = torch.Generator().manual_seed(2024)
+host = list(bench.synth_batch(args, B, 2024))
+devb = [t.to(dev) for t in host]
+for _ in range(3):
+    tr.step_device(*devb)
+torch.cuda.synchronize()
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    tr.step_device(*devb)
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+agg = {}
+for e in ev:
+    n = e.name.split("(")[0][:60]
+    a = agg.setdefault(n, [0.0, 0])
+    a[0] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+    a[1] += 1
+tot = sum(v[0] for v in agg.values())
+print("kernels: %d   summed device time: %.2f ms" % (len(ev), tot / 1000))
+for n, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:28]:
+    print("%-62s %9.3f ms %5.1f%% %6d launches %8.2f us" % (n, t / 1000, 100 * t / tot, c, t / c))

@@ -78,6 +78,12 @@ class EmuOps:
         pass
 
     # ------------------------------------------------------------------ weight staging
+    def fold_batch_begin(self, mode):
+        pass
+
+    def fold_batch_end(self):
+        pass
+
     def ln_fold_fwd(self, W, bias, gamma, beta, Wp, bp, row_map=(0, 0)):
         r = _remap(W.shape[0], *row_map)
         Wp[r, :W.shape[1]] = (W * gamma.unsqueeze(0)).to(Wp.dtype)
