@@ -45,7 +45,7 @@ struct TcGemmParams {
   int in_mode;            // 0 none, 1 residual (added), 2 gate (relu-backward mask from a saved activation)
   int reduce_add;
   float* colsum;          // fused bias gradient (wgrad only), or null
-  int dbg;                // diagnostic knobs (bpm_debug_set slot 0): 1 no TMA loads, 2 no MMAs, 4 no epilogue math, 8 no staging/store, 16 no tcgen05.ld, 32 MMA issuer skips the full-barrier wait, 64 no empty-barrier traffic
+  int dbg;                // diagnostic knobs (bpm_debug_set slot 0): 1 no TMA loads, 2 no MMAs, 4 no epilogue math, 8 no staging/store, 16 no tcgen05.ld, 32 MMA issuer skips the full-barrier wait, 64 no empty-barrier traffic, 128 never pair CTAs
   const float* bias; float alpha; int act; float gate_scale; int ldc;
   bpm_dropout_t drop;
 };
@@ -75,7 +75,10 @@ template <int CB> __device__ __forceinline__ uint32_t swz_off(int r, int u) {
 
 // ELEM: bytes per output element (2 = bf16, 4 = fp32); CB: bytes per row of one epilogue chunk (128, or 64 when BN * ELEM is not
 // a multiple of 128).  CW = CB / ELEM accumulator columns per chunk.
-template <int ELEM, int CB>
+// CG: 1 = one CTA per tile (M = 128);  2 = CTA pair (cluster of 2, tcgen05 cta_group::2): the pair owns a 256-row tile, each CTA loads
+// its 128 rows of A and HALF of the B tile, so the per-SM operand traffic from L2 (the measured bound of the 1-CTA main loop,
+// ~64 B/clk/SM) drops by a third; the leader CTA issues the MMAs, both CTAs run producer and epilogue warps on their own halves.
+template <int ELEM, int CB, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                const __grid_constant__ CUtensorMap tmI, const TcGemmParams p) {
@@ -102,20 +105,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb_total = (p.K + TC_BK - 1) / TC_BK;
-  const int tiles_mn = p.gx * p.gy;
+  const int tiles_mn = p.gx * p.gy;                  // p.gy counts (CG * 128)-row tiles
   const int total_tiles = tiles_mn * p.split;
   const int acc_stride = p.tmem_cols >> 1;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;       // 0 = leader of the pair
+  const int first_tile = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
+  const int m_sub = (int)cta_rank * TC_BM;                          // this CTA's rows inside the tile
+  const int bn_cta = p.BN / CG;                                     // B columns held by this CTA
+  const int n_sub = (int)cta_rank * bn_cta;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
     if (p.in_mode) tma_prefetch_desc(&tmI);
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), TC_EPI_WARPS); }
+    for (int a = 0; a < 2; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), CG * TC_EPI_WARPS); }
     for (int w = 0; w < TC_EPI_WARPS; w++)
       for (int b = 0; b < p.nb; b++) mbar_init(in_full(w, b), 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2cta(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  }
   if (warp >= 2 && p.colsum != nullptr) {                                   // 16 x 64 tile of bf16 ones (B operand of the colsum MMA)
     uint32_t* o = (uint32_t*)(base_gen + misc);
     for (int c = threadIdx.x - 64; c < 512; c += 32 * TC_EPI_WARPS) o[c] = 0x3F803F80u;
@@ -123,6 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();               // the peer's barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
   pdl_wait();                                   // everything above overlapped the previous kernel's tail; global memory from here on
@@ -130,12 +142,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
     {
-      const int b_chunks = (p.BN + 63) / 64;
+      const int b_chunks = (bn_cta + 63) / 64;
       const uint32_t tx = (uint32_t)stage_bytes;
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM, z = t / tiles_mn;
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
+        const int n0 = (t % p.gx) * p.BN + n_sub, m0 = ((t / p.gx) % p.gy) * (CG * TC_BM) + m_sub, z = t / tiles_mn;
         const int kb0 = z * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; kb++) {
           if (!(p.dbg & 64)) mbar_wait(empty_bar(s), ph ^ 1u);
@@ -144,7 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (elect_one()) {
             if (p.dbg & 1) {
               mbar_arrive(fb);
-            } else {
+            } else if (CG == 1) {
               mbar_expect_tx(fb, tx);
               const int k = kb * TC_BK;
               if (!p.a_mn) tma_load_2d(sa, &tmA, fb, k, m0);                                  // box {64 k, 128 m}
@@ -152,6 +164,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (!p.b_mn) tma_load_2d(sb, &tmB, fb, k, n0);                                  // box {64 k, BN n}
               else
                 for (int c = 0; c < b_chunks; c++) tma_load_2d(sb + c * 8192, &tmB, fb, n0 + 64 * c, k);   // box {64 n, 64 k}
+            } else {
+              // pair: the leader's barrier collects the bytes of BOTH CTAs (the leader alone arrives, expecting 2x; each CTA's loads
+              // land in its own shared memory and complete on the leader's barrier)
+              if (cta_rank == 0) mbar_expect_tx(fb, 2 * tx);
+              const uint32_t fl = mapa_rank(fb, 0);                                           // the leader's full barrier
+              const int k = kb * TC_BK;
+              if (!p.a_mn) tma_load_2d_2cta(sa, &tmA, fl, k, m0);
+              else { tma_load_2d_2cta(sa, &tmA, fl, m0, k); tma_load_2d_2cta(sa + 8192, &tmA, fl, m0 + 64, k); }
+              if (!p.b_mn) tma_load_2d_2cta(sb, &tmB, fl, k, n0);                             // box {64 k, BN/2 n}
+              else
+                for (int c = 0; c < b_chunks; c++) tma_load_2d_2cta(sb + c * 8192, &tmB, fl, n0 + 64 * c, k);
             }
           }
           __syncwarp();
@@ -160,8 +183,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (converged warp; one elected lane issues each k-block's batch) =====================
-    {
+    // ===================== MMA issuer (converged warp; one elected lane issues each k-block's batch); pair: leader CTA only =====================
+    if (CG == 1 || cta_rank == 0) {
       // descriptor templates: K-major SW128 (LBO 16, SBO 1024; +32 B per k16 step) or MN-major (LBO BK*128, SBO 1024; +2048 B per step)
       const uint64_t da_t = p.a_mn ? umma_desc(0, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(0, 16, 1024, BPM_SWZ_128B);
       const uint64_t db_t = p.b_mn ? umma_desc(0, TC_BK * 128, 1024, BPM_SWZ_128B) : umma_desc(0, 16, 1024, BPM_SWZ_128B);
@@ -170,16 +193,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool no_mma = (p.dbg & 2) != 0;
       int s = 0, tc = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tc++) {
-        const int z = t / tiles_mn;
-        const int kb0 = z * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-        const bool do_colsum = p.colsum != nullptr && (t % p.gx) == 0;
+      // tile state is prepared one tile AHEAD (while the tensor core still has the last k-block of the current tile queued): the
+      // divisions and the accumulator hand-shake of a tile boundary would otherwise idle the MMA pipe for several hundred cycles
+      int t = first_tile;
+      int kb0 = 0, kb1 = 0;
+      bool do_colsum = false;
+      auto tile_setup = [&](int tt, int tcc) {
+        const int z = tt / tiles_mn;
+        kb0 = z * p.kb_per_split;
+        kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        do_colsum = p.colsum != nullptr && (tt % p.gx) == 0;
+        mbar_wait(tmem_empty(tcc & 1), ((uint32_t)(tcc >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+        tc_fence_after();
+      };
+      if (t < total_tiles) tile_setup(t, 0);
+      while (t < total_tiles) {
         const int a = tc & 1;
         const uint32_t acc = tmem_base + (uint32_t)(a * acc_stride);
-        mbar_wait(tmem_empty(a), ((uint32_t)(tc >> 1) & 1u) ^ 1u);           // the epilogue has drained this accumulator
-        tc_fence_after();
+        const int kb_end = kb1;
+        const bool colsum_now = do_colsum;
         uint32_t accum = 0;
-        for (int kb = kb0; kb < kb1; kb++) {
+        for (int kb = kb0; kb < kb_end; kb++) {
+          if (kb == kb_end - 1 && t + tile_step < total_tiles) tile_setup(t + tile_step, tc + 1);
           if (!(p.dbg & 32)) {
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
@@ -190,20 +225,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!no_mma) {
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; k++) {
-                umma_bf16(acc, da, db, p.idesc, accum | (uint32_t)k);
+                if (CG == 2) umma_bf16_2cta(acc, da, db, p.idesc, accum | (uint32_t)k);
+                else umma_bf16(acc, da, db, p.idesc, accum | (uint32_t)k);
                 // column sums of dY: dY^T (this A tile) times a tile of ones -> 16 identical columns behind the accumulator
-                if (do_colsum) umma_bf16(acc + p.BN, da, d_ones + 2 * k, p.idesc_ones, accum | (uint32_t)k);
+                if (colsum_now) {
+                  if (CG == 2) umma_bf16_2cta(acc + p.BN, da, d_ones + 2 * k, p.idesc_ones, accum | (uint32_t)k);
+                  else umma_bf16(acc + p.BN, da, d_ones + 2 * k, p.idesc_ones, accum | (uint32_t)k);
+                }
                 da += da_k; db += db_k;
               }
             }
-            if (!(p.dbg & 64)) umma_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+            if (!(p.dbg & 64)) {                                      // frees the smem slot (in both CTAs) once these MMAs have read it
+              if (CG == 2) umma_commit_2cta(empty_bar(s));
+              else umma_commit(empty_bar(s));
+            }
           }
           __syncwarp();
           accum = 1;
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        if (elect_one()) umma_commit(tmem_full(a));              // accumulator complete
+        if (elect_one()) {                                        // accumulator complete (both CTAs' epilogues)
+          if (CG == 2) umma_commit_2cta(tmem_full(a));
+          else umma_commit(tmem_full(a));
+        }
         __syncwarp();
+        t += tile_step;
+        tc++;
       }
     }
   } else {
@@ -224,15 +271,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto chunk_ok = [&](int t, int c) { return c < p.n_chunks && (t % p.gx) * p.BN + c * CW < p.N; };
     auto advance = [&](int& t, int& c) {
       c += 2;
-      while (t < total_tiles && !chunk_ok(t, c)) { t += gridDim.x; c = half; }
+      while (t < total_tiles && !chunk_ok(t, c)) { t += tile_step; c = half; }
     };
     auto issue_in = [&](int t, int c, int idx) {                           // elected lane only
       const int b = idx % nb;
-      const int n = (t % p.gx) * p.BN + c * CW, m = ((t / p.gx) % p.gy) * TC_BM + quarter * 32;
+      const int n = (t % p.gx) * p.BN + c * CW, m = ((t / p.gx) % p.gy) * (CG * TC_BM) + m_sub + quarter * 32;
       mbar_expect_tx(in_full(ew, b), (uint32_t)EB);
       tma_load_2d(ebuf_s + b * EB, &tmI, in_full(ew, b), n, m);
     };
-    int pt = blockIdx.x, pc = half - 2, issued = 0;                        // prefetch cursor
+    int pt = first_tile, pc = half - 2, issued = 0;                        // prefetch cursor
     if (p.in_mode) {
       advance(pt, pc);
       for (int i = 0; i < dist && pt < total_tiles; i++) {
@@ -244,8 +291,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     int done = 0, tc = 0;                                                  // chunks processed by this warp; tiles seen
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tc++) {
-      const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * TC_BM + quarter * 32;
+    for (int t = first_tile; t < total_tiles; t += tile_step, tc++) {
+      const int n0 = (t % p.gx) * p.BN, m0 = ((t / p.gx) % p.gy) * (CG * TC_BM) + m_sub + quarter * 32;
       const int row = m0 + lane;
       const int a = tc & 1;
       const uint32_t acc = tmem_base + (uint32_t)(a * acc_stride) + lane_off;
@@ -263,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(a));
+        if (lane == 0) { if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tmem_empty(a), 0); else mbar_arrive(tmem_empty(a)); }
         continue;
       }
       for (int c = half; c <= last_c; c += 2, done++) {
@@ -286,7 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           tc_fence_before();                                                // this warp's part of the accumulator is in registers
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty(a));
+          if (lane == 0) { if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tmem_empty(a), 0); else mbar_arrive(tmem_empty(a)); }
           if (do_colsum && row < p.M) atomicAdd(p.colsum + row, cs0);
         }
         // ---- bias, alpha, relu, dropout
@@ -402,7 +449,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (CG == 2) cluster_sync_all();               // no CTA of the pair may exit (or free TMEM) while the other can still signal it
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
 
 // ---------------------------------------------------------------- host
@@ -457,16 +508,16 @@ static int pick_bn(int N, int max_bn) {
   return bn < 32 ? 32 : bn;
 }
 
-template <int ELEM, int CB>
+template <int ELEM, int CB, int CG>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmI, const TcGemmParams& p, int ctas,
                      size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ELEM, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ELEM, CB, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { bpm_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
     attr_set = true;
   }
-  cudaError_t le = bpm_launch(gemm_tc_kernel<ELEM, CB>, dim3(ctas), dim3(TC_THREADS), smem, stream, tmA, tmB, tmC, tmI, p);
+  cudaError_t le = bpm_launch_cluster(CG, gemm_tc_kernel<ELEM, CB, CG>, dim3(ctas), dim3(TC_THREADS), smem, stream, tmA, tmB, tmC, tmI, p);
   if (le != cudaSuccess) { bpm_set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
 }
@@ -494,10 +545,16 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   int max_bn = p.colsum ? 224 : 256;               // 2 x (224 + 16) TMEM columns still fit in 512
   if (bpm_debug_get(2) >= 32) max_bn = min(max_bn, bpm_debug_get(2));
   p.BN = pick_bn(g->N, max_bn);
+  // CTA pairs (256-row tiles) when the row count does not waste much more than 128-row tiles would (bpm_debug slot 0 bit 128: off)
+  const int waste1 = bpm_cdiv(g->M, TC_BM) * TC_BM, waste2 = bpm_cdiv(g->M, 2 * TC_BM) * 2 * TC_BM;
+  // ... and the main loop is long enough to matter: with K <= 384 the kernel is bound by its epilogue and pairing only couples the two
+  // CTAs' epilogues (measured: fc1 45 -> 50 us paired, fc2 49 -> 44 us, dgrad K = 1216 41 -> 34 us)
+  const int cg = (!(p.dbg & 128) && g->M > TC_BM && waste2 * 20 <= waste1 * 21 && bpm_num_sms() % 2 == 0 && (g->K >= 768 || (p.dbg & 256))) ? 2 : 1;
+  const int bn_cta = p.BN / cg;                     // B columns per CTA (BN is a multiple of 32)
   p.a_mn = g->ta ? 1 : 0;
   p.b_mn = g->tb ? 1 : 0;
   p.a_bytes = TC_BM * TC_BK * 2;
-  p.b_bytes = p.b_mn ? bpm_cdiv(p.BN, 64) * 8192 : bpm_cdiv(p.BN * 128, 1024) * 1024;
+  p.b_bytes = p.b_mn ? bpm_cdiv(bn_cta, 64) * 8192 : bpm_cdiv(bn_cta * 128, 1024) * 1024;
   const int stage_bytes = p.a_bytes + p.b_bytes;
   p.in_mode = g->residual ? 1 : (g->gate ? 2 : 0);
   p.reduce_add = g->accumulate ? 1 : 0;
@@ -516,11 +573,11 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   // two accumulators (one per in-flight tile); each BN (+16 for the fused column sum) columns wide
   p.tmem_cols = 64;
   while (p.tmem_cols < 2 * (p.BN + (p.colsum ? 16 : 0))) p.tmem_cols *= 2;
-  p.idesc = umma_idesc_bf16(TC_BM, p.BN, p.a_mn, p.b_mn);
-  p.idesc_ones = umma_idesc_bf16(TC_BM, 16, p.a_mn, 0);
+  p.idesc = umma_idesc_bf16(cg * TC_BM, p.BN, p.a_mn, p.b_mn);
+  p.idesc_ones = umma_idesc_bf16(cg * TC_BM, 16, p.a_mn, 0);
   p.bias = g->bias; p.alpha = g->alpha; p.act = g->act; p.gate_scale = g->gate_scale; p.ldc = g->ldc; p.drop = g->drop;
   int num_kb = bpm_cdiv(g->K, TC_BK);
-  int gx = bpm_cdiv(g->N, p.BN), gy = bpm_cdiv(g->M, TC_BM);
+  int gx = bpm_cdiv(g->N, p.BN), gy = bpm_cdiv(g->M, cg * TC_BM);
   int split = 1;
   if (g->accumulate) {
     if (g->split_k > 0) {
@@ -528,7 +585,7 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
     } else {
       // split K so that the persistent CTAs finish together: minimise (rounds of tiles per SM) x (k-blocks per tile + a few
       // k-block times of per-tile epilogue), instead of leaving a half-empty last round
-      const int sms = bpm_num_sms(), tiles_mn = gx * gy;
+      const int sms = bpm_num_sms() / cg, tiles_mn = gx * gy;
       int best_cost = 1 << 30;
       for (int s_ = 1; s_ <= max(1, min(num_kb / 4, (4 * sms) / tiles_mn)); s_++) {
         const int kbps = bpm_cdiv(num_kb, s_), real = bpm_cdiv(num_kb, kbps);
@@ -552,7 +609,7 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
     int rc = bpm_make_tmap_bf16(&tmA, g->A, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     // B: tb == 0 -> stored [N, K]: dims {K, N}, box {64, BN}.  tb == 1 -> stored [K, N]: dims {N, K}, box {64, 64}
-    if (!p.b_mn) { dims[0] = g->K; dims[1] = g->N; box[0] = TC_BK; box[1] = p.BN; }
+    if (!p.b_mn) { dims[0] = g->K; dims[1] = g->N; box[0] = TC_BK; box[1] = bn_cta; }
     else { dims[0] = g->N; dims[1] = g->K; box[0] = 64; box[1] = TC_BK; }
     str[0] = (uint64_t)g->ldb * 2;
     rc = bpm_make_tmap_bf16(&tmB, g->B, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -565,8 +622,13 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   size_t smem = (size_t)p.ring_bytes + TC_EPI_WARPS * p.nb * eb + fixed;
   BPM_REQUIRE(smem <= 227 * 1024 && p.tmem_cols <= 512, "gemm_tc: smem %zu / tmem %d too large", smem, p.tmem_cols);
   int total_tiles = gx * gy * split;
-  int ctas = min(total_tiles, bpm_num_sms());
-  if (elem == 4) return launch_tc<4, 128>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
-  if (cb == 128) return launch_tc<2, 128>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
-  return launch_tc<2, 64>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+  int ctas = cg * min(total_tiles, bpm_num_sms() / cg);
+  if (cg == 2) {
+    if (elem == 4) return launch_tc<4, 128, 2>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+    if (cb == 128) return launch_tc<2, 128, 2>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+    return launch_tc<2, 64, 2>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+  }
+  if (elem == 4) return launch_tc<4, 128, 1>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+  if (cb == 128) return launch_tc<2, 128, 1>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+  return launch_tc<2, 64, 1>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
 }

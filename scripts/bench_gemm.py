@@ -79,6 +79,10 @@ cases = [
     case("wgrad Wq 384 x320 x M colsum", d.HP, d.Dp, M, ta=1, tb=1, out_dtype=torch.float32, acc=True, colsum=True),
 ]
 knobs = [0] if len(sys.argv) < 2 else [int(x) for x in sys.argv[1].split(",")]
+if len(sys.argv) > 2:
+    ops.lib.bpm_debug_set(2, int(sys.argv[2]))      # max BN override
+if len(sys.argv) > 3:
+    ops.lib.bpm_debug_set(3, int(sys.argv[3]))      # staging buffers per epilogue warp
 print("%-40s" % "case" + "".join("  dbg=%-3d us (TF/s)" % k for k in knobs))
 for name, fn, fl in cases:
     row = "%-40s" % name
