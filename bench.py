@@ -165,6 +165,13 @@ def time_kernel(fn, n_rot, iters=20, warm=3):
     return e0.elapsed_time(e1) * 1e-3 / iters
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels below at the cfg-2 shape, from the `ncu --set full` captures of
+# this round (profiles/r01_ncu_full_summary.txt; scripts/gpu_ncu_full.sh).  Writes still resident in the 126 MB L2 when the kernel ends
+# are not counted by the DRAM counters, so output-heavy kernels show less traffic than their algorithmic bytes.
+NCU_DRAM_BYTES = {"xattn_bwd": 104.0e6 + 32.1e6, "xattn_fwd": 76.3e6 + 6.4e6, "gemm_fc1": 21.8e6 + 22.0e6, "layernorm_fwd": 42.0e6 + 0.3e6}
+MUFU_PER_CLK_SM = 16          # ex2 throughput of one B200 SM (guides/B300_MICROARCH: B300 has 2x this)
+
+
 def kernel_rooflines(ops, args, B, peaks):
     from bpmult_b200.engine import Dims
     from bpmult_b200.ops import Drop
@@ -213,6 +220,16 @@ def kernel_rooflines(ops, args, B, peaks):
     by = M * d.D * (4 + 2)
     out["layernorm_fwd"] = {"bound": "hbm", "achieved": by / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / t / 1e9 / peaks["hbm_gbs"],
                             "us": t * 1e6, "traffic": None, "note": "algorithmic rows*D*(4+2) B, rows=%d D=%d" % (M, d.D)}
+    for kname, v in out.items():
+        v["traffic"] = NCU_DRAM_BYTES.get(kname)
+    # the attention kernels are bounded by exponentials, not by the tensor pipe (head dim 32): report that bound beside the tensor one
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    mufu_peak = MUFU_PER_CLK_SM * sms * 1.965e9
+    n_exp = B * d.H * T * T * rho
+    for kname in ("xattn_fwd", "xattn_bwd"):
+        tt = out[kname]["us"] * 1e-6
+        out[kname]["exp_bound"] = {"achieved": n_exp / tt / 1e12, "peak": mufu_peak / 1e12, "unit": "Texp/s", "frac": n_exp / tt / mufu_peak,
+                                   "note": "one ex2 per unmasked score; peak = 16 /clk/SM x %d SMs x 1.965 GHz" % sms}
     return out
 
 
