@@ -97,39 +97,44 @@ extern "C" int bpm_unpack_matrix(const float* src_p, int rows_p, int cols_p, flo
 }
 
 __global__ void remap_batch_kernel(const bpm_remap_desc_t* __restrict__ descs, int mode) {
+  // one block per (padded / reference) destination row: the row mapping is computed once per row, the column mapping with 32-bit
+  // arithmetic once per element; threads run along the row (coalesced on both sides up to the 25 -> 32 head padding)
   const bpm_remap_desc_t d = descs[blockIdx.y];
-  if (mode == 0) {                                   // pack: one thread per destination (padded) element
-    int64_t n = (int64_t)d.rows_p * d.cols_p;
-    const float* src = (const float*)d.src;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      int rp = (int)(i / d.cols_p), cp = (int)(i % d.cols_p);
-      int r = rp, c = cp;
-      bool ok = true;
-      if (d.row_dh > 0) { int h = rp / d.row_dhp, j = rp % d.row_dhp; ok = ok && j < d.row_dh; r = h * d.row_dh + j; }
-      if (d.col_dh > 0) { int h = cp / d.col_dhp, j = cp % d.col_dhp; ok = ok && j < d.col_dh; c = h * d.col_dh + j; }
-      ok = ok && r < d.rows && c < d.cols;
-      float v = ok ? src[(int64_t)r * d.ld_src + c] : 0.f;
-      int64_t o = (int64_t)rp * d.ld_dst + cp;
-      if (d.dst_dtype == BPM_BF16) ((bf16*)d.dst)[o] = __float2bfloat16_rn(v);
-      else ((float*)d.dst)[o] = v;
+  const float* src = (const float*)d.src;
+  if (mode == 0) {                                   // pack: destination = padded layout
+    for (int rp = blockIdx.x; rp < d.rows_p; rp += gridDim.x) {
+      int r = rp;
+      bool rok = true;
+      if (d.row_dh > 0) { int h = rp / d.row_dhp, j = rp - h * d.row_dhp; rok = j < d.row_dh; r = h * d.row_dh + j; }
+      rok = rok && r < d.rows;
+      const float* srow = src + (int64_t)r * d.ld_src;
+      const int64_t ob = (int64_t)rp * d.ld_dst;
+      for (int cp = threadIdx.x; cp < d.cols_p; cp += blockDim.x) {
+        int c = cp;
+        bool ok = rok;
+        if (d.col_dh > 0) { int h = cp / d.col_dhp, j = cp - h * d.col_dhp; ok = ok && j < d.col_dh; c = h * d.col_dh + j; }
+        ok = ok && c < d.cols;
+        float v = ok ? srow[c] : 0.f;
+        if (d.dst_dtype == BPM_BF16) ((bf16*)d.dst)[ob + cp] = __float2bfloat16_rn(v);
+        else ((float*)d.dst)[ob + cp] = v;
+      }
     }
-  } else {                                           // unpack: one thread per destination (reference-layout) element
-    int64_t n = (int64_t)d.rows * d.cols;
-    const float* src = (const float*)d.src;
+  } else {                                           // unpack: destination = reference layout
     float* dst = (float*)d.dst;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      int r = (int)(i / d.cols), c = (int)(i % d.cols);
-      int rp = remap_fwd(r, d.row_dh, d.row_dhp), cp = remap_fwd(c, d.col_dh, d.col_dhp);
-      float v = src[(int64_t)rp * d.ld_src + cp] * d.scale;
-      float* o = dst + (int64_t)r * d.ld_dst + c;
-      *o = d.accumulate ? *o + v : v;
+    for (int r = blockIdx.x; r < d.rows; r += gridDim.x) {
+      const float* srow = src + (int64_t)remap_fwd(r, d.row_dh, d.row_dhp) * d.ld_src;
+      float* orow = dst + (int64_t)r * d.ld_dst;
+      for (int c = threadIdx.x; c < d.cols; c += blockDim.x) {
+        float v = srow[remap_fwd(c, d.col_dh, d.col_dhp)] * d.scale;
+        orow[c] = d.accumulate ? orow[c] + v : v;
+      }
     }
   }
 }
 
 extern "C" int bpm_remap_batch(const bpm_remap_desc_t* descs_dev, int n, int mode, void* stream) {
   BPM_REQUIRE(descs_dev && n > 0 && (mode == 0 || mode == 1), "remap_batch: bad args");
-  dim3 grid(16, n);
+  dim3 grid(32, n);
   remap_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, mode);
   BPM_CHECK_LAUNCH("remap_batch");
   return BPM_OK;
@@ -676,8 +681,9 @@ extern "C" int bpm_bce_fwd_bwd(const float* logits, int ldl, const float* target
 
 // ---------------------------------------------------------------- Adam
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
-                            float b1, float b2, float eps, float gs, const int64_t* __restrict__ step_ptr) {
+                            float b1, float b2, float eps, float gs, const int64_t* __restrict__ step_ptr, const float* __restrict__ lr_ptr) {
   float step = (float)(*step_ptr);
+  if (lr_ptr) lr = *lr_ptr;
   float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
   float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -689,9 +695,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 extern "C" int bpm_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                             float grad_scale, const int64_t* step_ptr, void* stream) {
+                             float grad_scale, const int64_t* step_ptr, const float* lr_ptr, void* stream) {
   BPM_REQUIRE(param && grad && m && v && step_ptr && n > 0, "adam: bad args");
-  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, grad_scale, step_ptr);
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, grad_scale, step_ptr, lr_ptr);
   BPM_CHECK_LAUNCH("adam");
   return BPM_OK;
 }

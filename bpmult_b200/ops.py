@@ -287,9 +287,10 @@ class CudaOps:
         self._ck(self.lib.bpm_bce_fwd_bwd(logits.data_ptr(), logits.stride(0), targets.data_ptr(), _ptr(pos_weight), B, Cc, float(grad_scale),
                                           loss.data_ptr(), dlogits.data_ptr(), self._s()), "bce_fwd_bwd")
 
-    def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t):
+    def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t, lr_t=None):
         self._ck(self.lib.bpm_adam_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), float(lr), float(beta1),
-                                        float(beta2), float(eps), float(grad_scale), step_t.data_ptr(), self._s()), "adam_step")
+                                        float(beta2), float(eps), float(grad_scale), step_t.data_ptr(),
+                                        0 if lr_t is None else lr_t.data_ptr(), self._s()), "adam_step")
 
     def zero_(self, t):
         """memset on the current stream (cudaMemsetAsync through torch; capturable)."""

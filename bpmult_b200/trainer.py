@@ -1,5 +1,6 @@
 """Graph-captured, data-parallel training step for the drop-in model (train.py:341-448 semantics: forward, BCEWithLogits,
-backward, Adam; gradient accumulation = 1).
+backward, Adam; `grad_accum` micro-batches per optimizer step as train.py:390-398; the learning rate lives in device memory so
+a ReduceLROnPlateau scheduler (train.py:128-136, 408) can change it between replays of the captured step -- see `set_lr`).
 
   * one process per GPU; gradients live in ONE flat fp32 buffer laid out in the order the encoders finish their backward
     (wave-2 first), so each encoder's bucket is all-reduced (NCCL, side stream) as soon as its last wgrad has landed, while the
@@ -17,11 +18,14 @@ from .modules import MultiprojectionMMTransformer3DGMUClf
 
 
 class Trainer:
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, pos_weight=None, seed=1234, use_graph=None):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, pos_weight=None, seed=1234, use_graph=None, grad_accum=1):
         assert isinstance(model, MultiprojectionMMTransformer3DGMUClf)
+        assert grad_accum >= 1
         self.model = model
         self.device = next(model.parameters()).device
         self.lr, self.betas, self.eps = lr, betas, eps
+        self.grad_accum, self.micro = int(grad_accum), 0
+        self.lr_t = torch.tensor([lr], dtype=torch.float32, device=self.device)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.eng = model.engine(self.device)
@@ -36,7 +40,7 @@ class Trainer:
         self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
         self.on_gpu = dev.type == "cuda"                     # (CPU only in the gloo host-logic tests, with the ops emulation)
         self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.on_gpu) else None
-        self.graph, self.static, self.shapes = None, None, None
+        self.graphs, self.static, self.shapes = {}, None, None
         self.loss_host = torch.zeros(1, dtype=torch.float32)
         if self.device.type == "cuda":
             self.loss_host = self.loss_host.pin_memory()
@@ -81,9 +85,14 @@ class Trainer:
         self.n_params = total
 
     # ---------------------------------------------------------------- one step (enqueue only)
-    def _enqueue(self, txt, img, audio, tgt):
+    def _enqueue(self, txt, img, audio, tgt, apply=True):
+        """one micro-batch: forward, loss, backward, gradients into the flat buffer; with `apply` also the all-reduces and Adam.
+        With grad_accum > 1 the flat gradient buffer ACCUMULATES over the micro-batches (it is cleared after Adam) and only the
+        last micro-batch reduces it across ranks -- the 1/grad_accum of train.py:391 rides on Adam's gradient scale."""
         eng, o = self.eng, self.ops
-        self.step_t += 1
+        acc = self.grad_accum > 1
+        if apply:
+            self.step_t += 1
         self.seed_t += 1
         eng.pack(self.params)
         logits, _ = eng.forward(txt, img, audio, training=True, seed=0, seed_ptr=self.seed_t)
@@ -93,7 +102,7 @@ class Trainer:
         bucket_of = {b[0]: b for b in self.buckets}
 
         def reduce_bucket(name):
-            if self.world == 1:
+            if self.world == 1 or not apply:
                 return
             _, s, e = bucket_of[name]
             if not self.on_gpu:
@@ -106,23 +115,50 @@ class Trainer:
                 dist.all_reduce(self.flat_g[s:e])
 
         def on_done(enc):
-            eng.enc[enc].unpack_grads(self.grads, "trans_%s." % enc)
+            eng.enc[enc].unpack_grads(self.grads, "trans_%s." % enc, accumulate=acc)
             reduce_bucket(enc)
         eng.backward(dlogits, None, on_done)
         o.batch_begin("unpack", "misc")
         for m, g in eng.gmu.items():
-            g.unpack_grads(self.grads, "gmu_%s." % m)
-        eng.head.unpack_grads(self.grads)
+            g.unpack_grads(self.grads, "gmu_%s." % m, accumulate=acc)
+        eng.head.unpack_grads(self.grads, accumulate=acc)
         for m in "lav":
             if eng.Gproj[m] is not None:
                 gw = self.grads["proj_%s.weight" % m]
-                o.unpack_matrix(eng.Gproj[m], gw.view(gw.shape[0], gw.shape[1]))
+                o.unpack_matrix(eng.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=acc)
         o.batch_end()
+        if not apply:
+            return loss
         reduce_bucket("misc")
         if self.world > 1 and self.on_gpu:
             cur.wait_stream(self.comm)
-        o.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world, self.step_t)
+        o.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
+                    1.0 / (self.world * self.grad_accum), self.step_t, self.lr_t)
+        if acc:
+            self.flat_g.zero_()
         return loss
+
+    # ---------------------------------------------------------------- learning rate / optimizer state (train.py:361-379,408,417-425)
+    def set_lr(self, lr):
+        """takes effect at the next optimizer step, captured graph or not (the kernel reads the rate from device memory)."""
+        self.lr = float(lr)
+        self.lr_t.fill_(self.lr)
+
+    def get_lr(self):
+        return self.lr
+
+    def optimizer_state_dict(self):
+        return dict(step=int(self.step_t.item()), lr=self.lr, betas=self.betas, eps=self.eps, exp_avg=self.flat_m.clone(),
+                    exp_avg_sq=self.flat_v.clone(), seed=int(self.seed_t.item()), micro=self.micro, grad=self.flat_g.clone())
+
+    def load_optimizer_state_dict(self, sd):
+        self.step_t.fill_(sd["step"])
+        self.seed_t.fill_(sd["seed"])
+        self.flat_m.copy_(sd["exp_avg"])
+        self.flat_v.copy_(sd["exp_avg_sq"])
+        self.flat_g.copy_(sd["grad"])
+        self.micro = sd["micro"]
+        self.set_lr(sd["lr"])
 
     # ---------------------------------------------------------------- public API
     def _ensure_static(self, txt, img, audio, tgt):
@@ -132,7 +168,7 @@ class Trainer:
             self.static = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
             self.pinned = [torch.zeros(s, dtype=torch.float32).pin_memory() if self.on_gpu else torch.zeros(s) for s in shapes]
             self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-            self.shapes, self.graph = shapes, None
+            self.shapes, self.graphs = shapes, {}
             self.warm = 0
 
     def step_device(self, txt, img, audio, tgt):
@@ -157,13 +193,15 @@ class Trainer:
         return float(self.loss_host[0])
 
     def _run(self):
+        apply = (self.micro + 1) % self.grad_accum == 0     # train.py:395-398: optimizer step every grad_accum micro-batches
+        self.micro = (self.micro + 1) % self.grad_accum
         if not self.use_graph:
-            self.loss_dev.copy_(self._enqueue(*self.static))
+            self.loss_dev.copy_(self._enqueue(*self.static, apply=apply))
             self.steps_done += 1
             return
-        if self.graph is None:
-            if self.warm < 2:                               # eager warm-up steps (allocate every arena buffer, NCCL init)
-                self.loss_dev.copy_(self._enqueue(*self.static))
+        if apply not in self.graphs:
+            if self.warm < 2 * self.grad_accum:             # eager warm-up steps (allocate every arena buffer, NCCL init)
+                self.loss_dev.copy_(self._enqueue(*self.static, apply=apply))
                 self.warm += 1
                 self.steps_done += 1
                 return
@@ -172,19 +210,23 @@ class Trainer:
             g = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self.loss_dev.copy_(self._enqueue(*self.static))
-                self.graph = g
+                    self.loss_dev.copy_(self._enqueue(*self.static, apply=apply))
+                self.graphs[apply] = g
                 self.launches_per_step = self.ops.launches
             except Exception as e:                         # e.g. a collective that cannot be captured on this stack
                 if self.rank == 0:
                     print("bpmult_b200.Trainer: CUDA-graph capture failed (%s); running eagerly" % str(e).splitlines()[0])
                 self.use_graph = False
                 torch.cuda.synchronize(self.device)
-                self.loss_dev.copy_(self._enqueue(*self.static))
+                self.loss_dev.copy_(self._enqueue(*self.static, apply=apply))
                 self.steps_done += 1
                 return
-        self.graph.replay()
+        self.graphs[apply].replay()
         self.steps_done += 1
+
+    @property
+    def graph(self):
+        return self.graphs.get(True)
 
     def bytes_in(self):
         return sum(t.numel() * 4 for t in self.static)

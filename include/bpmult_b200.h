@@ -204,9 +204,11 @@ int bpm_bce_fwd_bwd(const float* logits, int ldl, const float* targets, const fl
                     float grad_scale, float* loss, float* dlogits, void* stream);
 
 /* ---- optimiser: train.py:123-125 optim.Adam (default betas / eps, no weight decay) ----------------------------
- * step_ptr: device int64 step counter (already incremented); grad_scale multiplies the gradient (1/world, 1/accum). */
+ * step_ptr: device int64 step counter (already incremented); grad_scale multiplies the gradient (1/world, 1/accum).
+ * lr_ptr (nullable): device fp32 learning rate that overrides `lr` -- lets a ReduceLROnPlateau scheduler (train.py:128-136,
+ * 408) change the rate of a step that has been captured into a CUDA graph. */
 int bpm_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                  float eps, float grad_scale, const int64_t* step_ptr, void* stream);
+                  float eps, float grad_scale, const int64_t* step_ptr, const float* lr_ptr, void* stream);
 
 #ifdef __cplusplus
 }

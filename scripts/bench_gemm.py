@@ -66,6 +66,10 @@ def case(name, Mm, N, K, ta=0, tb=0, out_dtype=bf, bias=False, act=0, drop=False
 cases = [
     case("q      M x384 x320 bias", M, d.HP, d.Dp, bias=True),
     case("out    M x320 x384 bias drop res f32", M, d.Dp, d.HP, out_dtype=torch.float32, bias=True, drop=True, res=True),
+    case("out    M x320 x384 plain bf16", M, d.Dp, d.HP),
+    case("out    M x320 x384 plain f32", M, d.Dp, d.HP, out_dtype=torch.float32),
+    case("out    M x320 x384 bias res f32", M, d.Dp, d.HP, out_dtype=torch.float32, bias=True, res=True),
+    case("out    M x320 x384 bias drop f32", M, d.Dp, d.HP, out_dtype=torch.float32, bias=True, drop=True),
     case("fc1    M x1216x320 bias relu drop", M, d.FP, d.Dp, bias=True, act=1, drop=True),
     case("fc1    M x1216x320 bias relu", M, d.FP, d.Dp, bias=True, act=1),
     case("fc1    M x1216x320 plain", M, d.FP, d.Dp),
@@ -84,7 +88,10 @@ if len(sys.argv) > 2:
 if len(sys.argv) > 3:
     ops.lib.bpm_debug_set(3, int(sys.argv[3]))      # staging buffers per epilogue warp
 print("%-40s" % "case" + "".join("  dbg=%-3d us (TF/s)" % k for k in knobs))
+import os
 for name, fn, fl in cases:
+    if os.environ.get("BG_FILTER", "") not in name:
+        continue
     row = "%-40s" % name
     for k in knobs:
         has_in = ("res" in name) or ("gate" in name)

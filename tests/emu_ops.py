@@ -323,8 +323,10 @@ class EmuOps:
         dlogits.zero_()
         dlogits[:, :Cc] = x.grad * grad_scale
 
-    def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t):
+    def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t, lr_t=None):
         step = float(step_t.item())
+        if lr_t is not None:
+            lr = float(lr_t.item())
         g = grad * grad_scale
         m.mul_(beta1).add_(g, alpha=1 - beta1)
         v.mul_(beta2).addcmul_(g, g, value=1 - beta2)

@@ -312,6 +312,14 @@ def test_adam_matches_torch(ops):
         step += 1
         ops.adam_step(p, (g * (i + 1)).cuda(), m, v, 1e-3, 0.9, 0.999, 1e-8, 1.0, step)
     assert max_rel(p, ref.detach()) < 1e-6
+    # the device-resident rate overrides the scalar one
+    lr_t = torch.tensor([2e-3], device="cuda")
+    opt.param_groups[0]["lr"] = 2e-3
+    ref.grad = g
+    opt.step()
+    step += 1
+    ops.adam_step(p, g.cuda(), m, v, 123.0, 0.9, 0.999, 1e-8, 1.0, step, lr_t)
+    assert max_rel(p, ref.detach()) < 1e-6
 
 
 @pytest.mark.parametrize("dtype", [F32, BF16])

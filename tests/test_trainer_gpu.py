@@ -55,6 +55,36 @@ def test_trainer_e2e_host_api_and_dropout_determinism():
     assert len(set(round(x, 6) for x in runs[0])) > 1
 
 
+def test_gradient_accumulation_and_lr_change_under_graph_replay():
+    """train.py:390-398 with gradient_accumulation_steps=2: the accumulate-only and the apply micro-step are two captured graphs;
+    the learning rate is read from device memory, so set_lr() acts on a replayed graph"""
+    cfg = synth.tiny_cfg()
+    txt, img, audio, tgt = [t.cuda() for t in synth.mmtrvat_inputs(cfg, 4, 10, 30, 25)]
+    from bpmult_b200 import Trainer
+    a = _model(cfg, "fp32")
+    opt = torch.optim.Adam([p for p in a.parameters()], lr=1e-3)
+    tr = Trainer(_model(cfg, "fp32"), lr=1e-3, grad_accum=2)
+    la, lb = [], []
+    for it in range(5):                                        # 4 eager micro-steps, then both graphs captured and replayed
+        if it == 3:
+            tr.set_lr(5e-4)
+            opt.param_groups[0]["lr"] = 5e-4
+        opt.zero_grad()
+        loss = torch.nn.BCEWithLogitsLoss()(a(txt, None, None, img, audio), tgt)
+        loss.backward()
+        opt.step()
+        la.append(float(loss))
+        l0 = float(tr.step_device(txt[:2], img[:2], audio[:2], tgt[:2])[0])
+        l1 = float(tr.step_device(txt[2:], img[2:], audio[2:], tgt[2:])[0])
+        lb.append(0.5 * (l0 + l1))
+    assert set(tr.graphs) == {True, False}
+    assert max(abs(x - y) for x, y in zip(la, lb)) < 2e-5, (la, lb)
+    pa, pb = dict(a.named_parameters()), dict(tr.model.named_parameters())
+    num = sum(float((pb[n].detach() - pa[n].detach()).double().pow(2).sum()) for n in pa if pa[n].grad is not None)
+    den = sum(float(pa[n].detach().double().pow(2).sum()) for n in pa if pa[n].grad is not None)
+    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+
+
 def test_encoder_module_on_gpu_bf16_and_fp32():
     from bpmult_b200 import TransformerEncoder
     D, H, L, T, S, B = 300, 12, 2, 50, 70, 3
