@@ -29,6 +29,15 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of work
+__device__ __forceinline__ void ffma2(float& a0, float& a1, float b, float c) {
+  asm("{.reg .b64 x, y, z;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %2};\n mov.b64 z, {%3, %3};\n fma.rn.f32x2 x, x, y, z;\n mov.b64 {%0, %1}, x;}"
+      : "+f"(a0), "+f"(a1) : "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  asm("{.reg .b64 x, y;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %3};\n add.rn.f32x2 x, x, y;\n mov.b64 {%0, %1}, x;}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *(uint32_t*)&v;
@@ -45,13 +54,10 @@ struct AttnFwdSmem {
   static constexpr int TOTAL = BAR + 8 * AF_GROUPS * NBAR_G + 16;
 };
 
-// mask / dropout of one 32-column chunk of a score row (thread = query row qi, keys k0c .. k0c+31)
-template <bool MASKED>
-__device__ __forceinline__ void fwd_mask32(float* sv, int k0c, int row_lim) {
-  if (MASKED) {
+// causal mask of one 32-column chunk of a score row: column c is visible iff c <= lim (lim = last visible key - first key of the chunk)
+__device__ __forceinline__ void fwd_mask32(float* sv, int lim) {
 #pragma unroll
-    for (int c = 0; c < 32; c++) sv[c] = (k0c + c <= row_lim) ? sv[c] : -INFINITY;
-  }
+  for (int c = 0; c < 32; c++) sv[c] = (c <= lim) ? sv[c] : -INFINITY;
 }
 
 __global__ void __launch_bounds__(AF_THREADS, 1)
@@ -193,7 +199,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (!item_of(r, bh, qt)) break;
       const int b = bh / H, h = bh % H, q0 = qt * AT_BM, qi = q0 + rr, nt = tiles_of(qt);
       const int row_lim = (mask_off >= 0) ? min(qi + mask_off, S - 1) : S - 1;     // last visible key of this row
-      const int tile_lim = (mask_off >= 0) ? min(q0 + mask_off, S - 1) : S - 1;     // keys <= tile_lim are visible to every row of the tile
+      // warp-uniform visibility of a 32-key chunk: keys <= vis_all are visible to all 32 rows of this warp, keys > vis_any to none.
+      // Fully masked chunks (a suffix of the tile) cost no loads and no exponentials, fully visible ones no mask arithmetic.
+      const int vis_all = (mask_off >= 0) ? min(q0 + quarter * 32 + mask_off, S - 1) : S - 1;
+      const int vis_any = (mask_off >= 0) ? min(q0 + quarter * 32 + 31 + mask_off, S - 1) : S - 1;
       const uint64_t ebase = ((uint64_t)bh * T + (uint64_t)min(qi, T - 1)) * (uint64_t)S;
       float m = -INFINITY, l = 0.f;
       float oacc[AT_DH];
@@ -201,17 +210,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int d = 0; d < AT_DH; d++) oacc[d] = 0.f;
       for (int j = 0; j < nt; j++, tc++) {
         const int k0 = j * AT_BN;
-        const bool masked = k0 + AT_BN - 1 > tile_lim;
+        const int nvis = max(0, min(AT_BN / 32, (vis_any - k0 + 32) >> 5));   // chunks of this tile with at least one visible key
         mbar_wait(s_full, (uint32_t)tc & 1u);
         tc_fence_after();
         // ---- pass 1: row maximum
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < AT_BN; c += 32) {
+        for (int ci = 0; ci < nvis; ci++) {
+          const int c = ci * 32;
           float sv[32];
           tmem_ld32(tS + lane_off + c, sv);
           tmem_ld_wait();
-          if (masked) fwd_mask32<true>(sv, k0 + c, row_lim);
+          if (k0 + c + 31 > vis_all) fwd_mask32(sv, row_lim - (k0 + c));
           float m4[4] = {sv[0], sv[1], sv[2], sv[3]};
 #pragma unroll
           for (int e = 4; e < 32; e += 4) {
@@ -224,25 +234,44 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // P (single TMEM buffer) is free once the previous tile's PV has been issued AND completed; its result O_{j-1} is then ready too
         if (tc > 0) { mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u); tc_fence_after(); }
         // ---- pass 2: P = exp2(S log2e - m_new), row sum, dropout, packed bf16 back to TMEM
-        float rs = 0.f;
+        float rs0 = 0.f, rs1 = 0.f;
+        if (nvis == 0) {                                                   // nothing of this tile is visible to this warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
+        }
 #pragma unroll 1
-        for (int c = 0; c < AT_BN; c += 32) {
+        for (int ci = 0; ci < AT_BN / 32; ci++) {
+          const int c = ci * 32;
+          uint32_t pk[16];
+          if (ci >= nvis) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) pk[u] = 0u;
+            tmem_st16(tP + lane_off + (uint32_t)(c >> 1), pk);
+            continue;
+          }
           float sv[32];
           tmem_ld32(tS + lane_off + c, sv);
           tmem_ld_wait();
-          if (c + 32 == AT_BN) {                                           // the S tile is in registers / consumed: the next Q K^T may start
+          if (ci + 1 == nvis) {                                            // the S tile is in registers / consumed: the next Q K^T may start
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_free);
           }
-          if (masked) fwd_mask32<true>(sv, k0 + c, row_lim);
+          if (k0 + c + 31 > vis_all) fwd_mask32(sv, row_lim - (k0 + c));
           float r4[4] = {0.f, 0.f, 0.f, 0.f};
+          const float neg_m = -m_new;
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
+            ffma2(sv[e], sv[e + 1], LOG2E_F, neg_m);
+            ffma2(sv[e + 2], sv[e + 3], LOG2E_F, neg_m);
 #pragma unroll
-            for (int u = 0; u < 4; u++) { sv[e + u] = ex2f(fmaf(sv[e + u], LOG2E_F, -m_new)); r4[u] += sv[e + u]; }
+            for (int u = 0; u < 4; u++) sv[e + u] = ex2f(sv[e + u]);
+            fadd2(r4[0], r4[1], sv[e], sv[e + 1]);
+            fadd2(r4[2], r4[3], sv[e + 2], sv[e + 3]);
           }
-          rs += (r4[0] + r4[1]) + (r4[2] + r4[3]);
+          rs0 += r4[0] + r4[2];
+          rs1 += r4[1] + r4[3];
           if (dc.on) {
             // keep decisions of keys k0+c .. k0+c+31 (element index e = ebase + key): one 32-bit word per (query, 32-key group).
             // The 1/(1-p) scale is applied once to the output row (every kept probability of the row shares it).
@@ -267,11 +296,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             if (drop_bits != nullptr && qi < T && k0 + c < S) drop_bits[((int64_t)bh * T + qi) * (int64_t)W + ((k0 + c) >> 5)] = kb;
           }
-          uint32_t pk[16];
 #pragma unroll
           for (int u = 0; u < 16; u++) pk[u] = pack_bf16x2(sv[2 * u], sv[2 * u + 1]);
           tmem_st16(tP + lane_off + (uint32_t)(c >> 1), pk);
         }
+        const float rs = rs0 + rs1;
         l = fmaf(l, alpha, rs);
         m = m_new;
         tmem_st_wait();

@@ -1,6 +1,9 @@
 """mmtrvat (MultiprojectionMMTransformer3DGMUClf, models/mmtr.py:587-866) as an explicit forward / backward schedule over
 EncoderEngine / SeqGmuEngine / HeadEngine.  Owns the per-model buffers; parameters arrive as a dict of reference-named
 fp32 tensors and gradients leave the same way."""
+import contextlib
+import os
+
 import torch
 
 from .engine import Arena, Dims, EncoderEngine, HeadEngine, SeqGmuEngine, round_up
@@ -19,6 +22,44 @@ TARGETS = {"l": ("v_with_a", "a_with_v", "l_with_a2v", "l_with_v2a"),      # mmt
 HEAD_ORDER = ["l", "v", "a"]                                               # gmu([last_h_l, last_h_v, last_h_a]) :857
 
 
+class Lanes:
+    """Independent encoders of a wave are issued round-robin on `n` side streams (fork / join with events; inside the captured
+    step they become parallel branches of the CUDA graph).  The GEMM and attention kernels are persistent with one CTA per SM and
+    a static tile walk, so a kernel whose tile count is not a multiple of the SM count leaves part of the machine idle in its last
+    round (512 tiles on 148 SMs: 4 rounds for 3.46 rounds of work; attention backward: 768 (batch, head) items = 6 rounds for 5.19);
+    with two lanes the CTAs of the other lane's kernel start on the SMs that fall idle.  Every lane owns its scratch arena."""
+
+    def __init__(self, device, n):
+        self.on_gpu = torch.device(device).type == "cuda"
+        self.n = n                                            # (on the CPU the lanes are logical only: same buffers, no streams)
+        self.device = device
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(self.n)] if (self.n > 1 and self.on_gpu) else []
+
+    def on(self, k):
+        return torch.cuda.stream(self.streams[k % self.n]) if self.streams else contextlib.nullcontext()
+
+    def fork(self):
+        """the lanes wait for everything enqueued so far on the current stream"""
+        if self.streams:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            for s in self.streams:
+                s.wait_event(ev)
+
+    def join(self):
+        """the current stream waits for everything enqueued so far on the lanes"""
+        if self.streams:
+            cur = torch.cuda.current_stream(self.device)
+            for s in self.streams:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                cur.wait_event(ev)
+
+    def barrier(self):
+        self.join()
+        self.fork()
+
+
 def attn_dropout_for(name, args):
     """get_network (mmtr.py:691-697): attention dropout is chosen by the SOURCE modality of the stream."""
     src = name.split("_with_")[1][-1]
@@ -32,13 +73,20 @@ class MMTrVatEngine:
         self.d = Dims(D, H)
         self.orig = {"l": args.orig_d_l, "a": args.orig_d_a, "v": args.orig_d_v}
         self.Kp = {m: (self.d.Dp if self.orig[m] == D else round_up(self.orig[m], 64)) for m in "lav"}
-        self.shared = Arena(ops)
+        self.lanes = Lanes(ops.device, int(os.environ.get("BPM_LANES", "2")))
+        self.lane_shared = [Arena(ops) for _ in range(self.lanes.n)]
+        self.shared = self.lane_shared[0]
         self.arena = Arena(ops)
+        # lane of each encoder: wave 1 alternates, the two encoders of a target modality (p, q) sit on different lanes
+        self.lane_of = {n: i % self.lanes.n for i, n in enumerate(WAVE1)}
+        for i, m in enumerate(HEAD_ORDER):
+            u, w, pn, qn = TARGETS[m]
+            self.lane_of[pn], self.lane_of[qn] = (2 * i) % self.lanes.n, (2 * i + 1) % self.lanes.n
         self.enc = {}
         for i, n in enumerate(ENC_NAMES):
             self.enc[n] = EncoderEngine(ops, D, H, L, attn_dropout=attn_dropout_for(n, args), relu_dropout=args.relu_dropout,
                                         res_dropout=args.res_dropout, embed_dropout=args.embed_dropout, attn_mask=args.attn_mask,
-                                        biprojection=False, dtype=dtype, uid=i + 1, shared=self.shared)
+                                        biprojection=False, dtype=dtype, uid=i + 1, shared=self.lane_shared[self.lane_of[n]])
         self.gmu = {}
         for m in "lav":
             self.gmu[m + "_m"] = SeqGmuEngine(ops, D, dtype, True, self.shared, "gmu_%s_m" % m)
@@ -131,15 +179,24 @@ class MMTrVatEngine:
                 P[m] = X
         self.P = P
         h = {}
+        ln = self.lanes
+        ln.fork()
         for n, (qm, km) in WAVE1.items():
-            h[n] = self.enc[n].forward(P[qm], B, nv, src_k=P[km], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
+            with ln.on(self.lane_of[n]):
+                h[n] = self.enc[n].forward(P[qm], B, nv, src_k=P[km], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
+        ln.barrier()                                                            # wave 2 reads wave-1 outputs of either lane
+        for m in HEAD_ORDER:
+            u, w, pn, qn = TARGETS[m]
+            with ln.on(self.lane_of[pn]):
+                h[pn] = self.enc[pn].forward(P[m], B, nv, src_k=h[u], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
+            with ln.on(self.lane_of[qn]):
+                h[qn] = self.enc[qn].forward(P[m], B, nv, src_k=h[w], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
+        ln.join()
         cat = self.head.cat_buf(B)
         self.tops = {}
         for ci, m in enumerate(HEAD_ORDER):
             u, w, pn, qn = TARGETS[m]
-            hp = self.enc[pn].forward(P[m], B, nv, src_k=h[u], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
-            hq = self.enc[qn].forward(P[m], B, nv, src_k=h[w], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
-            h[pn], h[qn] = hp, hq
+            hp, hq = h[pn], h[qn]
             mid = self.gmu[m + "_m"].forward(h[u], h[w], M)                    # "GMU middle"
             a1 = A.get("a1_" + m, (M, d.Dp), self.T_)
             a2 = A.get("a2_" + m, (M, d.Dp), self.T_)
@@ -163,33 +220,46 @@ class MMTrVatEngine:
         M = B * nv
         f32 = torch.float32
         dcat = self.head.backward(dlogits)
-        dP = {m: A.get("dP_" + m, (M, d.Dp), f32) for m in "lav"}
+        ln = self.lanes
+        # every lane accumulates the projection-output gradients in its own buffers (two encoders of different lanes share a query
+        # stream); they are summed once at the end
+        dPl = [{m: A.get("dP%d_%s" % (k, m), (M, d.Dp), f32) for m in "lav"} for k in range(ln.n)]
+        dP = dPl[0]
         dh = {n: A.get("dh_" + n, (M, d.Dp), f32) for n in WAVE1}
-        for t in list(dP.values()) + list(dh.values()):
+        for t in [t for k in range(ln.n) for t in dPl[k].values()] + list(dh.values()):
             o.zero_(t)
         dtop = A.get("dtop", (M, d.Dp), f32)
-        da1 = A.get("da1", (M, d.Dp), f32)
-        da2 = A.get("da2", (M, d.Dp), f32)
-        for ci, m in reversed(list(enumerate(HEAD_ORDER))):
+        da1 = {m: A.get("da1_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
+        da2 = {m: A.get("da2_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
+        for ci, m in reversed(list(enumerate(HEAD_ORDER))):                      # gated fusion units: short, on the main stream
             u, w, pn, qn = TARGETS[m]
             o.zero_(dtop)
             o.pool_bwd(dcat, ci * d.Dp, B, nv, dtop)
-            o.zero_(da1)
-            o.zero_(da2)
-            self.gmu[m].backward(dtop, da1, da2)                                 # d(p+u), d(q+w)
+            o.zero_(da1[m])
+            o.zero_(da2[m])
+            self.gmu[m].backward(dtop, da1[m], da2[m])                           # d(p+u), d(q+w)
             self.gmu[m + "_m"].backward(dtop, dh[u], dh[w])                      # mid consumes u, w directly
-            o.axpy_f32(da1, dh[u], True)
-            o.axpy_f32(da2, dh[w], True)
-            self.enc[qn].backward(da2, dP[m], dh[w])
-            if on_done:
-                on_done(qn)
-            self.enc[pn].backward(da1, dP[m], dh[u])
-            if on_done:
-                on_done(pn)
+            o.axpy_f32(da1[m], dh[u], True)
+            o.axpy_f32(da2[m], dh[w], True)
+        ln.fork()
+        for m in reversed(HEAD_ORDER):
+            u, w, pn, qn = TARGETS[m]
+            for n, da, dsrc in ((qn, da2[m], dh[w]), (pn, da1[m], dh[u])):
+                with ln.on(self.lane_of[n]):
+                    self.enc[n].backward(da, dPl[self.lane_of[n]][m], dsrc)
+                    if on_done:
+                        on_done(n)
+        ln.barrier()                                                            # wave 1 consumes dh written on either lane
         for n, (qm, km) in reversed(list(WAVE1.items())):
-            self.enc[n].backward(dh[n], dP[qm], dP[km])
-            if on_done:
-                on_done(n)
+            k = self.lane_of[n]
+            with ln.on(k):
+                self.enc[n].backward(dh[n], dPl[k][qm], dPl[k][km])
+                if on_done:
+                    on_done(n)
+        ln.join()
+        for k in range(1, ln.n):
+            for m in "lav":
+                o.axpy_f32(dPl[k][m], dP[m], True)
         for m in "lav":
             if self.Wproj[m] is not None:
                 g = self.shared.get("dPc", (M, d.Dp), self.T_)

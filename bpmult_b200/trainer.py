@@ -109,7 +109,7 @@ class Trainer:
                 dist.all_reduce(self.flat_g[s:e])
                 return
             ev = torch.cuda.Event()
-            ev.record(cur)
+            ev.record(torch.cuda.current_stream(self.device))      # the lane stream this encoder's backward ran on
             with torch.cuda.stream(self.comm):
                 self.comm.wait_event(ev)
                 dist.all_reduce(self.flat_g[s:e])
