@@ -250,7 +250,7 @@ def run_ours(opt):
     model = MultiprojectionMMTransformer3DGMUClf(args, precision=opt.precision).to(dev)
     model.train()
     tr = Trainer(model, lr=1e-3, seed=1234)
-    host = synth_batch(args, B, 2024 + rank)
+    host = [t.pin_memory() for t in synth_batch(args, B, 2024 + rank)]     # as a DataLoader(pin_memory=True) hands them over
     devb = [t.to(dev) for t in host]
 
     def barrier():

@@ -73,7 +73,7 @@ class MMTrVatEngine:
         self.d = Dims(D, H)
         self.orig = {"l": args.orig_d_l, "a": args.orig_d_a, "v": args.orig_d_v}
         self.Kp = {m: (self.d.Dp if self.orig[m] == D else round_up(self.orig[m], 64)) for m in "lav"}
-        self.lanes = Lanes(ops.device, int(os.environ.get("BPM_LANES", "2")))
+        self.lanes = Lanes(ops.device, int(os.environ.get("BPM_LANES", "6")))
         self.lane_shared = [Arena(ops) for _ in range(self.lanes.n)]
         self.shared = self.lane_shared[0]
         self.arena = Arena(ops)

@@ -184,8 +184,11 @@ class Trainer:
         """end-to-end step from HOST tensors: pinned staging -> H2D -> step -> D2H of the loss.  Returns a python float."""
         self._ensure_static(txt, img, audio, tgt)
         for pbuf, s, t in zip(self.pinned, self.static, (txt, img, audio, tgt)):
-            pbuf.copy_(t)
-            s.copy_(pbuf, non_blocking=True)
+            if self.on_gpu and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous():
+                s.copy_(t, non_blocking=True)               # e.g. DataLoader(pin_memory=True): DMA straight from the caller's buffer
+            else:
+                pbuf.copy_(t)                               # pageable input: staged through this trainer's pinned buffers
+                s.copy_(pbuf, non_blocking=True)
         self._run()
         self.loss_host.copy_(self.loss_dev, non_blocking=True)
         if self.on_gpu:
