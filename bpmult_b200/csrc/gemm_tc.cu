@@ -78,10 +78,17 @@ template <int CB> __device__ __forceinline__ uint32_t swz_off(int r, int u) {
 // CG: 1 = one CTA per tile (M = 128);  2 = CTA pair (cluster of 2, tcgen05 cta_group::2): the pair owns a 256-row tile, each CTA loads
 // its 128 rows of A and HALF of the B tile, so the per-SM operand traffic from L2 (the measured bound of the 1-CTA main loop,
 // ~64 B/clk/SM) drops by a third; the leader CTA issues the MMAs, both CTAs run producer and epilogue warps on their own halves.
-template <int ELEM, int CB, int CG>
+// EPI: epilogue specialisation.  0 = everything decided at run time; the others compile only what one hot shape of the encoder layer
+// needs (a shorter instruction stream per chunk; the epilogue warps are instruction-fetch sensitive):
+//   1 plain / bias / bias + relu     2 + dropout (fc1)     3 relu-backward gate tile (dgrad into fc1)
+//   4 dropout + residual tile, fp32 out (out-proj, fc2)     5 fp32 reduce-add with fused column sums (wgrad)
+template <int ELEM, int CB, int CG, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                const __grid_constant__ CUtensorMap tmI, const TcGemmParams p) {
+  const int in_mode_ = EPI == 0 ? p.in_mode : (EPI == 3 ? 2 : (EPI == 4 ? 1 : 0));
+  float* const colsum_ = (EPI == 0 || EPI == 5) ? p.colsum : nullptr;
+
   constexpr int CW = CB / ELEM;
   constexpr int EB = 32 * CB;                                             // bytes of one staging buffer ({CW cols, 32 rows} box)
   extern __shared__ uint8_t smem_raw[];
@@ -116,7 +123,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
-    if (p.in_mode) tma_prefetch_desc(&tmI);
+    if (in_mode_) tma_prefetch_desc(&tmI);
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), CG * TC_EPI_WARPS); }
     for (int w = 0; w < TC_EPI_WARPS; w++)
@@ -127,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CG == 2) tmem_alloc_2cta(tmem_ptr_addr, (uint32_t)p.tmem_cols);
     else tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
   }
-  if (warp >= 2 && p.colsum != nullptr) {                                   // 16 x 64 tile of bf16 ones (B operand of the colsum MMA)
+  if (warp >= 2 && colsum_ != nullptr) {                                   // 16 x 64 tile of bf16 ones (B operand of the colsum MMA)
     uint32_t* o = (uint32_t*)(base_gen + misc);
     for (int c = threadIdx.x - 64; c < 512; c += 32 * TC_EPI_WARPS) o[c] = 0x3F803F80u;
     fence_async_smem();
@@ -202,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int z = tt / tiles_mn;
         kb0 = z * p.kb_per_split;
         kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-        do_colsum = p.colsum != nullptr && (tt % p.gx) == 0;
+        do_colsum = colsum_ != nullptr && (tt % p.gx) == 0;
         mbar_wait(tmem_empty(tcc & 1), ((uint32_t)(tcc >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
         tc_fence_after();
       };
@@ -260,7 +267,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;                                              // takes chunks half, half + 2, ...
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const DropCtx dc = make_drop(p.drop);
-    const float alpha = dc.on ? p.alpha * dc.inv_keep : p.alpha;
+    const bool drop_on = EPI == 0 ? dc.on : (EPI == 2 || EPI == 4);
+    const float alpha = drop_on ? p.alpha * dc.inv_keep : p.alpha;
     const int nb = p.nb;
     const int dist = nb - 1;                                               // residual / gate prefetch distance (chunks)
     uint8_t* const ebuf_gen = base_gen + ebuf_base + ew * nb * EB;
@@ -280,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_load_2d(ebuf_s + b * EB, &tmI, in_full(ew, b), n, m);
     };
     int pt = first_tile, pc = half - 2, issued = 0;                        // prefetch cursor
-    if (p.in_mode) {
+    if (in_mode_) {
       advance(pt, pc);
       for (int i = 0; i < dist && pt < total_tiles; i++) {
         if (elect_one()) issue_in(pt, pc, issued);
@@ -296,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m0 + lane;
       const int a = tc & 1;
       const uint32_t acc = tmem_base + (uint32_t)(a * acc_stride) + lane_off;
-      const bool do_colsum = p.colsum != nullptr && n0 == 0 && half == 0;
+      const bool do_colsum = colsum_ != nullptr && n0 == 0 && half == 0;
       int last_c = -1;
       for (int c = half; chunk_ok(t, c); c += 2) last_c = c;
       mbar_wait(tmem_full(a), (uint32_t)(tc >> 1) & 1u);
@@ -306,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float cs[16];
           tmem_ld16(acc + (uint32_t)p.BN, cs);
           tmem_ld_wait();
-          if (row < p.M) atomicAdd(p.colsum + row, cs[0]);
+          if (row < p.M) atomicAdd(colsum_ + row, cs[0]);
         }
         tc_fence_before();
         __syncwarp();
@@ -334,7 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_before();                                                // this warp's part of the accumulator is in registers
           __syncwarp();
           if (lane == 0) { if (CG == 2 && cta_rank != 0) mbar_arrive_remote(tmem_empty(a), 0); else mbar_arrive(tmem_empty(a)); }
-          if (do_colsum && row < p.M) atomicAdd(p.colsum + row, cs0);
+          if (do_colsum && row < p.M) atomicAdd(colsum_ + row, cs0);
         }
         // ---- bias, alpha, relu, dropout
         if (!skip_math) {
@@ -354,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int e = 0; e < CW; e++) v[e] = fmaxf(v[e], 0.f);
           }
-          if (dc.on) {
+          if (drop_on) {
             const uint64_t pair0 = ((uint64_t)row * (uint64_t)p.ldc + (uint64_t)n) >> 1;
             const uint32_t lo0 = (uint32_t)pair0;
             if (lo0 + (uint32_t)(CW / 2) >= lo0) {                           // no carry into the high counter word inside this chunk
@@ -379,7 +387,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (skip_store) continue;
         uint8_t* const st = ebuf_gen + b * EB;
-        if (p.in_mode) {
+        if (in_mode_) {
           // ---- relu-backward gate or residual from the tile the TMA unit placed in this warp's staging buffer
           mbar_wait(in_full(ew, b), (uint32_t)(done / nb) & 1u);
 #pragma unroll
@@ -390,7 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int e = 0; e < 4; e++) {
                 const float2 f = __bfloat1622float2(h2[e]);
-                if (p.in_mode == 2) {
+                if (in_mode_ == 2) {
                   v[u * 8 + 2 * e] = f.x > 0.f ? v[u * 8 + 2 * e] * p.gate_scale : 0.f;
                   v[u * 8 + 2 * e + 1] = f.y > 0.f ? v[u * 8 + 2 * e + 1] * p.gate_scale : 0.f;
                 } else {
@@ -402,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float* f = (const float*)&w;
 #pragma unroll
               for (int e = 0; e < 4; e++) {
-                if (p.in_mode == 2) v[u * 4 + e] = f[e] > 0.f ? v[u * 4 + e] * p.gate_scale : 0.f;
+                if (in_mode_ == 2) v[u * 4 + e] = f[e] > 0.f ? v[u * 4 + e] * p.gate_scale : 0.f;
                 else v[u * 4 + e] += f[e];
               }
             }
@@ -508,16 +516,16 @@ static int pick_bn(int N, int max_bn) {
   return bn < 32 ? 32 : bn;
 }
 
-template <int ELEM, int CB, int CG>
+template <int ELEM, int CB, int CG, int EPI>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmI, const TcGemmParams& p, int ctas,
                      size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ELEM, CB, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ELEM, CB, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { bpm_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
     attr_set = true;
   }
-  cudaError_t le = bpm_launch_cluster(CG, gemm_tc_kernel<ELEM, CB, CG>, dim3(ctas), dim3(TC_THREADS), smem, stream, tmA, tmB, tmC, tmI, p);
+  cudaError_t le = bpm_launch_cluster(CG, gemm_tc_kernel<ELEM, CB, CG, EPI>, dim3(ctas), dim3(TC_THREADS), smem, stream, tmA, tmB, tmC, tmI, p);
   if (le != cudaSuccess) { bpm_set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
 }
@@ -623,12 +631,31 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   BPM_REQUIRE(smem <= 227 * 1024 && p.tmem_cols <= 512, "gemm_tc: smem %zu / tmem %d too large", smem, p.tmem_cols);
   int total_tiles = gx * gy * split;
   int ctas = cg * min(total_tiles, bpm_num_sms() / cg);
-  if (cg == 2) {
-    if (elem == 4) return launch_tc<4, 128, 2>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
-    if (cb == 128) return launch_tc<2, 128, 2>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
-    return launch_tc<2, 64, 2>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+  const bool has_drop = g->drop.p > 0.f;
+  int epi = 0;
+  if (!(bpm_debug_get(0) & 512)) {
+    if (elem == 2) {
+      if (!has_drop && p.in_mode == 0 && p.colsum == nullptr) epi = 1;
+      else if (has_drop && p.in_mode == 0 && p.colsum == nullptr) epi = 2;
+      else if (!has_drop && p.in_mode == 2 && p.colsum == nullptr) epi = 3;
+    } else {
+      if (has_drop && p.in_mode == 1 && p.colsum == nullptr) epi = 4;
+      else if (!has_drop && p.in_mode == 0) epi = 5;
+    }
   }
-  if (elem == 4) return launch_tc<4, 128, 1>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
-  if (cb == 128) return launch_tc<2, 128, 1>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
-  return launch_tc<2, 64, 1>(tmA, tmB, tmC, tmI, p, ctas, smem, stream);
+#define TC_GO(E, C, G, X) return launch_tc<E, C, G, X>(tmA, tmB, tmC, tmI, p, ctas, smem, stream)
+#define TC_BF16(C, G) do { if (epi == 1) TC_GO(2, C, G, 1); if (epi == 2) TC_GO(2, C, G, 2); if (epi == 3) TC_GO(2, C, G, 3); TC_GO(2, C, G, 0); } while (0)
+#define TC_F32(G) do { if (epi == 4) TC_GO(4, 128, G, 4); if (epi == 5) TC_GO(4, 128, G, 5); TC_GO(4, 128, G, 0); } while (0)
+  if (cg == 2) {
+    if (elem == 4) TC_F32(2);
+    if (cb == 128) TC_BF16(128, 2);
+    TC_BF16(64, 2);
+  }
+  if (elem == 4) TC_F32(1);
+  if (cb == 128) TC_BF16(128, 1);
+  TC_BF16(64, 1);
+#undef TC_GO
+#undef TC_BF16
+#undef TC_F32
+
 }
