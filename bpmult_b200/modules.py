@@ -437,6 +437,24 @@ class TextShifting4Layer(_TextShiftingBase):                          # mmtr.py:
         self._build([size_in1, size_in2, size_in3, size_in4], size_out)
 
 
+class TextShiftingNLayer(nn.Module):                                  # mmtr.py:249-273
+    """N-input gate (`hybrid=True` head): parameters `hiddens.i.weight (out, in_i)`, `x_gates.i.weight (out, sum in)`, forward(*xs)."""
+
+    def __init__(self, sizes_in, size_out):
+        super().__init__()
+        self.sizes_in, self.size_out = list(sizes_in), size_out
+        assert all(s == size_out for s in self.sizes_in), "fused head kernel: equal sizes"
+        self.hiddens = nn.ModuleList([nn.Linear(s, size_out, bias=False) for s in self.sizes_in])
+        self.x_gates = nn.ModuleList([nn.Linear(sum(self.sizes_in), size_out, bias=False) for _ in self.sizes_in])
+        self._eng = None
+
+    def forward(self, *xs):
+        n = len(self.sizes_in)
+        assert len(xs) == n, "TextShiftingNLayer: expected %d inputs" % n
+        ws = [h.weight for h in self.hiddens] + [g.weight for g in self.x_gates]
+        return _TextShiftingFn.apply(self, n, *xs, *ws)
+
+
 class _TextShiftingFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, n, *args):
@@ -457,6 +475,7 @@ class _TextShiftingFn(torch.autograd.Function):
             cat[:, i * Dp:i * Dp + D] = xs[i].detach().float()
         fused, z = eng.gate_forward(B)
         ctx.mod, ctx.n, ctx.B = mod, n, B
+        ctx.wshapes = [tuple(w.shape) for w in ws]
         zz = z.view(B, n, Dp)[:, :, :D].reshape(B, n * D).clone()
         ctx.mark_non_differentiable(zz)
         return fused[:, :D].clone(), zz
@@ -473,11 +492,11 @@ class _TextShiftingFn(torch.autograd.Function):
         gx = tuple(dcat[:, i * Dp:i * Dp + D].clone() for i in range(n))
         gw = []
         for i in range(n):
-            t = torch.zeros_like(getattr(mod, "hidden%d" % (i + 1)).weight)
+            t = torch.zeros(ctx.wshapes[i], dtype=torch.float32, device=g.device)
             ops.unpack_matrix(eng.G["h"][i], t)
             gw.append(t)
         for i in range(n):
-            t = torch.zeros_like(getattr(mod, "x%d_gate" % (i + 1)).weight)
+            t = torch.zeros(ctx.wshapes[n + i], dtype=torch.float32, device=g.device)
             ops.unpack_matrix(eng.G["zg"][i], t, col_map=(D, Dp))
             gw.append(t)
         return (None, None) + gx + tuple(gw)

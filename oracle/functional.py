@@ -159,6 +159,17 @@ def text_shifting(sd, pfx, xs):
     return out, torch.cat(zs, -1)
 
 
+def text_shifting_n(sd, pfx, xs):
+    """models/mmtr.py:249-273 TextShiftingNLayer (ModuleList parameter names hiddens.i / x_gates.i; forward(*xs))."""
+    cat = torch.cat(xs, -1)
+    hs = [torch.tanh(F.linear(x, sd["%shiddens.%d.weight" % (pfx, i)])) for i, x in enumerate(xs)]
+    zs = [torch.sigmoid(F.linear(cat, sd["%sx_gates.%d.weight" % (pfx, i)])) for i in range(len(xs))]
+    out = zs[0] * hs[0]
+    for z, h in zip(zs[1:], hs[1:]):
+        out = out + z * h
+    return out, torch.cat(zs, -1)
+
+
 # ----------------------------------------------------------------------------- loss
 def bce_with_logits(logits, targets, pos_weight=None):
     """train.py:99-106,333: nn.BCEWithLogitsLoss(pos_weight=w), mean over (B, C)."""

@@ -146,6 +146,22 @@ def run_gmus(ref, seed):
         assert Fn.max_rel(o2, o) < TOL and Fn.max_rel(z2, z) < TOL
         rec["ts%d" % n_in] = dict(out=o.detach(), z=z.detach(), dx=[t.grad for t in xs],
                                   pgrads={n: p.grad.clone() for n, p in m.named_parameters()})
+    # TextShiftingNLayer (mmtr.py:249-273), N = 5 (one more than any fixed-arity class), varargs forward
+    n_in = 5
+    x5 = x + [synth.randn((M, D), seed + 4)]
+    m = ref.mmtr.TextShiftingNLayer([D] * n_in, D)
+    shp = {"hiddens.%d.weight" % i: (D, D) for i in range(n_in)}
+    shp.update({"x_gates.%d.weight" % i: (D, n_in * D) for i in range(n_in)})
+    sd = synth.make_state_dict(shp, seed + 20)
+    assert set(m.state_dict().keys()) == set(shp.keys())
+    m.load_state_dict(sd)
+    xs = [t.clone().requires_grad_() for t in x5]
+    o, z = m(*xs)
+    g = synth.randn(o.shape, seed + 9)
+    (o * g).sum().backward()
+    o2, z2 = Fn.text_shifting_n(sd, "", x5)
+    assert Fn.max_rel(o2, o) < TOL and Fn.max_rel(z2, z) < TOL
+    rec["tsN"] = dict(out=o.detach(), z=z.detach(), dx=[t.grad for t in xs], pgrads={n: p.grad.clone() for n, p in m.named_parameters()})
     rec["seed"], rec["dims"] = seed, (D, M)
     print("gmus ok")
     return rec

@@ -165,6 +165,31 @@ def test_gmu_modules_match_golden():
             assert Fn.rel_l2(p.grad, r["pgrads"][n]) < 5e-5, n
 
 
+def test_text_shifting_n_layer_matches_reference_golden():
+    """mmtr.py:249-273 (the `hybrid=True` head): ModuleList parameter names, varargs forward, N = 5 inputs"""
+    g = load_gold("modules.pt")["gmu"]
+    D, rows = g["dims"]
+    n_in = 5
+    x = [synth.randn((rows, D), g["seed"] + i) for i in range(n_in)]
+    m = M.TextShiftingNLayer([D] * n_in, D)
+    shp = {"hiddens.%d.weight" % i: (D, D) for i in range(n_in)}
+    shp.update({"x_gates.%d.weight" % i: (D, n_in * D) for i in range(n_in)})
+    assert set(m.state_dict().keys()) == set(shp.keys())
+    m.load_state_dict(synth.make_state_dict(shp, g["seed"] + 20))
+    xs = [t.clone().requires_grad_() for t in x]
+    o, z = m(*xs)
+    (o * synth.randn(o.shape, g["seed"] + 9)).sum().backward()
+    r = g["tsN"]
+    assert Fn.max_rel(o, r["out"]) < 2e-5 and Fn.max_rel(z, r["z"]) < 2e-5
+    for a, b in zip(xs, r["dx"]):
+        assert Fn.max_rel(a.grad, b) < 5e-5
+    for n, p in m.named_parameters():
+        assert Fn.rel_l2(p.grad, r["pgrads"][n]) < 5e-5, n
+    import pytest
+    with pytest.raises(AssertionError):
+        m(*xs[:3])
+
+
 def test_mmtrvat_module_autograd_matches_reference_golden():
     rec = load_gold("mmtrvat_tiny.pt")
     cfg = Namespace(**rec["cfg"])
