@@ -106,6 +106,19 @@ def _oracle_model_grads(rec, autocast):
     return logits.float().detach().cpu(), txt.grad.cpu(), {n: v.grad.cpu() for n, v in sdo.items() if v.grad is not None}
 
 
+@pytest.mark.parametrize("lanes", ["1", "3"])
+def test_mmtrvat_lane_counts_agree_with_the_golden(ops, lanes, monkeypatch):
+    """the encoder lanes (side streams, per-lane scratch and projection-gradient accumulators) are a scheduling choice only: a
+    single lane and an uneven lane count give the reference's result as well (the default of 6 is what the other tests run)"""
+    monkeypatch.setenv("BPM_LANES", lanes)
+    rec = load_gold("mmtrvat_tiny.pt")
+    logits, z, loss, dtxt, grads, eng = run_model_engine(ops, rec, dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert eng.lanes.n == int(lanes)
+    assert Fn.max_rel(logits, rec["logits"]) < 1e-4 and Fn.rel_l2(dtxt, rec["dtxt"]) < 2e-4
+    assert max(Fn.rel_l2(grads[n], ref) for n, ref in rec["pgrads"].items()) < 2e-4
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("gold", ["mmtrvat_tiny.pt", "mmtrvat_d96.pt"])
 def test_mmtrvat_vs_reference_golden(ops, gold, dtype):
