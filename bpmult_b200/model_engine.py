@@ -88,9 +88,11 @@ class MMTrVatEngine:
                                         res_dropout=args.res_dropout, embed_dropout=args.embed_dropout, attn_mask=args.attn_mask,
                                         biprojection=False, dtype=dtype, uid=i + 1, shared=self.lane_shared[self.lane_of[n]])
         self.gmu = {}
+        self.mod_lane = {m: i % self.lanes.n for i, m in enumerate(HEAD_ORDER)}      # lane of a modality's staging / gated units
         for m in "lav":
-            self.gmu[m + "_m"] = SeqGmuEngine(ops, D, dtype, True, self.shared, "gmu_%s_m" % m)
-            self.gmu[m] = SeqGmuEngine(ops, D, dtype, True, self.shared, "gmu_%s" % m)
+            sh = self.lane_shared[self.mod_lane[m]]
+            self.gmu[m + "_m"] = SeqGmuEngine(ops, D, dtype, True, sh, "gmu_%s_m" % m)
+            self.gmu[m] = SeqGmuEngine(ops, D, dtype, True, sh, "gmu_%s" % m)
         self.head = HeadEngine(ops, D, 3, args.n_classes, out_dropout=args.out_dropout)
         z = ops.zeros
         self.Wproj = {m: (z((self.d.Dp, self.Kp[m]), dtype) if self.orig[m] != D else None) for m in "lav"}
@@ -166,21 +168,23 @@ class MMTrVatEngine:
         self.in_shapes = {m: tuple(feats[m].shape) for m in "lav"}
         P = {}
         self.X = {}
+        ln = self.lanes
+        ln.fork()
         for m in "lav":
             # transpose / text embed-dropout / zero-pad to n_vec (mmtr.py:741-761), then Conv1d(k=1) as a row GEMM (:748-750)
             drop = Drop(self.args.embed_dropout, seed, seed_ptr, 7) if (m == "l" and training and self.args.embed_dropout > 0) else None
             X = A.get("X_" + m, (M, self.Kp[m]), self.T_)
-            o.stage_rows(feats[m], X, nv, drop)
-            self.X[m] = X
-            if self.Wproj[m] is not None:
-                P[m] = A.get("P_" + m, (M, d.Dp), self.T_)
-                o.gemm(X, self.Wproj[m], P[m], M, d.Dp, self.Kp[m])
-            else:
-                P[m] = X
+            with ln.on(self.mod_lane[m]):
+                o.stage_rows(feats[m], X, nv, drop)
+                self.X[m] = X
+                if self.Wproj[m] is not None:
+                    P[m] = A.get("P_" + m, (M, d.Dp), self.T_)
+                    o.gemm(X, self.Wproj[m], P[m], M, d.Dp, self.Kp[m])
+                else:
+                    P[m] = X
         self.P = P
         h = {}
-        ln = self.lanes
-        ln.fork()
+        ln.barrier()
         for n, (qm, km) in WAVE1.items():
             with ln.on(self.lane_of[n]):
                 h[n] = self.enc[n].forward(P[qm], B, nv, src_k=P[km], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
@@ -191,20 +195,22 @@ class MMTrVatEngine:
                 h[pn] = self.enc[pn].forward(P[m], B, nv, src_k=h[u], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
             with ln.on(self.lane_of[qn]):
                 h[qn] = self.enc[qn].forward(P[m], B, nv, src_k=h[w], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
-        ln.join()
+        ln.barrier()
         cat = self.head.cat_buf(B)
         self.tops = {}
-        for ci, m in enumerate(HEAD_ORDER):
+        for ci, m in enumerate(HEAD_ORDER):                                      # the three targets' gated units: one lane each
             u, w, pn, qn = TARGETS[m]
             hp, hq = h[pn], h[qn]
-            mid = self.gmu[m + "_m"].forward(h[u], h[w], M)                    # "GMU middle"
-            a1 = A.get("a1_" + m, (M, d.Dp), self.T_)
-            a2 = A.get("a2_" + m, (M, d.Dp), self.T_)
-            o.add(hp, h[u], a1)                                                  # residual level 1 -> 2 (:799-800)
-            o.add(hq, h[w], a2)
-            top = self.gmu[m].forward(a1, a2, M, addend=mid)                     # "GMU top" + residual level 1 -> 3 (:803-806)
-            self.tops[m] = top
-            o.pool_fwd(top, B, nv, cat, ci * d.Dp)                               # h[0] + h[-1] (:808)
+            with ln.on(self.mod_lane[m]):
+                mid = self.gmu[m + "_m"].forward(h[u], h[w], M)                    # "GMU middle"
+                a1 = A.get("a1_" + m, (M, d.Dp), self.T_)
+                a2 = A.get("a2_" + m, (M, d.Dp), self.T_)
+                o.add(hp, h[u], a1)                                                  # residual level 1 -> 2 (:799-800)
+                o.add(hq, h[w], a2)
+                top = self.gmu[m].forward(a1, a2, M, addend=mid)                     # "GMU top" + residual level 1 -> 3 (:803-806)
+                self.tops[m] = top
+                o.pool_fwd(top, B, nv, cat, ci * d.Dp)                               # h[0] + h[-1] (:808)
+        ln.join()
         self.h = h
         logits, z = self.head.forward(B, training, seed, seed_ptr)
         return logits, z
@@ -228,20 +234,22 @@ class MMTrVatEngine:
         dh = {n: A.get("dh_" + n, (M, d.Dp), f32) for n in WAVE1}
         for t in [t for k in range(ln.n) for t in dPl[k].values()] + list(dh.values()):
             o.zero_(t)
-        dtop = A.get("dtop", (M, d.Dp), f32)
+        dtop = {m: A.get("dtop_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
         da1 = {m: A.get("da1_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
         da2 = {m: A.get("da2_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
-        for ci, m in reversed(list(enumerate(HEAD_ORDER))):                      # gated fusion units: short, on the main stream
-            u, w, pn, qn = TARGETS[m]
-            o.zero_(dtop)
-            o.pool_bwd(dcat, ci * d.Dp, B, nv, dtop)
-            o.zero_(da1[m])
-            o.zero_(da2[m])
-            self.gmu[m].backward(dtop, da1[m], da2[m])                           # d(p+u), d(q+w)
-            self.gmu[m + "_m"].backward(dtop, dh[u], dh[w])                      # mid consumes u, w directly
-            o.axpy_f32(da1[m], dh[u], True)
-            o.axpy_f32(da2[m], dh[w], True)
         ln.fork()
+        for ci, m in reversed(list(enumerate(HEAD_ORDER))):                      # gated fusion units of the three targets: one lane each
+            u, w, pn, qn = TARGETS[m]
+            with ln.on(self.mod_lane[m]):
+                o.zero_(dtop[m])
+                o.pool_bwd(dcat, ci * d.Dp, B, nv, dtop[m])
+                o.zero_(da1[m])
+                o.zero_(da2[m])
+                self.gmu[m].backward(dtop[m], da1[m], da2[m])                    # d(p+u), d(q+w)
+                self.gmu[m + "_m"].backward(dtop[m], dh[u], dh[w])               # mid consumes u, w directly
+                o.axpy_f32(da1[m], dh[u], True)
+                o.axpy_f32(da2[m], dh[w], True)
+        ln.barrier()
         for m in reversed(HEAD_ORDER):
             u, w, pn, qn = TARGETS[m]
             for n, da, dsrc in ((qn, da2[m], dh[w]), (pn, da1[m], dh[u])):
@@ -256,21 +264,23 @@ class MMTrVatEngine:
                 self.enc[n].backward(dh[n], dPl[k][qm], dPl[k][km])
                 if on_done:
                     on_done(n)
+        ln.barrier()
+        for m in "lav":                                                          # input projections: one lane per modality
+            with ln.on(self.mod_lane[m]):
+                for k in range(1, ln.n):
+                    o.axpy_f32(dPl[k][m], dP[m], True)
+                if self.Wproj[m] is not None:
+                    sh = self.lane_shared[self.mod_lane[m]]
+                    g = sh.get("dPc", (M, d.Dp), self.T_)
+                    o.cast_drop(dP[m], g, None)
+                    o.gemm(g, self.X[m], self.Gproj[m], d.Dp, self.Kp[m], M, ta=1, tb=1, accumulate=True)     # dW = dP^T X
+                    if d_inputs is not None and m in d_inputs:
+                        dX = sh.get("dX_" + m, (M, self.Kp[m]), f32)
+                        o.gemm(g, self.Wproj[m], dX, M, self.Kp[m], d.Dp, tb=1)
+                        self._unstage(m, dX, d_inputs[m])
+                elif d_inputs is not None and m in d_inputs:
+                    self._unstage(m, dP[m], d_inputs[m])
         ln.join()
-        for k in range(1, ln.n):
-            for m in "lav":
-                o.axpy_f32(dPl[k][m], dP[m], True)
-        for m in "lav":
-            if self.Wproj[m] is not None:
-                g = self.shared.get("dPc", (M, d.Dp), self.T_)
-                o.cast_drop(dP[m], g, None)
-                o.gemm(g, self.X[m], self.Gproj[m], d.Dp, self.Kp[m], M, ta=1, tb=1, accumulate=True)     # dW = dP^T X
-                if d_inputs is not None and m in d_inputs:
-                    dX = self.shared.get("dX_" + m, (M, self.Kp[m]), f32)
-                    o.gemm(g, self.Wproj[m], dX, M, self.Kp[m], d.Dp, tb=1)
-                    self._unstage(m, dX, d_inputs[m])
-            elif d_inputs is not None and m in d_inputs:
-                self._unstage(m, dP[m], d_inputs[m])
 
     def backward_order(self):
         """encoder names in the order their gradients complete during backward (bucket launch order)"""
