@@ -38,6 +38,12 @@ __device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) 
   asm("{.reg .b64 x, y;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %3};\n add.rn.f32x2 x, x, y;\n mov.b64 {%0, %1}, x;}"
       : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
 }
+__device__ __forceinline__ void fmul2(float& a0, float& a1, float b) {
+  asm("{.reg .b64 x, y;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %2};\n mul.rn.f32x2 x, x, y;\n mov.b64 {%0, %1}, x;}" : "+f"(a0), "+f"(a1) : "f"(b));
+}
+__device__ __forceinline__ void fmul2v(float& a0, float& a1, float b0, float b1) {
+  asm("{.reg .b64 x, y;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %3};\n mul.rn.f32x2 x, x, y;\n mov.b64 {%0, %1}, x;}" : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *(uint32_t*)&v;
@@ -468,10 +474,25 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
 //   DROP: 0 no dropout, 1 keep bits staged in shared memory by TMA (word (query, 32-key group), bit = key lane),
 //         2 keep bits fetched from global memory into mw (one word per lane = query), 3 regenerate the decisions.
 //   MASKED: the tile touches the mask diagonal or the end of the key sequence.
-template <int DROP, bool MASKED, int NC>
+//   FOLD (no dropout only): -lse and -delta already sit inside the MMA results (two padding columns of the head dimension carry them
+//         as bf16 hi + lo parts against ones in K / V, see the S^T issuer), so sv = S^T - lse and dpv = dP^T - delta on entry:
+//         per element one multiply, one ex2, one multiply, and no shared-memory operands.
+template <int DROP, bool MASKED, int NC, bool FOLD>
 __device__ __forceinline__ void bwd_chunk_math(float* sv, float* dpv, const float* __restrict__ lse_c, const float* __restrict__ del_c, int c_lo, int cmin,
                                                bool key_oob, bool diag, const DropCtx& dc, const uint32_t* __restrict__ bits_c, uint32_t mw, int lane,
                                                uint64_t e_row, int q_lo, int T, int S) {
+  if (FOLD) {
+#pragma unroll
+    for (int c = 0; c < NC; c += 2) {
+      float t0 = sv[c], t1 = sv[c + 1];
+      fmul2(t0, t1, LOG2E_F);
+      float p0 = ex2f(t0), p1 = ex2f(t1);
+      if (MASKED) { p0 = (c < cmin) ? 0.f : p0; p1 = (c + 1 < cmin) ? 0.f : p1; }
+      sv[c] = p0; sv[c + 1] = p1;
+      fmul2v(dpv[c], dpv[c + 1], p0, p1);
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < NC; c += 4) {
     const float4 l4 = *(const float4*)(lse_c + c);
@@ -499,7 +520,12 @@ __device__ __forceinline__ void bwd_chunk_math(float* sv, float* dpv, const floa
 // DM = 0: instantiation without any dropout code (two thirds of the calls of the training step: 20% faster than the general one,
 // whose hot loop with all four dropout modes does not fit the instruction cache as well); DM = 1: dropout mode resolved at run time.
 // (A third instantiation with only the TMA-staged keep bits was measured 15% SLOWER than the general one and is not kept.)
-template <int DM>
+// FOLD (with DM = 0, head dim <= 26 of 32): the S^T issuer warp patches two padding columns of every operand tile in shared memory
+// before it issues the MMAs -- Q rows get (-lse) and dO rows get (-delta), each as bf16 hi + lo, K and V rows get ones -- so the
+// tensor core delivers S^T - lse and dP^T - delta directly.  The garbage this leaves in the same two columns of dQ / dK / dV is
+// zeroed when the accumulators are drained.
+#define AB_PAD0 26                       // patched head-dim columns (AB_PAD0, AB_PAD0 + 1): 4-byte aligned inside the 64-byte row
+template <int DM, bool FOLD>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmBits, const int bits_tma,
@@ -624,14 +650,50 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     {   // converged warp; one elected lane issues
       const uint32_t id_st = umma_idesc_bf16(128, 128, 0, 0);
       const uint64_t d_k64 = umma_desc(0, 16, 512, BPM_SWZ_64B);          // K-major 64-byte rows; +32 B per k16
-      int pc = 0;
+      int pc = 0, bcs = -1, cur_bh = -1;
+      // patched word of tile row r: 16-byte unit 3 of the 64-byte row (SWIZZLE_64B: unit ^ ((r >> 1) & 3)), bytes 4..7 = columns 26, 27
+      auto pad_word = [&](int tile_off, int r) { return (uint32_t*)(base_gen + tile_off + r * 64 + ((3 ^ ((r >> 1) & 3)) << 4) + 4); };
+      auto hi_lo = [](float x) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+        return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+      };
       for (Pair p = first_pair(); p.bh < nbh; next_pair(p), pc++) {
         const int ks = p.jc & 1, qs = pc % AB_QD_STAGES;
         TRACE(1, 10);
-        if (p.i == i_min_of(p.j)) mbar_wait(kv_full(ks), (uint32_t)(p.jc >> 1) & 1u);
+        if (FOLD && p.bh != cur_bh) {                          // this (b,h)'s lse / delta rows (the compute warps release the buffer)
+          cur_bh = p.bh; bcs++;
+          mbar_wait(ld_full(bcs & 1), (uint32_t)(bcs >> 1) & 1u);
+        }
+        if (p.i == i_min_of(p.j)) {
+          mbar_wait(kv_full(ks), (uint32_t)(p.jc >> 1) & 1u);
+          if (FOLD) {
+            const int kt = AttnBwdSmem::KV + ks * 16384;
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+              *pad_word(kt, rr * 32 + lane) = 0x3F803F80u;             // K: (1, 1)
+              *pad_word(kt + 8192, rr * 32 + lane) = 0x3F803F80u;      // V: (1, 1)
+            }
+          }
+        }
         const uint32_t ka = base + AttnBwdSmem::KV + ks * 16384, va = ka + 8192;
         const uint32_t qa = base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, ga = qa + 8192;
         mbar_wait(q_full(qs), (uint32_t)(pc / AB_QD_STAGES) & 1u);
+        if (FOLD) {
+          const float* lse_s = (const float*)(base_gen + AttnBwdSmem::LD + (bcs & 1) * 4096);
+          const float* del_s = lse_s + 512;
+          const int qt = AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE;
+#pragma unroll
+          for (int rr = 0; rr < 4; rr++) {
+            const int row = rr * 32 + lane, qi = p.i * 128 + row;
+            const float l2 = lse_s[qi];                                 // lse * log2e, +inf beyond T
+            const bool live = qi < T && l2 < 1e30f;
+            *pad_word(qt, row) = live ? hi_lo(-l2 * LN2_F) : 0x0000C6EAu;   // (-30000, 0): exp2 underflows to 0 for dead query rows
+            *pad_word(qt + 8192, row) = live ? hi_lo(-del_s[qi]) : 0u;
+          }
+          fence_async_smem();                                          // generic-proxy writes -> visible to the MMAs' operand reads
+          __syncwarp();
+        }
         TRACE(1, 11);
         mbar_wait(st_free, ((uint32_t)pc & 1u) ^ 1u);
         TRACE(1, 12);
@@ -733,6 +795,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(tDQ + 32 * i + lane_off, acc);
         tmem_ld_wait();
         const int qi = i * 128 + r;
+        if (FOLD) acc[AB_PAD0] = acc[AB_PAD0 + 1] = 0.f;
         if (qi < T) {
           bf16* dst = dq + ((int64_t)pend_q_b * T + qi) * HP + pend_q_h * AT_DH;
 #pragma unroll
@@ -756,6 +819,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dkv_free);
+      if (FOLD) {
+        static_assert(!FOLD || DCOL == 32, "the patched columns are addressed inside a 32-column drain");
+        acc[AB_PAD0 % DCOL] = acc[(AB_PAD0 + 1) % DCOL] = 0.f;
+      }
       if (pend_key < S) {
         bf16* dst = (drain_dv ? dv : dk) + ((int64_t)pend_b * S + pend_key) * ld_dkv + pend_h * AT_DH + dcol0;
 #pragma unroll
@@ -837,8 +904,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               const int cm = key_oob ? 0x40000000 : (diag ? cmin - cs : -0x40000000);
 #define BWD_MATH(DROP)                                                                                                                        \
   do {                                                                                                                                        \
-    if (need_mask) bwd_chunk_math<DROP, true, 16>(sv, dpv, lse_c, del_c, cs, cm, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S); \
-    else bwd_chunk_math<DROP, false, 16>(sv, dpv, lse_c, del_c, cs, cmin, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S);       \
+    if (need_mask) bwd_chunk_math<DROP, true, 16, FOLD && DROP == 0>(sv, dpv, lse_c, del_c, cs, cm, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S); \
+    else bwd_chunk_math<DROP, false, 16, FOLD && DROP == 0>(sv, dpv, lse_c, del_c, cs, cmin, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S);       \
   } while (0)
               if (drop_mode == 0) BWD_MATH(0);
               else if (drop_mode == 1) BWD_MATH(1);
@@ -938,9 +1005,10 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     BPM_REQUIRE(r == CUDA_SUCCESS, "xattn_bwd: tensor map for the dropout bits failed (%d)", (int)r);
   }
   size_t smem = AttnBwdSmem::TOTAL + 1024;
-  const int dm = !(a->drop.p > 0.f) ? 0 : 1;
-  auto kern = dm == 0 ? attn_bwd_tc_kernel<0> : attn_bwd_tc_kernel<1>;
-  static bool attr_set[2] = {false, false};
+  // 0: no dropout, -lse / -delta folded into the MMAs (needs two free padding columns);  1: dropout;  2: no dropout, no fold
+  const int dm = a->drop.p > 0.f ? 1 : ((a->dh <= AB_PAD0 && !(bpm_debug_get(1) & 2048)) ? 0 : 2);
+  auto kern = dm == 0 ? attn_bwd_tc_kernel<0, true> : (dm == 1 ? attn_bwd_tc_kernel<1, false> : attn_bwd_tc_kernel<0, false>);
+  static bool attr_set[3] = {false, false, false};
   if (!attr_set[dm]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bpm_set_error("xattn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }

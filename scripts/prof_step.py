@@ -6,7 +6,8 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-os.environ["BPM_NO_GRAPH"] = "1"
+if os.environ.get("PROF_GRAPH", "1") != "1":            # default: profile the replayed CUDA graph (what bench.py times)
+    os.environ["BPM_NO_GRAPH"] = "1"
 import bench  # noqa: E402
 from bpmult_b200 import MultiprojectionMMTransformer3DGMUClf  # noqa: E402
 from bpmult_b200 import Trainer  # noqa: E402
@@ -21,7 +22,7 @@ tr = Trainer(model, lr=1e-3)
 g = torch.Generator().manual_seed(2024)
 host = list(bench.synth_batch(args, B, 2024))
 devb = [t.to(dev) for t in host]
-for _ in range(3):
+for _ in range(5):
     tr.step_device(*devb)
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
@@ -39,3 +40,27 @@ tot = sum(v[0] for v in agg.values())
 print("kernels: %d   summed device time: %.2f ms" % (len(ev), tot / 1000))
 for n, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:28]:
     print("%-62s %9.3f ms %5.1f%% %6d launches %8.2f us" % (n, t / 1000, 100 * t / tot, c, t / c))
+
+# ---- concurrency: how much of the step has 1, 2, ... kernels in flight, and which kernels run ALONE (serialisation points)
+iv = sorted((e.time_range.start, e.time_range.end, e.name.split("(")[0][:60]) for e in ev)
+pts = []
+for s, t, n in iv:
+    pts.append((s, 1, n))
+    pts.append((t, -1, n))
+pts.sort(key=lambda p: (p[0], p[1]))
+active, last, hist, alone = {}, None, {}, {}
+for t, d, n in pts:
+    k = sum(active.values())
+    if last is not None and t > last and k > 0:
+        hist[k] = hist.get(k, 0.0) + (t - last)
+        if k == 1:
+            nm = next(a for a, c in active.items() if c > 0)
+            alone[nm] = alone.get(nm, 0.0) + (t - last)
+    active[n] = active.get(n, 0) + d
+    last = t
+span = iv[-1][1] - iv[0][0] if iv else 0
+print("\nstep span %.2f ms; kernels in flight -> ms: %s; idle %.2f ms" % (
+    span / 1000, {k: round(v / 1000, 2) for k, v in sorted(hist.items())}, (span - sum(hist.values())) / 1000))
+print("time with exactly ONE kernel in flight, by kernel:")
+for n, t in sorted(alone.items(), key=lambda kv: -kv[1])[:14]:
+    print("   %-60s %8.3f ms" % (n, t / 1000))
