@@ -432,11 +432,13 @@ struct AttnBwdSmem {
   static constexpr int QD = KV + 2 * 2 * 128 * 64;
   static constexpr int DST = QD + AB_QD_STAGES * QD_STAGE;      // 2 buffers x (2 chunk tiles x 16 KB)
   static constexpr int LD = DST + 2 * 2 * 128 * 128;            // 2 buffers x (512 floats lse*log2e (+inf beyond T) + 512 floats delta)
-  static constexpr int BAR = LD + 2 * 4096;
+  static constexpr int STG = LD + 2 * 4096;                     // per compute warp: 2 staging slices of 32 rows x 64 B for the dQ / dK / dV TMA stores
+  static constexpr int BAR = STG + AB_CW * 2 * 2048;
   static constexpr int NBAR = 4 + 2 * AB_QD_STAGES + 16;
   static constexpr int TOTAL = BAR + 8 * NBAR + 16;
 };
-static_assert(AttnBwdSmem::DST % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+static_assert(AttnBwdSmem::DST % 1024 == 0 && AttnBwdSmem::STG % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+static_assert(AttnBwdSmem::TOTAL + 1024 <= 227 * 1024, "shared memory budget");
 
 __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ ws,
                                   int B, int T, int H) {
@@ -528,7 +530,8 @@ __device__ __forceinline__ void bwd_chunk_math(float* sv, float* dpv, const floa
 template <int DM, bool FOLD>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmBits, const int bits_tma,
+                   const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmBits, const __grid_constant__ CUtensorMap tmDQ,
+                   const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const int bits_tma,
                    const float* __restrict__ ws, bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T,
                    int S, int H, int mask_off, bpm_dropout_t drop, const uint32_t* __restrict__ drop_bits, const int ld_dkv, const int dbg,
                    unsigned long long* __restrict__ trace) {
@@ -787,22 +790,40 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int pend_jc = -1, pend_b = 0, pend_h = 0, pend_key = 0;
     // dQ of a finished (b,h) is drained after the first pair of the NEXT (b,h) has been computed, for the same reason
     int pend_q_bc = -1, pend_q_b = 0, pend_q_h = 0;
+    // accumulator rows leave through shared memory and the TMA unit: a thread owns one 64-byte row, so direct stores would be 32
+    // half-used sectors per instruction (measured: 3 k clk per (b,h) for dQ, 1 k per key tile for dK / dV); staged and stored as
+    // {32 columns, 32 rows} boxes they are fully coalesced, asynchronous, and rows beyond T / S are clipped by the tensor map
+    uint8_t* const stg_gen = base_gen + AttnBwdSmem::STG + cw * 4096;
+    const uint32_t stg_s = base + AttnBwdSmem::STG + cw * 4096;
+    int stg_n = 0;                                            // staging slices used so far (slice = stg_n & 1)
+    auto stage_store = [&](const float* acc, float scale, const CUtensorMap* map, int c0, int row0, int bidx) {
+      const int sl = stg_n & 1;
+      stg_n++;
+      if (elect_one()) bulk_wait_read<1>();                   // the store that last used this slice has read it
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        *(uint4*)(stg_gen + sl * 2048 + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) =
+            make_uint4(pack_bf16x2(acc[u * 8] * scale, acc[u * 8 + 1] * scale), pack_bf16x2(acc[u * 8 + 2] * scale, acc[u * 8 + 3] * scale),
+                       pack_bf16x2(acc[u * 8 + 4] * scale, acc[u * 8 + 5] * scale), pack_bf16x2(acc[u * 8 + 6] * scale, acc[u * 8 + 7] * scale));
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_3d(map, stg_s + sl * 2048, c0, row0, bidx);
+        bulk_commit();
+      }
+      __syncwarp();
+    };
     auto drain_dq = [&]() {
       mbar_wait(dq_full, (uint32_t)pend_q_bc & 1u);
       tc_fence_after();
+      TRACE(3 + (colq & 1), 35);
       for (int i = colq; i < nq; i += NCG) {                  // query tile i is drained by column group i % NCG
         float acc[AT_DH];
         tmem_ld32(tDQ + 32 * i + lane_off, acc);
         tmem_ld_wait();
-        const int qi = i * 128 + r;
         if (FOLD) acc[AB_PAD0] = acc[AB_PAD0 + 1] = 0.f;
-        if (qi < T) {
-          bf16* dst = dq + ((int64_t)pend_q_b * T + qi) * HP + pend_q_h * AT_DH;
-#pragma unroll
-          for (int u = 0; u < AT_DH / 8; u++)
-            *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8] * dq_scale, acc[u * 8 + 1] * dq_scale), pack_bf16x2(acc[u * 8 + 2] * dq_scale, acc[u * 8 + 3] * dq_scale),
-                                                pack_bf16x2(acc[u * 8 + 4] * dq_scale, acc[u * 8 + 5] * dq_scale), pack_bf16x2(acc[u * 8 + 6] * dq_scale, acc[u * 8 + 7] * dq_scale));
-        }
+        stage_store(acc, dq_scale, &tmDQ, pend_q_h * AT_DH, i * 128 + quarter * 32, pend_q_b);
       }
       tc_fence_before();
       __syncwarp();
@@ -810,26 +831,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       pend_q_bc = -1;
     };
     auto drain_dkv = [&]() {
+      static_assert(DCOL == 32, "one warp drains all 32 columns of dK or of dV");
       mbar_wait(dkv_full, (uint32_t)pend_jc & 1u);
       tc_fence_after();
+      TRACE(3 + (colq & 1), 36);
       float acc[DCOL];
-      if (DCOL == 32) tmem_ld32((drain_dv ? tDV : tDK) + lane_off, acc);
-      else tmem_ld16((drain_dv ? tDV : tDK) + (uint32_t)dcol0 + lane_off, acc);
+      tmem_ld32((drain_dv ? tDV : tDK) + lane_off, acc);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dkv_free);
-      if (FOLD) {
-        static_assert(!FOLD || DCOL == 32, "the patched columns are addressed inside a 32-column drain");
-        acc[AB_PAD0 % DCOL] = acc[(AB_PAD0 + 1) % DCOL] = 0.f;
-      }
-      if (pend_key < S) {
-        bf16* dst = (drain_dv ? dv : dk) + ((int64_t)pend_b * S + pend_key) * ld_dkv + pend_h * AT_DH + dcol0;
-#pragma unroll
-        for (int u = 0; u < DCOL / 8; u++)
-          *(uint4*)(dst + u * 8) = make_uint4(pack_bf16x2(acc[u * 8], acc[u * 8 + 1]), pack_bf16x2(acc[u * 8 + 2], acc[u * 8 + 3]),
-                                              pack_bf16x2(acc[u * 8 + 4], acc[u * 8 + 5]), pack_bf16x2(acc[u * 8 + 6], acc[u * 8 + 7]));
-      }
+      if (FOLD) acc[AB_PAD0] = acc[AB_PAD0 + 1] = 0.f;
+      stage_store(acc, 1.f, drain_dv ? &tmDV : &tmDK, pend_h * AT_DH, pend_key - lane, pend_b);
       pend_jc = -1;
     };
     for (int bh = blockIdx.x; bh < nbh; bh += gridDim.x, bc++) {
@@ -939,7 +952,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           TRACE(3 + (colq & 1), 30);
           if (pend_jc >= 0) drain_dkv();                      // previous key tile's dK / dV: its MMAs finished while this pair was computed
+          TRACE(3 + (colq & 1), 32);
           if (pend_q_bc >= 0) drain_dq();                     // previous (b,h)'s dQ
+          TRACE(3 + (colq & 1), 33);
           tmem_st_wait();
           tc_fence_before();
           fence_async_smem();
@@ -962,6 +977,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (pend_jc >= 0) drain_dkv();
       drain_dq();
     }
+    if (elect_one()) bulk_wait_read<0>();                     // the staging slices must outlive the last TMA stores' reads
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -985,10 +1002,13 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     cudaError_t le = bpm_launch(attn_delta_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)out, (const bf16*)dout, lse, delta, a->B, a->T, a->H);
     if (le != cudaSuccess) { bpm_set_error("xattn_delta: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   }
-  CUtensorMap tq, tk, tv, tg;
+  CUtensorMap tq, tk, tv, tg, tdq, tdk, tdv;
   int rc;
   if ((rc = make_qkv_map(&tq, q, a->B, a->T, HP, 128))) return rc;
   BPM_REQUIRE(a->ld_kv % 8 == 0 && a->ld_dkv % 8 == 0, "xattn_bwd: ld_kv / ld_dkv must be multiples of 8 elements");
+  if ((rc = make_qkv_map(&tdq, dq, a->B, a->T, HP, 32))) return rc;                       // outputs: {32 columns, 32 rows} store boxes
+  if ((rc = make_qkv_map(&tdk, dk, a->B, a->S, HP, 32, a->ld_dkv))) return rc;
+  if ((rc = make_qkv_map(&tdv, dv, a->B, a->S, HP, 32, a->ld_dkv))) return rc;
   if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, 128, a->ld_kv))) return rc;
   if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, 128, a->ld_kv))) return rc;
   if ((rc = make_qkv_map(&tg, dout, a->B, a->T, HP, 128))) return rc;
@@ -1015,7 +1035,7 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     attr_set[dm] = true;
   }
   const int ctas = min(a->B * a->H, bpm_num_sms());
-  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AB_THREADS), smem, stream, tq, tk, tv, tg, tb, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
+  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AB_THREADS), smem, stream, tq, tk, tv, tg, tb, tdq, tdk, tdv, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
                                                          a->mask_off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr());
   if (le != cudaSuccess) { bpm_set_error("xattn_bwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;

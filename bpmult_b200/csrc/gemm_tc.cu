@@ -59,14 +59,6 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
                "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_read_n(int n) {
-  if (n <= 0) bulk_wait_read<0>();
-  else if (n == 1) bulk_wait_read<1>();
-  else if (n == 2) bulk_wait_read<2>();
-  else bulk_wait_read<3>();
-}
 
 // byte offset of 16-byte unit u of row r inside a swizzled [32 rows x CB] box (TMA SWIZZLE_128B / SWIZZLE_64B)
 template <int CB> __device__ __forceinline__ uint32_t swz_off(int r, int u) {

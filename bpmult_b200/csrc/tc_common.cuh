@@ -68,6 +68,21 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
                : "memory");
 }
 
+// shared memory -> global through the TMA unit (bulk async group of the issuing thread); rows / columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)m), "r"(smem_src), "r"(c0), "r"(c1),
+               "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_read_n(int n) {
+  if (n <= 0) bulk_wait_read<0>();
+  else if (n == 1) bulk_wait_read<1>();
+  else if (n == 2) bulk_wait_read<2>();
+  else bulk_wait_read<3>();
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
