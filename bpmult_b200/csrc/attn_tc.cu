@@ -412,8 +412,8 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
 // TMEM: S^T 128 + dP^T 128 + P~^T 64 (bf16 pairs) + dK 32 + dV 32 + dQ 4x32 = 512 columns.
 // The pre-kernel computes delta = rowsum(dO * O) and lse * log2e into the [2, B, H, T] workspace.
 // =====================================================================================================================
-#define AB_CW 8                           // compute warps: AB_CW/4 per TMEM lane quarter, 128/(AB_CW/4) query columns each
-#define AB_THREADS (96 + 32 * AB_CW)
+// CW compute warps (template parameter: 8, or 16 for the light folded math): CW/4 per TMEM lane quarter, 128/(CW/4) query columns each
+#define AB_THREADS(CW) (96 + 32 * (CW))
 #define AB_MAXQT 4
 #define AB_QD_STAGES 4
 // optional per-role event trace of CTA 0 (bpm_debug_set_ptr; scripts/trace_attn.py): entry = (clock64 << 8) | event id
@@ -433,7 +433,7 @@ struct AttnBwdSmem {
   static constexpr int DST = QD + AB_QD_STAGES * QD_STAGE;      // 2 buffers x (2 chunk tiles x 16 KB)
   static constexpr int LD = DST + 2 * 2 * 128 * 128;            // 2 buffers x (512 floats lse*log2e (+inf beyond T) + 512 floats delta)
   static constexpr int STG = LD + 2 * 4096;                     // per compute warp: 2 staging slices of 32 rows x 64 B for the dQ / dK / dV TMA stores
-  static constexpr int BAR = STG + AB_CW * 2 * 2048;
+  static constexpr int BAR = STG + 8 * 2 * 2048;                // 32 KB: 2 slices per warp with 8 compute warps, 1 with 16
   static constexpr int NBAR = 4 + 2 * AB_QD_STAGES + 16;
   static constexpr int TOTAL = BAR + 8 * NBAR + 16;
 };
@@ -527,8 +527,8 @@ __device__ __forceinline__ void bwd_chunk_math(float* sv, float* dpv, const floa
 // tensor core delivers S^T - lse and dP^T - delta directly.  The garbage this leaves in the same two columns of dQ / dK / dV is
 // zeroed when the accumulators are drained.
 #define AB_PAD0 26                       // patched head-dim columns (AB_PAD0, AB_PAD0 + 1): 4-byte aligned inside the 64-byte row
-template <int DM, bool FOLD>
-__global__ void __launch_bounds__(AB_THREADS, 1)
+template <int DM, bool FOLD, int CW>
+__global__ void __launch_bounds__(AB_THREADS(CW), 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmBits, const __grid_constant__ CUtensorMap tmDQ,
                    const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const int bits_tma,
@@ -583,18 +583,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     for (int s = 0; s < 2; s++) {
       mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1);
-      mbar_init(pt_full(s), AB_CW); mbar_init(ds_free(s), 1);
-      mbar_init(ld_full(s), 1); mbar_init(ld_empty(s), AB_CW);
+      mbar_init(pt_full(s), CW); mbar_init(ds_free(s), 1);
+      mbar_init(ld_full(s), 1); mbar_init(ld_empty(s), CW);
     }
     for (int s = 0; s < AB_QD_STAGES; s++) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
-    mbar_init(st_full, 1); mbar_init(st_free, AB_CW); mbar_init(pv_free, 1);
-    mbar_init(dkv_full, 1); mbar_init(dkv_free, AB_CW);
-    mbar_init(dq_full, 1); mbar_init(dq_free, AB_CW);
+    mbar_init(st_full, 1); mbar_init(st_free, CW); mbar_init(pv_free, 1);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, 8);              // drained by 8 warps: (lane quarter) x (dK | dV)
+    mbar_init(dq_full, 1); mbar_init(dq_free, CW);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, 512);
   // query columns beyond T: lse = +inf (exp2(x - inf) = 0), delta = 0; the bulk copies only ever write the first T entries
-  for (int t = threadIdx.x; t < 2 * 1024; t += AB_THREADS) {
+  for (int t = threadIdx.x; t < 2 * 1024; t += AB_THREADS(CW)) {
     float* ld = (float*)(base_gen + AttnBwdSmem::LD);
     ld[t] = ((t & 1023) < 512) ? INFINITY : 0.f;
   }
@@ -768,7 +768,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ===================== compute warps =====================
-    constexpr int NCG = AB_CW / 4;                          // column groups (warps per lane quarter)
+    constexpr int NCG = CW / 4;                             // column groups (warps per lane quarter)
     constexpr int NCOL = 128 / NCG;                         // query columns per warp
     const int cw = warp - 3;
     const int quarter = warp & 3, colq = cw >> 2;          // TMEM lane quarter; column group [NCOL*colq, +NCOL) of the pair tile
@@ -783,23 +783,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
     int pc = 0, jc = 0, bc = 0;
     // dK / dV of a finished key tile are drained while the NEXT pair is being computed (no stall on the last accumulate MMAs):
-    // the 32 dK and 32 dV columns are split evenly over the NCG warps of a lane quarter (first half of the groups dK, second half dV)
-    constexpr int DCOL = 64 / NCG;                          // accumulator columns per warp: 32 (NCG = 2) or 16 (NCG = 4)
+    // dK (all 32 columns) is drained by the first column group of each lane quarter, dV by group NCG/2; the others only compute
+    constexpr int DCOL = 32;
     const bool drain_dv = colq >= NCG / 2;
-    const int dcol0 = (colq % (NCG / 2)) * DCOL;
+    const bool drains_kv = (colq % (NCG / 2)) == 0;
+    const int dcol0 = 0;
     int pend_jc = -1, pend_b = 0, pend_h = 0, pend_key = 0;
     // dQ of a finished (b,h) is drained after the first pair of the NEXT (b,h) has been computed, for the same reason
     int pend_q_bc = -1, pend_q_b = 0, pend_q_h = 0;
     // accumulator rows leave through shared memory and the TMA unit: a thread owns one 64-byte row, so direct stores would be 32
     // half-used sectors per instruction (measured: 3 k clk per (b,h) for dQ, 1 k per key tile for dK / dV); staged and stored as
     // {32 columns, 32 rows} boxes they are fully coalesced, asynchronous, and rows beyond T / S are clipped by the tensor map
-    uint8_t* const stg_gen = base_gen + AttnBwdSmem::STG + cw * 4096;
-    const uint32_t stg_s = base + AttnBwdSmem::STG + cw * 4096;
-    int stg_n = 0;                                            // staging slices used so far (slice = stg_n & 1)
+    constexpr int NSL = 16 / CW;                              // staging slices per warp (2 KB each)
+    uint8_t* const stg_gen = base_gen + AttnBwdSmem::STG + cw * NSL * 2048;
+    const uint32_t stg_s = base + AttnBwdSmem::STG + cw * NSL * 2048;
+    int stg_n = 0;                                            // staging slices used so far (slice = stg_n % NSL)
     auto stage_store = [&](const float* acc, float scale, const CUtensorMap* map, int c0, int row0, int bidx) {
-      const int sl = stg_n & 1;
+      const int sl = stg_n % NSL;
       stg_n++;
-      if (elect_one()) bulk_wait_read<1>();                   // the store that last used this slice has read it
+      if (elect_one()) bulk_wait_read<NSL - 1>();             // the store that last used this slice has read it
       __syncwarp();
 #pragma unroll
       for (int u = 0; u < 4; u++)
@@ -831,7 +833,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       pend_q_bc = -1;
     };
     auto drain_dkv = [&]() {
-      static_assert(DCOL == 32, "one warp drains all 32 columns of dK or of dV");
+      if (!drains_kv) { pend_jc = -1; return; }
       mbar_wait(dkv_full, (uint32_t)pend_jc & 1u);
       tc_fence_after();
       TRACE(3 + (colq & 1), 36);
@@ -854,7 +856,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int key = j * 128 + r;
         const int imin = i_min_of(j);
         if (imin >= nq) {                                     // no query sees this key tile: dK = dV = 0
-          if (key < S) {
+          if (key < S && drains_kv) {
             bf16* dst = (drain_dv ? dv : dk) + ((int64_t)b * S + key) * ld_dkv + h * AT_DH + dcol0;
 #pragma unroll
             for (int u = 0; u < DCOL / 8; u++) *(uint4*)(dst + u * 8) = make_uint4(0, 0, 0, 0);
@@ -1027,15 +1029,18 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   size_t smem = AttnBwdSmem::TOTAL + 1024;
   // 0: no dropout, -lse / -delta folded into the MMAs (needs two free padding columns);  1: dropout;  2: no dropout, no fold
   const int dm = a->drop.p > 0.f ? 1 : ((a->dh <= AB_PAD0 && !(bpm_debug_get(1) & 2048)) ? 0 : 2);
-  auto kern = dm == 0 ? attn_bwd_tc_kernel<0, true> : (dm == 1 ? attn_bwd_tc_kernel<1, false> : attn_bwd_tc_kernel<0, false>);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[dm]) {
+  const int cw = (dm == 0 && !(bpm_debug_get(1) & 4096)) ? 16 : 8;
+  auto kern = dm == 0 ? (cw == 16 ? attn_bwd_tc_kernel<0, true, 16> : attn_bwd_tc_kernel<0, true, 8>)
+                      : (dm == 1 ? attn_bwd_tc_kernel<1, false, 8> : attn_bwd_tc_kernel<0, false, 8>);
+  static bool attr_set[4] = {false, false, false, false};
+  const int ki = dm == 0 && cw == 8 ? 3 : dm;
+  if (!attr_set[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bpm_set_error("xattn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
-    attr_set[dm] = true;
+    attr_set[ki] = true;
   }
   const int ctas = min(a->B * a->H, bpm_num_sms());
-  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AB_THREADS), smem, stream, tq, tk, tv, tg, tb, tdq, tdk, tdv, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
+  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AB_THREADS(cw)), smem, stream, tq, tk, tv, tg, tb, tdq, tdk, tdv, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
                                                          a->mask_off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr());
   if (le != cudaSuccess) { bpm_set_error("xattn_bwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
