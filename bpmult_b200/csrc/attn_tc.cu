@@ -416,8 +416,10 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
 #define AB_THREADS(CW) (96 + 32 * (CW))
 #define AB_MAXQT 4
 #define AB_QD_STAGES 4
-// optional per-role event trace of CTA 0 (bpm_debug_set_ptr; scripts/trace_attn.py): entry = (clock64 << 8) | event id
+// optional per-role event trace of CTA 0 (bpm_debug_set_ptr; scripts/trace_attn.py): entry = (clock64 << 8) | event id.
+// Compiled in only with `make EXTRA=-DBPM_ATTN_TRACE` (the checks cost ~5 % of the kernel when they sit in the pair loop).
 #define AB_TRACE_N 4096
+#ifdef BPM_ATTN_TRACE
 #define TRACE(role, id)                                                                 \
   do {                                                                                  \
     if (trace != nullptr && blockIdx.x == 0 && tr_n < AB_TRACE_N) {                     \
@@ -425,6 +427,9 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
       tr_n++;                                                                           \
     }                                                                                   \
   } while (0)
+#else
+#define TRACE(role, id) do { (void)tr_n; } while (0)
+#endif
 
 struct AttnBwdSmem {
   static constexpr int KV = 0;                                  // 2 stages x (K 8 KB + V 8 KB)

@@ -1,4 +1,5 @@
-"""Dumps the per-role event trace of CTA 0 of the attention backward kernel (diagnostics only)."""
+"""Dumps the per-role event trace of CTA 0 of the attention backward kernel (diagnostics only).
+Needs a library built with the trace points compiled in:  make -C bpmult_b200/csrc clean && make -C bpmult_b200/csrc EXTRA=-DBPM_ATTN_TRACE"""
 import sys
 
 import torch
