@@ -55,7 +55,8 @@ struct AttnFwdSmem {
   static constexpr int K = Q + 2 * AT_BM * 64;                  // stages x 128 x 64 B
   static constexpr int V = K + AT_KV_STAGES * AT_BN * 64;
   static constexpr int GROUP = V + AT_KV_STAGES * AT_BN * 64;   // 64 KB
-  static constexpr int BAR = AF_GROUPS * GROUP;
+  static constexpr int STG = AF_GROUPS * GROUP;                 // output staging: one 32-row x 64-byte slice per softmax warp (TMA store)
+  static constexpr int BAR = STG + AF_GROUPS * 4 * 2048;
   static constexpr int NBAR_G = 4 + 2 * AT_KV_STAGES + 2 + 1 + 2;   // q_full[2], q_free[2], kv_full/empty, s_full, s_free, p_full, o_full[2]
   static constexpr int TOTAL = BAR + 8 * AF_GROUPS * NBAR_G + 16;
 };
@@ -66,10 +67,14 @@ __device__ __forceinline__ void fwd_mask32(float* sv, int lim) {
   for (int c = 0; c < 32; c++) sv[c] = (c <= lim) ? sv[c] : -INFINITY;
 }
 
-template <bool DROP>
+// ONES (no dropout, head dim <= 26 of 32): the MMA warp writes ones into two padding columns of every V tile in shared memory, so
+// column AF_PAD0 of the P V accumulator is the row sum of P -- rescaled with the other columns, summed by the tensor core from the
+// same bf16 probabilities that weight V -- and the softmax warps need no add per probability.
+#define AF_PAD0 26
+template <bool DROP, bool ONES>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   bf16* __restrict__ out, float* __restrict__ lse, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
+                   const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
                    uint32_t* __restrict__ drop_bits) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -166,6 +171,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       auto issue_s = [&](int kcj, int tcj, bool last) {
         const int s = kcj % AT_KV_STAGES;
         mbar_wait(kv_full(s), (uint32_t)(kcj / AT_KV_STAGES) & 1u);
+        if (ONES) {                                                        // V[:, AF_PAD0 .. +1] = 1 (16-byte unit 3 of the swizzled 64-byte row)
+          uint8_t* vt = base_gen + (gbase - base) + AttnFwdSmem::V + s * AT_BN * 64;
+#pragma unroll
+          for (int rr = 0; rr < 4; rr++) {
+            const int r = rr * 32 + lane;
+            *(uint32_t*)(vt + r * 64 + ((3 ^ ((r >> 1) & 3)) << 4) + 4) = 0x3F803F80u;
+          }
+          fence_async_smem();
+          __syncwarp();
+        }
         mbar_wait(s_free, ((uint32_t)tcj & 1u) ^ 1u);                      // the softmax warps have read the previous S tile
         tc_fence_after();
         if (elect_one()) {
@@ -274,8 +289,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ffma2(sv[e + 2], sv[e + 3], LOG2E_F, neg_m);
 #pragma unroll
             for (int u = 0; u < 4; u++) sv[e + u] = ex2f(sv[e + u]);
-            fadd2(r4[0], r4[1], sv[e], sv[e + 1]);
-            fadd2(r4[2], r4[3], sv[e + 2], sv[e + 3]);
+            if (!ONES) {
+              fadd2(r4[0], r4[1], sv[e], sv[e + 1]);
+              fadd2(r4[2], r4[3], sv[e + 2], sv[e + 3]);
+            }
           }
           rs0 += r4[0] + r4[2];
           rs1 += r4[1] + r4[3];
@@ -330,22 +347,40 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(tO0 + 32 * ((tc - 1) & 1) + lane_off, ov);
         tmem_ld_wait();
         tc_fence_before();
+        if (ONES) {                                                        // the ones column of V: row sum of the bf16 probabilities
+          l = oacc[AF_PAD0] + ov[AF_PAD0];
+          oacc[AF_PAD0] = oacc[AF_PAD0 + 1] = 0.f;
+          ov[AF_PAD0] = ov[AF_PAD0 + 1] = 0.f;
+        }
         const float inv_l = (DROP ? dc.inv_keep : 1.f) / l;
 #pragma unroll
         for (int d = 0; d < AT_DH; d++) oacc[d] = (oacc[d] + ov[d]) * inv_l;
       }
-      if (qi < T) {
-        bf16* orow = out + ((int64_t)b * T + qi) * (int64_t)(H * AT_DH) + h * AT_DH;
+      {
+        // the 32 output rows of this warp leave through shared memory and one TMA store (a thread owns a 64-byte row: direct stores
+        // would be 32 half-used sectors per instruction); rows beyond T are clipped by the tensor map
+        uint8_t* const stg = base_gen + AttnFwdSmem::STG + (grp * 4 + (gw - 2)) * 2048;
+        if (elect_one()) bulk_wait_read<0>();                              // the previous item's store has read the slice
+        __syncwarp();
 #pragma unroll
         for (int u = 0; u < AT_DH / 8; u++) {
           uint4 w;
           w.x = pack_bf16x2(oacc[u * 8 + 0], oacc[u * 8 + 1]); w.y = pack_bf16x2(oacc[u * 8 + 2], oacc[u * 8 + 3]);
           w.z = pack_bf16x2(oacc[u * 8 + 4], oacc[u * 8 + 5]); w.w = pack_bf16x2(oacc[u * 8 + 6], oacc[u * 8 + 7]);
-          *(uint4*)(orow + u * 8) = w;
+          *(uint4*)(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = w;
         }
-        lse[(int64_t)bh * T + qi] = (m + log2f(l)) * LN2_F;
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_3d(&tmO, base + AttnFwdSmem::STG + (grp * 4 + (gw - 2)) * 2048, h * AT_DH, q0 + quarter * 32, b);
+          bulk_commit();
+        }
+        __syncwarp();
+        if (qi < T) lse[(int64_t)bh * T + qi] = (m + log2f(l)) * LN2_F;
       }
     }
+    if (elect_one()) bulk_wait_read<0>();                                 // the staging slice must outlive the last TMA store's read
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -375,9 +410,12 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, AT_BN, a->ld_kv))) return rc;
   if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, AT_BN, a->ld_kv))) return rc;
   size_t smem = AttnFwdSmem::TOTAL + 1024;
-  const int dm = a->drop.p > 0.f ? 1 : 0;                // the instantiation without dropout code is smaller and faster
-  auto kern = dm ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>;
-  static bool attr_set[2] = {false, false};
+  // 0: no dropout, row sums through a ones column of V (needs two free padding columns);  1: dropout;  2: no dropout, no ones column
+  const int dm = a->drop.p > 0.f ? 1 : ((a->dh <= AF_PAD0 && !(bpm_debug_get(1) & 8192)) ? 0 : 2);
+  auto kern = dm == 1 ? attn_fwd_tc_kernel<true, false> : (dm == 0 ? attn_fwd_tc_kernel<false, true> : attn_fwd_tc_kernel<false, false>);
+  CUtensorMap to;
+  if ((rc = make_qkv_map(&to, out, a->B, a->T, HP, 32))) return rc;                      // output: {32 columns, 32 rows} store boxes
+  static bool attr_set[3] = {false, false, false};
   if (!attr_set[dm]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bpm_set_error("xattn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
@@ -385,7 +423,7 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   }
   const int n_items = a->B * a->H * bpm_cdiv(a->T, AT_BM);
   const int ctas = min(bpm_num_sms(), bpm_cdiv(n_items, AF_GROUPS));
-  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AF_THREADS), smem, stream, tq, tk, tv, (bf16*)out, lse, a->B, a->T, a->S, a->H,
+  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AF_THREADS), smem, stream, tq, tk, tv, to, lse, a->B, a->T, a->S, a->H,
                               a->mask_off, a->drop, a->drop_bits);
   if (le != cudaSuccess) { bpm_set_error("xattn_fwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
