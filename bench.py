@@ -280,7 +280,7 @@ def run_ours(opt):
     loss_dev = float(tr.loss_dev[0])
     # e2e: public API with host tensors, H2D + D2H inside the timed region
     tr.step(*host)
-    ms_e2e = timed(lambda: tr.step(*host), opt.steps)
+    ms_e2e = timed(lambda: tr.step(*host), opt.steps)           # blocking API: the loss of every step is read before the next is enqueued
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -301,7 +301,8 @@ def run_ours(opt):
     line = {"metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": opt.steps, "warmup": max(opt.warmup, 3),
             "ms_per_step": ms / opt.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if opt.precision == "bf16" else "f32", "data": "synthetic", "config": workload_config(args, B, world),
-            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": tr.bytes_in(), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / opt.steps},
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": tr.bytes_in(), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / opt.steps,
+                    "api": "Trainer.step(pinned host tensors) -> float: H2D of the batch and D2H of the loss every step, blocking"},
             "gpu_launches": int(getattr(tr, "launches_per_step", 0)) * opt.steps, "launches_per_step": int(getattr(tr, "launches_per_step", 0)),
             "cuda_graph": bool(tr.use_graph), "loss": loss_dev, "params": tr.n_params,
             "clocks": sampler.summary() if sampler else None}

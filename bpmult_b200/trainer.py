@@ -17,6 +17,18 @@ import torch.distributed as dist
 from .modules import MultiprojectionMMTransformer3DGMUClf
 
 
+class _Loss:
+    """handle of an enqueued step: item() waits for that step and returns its loss"""
+
+    def __init__(self, host, event):
+        self.host, self.event = host, event
+
+    def item(self):
+        if self.event is not None:
+            self.event.synchronize()
+        return float(self.host[0])
+
+
 class Trainer:
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, pos_weight=None, seed=1234, use_graph=None, grad_accum=1):
         assert isinstance(model, MultiprojectionMMTransformer3DGMUClf)
@@ -41,9 +53,11 @@ class Trainer:
         self.on_gpu = dev.type == "cuda"                     # (CPU only in the gloo host-logic tests, with the ops emulation)
         self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.on_gpu) else None
         self.graphs, self.static, self.shapes = {}, None, None
-        self.loss_host = torch.zeros(1, dtype=torch.float32)
+        self.loss_slots = [torch.zeros(1, dtype=torch.float32) for _ in range(2)]     # two steps may be in flight (step_async)
         if self.device.type == "cuda":
-            self.loss_host = self.loss_host.pin_memory()
+            self.loss_slots = [t.pin_memory() for t in self.loss_slots]
+        self.loss_host = self.loss_slots[0]
+        self._h2d_done = None
         self.steps_done = 0
 
     # ---------------------------------------------------------------- flat parameter / gradient buffers
@@ -181,19 +195,34 @@ class Trainer:
         return self.loss_dev
 
     def step(self, txt, img, audio, tgt):
-        """end-to-end step from HOST tensors: pinned staging -> H2D -> step -> D2H of the loss.  Returns a python float."""
+        """end-to-end step from HOST tensors: pinned staging -> H2D -> step -> D2H of the loss.  Returns a python float (blocks until
+        the step has finished, like the `loss.item()` of train.py:393)."""
+        return self.step_async(txt, img, audio, tgt).item()
+
+    def step_async(self, txt, img, audio, tgt):
+        """same as step() but returns at once with a handle; `handle.item()` blocks for THIS step's loss.  Reading the loss one step late
+        (enqueue step k+1, then `item()` of step k) keeps the GPU busy while the host prepares the next launch.  Pinned inputs are
+        read by DMA straight from the caller's tensors: keep them unchanged until the handle has been read."""
         self._ensure_static(txt, img, audio, tgt)
+        if self.on_gpu and self._h2d_done is not None:
+            self._h2d_done.synchronize()                    # the previous step's copies out of the staging buffers have finished
         for pbuf, s, t in zip(self.pinned, self.static, (txt, img, audio, tgt)):
             if self.on_gpu and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous():
                 s.copy_(t, non_blocking=True)               # e.g. DataLoader(pin_memory=True): DMA straight from the caller's buffer
             else:
                 pbuf.copy_(t)                               # pageable input: staged through this trainer's pinned buffers
                 s.copy_(pbuf, non_blocking=True)
-        self._run()
-        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        slot = self._loss_slot = (getattr(self, "_loss_slot", 1) + 1) & 1
         if self.on_gpu:
-            torch.cuda.current_stream(self.device).synchronize()
-        return float(self.loss_host[0])
+            self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(torch.cuda.current_stream(self.device))
+        self._run()
+        self.loss_slots[slot].copy_(self.loss_dev, non_blocking=True)
+        ev = None
+        if self.on_gpu:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        return _Loss(self.loss_slots[slot], ev)
 
     def _run(self):
         apply = (self.micro + 1) % self.grad_accum == 0     # train.py:395-398: optimizer step every grad_accum micro-batches

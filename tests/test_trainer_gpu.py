@@ -55,6 +55,23 @@ def test_trainer_e2e_host_api_and_dropout_determinism():
     assert len(set(round(x, 6) for x in runs[0])) > 1
 
 
+def test_step_async_reads_each_loss_one_step_late_and_matches_step():
+    cfg = synth.tiny_cfg()
+    host = synth.mmtrvat_inputs(cfg, 2, 10, 30, 25)
+    pinned = [t.pin_memory() for t in host]
+    from bpmult_b200 import Trainer
+    a, b = Trainer(_model(cfg, "fp32"), lr=1e-3, seed=5), Trainer(_model(cfg, "fp32"), lr=1e-3, seed=5)
+    la = [a.step(*host) for _ in range(5)]                    # pageable inputs, blocking
+    lb, pend = [], []
+    for _ in range(5):                                         # pinned inputs, two steps in flight
+        pend.append(b.step_async(*pinned))
+        if len(pend) > 1:
+            lb.append(pend.pop(0).item())
+    lb.append(pend.pop(0).item())
+    assert max(abs(x - y) for x, y in zip(la, lb)) < 1e-6, (la, lb)
+    assert len(set(lb)) == 5
+
+
 def test_gradient_accumulation_and_lr_change_under_graph_replay():
     """train.py:390-398 with gradient_accumulation_steps=2: the accumulate-only and the apply micro-step are two captured graphs;
     the learning rate is read from device memory, so set_lr() acts on a replayed graph"""
