@@ -68,6 +68,8 @@ SIGNATURES = {
     "bpm_tsgate_fwd": [_P, _P, _I, _I, _I, _P, _P, _P],
     "bpm_tsgate_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P],
     "bpm_bce_fwd_bwd": [_P, _I, _P, _P, _I, _I, _F, _P, _P, _P],
+    "bpm_timelin_fwd": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "bpm_timelin_bwd": [_I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "bpm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P, _P, _P],
 }
 _RESTYPE = {"bpm_last_error": C.c_char_p}

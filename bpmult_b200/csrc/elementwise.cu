@@ -406,6 +406,109 @@ extern "C" int bpm_add(int dtype, const void* a, const void* b, void* y, int64_t
   return BPM_OK;
 }
 
+// ---------------------------------------------------------------- time-axis Linear (mmtr.py:507-508,530,553: x.permute(2,1,0) -> Linear(T -> T2) -> permute back)
+// y[b, t2, d] = bias[t2] + sum_t W[t2, t] * x[b, t, d]   on batch-major [B, T, ld] rows (columns >= D are written as zeros).
+// One block per (t2, b): the weight row sits in shared memory, threads run along d (coalesced).  TRANSPOSED = the input-gradient
+// form dx[b, t, d] (+)= sum_t2 W[t2, t] * dy[b, t2, d]  (same kernel, weight read down a column, no bias).
+template <typename T, bool TRANSPOSED>
+__global__ void timelin_kernel(const T* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, T* __restrict__ y, int Tin, int Tout,
+                               int D, int ld, int w_in, int accumulate) {
+  extern __shared__ float wrow[];
+  const int to = blockIdx.x, b = blockIdx.y;
+  for (int t = threadIdx.x; t < Tin; t += blockDim.x) wrow[t] = TRANSPOSED ? W[(int64_t)t * w_in + to] : W[(int64_t)to * w_in + t];
+  __syncthreads();
+  const T* xb = x + (int64_t)b * Tin * ld;
+  T* yr = y + ((int64_t)b * Tout + to) * ld;
+  const float b0 = (!TRANSPOSED && bias != nullptr) ? bias[to] : 0.f;
+  for (int d0 = threadIdx.x * 8; d0 < ld; d0 += blockDim.x * 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = b0;
+    for (int t = 0; t < Tin; t++) {
+      Vec8<T> v; v.load(xb + (int64_t)t * ld + d0);
+      const float w = wrow[t];
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] = fmaf(w, v.v[j], acc[j]);
+    }
+    Vec8<T> o;
+    if (accumulate) o.load(yr + d0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float r = (d0 + j < D) ? acc[j] : 0.f;
+      o.v[j] = accumulate ? o.v[j] + r : r;
+    }
+    o.store(yr + d0);
+  }
+}
+
+// dW[t2, t] += sum_{b, d < D} dy[b, t2, d] * x[b, t, d];  db[t2] += sum_{b, d < D} dy[b, t2, d].  One block per (t2, 8 input steps).
+template <typename T>
+__global__ void timelin_wgrad_kernel(const float* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dW, float* __restrict__ db, int B, int Tin,
+                                     int Tout, int D, int ld) {
+  const int t2 = blockIdx.x, tb = blockIdx.y * 8;
+  float acc[8], accb = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = 0.f;
+  for (int b = 0; b < B; b++) {
+    const float* dyr = dy + ((int64_t)b * Tout + t2) * ld;
+    const T* xb = x + (int64_t)b * Tin * ld;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float g = dyr[d];
+      accb += g;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (tb + k < Tin) acc[k] = fmaf(g, (float)xb[(int64_t)(tb + k) * ld + d], acc[k]);
+    }
+  }
+  __shared__ float red[9][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    float v = k < 8 ? acc[k] : accb;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float v = 0.f;
+    for (int w = 0; w < nw; w++) v += red[threadIdx.x][w];
+    if (threadIdx.x < 8) { if (tb + (int)threadIdx.x < Tin) dW[(int64_t)t2 * Tin + tb + threadIdx.x] += v; }
+    else if (blockIdx.y == 0 && db != nullptr) db[t2] += v;
+  }
+}
+
+extern "C" int bpm_timelin_fwd(int dtype, const void* x, const float* W, const float* bias, void* y, int B, int Tin, int Tout, int D, int ld,
+                               void* stream) {
+  BPM_REQUIRE(x && W && y && B > 0 && Tin > 0 && Tout > 0 && D > 0 && ld >= D && ld % 8 == 0, "timelin_fwd: bad args");
+  dim3 grid(Tout, B);
+  const size_t sm = (size_t)Tin * sizeof(float);
+  if (dtype == BPM_BF16)
+    timelin_kernel<bf16, false><<<grid, 128, sm, (cudaStream_t)stream>>>((const bf16*)x, W, bias, (bf16*)y, Tin, Tout, D, ld, Tin, 0);
+  else
+    timelin_kernel<float, false><<<grid, 128, sm, (cudaStream_t)stream>>>((const float*)x, W, bias, (float*)y, Tin, Tout, D, ld, Tin, 0);
+  BPM_CHECK_LAUNCH("timelin_fwd");
+  return BPM_OK;
+}
+
+/* dy fp32 [B, Tout, ld], x [B, Tin, ld] (x_dtype: the saved forward input) -> dx fp32 [B, Tin, ld] (+)=, dW fp32 [Tout, Tin] +=, db fp32 [Tout] += */
+extern "C" int bpm_timelin_bwd(int x_dtype, const float* dy, const void* x, const float* W, float* dx, int accumulate_dx, float* dW, float* db, int B,
+                               int Tin, int Tout, int D, int ld, void* stream) {
+  BPM_REQUIRE(dy && x && W && B > 0 && Tin > 0 && Tout > 0 && D > 0 && ld >= D && ld % 8 == 0, "timelin_bwd: bad args");
+  if (dx != nullptr) {
+    dim3 grid(Tin, B);
+    timelin_kernel<float, true><<<grid, 128, (size_t)Tout * sizeof(float), (cudaStream_t)stream>>>(dy, W, nullptr, dx, Tout, Tin, D, ld, Tin,
+                                                                                                    accumulate_dx);
+    BPM_CHECK_LAUNCH("timelin_bwd(dx)");
+  }
+  if (dW != nullptr) {
+    dim3 grid(Tout, bpm_cdiv(Tin, 8));
+    if (x_dtype == BPM_BF16) timelin_wgrad_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, (const bf16*)x, dW, db, B, Tin, Tout, D, ld);
+    else timelin_wgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, (const float*)x, dW, db, B, Tin, Tout, D, ld);
+    BPM_CHECK_LAUNCH("timelin_bwd(dW)");
+  }
+  return BPM_OK;
+}
+
 template <typename T>
 __global__ void axpy_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n8, int accumulate) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {

@@ -287,6 +287,16 @@ class CudaOps:
         self._ck(self.lib.bpm_bce_fwd_bwd(logits.data_ptr(), logits.stride(0), targets.data_ptr(), _ptr(pos_weight), B, Cc, float(grad_scale),
                                           loss.data_ptr(), dlogits.data_ptr(), self._s()), "bce_fwd_bwd")
 
+    def timelin_fwd(self, x, W, bias, y, B, Tin, Tout, D):
+        """y[b, t2, :] = bias[t2] + sum_t W[t2, t] x[b, t, :]   (x [B*Tin, ld], y [B*Tout, ld], W fp32 [Tout, Tin])"""
+        self._ck(self.lib.bpm_timelin_fwd(_dt(x), x.data_ptr(), W.data_ptr(), 0 if bias is None else bias.data_ptr(), y.data_ptr(), B, Tin, Tout, D,
+                                          x.shape[1], self._s()), "timelin_fwd")
+
+    def timelin_bwd(self, dy, x, W, dx, accumulate_dx, dW, db, B, Tin, Tout, D):
+        self._ck(self.lib.bpm_timelin_bwd(_dt(x), dy.data_ptr(), x.data_ptr(), W.data_ptr(), 0 if dx is None else dx.data_ptr(), int(accumulate_dx),
+                                          0 if dW is None else dW.data_ptr(), 0 if db is None else db.data_ptr(), B, Tin, Tout, D, x.shape[1],
+                                          self._s()), "timelin_bwd")
+
     def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t, lr_t=None):
         self._ck(self.lib.bpm_adam_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), float(lr), float(beta1),
                                         float(beta2), float(eps), float(grad_scale), step_t.data_ptr(),

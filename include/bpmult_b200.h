@@ -198,6 +198,14 @@ int bpm_tsgate_fwd(const float* hpre, const float* zpre, int n_in, int B, int Dp
 int bpm_tsgate_bwd(const float* hpre, const float* zpre, const float* dfused, int n_in, int B, int Dp, float* dhpre,
                    float* dzpre, void* stream);
 
+/* ---- time-axis Linear of the 4-modality model: mmtr.py:507-508,530,553  transfm_x2y(h.permute(2,1,0)).permute(2,1,0) ------
+ * y[b, t2, d] = bias[t2] + sum_t W[t2, t] x[b, t, d] on batch-major [B, T, ld] rows (W = the nn.Linear weight [Tout, Tin], fp32;
+ * columns D..ld are written as zeros).  Backward: dy fp32 -> dx fp32 (+= when accumulate_dx), dW += , db += (NULL pointers skip). */
+int bpm_timelin_fwd(int dtype, const void* x, const float* W, const float* bias, void* y, int B, int Tin, int Tout, int D, int ld,
+                    void* stream);
+int bpm_timelin_bwd(int x_dtype, const float* dy, const void* x, const float* W, float* dx, int accumulate_dx, float* dW, float* db,
+                    int B, int Tin, int Tout, int D, int ld, void* stream);
+
 /* ---- loss: train.py:99-106,333 nn.BCEWithLogitsLoss(pos_weight), mean over (B, C) -----------------------------
  * loss (fp32 scalar, overwritten) and dlogits = dloss/dlogits * grad_scale (fp32 [B, ldl]) in one launch. */
 int bpm_bce_fwd_bwd(const float* logits, int ldl, const float* targets, const float* pos_weight, int B, int C,

@@ -239,6 +239,69 @@ def mmtrvat_forward(sd, cfg, txt, img, audio, n_vec=512, return_intermediates=Fa
     return logits, z
 
 
+# ----------------------------------------------------------------------------- mmtrvapt
+def time_linear(sd, name, h):
+    """models/mmtr.py:507-508,530,553: transfm_x2y(h.permute(2,1,0)).permute(2,1,0) -- nn.Linear over the TIME axis of (T, B, D)."""
+    return F.linear(h.permute(2, 1, 0), sd["transfm_%s.weight" % name], sd["transfm_%s.bias" % name]).permute(2, 1, 0)
+
+
+def mmtrvapt_forward(sd, cfg, txt, img, audio, poster, nv=(512, 200, 200)):
+    """models/mmtr.py:444-583 MultiprojectionMMTransformerGMUClf.forward, hybrid = False, dropout = 0, BERT and AudioEncoder bypassed
+    (txt float (B, T_l, orig_d_l); audio float (B, T_a, orig_d_a) post-encoder); wave-2 encoders are biprojection layers (:342-353)."""
+    D, H, L, am = cfg.hidden_sz, cfg.num_heads, cfg.layers, cfg.attn_mask
+    nl, na, nvv = nv
+
+    def proj(x, key, orig_d, n):                                           # :448-468
+        x = x.transpose(1, 2)
+        if orig_d != D:
+            x = F.conv1d(x, sd[key])
+        return _pad_time(x.permute(2, 0, 1), n)
+
+    p_l = proj(txt, "proj_l.weight", cfg.orig_d_l, nl)
+    p_a = proj(audio, "proj_a.weight", cfg.orig_d_a, na)
+    p_v = proj(img, "proj_v.weight", cfg.orig_d_v, nvv)
+    post = F.linear(poster, sd["proj_poster.weight"])                      # :486
+    enc = lambda name, q, kv, bi=False: transformer_encoder(sd, "trans_%s." % name, q, kv, kv, H, L, am, biprojection=bi)
+    h = {}
+    h["v_with_a"] = enc("v_with_a", p_v, p_a)                              # :491-498
+    h["a_with_v"] = enc("a_with_v", p_a, p_v)
+    h["v_with_l"] = enc("v_with_l", p_v, p_l)
+    h["l_with_v"] = enc("l_with_v", p_l, p_v)
+    h["a_with_l"] = enc("a_with_l", p_a, p_l)
+    h["l_with_a"] = enc("l_with_a", p_l, p_a)
+    # target l (:501-523)
+    l_v2a = enc("l_with_v2a", p_l, h["a_with_v"], True)
+    l_a2v = enc("l_with_a2v", p_l, h["v_with_a"], True)
+    t_a = time_linear(sd, "a2l", h["a_with_v"])
+    t_v = time_linear(sd, "v2l", h["v_with_a"])
+    mid, _ = gmu_features(sd, "gmu_l_m.", t_v, t_a)
+    top, _ = gmu_features(sd, "gmu_l.", l_a2v + t_v, l_v2a + t_a)
+    top = top + mid
+    last_l = top[0] + top[-1]
+    # target a (:525-546)
+    a_v2l = enc("a_with_v2l", p_a, h["l_with_v"], True)
+    a_l2v = enc("a_with_l2v", p_a, h["v_with_l"], True)
+    t_l = time_linear(sd, "l2a", h["l_with_v"])
+    t_v = h["v_with_l"]
+    mid, _ = gmu_features(sd, "gmu_a_m.", t_l, t_v)
+    top, _ = gmu_features(sd, "gmu_a.", a_v2l + t_l, a_l2v + t_v)
+    top = top + mid
+    last_a = top[0] + top[-1]
+    # target v (:548-569)
+    v_a2l = enc("v_with_a2l", p_v, h["l_with_a"], True)
+    v_l2a = enc("v_with_l2a", p_v, h["a_with_l"], True)
+    t_l = time_linear(sd, "l2v", h["l_with_a"])
+    t_a = h["a_with_l"]
+    mid, _ = gmu_features(sd, "gmu_v_m.", t_l, t_a)
+    top, _ = gmu_features(sd, "gmu_v.", v_a2l + t_l, v_l2a + t_a)
+    top = top + mid
+    last_v = top[0] + top[-1]
+    # head (:574-583)
+    fused, z = text_shifting(sd, "gmu.", [last_l, last_v, last_a, post])
+    y = F.linear(F.relu(F.linear(fused, sd["proj1.weight"], sd["proj1.bias"])), sd["proj2.weight"], sd["proj2.bias"]) + fused
+    return F.linear(y, sd["out_layer.weight"], sd["out_layer.bias"]), z
+
+
 # ----------------------------------------------------------------------------- error metrics (SURVEY 8c)
 def max_rel(a, b):
     """max|a-b| / max|b| per tensor (logits / activations)."""

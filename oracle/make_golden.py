@@ -179,6 +179,41 @@ def run_bce(seed):
     return dict(seed=seed, x=x.detach(), y=y, w=w, loss=loss.detach(), dx=x.grad)
 
 
+def run_mmtrvapt(ref, cfg, B, T_l, T_a, T_v, seed):
+    """4-modality model (mmtr.py:278-583): lengths 512 / 200 / 200, biprojection wave-2 encoders, time-axis transfm_* linears, poster,
+    TextShifting4Layer head.  Parameter gradients are stored as fingerprints (norm + strided sample) to keep the fixture small."""
+    shapes = synth.mmtrvapt_shapes(cfg)
+    sd = synth.make_state_dict(shapes, seed)
+    m = ref.mmtr.MultiprojectionMMTransformerGMUClf(cfg)
+    ref_keys = {k for k in m.state_dict().keys() if not (k.endswith(".version") or k.endswith("_float_tensor"))}
+    assert ref_keys == set(shapes.keys()), sorted(ref_keys ^ set(shapes.keys()))[:10]
+    m.load_state_dict(sd, strict=False)
+    m.train()
+    txt, img, audio, poster, tgt = synth.mmtrvapt_inputs(cfg, B, T_l, T_a, T_v)
+    pw = torch.linspace(0.5, 2.0, cfg.n_classes)
+    txt_r = txt.clone().requires_grad_()
+    logits, z = m(txt_r, None, None, img, audio, poster, output_gate=True)
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=pw)(logits, tgt)
+    loss.backward()
+    rgr = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    nograd = sorted(n for n, p in m.named_parameters() if p.grad is None)
+    sdo = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    l2, z2 = Fn.mmtrvapt_forward(sdo, cfg, txt, img, audio, poster)
+    loss2 = Fn.bce_with_logits(l2, tgt, pw)
+    loss2.backward()
+    e = Fn.max_rel(l2, logits)
+    assert e < 2e-5, ("logits", e)
+    assert Fn.max_rel(z2, z) < 2e-5
+    worst = 0.0
+    for n in rgr:
+        ee = Fn.rel_l2(sdo[n].grad, rgr[n])
+        worst = max(worst, ee)
+        assert ee < 1e-4, (n, ee)
+    print("mmtrvapt D=%d L=%d ok  logits err %.2e  worst grad rel-l2 %.2e  (no-grad params: %d)" % (cfg.hidden_sz, cfg.layers, e, worst, len(nograd)))
+    return dict(cfg=vars(cfg), dims=(B, T_l, T_a, T_v), seed=seed, pos_weight=pw, logits=logits.detach(), z=z.detach(), loss=loss.detach(),
+                dtxt=txt_r.grad, nograd=nograd, pgrad_fp={n: synth.summarize(g) for n, g in rgr.items()})
+
+
 def run_mmtrvat(ref, cfg, B, T_l, T_a, T_v, seed, full_pgrads):
     shapes = synth.mmtrvat_shapes(cfg)
     sd = synth.make_state_dict(shapes, seed)
@@ -232,6 +267,8 @@ def main():
     torch.save(run_mmtrvat(ref, synth.tiny_cfg(), 2, 10, 30, 25, 77, True), os.path.join(OUT, "mmtrvat_tiny.pt"))
     cfg = synth.tiny_cfg(orig_d_l=96, orig_d_v=35, orig_d_a=74, hidden_sz=96, num_heads=4, layers=1)
     torch.save(run_mmtrvat(ref, cfg, 2, 50, 60, 40, 78, False), os.path.join(OUT, "mmtrvat_d96.pt"))
+    cfg = synth.tiny_cfg(layers=1, n_classes=13, orig_d_p=48)
+    torch.save(run_mmtrvapt(ref, cfg, 2, 20, 30, 25, 79), os.path.join(OUT, "mmtrvapt_tiny.pt"))
     # state_dict contract: key names + shapes of the reference model, and its init under the default seed
     import json
     from oracle.ref_shim import mmtrvat_args

@@ -75,6 +75,14 @@ def load_reference(patch_cuda=True):
             return txt
     mmtr.BertEncoder = FeatEnc
 
+    class AudioFeat(torch.nn.Module):                                            # AudioEncoder bypass (mmtr.py:452-453): audio arrives as
+        def __init__(self, args):                                               # post-encoder features (B, T_a, orig_d_a)
+            super().__init__()
+
+        def forward(self, audio):
+            return audio.transpose(1, 2)
+    mmtr.AudioEncoder = AudioFeat
+
     _LOADED = Namespace(root=root, pe=pe, mha=mha, mmtr=mmtr, tr=tr)
     return _LOADED
 

@@ -57,6 +57,47 @@ def mmtrvat_shapes(cfg, n_vec=512):
     return s
 
 
+BIPROJ = ("l_with_v2a", "l_with_a2v", "v_with_l2a", "v_with_a2l", "a_with_v2l", "a_with_l2v")      # mmtr.py:342-353
+NV = {"l": 512, "a": 200, "v": 200}                                          # mmtr.py:371-373 num_vectors_{l,a,v}
+
+
+def mmtrvapt_shapes(cfg):
+    """state_dict of MultiprojectionMMTransformerGMUClf (mmtr.py:278-396), hybrid = False, BERT / AudioEncoder bypassed"""
+    D, C = cfg.hidden_sz, cfg.n_classes
+    s = {"proj_poster.weight": (D, cfg.orig_d_p)}
+    for m in ("l_m", "v_m", "a_m", "l", "v", "a"):
+        s["gmu_%s.hidden1.weight" % m] = (D, D)
+        s["gmu_%s.hidden2.weight" % m] = (D, D)
+        s["gmu_%s.x_gate.weight" % m] = (D, 2 * D)
+    s["proj_l.weight"] = (D, cfg.orig_d_l, 1)
+    s["proj_v.weight"] = (D, cfg.orig_d_v, 1)
+    s["proj_a.weight"] = (D, cfg.orig_d_a, 1)
+    for n in ENC_NAMES:
+        s.update(encoder_shapes(D, cfg.layers, n in BIPROJ, "trans_%s." % n))
+    s["proj1.weight"] = (D, D); s["proj1.bias"] = (D,)
+    s["proj2.weight"] = (D, D); s["proj2.bias"] = (D,)
+    s["out_layer.weight"] = (C, D); s["out_layer.bias"] = (C,)
+    for i in (1, 2, 3, 4):
+        s["gmu.hidden%d.weight" % i] = (D, D)
+    for i in (1, 2, 3, 4):
+        s["gmu.x%d_gate.weight" % i] = (D, 4 * D)
+    for n, (ti, to) in (("a2l", (NV["a"], NV["l"])), ("v2l", (NV["v"], NV["l"])), ("l2a", (NV["l"], NV["a"])), ("l2v", (NV["l"], NV["v"]))):
+        s["transfm_%s.weight" % n] = (to, ti)
+        s["transfm_%s.bias" % n] = (to,)
+    return s
+
+
+def mmtrvapt_inputs(cfg, B, T_l, T_a, T_v, seed=2024):
+    """text (B, T_l, orig_d_l), video (B, T_v, orig_d_v), audio (B, T_a, orig_d_a) post-encoder features, poster (B, orig_d_p), targets"""
+    g = torch.Generator().manual_seed(seed)
+    txt = torch.randn(B, T_l, cfg.orig_d_l, generator=g)
+    img = torch.randn(B, T_v, cfg.orig_d_v, generator=g)
+    audio = torch.randn(B, T_a, cfg.orig_d_a, generator=g)
+    poster = torch.randn(B, cfg.orig_d_p, generator=g)
+    tgt = (torch.rand(B, cfg.n_classes, generator=g) < 0.3).float()
+    return txt, img, audio, poster, tgt
+
+
 def make_state_dict(shapes, seed, dtype=torch.float32, gain=1.0):
     """randn / sqrt(fan_in) matrices, LayerNorm weight 1 + 0.1 randn, non-zero biases 0.1 randn --
     biases are zero at reference init (transformer.py:219-224) but a trained checkpoint has them,

@@ -323,6 +323,26 @@ class EmuOps:
         dlogits.zero_()
         dlogits[:, :Cc] = x.grad * grad_scale
 
+    def timelin_fwd(self, x, W, bias, y, B, Tin, Tout, D):
+        xb = x.float().view(B, Tin, -1)
+        r = torch.einsum("ot,btd->bod", W, xb)
+        if bias is not None:
+            r = r + bias.view(1, -1, 1)
+        r[:, :, D:] = 0
+        y.copy_(r.reshape(B * Tout, -1).to(y.dtype))
+
+    def timelin_bwd(self, dy, x, W, dx, accumulate_dx, dW, db, B, Tin, Tout, D):
+        g = dy.float().view(B, Tout, -1).clone()
+        g[:, :, D:] = 0
+        xb = x.float().view(B, Tin, -1)
+        if dx is not None:
+            r = torch.einsum("ot,bod->btd", W, g).reshape(B * Tin, -1)
+            dx.copy_(dx + r if accumulate_dx else r)
+        if dW is not None:
+            dW += torch.einsum("bod,btd->ot", g, xb)
+        if db is not None:
+            db += g.sum(dim=(0, 2))
+
     def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t, lr_t=None):
         step = float(step_t.item())
         if lr_t is not None:

@@ -75,3 +75,17 @@ def run_model_engine(ops, rec, dtype=torch.float32, full=True):
     return logits[:, :C].cpu(), zz.cpu(), loss.cpu(), dtxt.cpu(), {n: v.cpu() for n, v in grads.items()}, eng
 
 
+
+
+def check_fingerprints(grads, fps, tol):
+    """gradients against the stored fingerprints (norm + strided sample, oracle/synth.py:summarize) of the reference's"""
+    worst = (0.0, "")
+    for n, fp in fps.items():
+        g = grads[n].detach().reshape(-1).double().cpu()
+        ref = fp["val"].double()
+        e = float((g[fp["idx"]] - ref).norm() / ref.norm().clamp_min(1e-30))
+        en = abs(float(g.norm()) - fp["norm"]) / max(fp["norm"], 1e-30)
+        worst = max(worst, (max(e, en), n))
+        assert tuple(grads[n].shape) == tuple(fp["shape"]), n
+    assert worst[0] < tol, worst
+    return worst

@@ -36,6 +36,24 @@ def test_encoder_engine_fp32_matches_reference_golden(rec):
             assert torch.allclose(f[s["idx"]].float(), s["val"], rtol=2e-3, atol=2e-5 * max(1e-6, s["norm"])), n
 
 
+def test_oracle_mmtrvapt_restatement_matches_reference_golden():
+    """the 4-modality model (mmtr.py:278-583): oracle restatement against the fixture generated from the shimmed reference"""
+    from argparse import Namespace
+    from helpers import check_fingerprints
+    rec = load_gold("mmtrvapt_tiny.pt")
+    cfg = Namespace(**rec["cfg"])
+    B, T_l, T_a, T_v = rec["dims"]
+    sd = {k: v.requires_grad_() for k, v in synth.make_state_dict(synth.mmtrvapt_shapes(cfg), rec["seed"]).items()}
+    txt, img, audio, poster, tgt = synth.mmtrvapt_inputs(cfg, B, T_l, T_a, T_v)
+    txt.requires_grad_()
+    logits, z = Fn.mmtrvapt_forward(sd, cfg, txt, img, audio, poster)
+    loss = Fn.bce_with_logits(logits, tgt, rec["pos_weight"])
+    loss.backward()
+    assert Fn.max_rel(logits, rec["logits"]) < 2e-5 and Fn.max_rel(z, rec["z"]) < 2e-5
+    assert abs(loss.item() - rec["loss"].item()) < 1e-6 and Fn.rel_l2(txt.grad, rec["dtxt"]) < 1e-4
+    check_fingerprints({n: v.grad for n, v in sd.items()}, rec["pgrad_fp"], 1e-4)
+
+
 def test_mmtrvat_engine_fp32_matches_reference_golden():
     rec = load_gold("mmtrvat_tiny.pt")
     logits, z, loss, dtxt, grads, eng = run_model_engine(EmuOps(), rec)

@@ -300,6 +300,35 @@ def test_bce_matches_golden_and_torch(ops):
     assert max_rel(dl[:, :C], g["dx"]) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("Tin,Tout", [(200, 512), (512, 200), (7, 5)])
+def test_time_axis_linear(ops, dtype, Tin, Tout):
+    """transfm_x2y of the 4-modality model (mmtr.py:507-508): Linear over the TIME axis, on batch-major padded rows"""
+    B, D, ld = 3, 45, 64
+    x = torch.zeros(B, Tin, ld)
+    x[:, :, :D] = rnd((B, Tin, D), 70)
+    W, bias = rnd((Tout, Tin), 71) * 0.1, rnd((Tout,), 72)
+    xr, Wr, br = x[:, :, :D].clone().requires_grad_(), W.clone().requires_grad_(), bias.clone().requires_grad_()
+    if dtype == BF16:
+        xr = x[:, :, :D].to(BF16).float().requires_grad_()
+    yr = torch.nn.functional.linear(xr.permute(2, 0, 1), Wr, br).permute(1, 2, 0)          # [D, B, T] -> Linear -> [B, T2, D]
+    gy = rnd((B, Tout, D), 73)
+    yr.backward(gy)
+    xg = x.reshape(B * Tin, ld).to(dtype).cuda()
+    y = torch.full((B * Tout, ld), 7.0, dtype=dtype, device="cuda")
+    ops.timelin_fwd(xg, W.cuda(), bias.cuda(), y, B, Tin, Tout, D)
+    yv = y.float().cpu().view(B, Tout, ld)
+    assert max_rel(yv[:, :, :D], yr.detach()) < (1e-5 if dtype == F32 else 1e-2)
+    assert float(yv[:, :, D:].abs().max()) == 0.0
+    dy = torch.zeros(B * Tout, ld, device="cuda")
+    dy.view(B, Tout, ld)[:, :, :D] = gy.cuda()
+    dx = torch.ones(B * Tin, ld, device="cuda")
+    dW, db = torch.zeros(Tout, Tin, device="cuda"), torch.zeros(Tout, device="cuda")
+    ops.timelin_bwd(dy, xg, W.cuda(), dx, True, dW, db, B, Tin, Tout, D)
+    assert max_rel(dx.cpu().view(B, Tin, ld)[:, :, :D] - 1.0, xr.grad) < 1e-4
+    assert max_rel(dW.cpu(), Wr.grad) < 1e-4 and max_rel(db.cpu(), br.grad) < 1e-4
+
+
 def test_adam_matches_torch(ops):
     p0, g = rnd((1000,), 90), rnd((1000,), 91)
     ref = torch.nn.Parameter(p0.clone())
