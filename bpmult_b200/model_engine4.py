@@ -1,0 +1,252 @@
+"""mmtrvapt (MultiprojectionMMTransformerGMUClf, models/mmtr.py:278-583): the 4-modality model (text, video, audio, poster) as an
+explicit forward / backward schedule over the same engines as mmtrvat.  Differences to model_engine.MMTrVatEngine:
+  * per-modality sequence lengths 512 / 200 / 200 (mmtr.py:371-373), so the crossmodal encoders run with T != S;
+  * the wave-2 encoders are biprojection stacks (self-attention, then cross-attention with the same weights, 3 LayerNorms; :342-353);
+  * wave-1 outputs reach the text-length (or audio / video-length) gated units through nn.Linear layers over the TIME axis
+    (transfm_a2l, transfm_v2l : 200 -> 512;  transfm_l2a, transfm_l2v : 512 -> 200; :375-378, 507-508, 530, 553);
+  * the poster vector joins at the head: proj_poster (Linear 4096 -> D, no bias, :310,486) and a 4-input TextShifting4Layer (:369,574).
+BERT and the AudioEncoder sit upstream of this path (out of scope): text and audio arrive as feature sequences.
+hybrid = True is not supported (broken in the reference).  Single stream (this model is a "next" row, not the benchmark)."""
+import torch
+
+from .engine import Arena, Dims, EncoderEngine, HeadEngine, SeqGmuEngine, round_up
+from .model_engine import ENC_NAMES, HEAD_ORDER, TARGETS, WAVE1, attn_dropout_for
+from .ops import Drop
+
+BIPROJ = ("l_with_v2a", "l_with_a2v", "v_with_l2a", "v_with_a2l", "a_with_v2l", "a_with_l2v")
+NV = {"l": 512, "a": 200, "v": 200}                                          # mmtr.py:371-373
+# time-axis linears: name -> (source modality length, target modality length)
+TRANSFM = {"a2l": ("a", "l"), "v2l": ("v", "l"), "l2a": ("l", "a"), "l2v": ("l", "v")}
+
+
+def _mod_of(enc_name):
+    """query modality of an encoder = its sequence length (trans_<q>_with_<src>)"""
+    return enc_name[0]
+
+
+class MMTrVaptEngine:
+    def __init__(self, ops, args, dtype=torch.bfloat16):
+        assert not getattr(args, "hybrid", False), "hybrid=True is broken in the reference (mmtr.py:572) and not supported"
+        self.ops, self.args, self.T_ = ops, args, dtype
+        D, H, L = args.hidden_sz, args.num_heads, args.layers
+        self.d = Dims(D, H)
+        self.orig = {"l": args.orig_d_l, "a": args.orig_d_a, "v": args.orig_d_v}
+        self.Kp = {m: (self.d.Dp if self.orig[m] == D else round_up(self.orig[m], 64)) for m in "lav"}
+        self.Kpp = round_up(args.orig_d_p, 64)
+        self.shared = Arena(ops)
+        self.arena = Arena(ops)
+        self.enc = {}
+        for i, n in enumerate(ENC_NAMES):
+            self.enc[n] = EncoderEngine(ops, D, H, L, attn_dropout=attn_dropout_for(n, args), relu_dropout=args.relu_dropout,
+                                        res_dropout=args.res_dropout, embed_dropout=args.embed_dropout, attn_mask=args.attn_mask,
+                                        biprojection=n in BIPROJ, dtype=dtype, uid=i + 1, shared=self.shared)
+        self.gmu = {}
+        for m in "lav":
+            self.gmu[m + "_m"] = SeqGmuEngine(ops, D, dtype, True, self.shared, "gmu_%s_m" % m)
+            self.gmu[m] = SeqGmuEngine(ops, D, dtype, True, self.shared, "gmu_%s" % m)
+        self.head = HeadEngine(ops, D, 4, args.n_classes, out_dropout=args.out_dropout)
+        z = ops.zeros
+        self.Wproj = {m: (z((self.d.Dp, self.Kp[m]), dtype) if self.orig[m] != D else None) for m in "lav"}
+        self.Gproj = {m: (z((self.d.Dp, self.Kp[m]), torch.float32) if self.orig[m] != D else None) for m in "lav"}
+        self.Wpost = z((self.d.Dp, self.Kpp), dtype)
+        self.Gpost = z((self.d.Dp, self.Kpp), torch.float32)
+        # time-axis linears stay fp32 in the reference layout [T_out, T_in] (small, SIMT kernel)
+        self.Wt = {n: (z((NV[to], NV[ti]), torch.float32), z((NV[to],), torch.float32)) for n, (ti, to) in TRANSFM.items()}
+        self.Gt = {n: (z((NV[to], NV[ti]), torch.float32), z((NV[to],), torch.float32)) for n, (ti, to) in TRANSFM.items()}
+
+    # ---------------------------------------------------------------- parameters
+    def param_shapes(self):
+        s = {"proj_poster.weight": (self.d.D, self.args.orig_d_p)}
+        D = self.d.D
+        for m in ("l_m", "v_m", "a_m", "l", "v", "a"):
+            for k, v in self.gmu[m].param_shapes().items():
+                s["gmu_%s.%s" % (m, k)] = v
+        for m in "lva":
+            s["proj_%s.weight" % m] = (D, self.orig[m], 1)
+        for n in ENC_NAMES:
+            for k, v in self.enc[n].param_shapes().items():
+                s["trans_%s.%s" % (n, k)] = v
+        s.update(self.head.param_shapes())
+        for n, (ti, to) in TRANSFM.items():
+            s["transfm_%s.weight" % n] = (NV[to], NV[ti])
+            s["transfm_%s.bias" % n] = (NV[to],)
+        return s
+
+    def unused_params(self):
+        return ["proj_%s.weight" % m for m in "lav" if self.orig[m] == self.d.D]
+
+    def pack(self, params):
+        o = self.ops
+        o.batch_begin("pack", "model4")
+        for n in ENC_NAMES:
+            self.enc[n].pack(params, "trans_%s." % n)
+        for m, g in self.gmu.items():
+            g.pack(params, "gmu_%s." % m)
+        self.head.pack(params)
+        for m in "lav":
+            if self.Wproj[m] is not None:
+                w = params["proj_%s.weight" % m]
+                o.pack_matrix(w.view(w.shape[0], w.shape[1]), self.Wproj[m])
+        o.pack_matrix(params["proj_poster.weight"], self.Wpost)
+        o.batch_end()
+        for n in TRANSFM:
+            self.Wt[n][0].copy_(params["transfm_%s.weight" % n])
+            self.Wt[n][1].copy_(params["transfm_%s.bias" % n])
+
+    def zero_grads(self):
+        for e in self.enc.values():
+            e.zero_grads()
+        for g in self.gmu.values():
+            g.zero_grads()
+        self.head.zero_grads()
+        for m in "lav":
+            if self.Gproj[m] is not None:
+                self.ops.zero_(self.Gproj[m])
+        self.ops.zero_(self.Gpost)
+        for gw, gb in self.Gt.values():
+            self.ops.zero_(gw)
+            self.ops.zero_(gb)
+
+    def unpack_grads(self, grads, accumulate=False):
+        o = self.ops
+        o.batch_begin("unpack", "model4")
+        for n in ENC_NAMES:
+            self.enc[n].unpack_grads(grads, "trans_%s." % n, accumulate)
+        for m, g in self.gmu.items():
+            g.unpack_grads(grads, "gmu_%s." % m, accumulate)
+        self.head.unpack_grads(grads, accumulate)
+        for m in "lav":
+            if self.Gproj[m] is not None:
+                gw = grads["proj_%s.weight" % m]
+                o.unpack_matrix(self.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=accumulate)
+        o.unpack_matrix(self.Gpost, grads["proj_poster.weight"], accumulate=accumulate)
+        o.batch_end()
+        for n in TRANSFM:
+            for src, key in ((self.Gt[n][0], "weight"), (self.Gt[n][1], "bias")):
+                dst = grads["transfm_%s.%s" % (n, key)]
+                dst.copy_(dst + src if accumulate else src)
+
+    # ---------------------------------------------------------------- pieces
+    def _time_linear(self, name, h, B):
+        ti, to = TRANSFM[name]
+        y = self.arena.get("t_" + name, (B * NV[to], self.d.Dp), self.T_)
+        self.ops.timelin_fwd(h, self.Wt[name][0], self.Wt[name][1], y, B, NV[ti], NV[to], self.d.D)
+        return y
+
+    def _time_linear_bwd(self, name, dy, h, dh, B):
+        """dy fp32 [B*T_out, Dp] -> dh fp32 [B*T_in, Dp] += ; weight / bias gradients accumulate"""
+        ti, to = TRANSFM[name]
+        self.ops.timelin_bwd(dy, h, self.Wt[name][0], dh, True, self.Gt[name][0], self.Gt[name][1], B, NV[ti], NV[to], self.d.D)
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, txt, img, audio, poster, training=True, seed=0, seed_ptr=None):
+        """txt (B, T_l<=512, orig_d_l), img (B, T_v<=200, orig_d_v), audio (B, T_a<=200, orig_d_a), poster (B, orig_d_p): fp32 device tensors.
+        Returns (logits [B, Cp], z [B, 4*Dp]) views of internal buffers."""
+        o, d, A = self.ops, self.d, self.arena
+        B = txt.shape[0]
+        self.B, self.training, self.seed, self.seed_ptr = B, training, seed, seed_ptr
+        feats = {"l": txt, "a": audio, "v": img}
+        self.in_shapes = {m: tuple(feats[m].shape) for m in "lav"}
+        P = {}
+        self.X = {}
+        for m in "lav":
+            drop = Drop(self.args.embed_dropout, seed, seed_ptr, 7) if (m == "l" and training and self.args.embed_dropout > 0) else None
+            X = A.get("X_" + m, (B * NV[m], self.Kp[m]), self.T_)
+            o.stage_rows(feats[m], X, NV[m], drop)                              # transpose / embed-dropout / zero-pad to num_vectors_m
+            self.X[m] = X
+            if self.Wproj[m] is not None:
+                P[m] = A.get("P_" + m, (B * NV[m], d.Dp), self.T_)
+                o.gemm(X, self.Wproj[m], P[m], B * NV[m], d.Dp, self.Kp[m])
+            else:
+                P[m] = X
+        self.P = P
+        h = {}
+        for n, (qm, km) in WAVE1.items():
+            h[n] = self.enc[n].forward(P[qm], B, NV[qm], src_k=P[km], S=NV[km], training=training, seed=seed, seed_ptr=seed_ptr)
+        cat = self.head.cat_buf(B)
+        self.tsrc = {}
+        for ci, m in enumerate(HEAD_ORDER):
+            u, w, pn, qn = TARGETS[m]
+            Mm = B * NV[m]
+            su, sw = NV[_mod_of(u)], NV[_mod_of(w)]
+            hp = self.enc[pn].forward(P[m], B, NV[m], src_k=h[u], S=su, training=training, seed=seed, seed_ptr=seed_ptr)
+            hq = self.enc[qn].forward(P[m], B, NV[m], src_k=h[w], S=sw, training=training, seed=seed, seed_ptr=seed_ptr)
+            h[pn], h[qn] = hp, hq
+            # wave-1 outputs at this target's length: through the time-axis linear when the lengths differ (:507-508,530,553)
+            tname_u = "%s2%s" % (_mod_of(u), m) if su != NV[m] else None
+            tname_w = "%s2%s" % (_mod_of(w), m) if sw != NV[m] else None
+            tu = self._time_linear(tname_u, h[u], B) if tname_u else h[u]
+            tw = self._time_linear(tname_w, h[w], B) if tname_w else h[w]
+            self.tsrc[m] = (tname_u, tname_w, tu, tw)
+            mid = self.gmu[m + "_m"].forward(tu, tw, Mm)                          # "GMU middle"
+            a1 = A.get("a1_" + m, (Mm, d.Dp), self.T_)
+            a2 = A.get("a2_" + m, (Mm, d.Dp), self.T_)
+            o.add(hp, tu, a1)                                                    # residual level 1 -> 2
+            o.add(hq, tw, a2)
+            top = self.gmu[m].forward(a1, a2, Mm, addend=mid)                    # "GMU top" + residual level 1 -> 3
+            o.pool_fwd(top, B, NV[m], cat, ci * d.Dp)                            # h[0] + h[-1]
+        # poster: Linear(orig_d_p -> D, no bias) straight into the 4th block of the head's input
+        Xp = A.get("X_p", (B, self.Kpp), self.T_)
+        o.stage_rows(poster.view(B, 1, -1), Xp, 1, None)
+        self.Xp = Xp
+        o.gemm(Xp, self.Wpost, cat[:, 3 * d.Dp:], B, d.Dp, self.Kpp)
+        self.h = h
+        return self.head.forward(B, training, seed, seed_ptr)
+
+    def loss(self, logits, targets, pos_weight=None, grad_scale=1.0):
+        return self.head.loss(logits, targets, pos_weight, grad_scale)
+
+    # ---------------------------------------------------------------- backward
+    def backward(self, dlogits, d_inputs=None):
+        """dlogits fp32 [B, Cp].  Parameter gradients accumulate in the padded buffers (see unpack_grads).
+        d_inputs: optional dict m -> fp32 tensor shaped like the input features ("l", "a", "v"), overwritten with input gradients."""
+        o, d, A, B, h = self.ops, self.d, self.arena, self.B, self.h
+        f32 = torch.float32
+        dcat = self.head.backward(dlogits)
+        # poster projection: dW = dpost^T Xp
+        gpo = A.get("dpost", (B, d.Dp), self.T_)
+        gpo.copy_(dcat[:, 3 * d.Dp:])                                            # (strided slice + cast: a torch copy, off the hot path)
+        o.gemm(gpo, self.Xp, self.Gpost, d.Dp, self.Kpp, B, ta=1, tb=1, accumulate=True)
+        dP = {m: A.get("dP_" + m, (B * NV[m], d.Dp), f32) for m in "lav"}
+        dh = {n: A.get("dh_" + n, (B * NV[_mod_of(n)], d.Dp), f32) for n in WAVE1}
+        for t in list(dP.values()) + list(dh.values()):
+            o.zero_(t)
+        for ci, m in reversed(list(enumerate(HEAD_ORDER))):
+            u, w, pn, qn = TARGETS[m]
+            Mm = B * NV[m]
+            tname_u, tname_w, tu, tw = self.tsrc[m]
+            dtop = A.get("dtop_" + m, (Mm, d.Dp), f32)
+            da1 = A.get("da1_" + m, (Mm, d.Dp), f32)
+            da2 = A.get("da2_" + m, (Mm, d.Dp), f32)
+            dtu = A.get("dtu_" + m, (Mm, d.Dp), f32) if tname_u else dh[u]       # gradient wrt the (time-mapped) wave-1 outputs
+            dtw = A.get("dtw_" + m, (Mm, d.Dp), f32) if tname_w else dh[w]
+            for t in [dtop, da1, da2] + ([dtu] if tname_u else []) + ([dtw] if tname_w else []):
+                o.zero_(t)
+            o.pool_bwd(dcat, ci * d.Dp, B, NV[m], dtop)
+            self.gmu[m].backward(dtop, da1, da2)                                 # d(p + tu), d(q + tw)
+            self.gmu[m + "_m"].backward(dtop, dtu, dtw)
+            o.axpy_f32(da1, dtu, True)
+            o.axpy_f32(da2, dtw, True)
+            if tname_u:
+                self._time_linear_bwd(tname_u, dtu, h[u], dh[u], B)
+            if tname_w:
+                self._time_linear_bwd(tname_w, dtw, h[w], dh[w], B)
+            self.enc[qn].backward(da2, dP[m], dh[w])
+            self.enc[pn].backward(da1, dP[m], dh[u])
+        for n, (qm, km) in reversed(list(WAVE1.items())):
+            self.enc[n].backward(dh[n], dP[qm], dP[km])
+        for m in "lav":
+            if self.Wproj[m] is not None:
+                g = self.shared.get("dPc_" + m, (B * NV[m], d.Dp), self.T_)
+                o.cast_drop(dP[m], g, None)
+                o.gemm(g, self.X[m], self.Gproj[m], d.Dp, self.Kp[m], B * NV[m], ta=1, tb=1, accumulate=True)     # dW = dP^T X
+                if d_inputs is not None and m in d_inputs:
+                    dX = self.shared.get("dX_" + m, (B * NV[m], self.Kp[m]), f32)
+                    o.gemm(g, self.Wproj[m], dX, B * NV[m], self.Kp[m], d.Dp, tb=1)
+                    self._unstage(m, dX, d_inputs[m])
+            elif d_inputs is not None and m in d_inputs:
+                self._unstage(m, dP[m], d_inputs[m])
+
+    def _unstage(self, m, g, dst):
+        drop = Drop(self.args.embed_dropout, self.seed, self.seed_ptr, 7) if (m == "l" and self.training and self.args.embed_dropout > 0) else None
+        self.ops.unstage_rows(g, dst, NV[m], False, drop)

@@ -613,7 +613,123 @@ class _MMTrVatFn(torch.autograd.Function):
         return (None, None, d_in.get("l"), d_in.get("v"), d_in.get("a")) + tuple(grads.get(n) for n in names)
 
 
-MODELS = {"mmtrvat": MultiprojectionMMTransformer3DGMUClf}            # models/__init__.py:6-9 ("mmtrvapt": next round)
+class AudioFeatures(nn.Module):
+    """stands in for mmtr.AudioEncoder (mmtr.py:452): the audio arrives as post-encoder features (B, T_a, orig_d_a)."""
+
+    def __init__(self, args=None):
+        super().__init__()
+
+    def forward(self, audio):
+        return audio
+
+
+class MultiprojectionMMTransformerGMUClf(nn.Module):
+    """"mmtrvapt" -- mmtr.py:278-583.  forward(txt, mask, segment, img, audio, poster, output_gate=False) -> logits (B, C) [, z (B, 4*D)].
+    txt (B, L <= 512, orig_d_l) float, img (B, T_v <= 200, orig_d_v), audio (B, T_a <= 200, orig_d_a) post-encoder features,
+    poster (B, orig_d_p).  Sequences are zero-padded to 512 / 200 / 200 inside (mmtr.py:371-373, 461-466)."""
+
+    def __init__(self, args, precision="bf16"):
+        super().__init__()
+        from .model_engine4 import BIPROJ, NV, TRANSFM
+        self.args = args
+        self.orig_d_l, self.orig_d_v, self.orig_d_a, self.orig_d_p = args.orig_d_l, args.orig_d_v, args.orig_d_a, args.orig_d_p
+        self.d_l = self.d_a = self.d_v = D = args.hidden_sz
+        self.vonly, self.lonly, self.aonly = args.vonly, args.lonly, args.aonly
+        if not (self.vonly and self.lonly and self.aonly):
+            raise NotImplementedError("the reference forward itself requires lonly = aonly = vonly (last_h_* undefined otherwise, mmtr.py:572)")
+        if getattr(args, "hybrid", False):
+            raise NotImplementedError("hybrid=True is broken in the reference (list-vs-varargs call sites, mmtr.py:572); not implemented")
+        self.precision = precision
+        self.enc = FeatureEncoder(args)
+        self.audio_enc = AudioFeatures(args)
+        self.proj_poster = nn.Linear(self.orig_d_p, D, bias=False)             # construction order = reference (mmtr.py:310-378)
+        mk = lambda: GatedMultimodalLayerFeatures(D, D, D)
+        self.gmu_l_m, self.gmu_v_m, self.gmu_a_m = mk(), mk(), mk()
+        self.gmu_l, self.gmu_v, self.gmu_a = mk(), mk(), mk()
+        self.proj_l = nn.Conv1d(self.orig_d_l, D, kernel_size=1, padding=0, bias=False)
+        self.proj_v = nn.Conv1d(self.orig_d_v, D, kernel_size=1, padding=0, bias=False)
+        self.proj_a = nn.Conv1d(self.orig_d_a, D, kernel_size=1, padding=0, bias=False)
+        for n in ("l_with_a", "l_with_v", "l_with_v2a", "l_with_a2v", "v_with_l", "v_with_a", "v_with_l2a", "v_with_a2l",
+                  "a_with_l", "a_with_v", "a_with_v2l", "a_with_l2v"):
+            setattr(self, "trans_" + n, self.get_network(n, biprojection=n in BIPROJ))
+        self.proj1 = nn.Linear(D, D)
+        self.proj2 = nn.Linear(D, D)
+        self.out_layer = nn.Linear(D, args.n_classes)
+        self.gmu = TextShifting4Layer(D, D, D, D, D)
+        self.num_vectors_l, self.num_vectors_a, self.num_vectors_v = NV["l"], NV["a"], NV["v"]
+        for n in ("a2l", "v2l", "l2a", "l2v"):
+            ti, to = TRANSFM[n]
+            setattr(self, "transfm_" + n, nn.Linear(NV[ti], NV[to]))
+        self._eng = None
+
+    def get_network(self, name, biprojection=False):
+        a = self.args
+        return TransformerEncoder(embed_dim=a.hidden_sz, num_heads=a.num_heads, layers=a.layers, attn_dropout=attn_dropout_for(name, a),
+                                  relu_dropout=a.relu_dropout, res_dropout=a.res_dropout, embed_dropout=a.embed_dropout,
+                                  attn_mask=a.attn_mask, biprojection=biprojection)
+
+    def trunk_named_parameters(self):
+        skip = ("_float_tensor", "version")
+        return [(n, p) for n, p in self.named_parameters() if not n.endswith(skip)]
+
+    def engine(self, device=None):
+        from .model_engine4 import MMTrVaptEngine
+        device = device or next(self.parameters()).device
+        ops = _ops_for(device)
+        dt = _DT[self.precision]
+        if self._eng is None or self._eng.T_ != dt or self._eng.ops is not ops:
+            self._eng = MMTrVaptEngine(ops, self.args, dtype=dt)
+        return self._eng
+
+    def forward(self, txt, mask, segment, img, audio, poster, output_gate=False):
+        x_l = self.enc(txt, mask, segment)
+        x_a = self.audio_enc(audio)
+        named = self.trunk_named_parameters()
+        names = [n for n, _ in named]
+        logits, z = _MMTrVaptFn.apply(self, names, x_l, img, x_a, poster, *[p for _, p in named])
+        return (logits, z) if output_gate else logits
+
+
+class _MMTrVaptFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, names, txt, img, audio, poster, *params):
+        eng = mod.engine(txt.device)
+        for nm, t, dim in (("text", txt, mod.orig_d_l), ("img", img, mod.orig_d_v), ("audio", audio, mod.orig_d_a)):
+            assert t.dim() == 3 and t.shape[2] == dim, "%s features must be (B, T, %d)" % (nm, dim)
+        assert poster.dim() == 2 and poster.shape[1] == mod.orig_d_p, "poster must be (B, %d)" % mod.orig_d_p
+        assert txt.shape[1] <= mod.num_vectors_l and audio.shape[1] <= mod.num_vectors_a and img.shape[1] <= mod.num_vectors_v, \
+            "a sequence exceeds its fixed length (the reference raises on a negative pad size, mmtr.py:431-441)"
+        eng.pack({n: p.detach() for n, p in zip(names, params)})
+        logits, z = eng.forward(txt.detach().float(), img.detach().float(), audio.detach().float(), poster.detach().float(),
+                                training=mod.training, seed=_next_seed())
+        B, C, D, Dp = txt.shape[0], mod.args.n_classes, mod.args.hidden_sz, eng.d.Dp
+        ctx.mod, ctx.names, ctx.shapes = mod, names, (txt.shape, img.shape, audio.shape)
+        ctx.need_in = (txt.requires_grad, img.requires_grad, audio.requires_grad)
+        zz = z.view(B, 4, Dp)[:, :, :D].reshape(B, 4 * D).clone()
+        ctx.mark_non_differentiable(zz)
+        return logits[:, :C].clone(), zz
+
+    @staticmethod
+    def backward(ctx, g, _gz):
+        mod, names = ctx.mod, ctx.names
+        eng = mod._eng
+        ops = eng.ops
+        B, C = g.shape
+        dl = ops.zeros((B, eng.head.Cp), torch.float32)
+        dl[:, :C] = g.float()
+        eng.zero_grads()
+        d_in = {}
+        for m, need, shp in zip("lva", ctx.need_in, ctx.shapes):
+            if need:
+                d_in[m] = ops.zeros(tuple(shp), torch.float32)
+        eng.backward(dl, d_in)
+        pmap = dict(mod.trunk_named_parameters())
+        grads = {n: torch.zeros_like(pmap[n]) for n in eng.param_shapes()}
+        eng.unpack_grads(grads)
+        return (None, None, d_in.get("l"), d_in.get("v"), d_in.get("a"), None) + tuple(grads.get(n) for n in names)     # (no poster input gradient)
+
+
+MODELS = {"mmtrvat": MultiprojectionMMTransformer3DGMUClf, "mmtrvapt": MultiprojectionMMTransformerGMUClf}    # models/__init__.py:6-9
 
 
 def get_model(args):                                                   # models/__init__.py:12-14

@@ -89,3 +89,30 @@ def check_fingerprints(grads, fps, tol):
         assert tuple(grads[n].shape) == tuple(fp["shape"]), n
     assert worst[0] < tol, worst
     return worst
+
+
+def run_model4_engine(ops, rec, dtype=torch.float32):
+    """MMTrVaptEngine on a golden record: returns logits, z, loss, dtxt, reference-layout parameter gradients"""
+    from argparse import Namespace
+    from bpmult_b200.model_engine4 import MMTrVaptEngine
+    cfg = Namespace(**rec["cfg"])
+    B, T_l, T_a, T_v = rec["dims"]
+    sd = synth.make_state_dict(synth.mmtrvapt_shapes(cfg), rec["seed"])
+    txt, img, audio, poster, tgt = synth.mmtrvapt_inputs(cfg, B, T_l, T_a, T_v)
+    eng = MMTrVaptEngine(ops, cfg, dtype=dtype)
+    dev = ops.device
+    params = {k: v.to(dev) for k, v in sd.items()}
+    assert set(eng.param_shapes().keys()) == set(sd.keys()), set(eng.param_shapes().keys()) ^ set(sd.keys())
+    for k, shp in eng.param_shapes().items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    eng.pack(params)
+    logits, z = eng.forward(txt.to(dev), img.to(dev), audio.to(dev), poster.to(dev), training=True)
+    loss, dlogits = eng.loss(logits, tgt.to(dev), rec["pos_weight"].to(dev))
+    eng.zero_grads()
+    dtxt = torch.zeros_like(txt, device=dev)
+    eng.backward(dlogits, {"l": dtxt})
+    grads = {n: torch.zeros(s, device=dev) for n, s in eng.param_shapes().items()}
+    eng.unpack_grads(grads)
+    D, Dp, C = cfg.hidden_sz, eng.d.Dp, cfg.n_classes
+    zz = z.view(B, 4, Dp)[:, :, :D].reshape(B, 4 * D)
+    return logits[:, :C].cpu(), zz.cpu(), loss.cpu(), dtxt.cpu(), {n: v.cpu() for n, v in grads.items()}, eng

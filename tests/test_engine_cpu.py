@@ -54,6 +54,17 @@ def test_oracle_mmtrvapt_restatement_matches_reference_golden():
     check_fingerprints({n: v.grad for n, v in sd.items()}, rec["pgrad_fp"], 1e-4)
 
 
+def test_mmtrvapt_engine_fp32_matches_reference_golden():
+    """host schedule of the 4-modality model (device ops emulated): T != S encoders, biprojection wave 2, time-axis linears, poster"""
+    from helpers import check_fingerprints, run_model4_engine
+    rec = load_gold("mmtrvapt_tiny.pt")
+    logits, z, loss, dtxt, grads, eng = run_model4_engine(EmuOps(), rec)
+    assert Fn.max_rel(logits, rec["logits"]) < 2e-5 and Fn.max_rel(z, rec["z"]) < 2e-5
+    assert abs(loss.item() - rec["loss"].item()) < 1e-6
+    assert Fn.rel_l2(dtxt, rec["dtxt"]) < 1e-4
+    check_fingerprints(grads, rec["pgrad_fp"], 2e-4)
+
+
 def test_mmtrvat_engine_fp32_matches_reference_golden():
     rec = load_gold("mmtrvat_tiny.pt")
     logits, z, loss, dtxt, grads, eng = run_model_engine(EmuOps(), rec)

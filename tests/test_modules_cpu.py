@@ -190,6 +190,29 @@ def test_text_shifting_n_layer_matches_reference_golden():
         m(*xs[:3])
 
 
+def test_mmtrvapt_module_autograd_matches_reference_golden():
+    """the 4-modality model behind the reference's module API (mmtr.py:278-583): state_dict names, forward signature with poster"""
+    from helpers import check_fingerprints
+    rec = load_gold("mmtrvapt_tiny.pt")
+    cfg = Namespace(**rec["cfg"])
+    m = M.MultiprojectionMMTransformerGMUClf(cfg, precision="fp32")
+    shapes = synth.mmtrvapt_shapes(cfg)
+    keys = {k for k in m.state_dict().keys() if not (k.endswith(".version") or k.endswith("_float_tensor"))}
+    assert keys == set(shapes.keys()), sorted(keys ^ set(shapes.keys()))[:8]
+    m.load_state_dict(synth.make_state_dict(shapes, rec["seed"]), strict=False)
+    m.train()
+    B, T_l, T_a, T_v = rec["dims"]
+    txt, img, audio, poster, tgt = synth.mmtrvapt_inputs(cfg, B, T_l, T_a, T_v)
+    txt.requires_grad_()
+    logits, z = m(txt, None, None, img, audio, poster, output_gate=True)
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=rec["pos_weight"])(logits, tgt)
+    loss.backward()
+    assert Fn.max_rel(logits, rec["logits"]) < 2e-5 and Fn.max_rel(z, rec["z"]) < 2e-5
+    assert Fn.max_rel(txt.grad, rec["dtxt"]) < 1e-4
+    check_fingerprints({n: p.grad for n, p in m.named_parameters()}, rec["pgrad_fp"], 2e-4)
+    assert M.get_model(Namespace(model="mmtrvapt", **rec["cfg"])).__class__ is M.MultiprojectionMMTransformerGMUClf
+
+
 def test_mmtrvat_module_autograd_matches_reference_golden():
     rec = load_gold("mmtrvat_tiny.pt")
     cfg = Namespace(**rec["cfg"])
