@@ -122,6 +122,29 @@ def test_encoder_module_on_gpu_bf16_and_fp32():
         assert Fn.rel_l2(xg.grad.cpu(), xo.grad) < (2e-4 if prec == "fp32" else 5e-2)
 
 
+def test_mmtrvapt_module_on_gpu_matches_reference_golden():
+    """the 4-modality model through the nn.Module API on the GPU (fp32 precision mode)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import check_fingerprints, load_gold
+    from bpmult_b200 import MultiprojectionMMTransformerGMUClf
+    rec = load_gold("mmtrvapt_tiny.pt")
+    cfg = Namespace(**rec["cfg"])
+    m = MultiprojectionMMTransformerGMUClf(cfg, precision="fp32")
+    m.load_state_dict(synth.make_state_dict(synth.mmtrvapt_shapes(cfg), rec["seed"]), strict=False)
+    m.cuda().train()
+    B, T_l, T_a, T_v = rec["dims"]
+    txt, img, audio, poster, tgt = [t.cuda() for t in synth.mmtrvapt_inputs(cfg, B, T_l, T_a, T_v)]
+    txt.requires_grad_()
+    logits, z = m(txt, None, None, img, audio, poster, output_gate=True)
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=rec["pos_weight"].cuda())(logits, tgt)
+    loss.backward()
+    assert Fn.max_rel(logits.detach().cpu(), rec["logits"]) < 1e-4 and Fn.max_rel(z.cpu(), rec["z"]) < 1e-4
+    assert Fn.rel_l2(txt.grad.cpu(), rec["dtxt"]) < 2e-4
+    check_fingerprints({n: p.grad for n, p in m.named_parameters()}, rec["pgrad_fp"], 5e-4)
+
+
 def test_no_cpu_fallback():
     from bpmult_b200 import TransformerEncoder
     m = TransformerEncoder(40, 4, 1)
