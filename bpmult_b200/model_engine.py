@@ -156,6 +156,19 @@ class MMTrVatEngine:
                 self.ops.unpack_matrix(self.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=accumulate)
         self.ops.batch_end()
 
+    def unpack_misc(self, grads, accumulate=False):
+        """gradients of everything but the encoders (the encoders' leave per bucket during backward, see Trainer)"""
+        o = self.ops
+        o.batch_begin("unpack", "misc")
+        for m, g in self.gmu.items():
+            g.unpack_grads(grads, "gmu_%s." % m, accumulate=accumulate)
+        self.head.unpack_grads(grads, accumulate=accumulate)
+        for m in "lav":
+            if self.Gproj[m] is not None:
+                gw = grads["proj_%s.weight" % m]
+                o.unpack_matrix(self.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=accumulate)
+        o.batch_end()
+
     # ---------------------------------------------------------------- forward
     def forward(self, txt, img, audio, training=True, seed=0, seed_ptr=None):
         """txt (B, T_l, orig_d_l), img (B, T_v, orig_d_v), audio (B, T_a, orig_d_a): fp32 device tensors (any strides).

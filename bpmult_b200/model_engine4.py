@@ -108,10 +108,14 @@ class MMTrVaptEngine:
             self.ops.zero_(gb)
 
     def unpack_grads(self, grads, accumulate=False):
-        o = self.ops
-        o.batch_begin("unpack", "model4")
         for n in ENC_NAMES:
             self.enc[n].unpack_grads(grads, "trans_%s." % n, accumulate)
+        self.unpack_misc(grads, accumulate)
+
+    def unpack_misc(self, grads, accumulate=False):
+        """gradients of everything but the encoders"""
+        o = self.ops
+        o.batch_begin("unpack", "misc4")
         for m, g in self.gmu.items():
             g.unpack_grads(grads, "gmu_%s." % m, accumulate)
         self.head.unpack_grads(grads, accumulate)
@@ -197,9 +201,18 @@ class MMTrVaptEngine:
         return self.head.loss(logits, targets, pos_weight, grad_scale)
 
     # ---------------------------------------------------------------- backward
-    def backward(self, dlogits, d_inputs=None):
+    def backward_order(self):
+        """encoder names in the order their gradients complete during backward (gradient-bucket order of the Trainer)"""
+        order = []
+        for m in reversed(HEAD_ORDER):
+            u, w, pn, qn = TARGETS[m]
+            order += [qn, pn]
+        return order + list(reversed(list(WAVE1.keys())))
+
+    def backward(self, dlogits, d_inputs=None, on_done=None):
         """dlogits fp32 [B, Cp].  Parameter gradients accumulate in the padded buffers (see unpack_grads).
-        d_inputs: optional dict m -> fp32 tensor shaped like the input features ("l", "a", "v"), overwritten with input gradients."""
+        d_inputs: optional dict m -> fp32 tensor shaped like the input features ("l", "a", "v"), overwritten with input gradients.
+        on_done(name): called when an encoder's parameter gradients are complete."""
         o, d, A, B, h = self.ops, self.d, self.arena, self.B, self.h
         f32 = torch.float32
         dcat = self.head.backward(dlogits)
@@ -232,9 +245,15 @@ class MMTrVaptEngine:
             if tname_w:
                 self._time_linear_bwd(tname_w, dtw, h[w], dh[w], B)
             self.enc[qn].backward(da2, dP[m], dh[w])
+            if on_done:
+                on_done(qn)
             self.enc[pn].backward(da1, dP[m], dh[u])
+            if on_done:
+                on_done(pn)
         for n, (qm, km) in reversed(list(WAVE1.items())):
             self.enc[n].backward(dh[n], dP[qm], dP[km])
+            if on_done:
+                on_done(n)
         for m in "lav":
             if self.Wproj[m] is not None:
                 g = self.shared.get("dPc_" + m, (B * NV[m], d.Dp), self.T_)

@@ -14,7 +14,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from .modules import MultiprojectionMMTransformer3DGMUClf
+from .modules import MultiprojectionMMTransformer3DGMUClf, MultiprojectionMMTransformerGMUClf
 
 
 class _Loss:
@@ -31,7 +31,7 @@ class _Loss:
 
 class Trainer:
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, pos_weight=None, seed=1234, use_graph=None, grad_accum=1):
-        assert isinstance(model, MultiprojectionMMTransformer3DGMUClf)
+        assert isinstance(model, (MultiprojectionMMTransformer3DGMUClf, MultiprojectionMMTransformerGMUClf))
         assert grad_accum >= 1
         self.model = model
         self.device = next(model.parameters()).device
@@ -99,7 +99,7 @@ class Trainer:
         self.n_params = total
 
     # ---------------------------------------------------------------- one step (enqueue only)
-    def _enqueue(self, txt, img, audio, tgt, apply=True):
+    def _enqueue(self, *batch, apply=True):
         """one micro-batch: forward, loss, backward, gradients into the flat buffer; with `apply` also the all-reduces and Adam.
         With grad_accum > 1 the flat gradient buffer ACCUMULATES over the micro-batches (it is cleared after Adam) and only the
         last micro-batch reduces it across ranks -- the 1/grad_accum of train.py:391 rides on Adam's gradient scale."""
@@ -109,7 +109,8 @@ class Trainer:
             self.step_t += 1
         self.seed_t += 1
         eng.pack(self.params)
-        logits, _ = eng.forward(txt, img, audio, training=True, seed=0, seed_ptr=self.seed_t)
+        *feats, tgt = batch                             # (txt, img, audio[, poster]), targets
+        logits, _ = eng.forward(*feats, training=True, seed=0, seed_ptr=self.seed_t)
         loss, dlogits = eng.loss(logits, tgt, self.pos_weight, 1.0)
         eng.zero_grads()
         cur = torch.cuda.current_stream(self.device) if self.on_gpu else None
@@ -132,15 +133,7 @@ class Trainer:
             eng.enc[enc].unpack_grads(self.grads, "trans_%s." % enc, accumulate=acc)
             reduce_bucket(enc)
         eng.backward(dlogits, None, on_done)
-        o.batch_begin("unpack", "misc")
-        for m, g in eng.gmu.items():
-            g.unpack_grads(self.grads, "gmu_%s." % m, accumulate=acc)
-        eng.head.unpack_grads(self.grads, accumulate=acc)
-        for m in "lav":
-            if eng.Gproj[m] is not None:
-                gw = self.grads["proj_%s.weight" % m]
-                o.unpack_matrix(eng.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=acc)
-        o.batch_end()
+        eng.unpack_misc(self.grads, accumulate=acc)              # everything but the encoders (gated units, head, projections)
         if not apply:
             return loss
         reduce_bucket("misc")
@@ -175,8 +168,8 @@ class Trainer:
         self.set_lr(sd["lr"])
 
     # ---------------------------------------------------------------- public API
-    def _ensure_static(self, txt, img, audio, tgt):
-        shapes = tuple(tuple(t.shape) for t in (txt, img, audio, tgt))
+    def _ensure_static(self, *batch):
+        shapes = tuple(tuple(t.shape) for t in batch)
         if self.shapes != shapes:
             dev = self.device
             self.static = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
@@ -185,28 +178,29 @@ class Trainer:
             self.shapes, self.graphs = shapes, {}
             self.warm = 0
 
-    def step_device(self, txt, img, audio, tgt):
-        """inputs already resident on the device (fp32).  Returns the device loss tensor (no sync)."""
-        self._ensure_static(txt, img, audio, tgt)
-        for s, t in zip(self.static, (txt, img, audio, tgt)):
+    def step_device(self, *batch):
+        """batch = (txt, img, audio, targets) for mmtrvat, (txt, img, audio, poster, targets) for mmtrvapt, already resident on the
+        device (fp32).  Returns the device loss tensor (no sync)."""
+        self._ensure_static(*batch)
+        for s, t in zip(self.static, batch):
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
         self._run()
         return self.loss_dev
 
-    def step(self, txt, img, audio, tgt):
+    def step(self, *batch):
         """end-to-end step from HOST tensors: pinned staging -> H2D -> step -> D2H of the loss.  Returns a python float (blocks until
         the step has finished, like the `loss.item()` of train.py:393)."""
-        return self.step_async(txt, img, audio, tgt).item()
+        return self.step_async(*batch).item()
 
-    def step_async(self, txt, img, audio, tgt):
+    def step_async(self, *batch):
         """same as step() but returns at once with a handle; `handle.item()` blocks for THIS step's loss.  Reading the loss one step late
         (enqueue step k+1, then `item()` of step k) keeps the GPU busy while the host prepares the next launch.  Pinned inputs are
         read by DMA straight from the caller's tensors: keep them unchanged until the handle has been read."""
-        self._ensure_static(txt, img, audio, tgt)
+        self._ensure_static(*batch)
         if self.on_gpu and self._h2d_done is not None:
             self._h2d_done.synchronize()                    # the previous step's copies out of the staging buffers have finished
-        for pbuf, s, t in zip(self.pinned, self.static, (txt, img, audio, tgt)):
+        for pbuf, s, t in zip(self.pinned, self.static, batch):
             if self.on_gpu and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous():
                 s.copy_(t, non_blocking=True)               # e.g. DataLoader(pin_memory=True): DMA straight from the caller's buffer
             else:

@@ -145,6 +145,35 @@ def test_mmtrvapt_module_on_gpu_matches_reference_golden():
     check_fingerprints({n: p.grad for n, p in m.named_parameters()}, rec["pgrad_fp"], 5e-4)
 
 
+def test_trainer_runs_the_4_modality_model_under_graph_replay():
+    """mmtrvapt through the same Trainer (flat buffers, buckets in backward order, fused Adam, CUDA graph): 5-tensor batch"""
+    from bpmult_b200 import MultiprojectionMMTransformerGMUClf, Trainer
+    cfg = synth.tiny_cfg(layers=1, n_classes=13, orig_d_p=48)
+
+    def mk():
+        m = MultiprojectionMMTransformerGMUClf(Namespace(**vars(cfg)), precision="fp32")
+        m.load_state_dict(synth.make_state_dict(synth.mmtrvapt_shapes(cfg), 5), strict=False)
+        return m.cuda().train()
+    txt, img, audio, poster, tgt = [t.cuda() for t in synth.mmtrvapt_inputs(cfg, 2, 20, 30, 25)]
+    a, b = mk(), mk()
+    opt = torch.optim.Adam([p for p in a.parameters()], lr=1e-3)
+    tr = Trainer(b, lr=1e-3)
+    la, lb = [], []
+    for _ in range(5):
+        opt.zero_grad()
+        loss = torch.nn.BCEWithLogitsLoss()(a(txt, None, None, img, audio, poster), tgt)
+        loss.backward()
+        opt.step()
+        la.append(float(loss))
+        lb.append(float(tr.step_device(txt, img, audio, poster, tgt)[0]))
+    assert tr.graph is not None and tr.use_graph
+    assert max(abs(x - y) for x, y in zip(la, lb)) < 2e-5, (la, lb)
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    num = sum(float((pb[n].detach() - pa[n].detach()).double().pow(2).sum()) for n in pa if pa[n].grad is not None)
+    den = sum(float(pa[n].detach().double().pow(2).sum()) for n in pa if pa[n].grad is not None)
+    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+
+
 def test_no_cpu_fallback():
     from bpmult_b200 import TransformerEncoder
     m = TransformerEncoder(40, 4, 1)
