@@ -46,3 +46,22 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 print("mmtrvapt cfg 3  B=%d  fwd+bwd %.1f ms  (%.1f samples/s, eager launches, no optimizer)  loss %.4f" % (B, ms, B / ms * 1e3, float(loss)))
+
+# full training step (Adam, CUDA graph) through the module API + Trainer
+del eng
+torch.cuda.empty_cache()
+from bpmult_b200 import MultiprojectionMMTransformerGMUClf, Trainer  # noqa: E402
+torch.manual_seed(1234)
+model = MultiprojectionMMTransformerGMUClf(cfg, precision="bf16").to(dev).train()
+tr = Trainer(model, lr=1e-4)
+for _ in range(4):
+    tr.step_device(txt, img, audio, poster, tgt)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(n):
+    tr.step_device(txt, img, audio, poster, tgt)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+print("mmtrvapt cfg 3  B=%d  train step (fwd + BCE + bwd + Adam, CUDA graph %s) %.1f ms  (%.1f samples/s)  params %.1f M  loss %.4f" % (
+    B, tr.graph is not None, ms, B / ms * 1e3, tr.n_params / 1e6, float(tr.loss_dev[0])))
