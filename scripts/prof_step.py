@@ -64,3 +64,16 @@ print("\nstep span %.2f ms; kernels in flight -> ms: %s; idle %.2f ms" % (
 print("time with exactly ONE kernel in flight, by kernel:")
 for n, t in sorted(alone.items(), key=lambda kv: -kv[1])[:14]:
     print("   %-60s %8.3f ms" % (n, t / 1000))
+
+# ---- largest idle gaps (no kernel in flight) and what surrounds them
+ends = []
+cur_end, gaps = iv[0][1], []
+last_name = iv[0][2]
+for s, t, n in iv[1:]:
+    if s > cur_end:
+        gaps.append((s - cur_end, last_name, n, cur_end - iv[0][0]))
+    if t > cur_end:
+        cur_end, last_name = t, n
+print("idle gaps > 20 us: %d, total %.2f ms" % (sum(1 for g in gaps if g[0] > 20), sum(g[0] for g in gaps if g[0] > 20) / 1000))
+for g in sorted(gaps, reverse=True)[:14]:
+    print("   %7.1f us at t=%8.2f ms   after %-40s before %s" % (g[0], g[3] / 1000, g[1][:40], g[2][:40]))
