@@ -168,7 +168,8 @@ def time_kernel(fn, n_rot, iters=20, warm=3):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels below at the cfg-2 shape, from the `ncu --set full` captures of
 # this round (profiles/r01_ncu_full_summary.txt; scripts/gpu_ncu_full.sh).  Writes still resident in the 126 MB L2 when the kernel ends
 # are not counted by the DRAM counters, so output-heavy kernels show less traffic than their algorithmic bytes.
-NCU_DRAM_BYTES = {"xattn_bwd": 104.0e6 + 32.1e6, "xattn_fwd": 76.3e6 + 6.4e6, "gemm_fc1": 21.8e6 + 22.0e6, "layernorm_fwd": 42.0e6 + 0.3e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` of the same shapes (profiles/r01_ncu_full_summary_v2.txt)
+NCU_DRAM_BYTES = {"xattn_bwd": 103.9e6 + 41.0e6, "xattn_fwd": 76.9e6 + 8.7e6, "gemm_fc1": 21.8e6 + 21.8e6, "layernorm_fwd": 42.0e6 + 0.3e6}
 MUFU_PER_CLK_SM = 16          # ex2 throughput of one B200 SM (guides/B300_MICROARCH: B300 has 2x this)
 
 
