@@ -203,6 +203,8 @@ def test_colsum(ops):
 ATTN_CASES = [  # B, T, S, H, dh, dhp, mask_off, p
     (2, 12, 12, 4, 10, 32, 0, 0.0), (2, 6, 4, 4, 10, 32, 2, 0.0), (3, 4, 6, 4, 10, 32, 2, 0.0), (2, 9, 17, 4, 10, 32, -1, 0.0),
     (2, 130, 200, 12, 25, 32, 70, 0.1), (1, 256, 256, 12, 25, 32, 0, 0.0), (1, 200, 512, 6, 128, 128, -1, 0.1), (2, 512, 512, 2, 25, 32, 0, 0.2),
+    # head dims without two free padding columns: the instantiations that do NOT fold lse / delta / row sums into the MMAs
+    (2, 140, 140, 3, 30, 32, 0, 0.0), (1, 64, 200, 2, 32, 32, -1, 0.0),
 ]
 
 
