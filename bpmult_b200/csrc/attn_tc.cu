@@ -19,8 +19,7 @@
 #define AT_DH 32
 #define AT_KV_STAGES 3
 #define AF_GROUPS 2
-#define AF_GROUP_WARPS 6
-#define AF_THREADS (32 * AF_GROUPS * AF_GROUP_WARPS)
+#define AF_THREADS(SW) (32 * AF_GROUPS * (2 + (SW)))     // per group: 1 producer, 1 MMA issuer, SW softmax warps (4, or 8 = two per TMEM lane quarter)
 #define LOG2E_F 1.4426950408889634f
 #define LN2_F 0.6931471805599453f
 
@@ -55,8 +54,10 @@ struct AttnFwdSmem {
   static constexpr int K = Q + 2 * AT_BM * 64;                  // stages x 128 x 64 B
   static constexpr int V = K + AT_KV_STAGES * AT_BN * 64;
   static constexpr int GROUP = V + AT_KV_STAGES * AT_BN * 64;   // 64 KB
-  static constexpr int STG = AF_GROUPS * GROUP;                 // output staging: one 32-row x 64-byte slice per softmax warp (TMA store)
-  static constexpr int BAR = STG + AF_GROUPS * 4 * 2048;
+  static constexpr int STG = AF_GROUPS * GROUP;                 // output staging: one 32-row x 64-byte slice per (group, lane quarter) (TMA store)
+  static constexpr int XCH = STG + AF_GROUPS * 4 * 2048;        // SW = 8: row-max exchange [2 tile parities][2 halves][128] + row sums [128], per group
+  static constexpr int XCH_G = (2 * 2 * AT_BM + AT_BM) * 4;
+  static constexpr int BAR = XCH + AF_GROUPS * XCH_G;
   static constexpr int NBAR_G = 4 + 2 * AT_KV_STAGES + 2 + 1 + 2;   // q_full[2], q_free[2], kv_full/empty, s_full, s_free, p_full, o_full[2]
   static constexpr int TOTAL = BAR + 8 * AF_GROUPS * NBAR_G + 16;
 };
@@ -71,8 +72,11 @@ __device__ __forceinline__ void fwd_mask32(float* sv, int lim) {
 // column AF_PAD0 of the P V accumulator is the row sum of P -- rescaled with the other columns, summed by the tensor core from the
 // same bf16 probabilities that weight V -- and the softmax warps need no add per probability.
 #define AF_PAD0 26
-template <bool DROP, bool ONES>
-__global__ void __launch_bounds__(AF_THREADS, 1)
+// SW = 8 (with ONES): two softmax warps per TMEM lane quarter, 64 of the tile's 128 key columns and 16 of the 32 output columns
+// each; the pair shares the row maximum through shared memory (one 64-thread named barrier per tile).  The kernel is bound by the
+// serial latency of a tile's softmax, not by a pipe (35 % issue slots, 41 % MUFU with SW = 4): halving the columns per warp shortens it.
+template <bool DROP, bool ONES, int SW>
+__global__ void __launch_bounds__(AF_THREADS(SW), 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
                    uint32_t* __restrict__ drop_bits) {
@@ -81,7 +85,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = warp / AF_GROUP_WARPS, gw = warp % AF_GROUP_WARPS;      // group, role inside the group (0 producer, 1 MMA, 2..5 softmax)
+  static_assert(SW == 4 || (SW == 8 && ONES && !DROP), "8 softmax warps per group: only the light no-dropout / ones-column math fits 96 registers");
+  constexpr int GW = 2 + SW;
+  const int grp = warp / GW, gw = warp % GW;                              // group, role inside the group (0 producer, 1 MMA, 2.. softmax)
   const uint32_t gbase = base + grp * AttnFwdSmem::GROUP;
   const uint32_t bar0 = base + AttnFwdSmem::BAR + 8u * grp * AttnFwdSmem::NBAR_G;
   auto q_full = [&](int s) { return bar0 + 8u * s; };
@@ -117,7 +123,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int s = 0; s < 2; s++) { mbar_init(b0 + 8u * s, 1); mbar_init(b0 + 8u * (2 + s), 1); }
       for (int s = 0; s < AT_KV_STAGES; s++) { mbar_init(b0 + 8u * (4 + s), 1); mbar_init(b0 + 8u * (4 + AT_KV_STAGES + s), 1); }
       const uint32_t sf = b0 + 8u * (4 + 2 * AT_KV_STAGES);
-      mbar_init(sf, 1); mbar_init(sf + 8u, 4); mbar_init(sf + 16u, 4); mbar_init(sf + 24u, 1); mbar_init(sf + 32u, 1);
+      mbar_init(sf, 1); mbar_init(sf + 8u, SW); mbar_init(sf + 16u, SW); mbar_init(sf + 24u, 1); mbar_init(sf + 32u, 1);
     }
     mbar_fence_init();
   }
@@ -211,8 +217,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else {
     // ===================== softmax warps: one thread per query row =====================
     const int quarter = warp & 3;                                          // TMEM lane quarter this warp may access
+    const int half = (gw - 2) >> 2;                                        // SW = 8: key-column half / output-column half of this warp
+    constexpr int NCH = SW == 8 ? 2 : 4;                                   // 32-key chunks of a tile per warp
+    constexpr int OC = SW == 8 ? 16 : 32;                                  // output columns per warp
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int rr = quarter * 32 + lane;
+    float* const xmax = (float*)(base_gen + AttnFwdSmem::XCH + grp * AttnFwdSmem::XCH_G);
+    float* const xsum = xmax + 2 * 2 * AT_BM;
+    const int pair_bar = 1 + grp * 4 + quarter;                            // named barrier of this (group, quarter) pair of warps
+    auto pair_sync = [&]() { if (SW == 8) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
     const DropCtx dc = make_drop(drop);
     const int W = (S + 31) >> 5;
     int tc = 0;
@@ -227,19 +240,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int vis_any = (mask_off >= 0) ? min(q0 + quarter * 32 + 31 + mask_off, S - 1) : S - 1;
       const uint64_t ebase = ((uint64_t)bh * T + (uint64_t)min(qi, T - 1)) * (uint64_t)S;
       float m = -INFINITY, l = 0.f;
-      float oacc[AT_DH];
+      float oacc[OC];
 #pragma unroll
-      for (int d = 0; d < AT_DH; d++) oacc[d] = 0.f;
+      for (int d = 0; d < OC; d++) oacc[d] = 0.f;
       for (int j = 0; j < nt; j++, tc++) {
         const int k0 = j * AT_BN;
-        const int nvis = max(0, min(AT_BN / 32, (vis_any - k0 + 32) >> 5));   // chunks of this tile with at least one visible key
+        const int nvis_t = max(0, min(AT_BN / 32, (vis_any - k0 + 32) >> 5));  // chunks of this tile with at least one visible key
+        const int c_lo = SW == 8 ? 2 * half : 0;                               // this warp's chunks: [c_lo, c_lo + NCH)
+        const int nvis = max(0, min(NCH, nvis_t - c_lo));                      // ... of which the first nvis have visible keys
         mbar_wait(s_full, (uint32_t)tc & 1u);
         tc_fence_after();
         // ---- pass 1: row maximum
         float mx = -INFINITY;
 #pragma unroll 1
         for (int ci = 0; ci < nvis; ci++) {
-          const int c = ci * 32;
+          const int c = (c_lo + ci) * 32;
           float sv[32];
           tmem_ld32(tS + lane_off + c, sv);
           tmem_ld_wait();
@@ -250,6 +265,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             m4[0] = fmaxf(m4[0], sv[e]); m4[1] = fmaxf(m4[1], sv[e + 1]); m4[2] = fmaxf(m4[2], sv[e + 2]); m4[3] = fmaxf(m4[3], sv[e + 3]);
           }
           mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+        if (SW == 8) {                                                     // row maximum over both column halves
+          float* xm = xmax + (tc & 1) * 2 * AT_BM;
+          xm[half * AT_BM + rr] = mx;
+          pair_sync();
+          mx = fmaxf(mx, xm[(half ^ 1) * AT_BM + rr]);
         }
         const float m_new = fmaxf(m, mx * LOG2E_F);
         const float alpha = ex2f(m - m_new);
@@ -263,8 +284,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (lane == 0) mbar_arrive(s_free);
         }
 #pragma unroll 1
-        for (int ci = 0; ci < AT_BN / 32; ci++) {
-          const int c = ci * 32;
+        for (int ci = 0; ci < NCH; ci++) {
+          const int c = (c_lo + ci) * 32;
           uint32_t pk[16];
           if (ci >= nvis) {
 #pragma unroll
@@ -333,50 +354,63 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) mbar_arrive(p_full);
         // ---- fold the previous tile's P V into the register accumulator, then rescale to the new max
         if (j > 0) {
-          float ov[AT_DH];
-          tmem_ld32(tO0 + 32 * ((tc - 1) & 1) + lane_off, ov);
+          float ov[OC];
+          if (SW == 8) tmem_ld16(tO0 + 32 * ((tc - 1) & 1) + 16 * half + lane_off, ov);
+          else tmem_ld32(tO0 + 32 * ((tc - 1) & 1) + lane_off, ov);
           tmem_ld_wait();
 #pragma unroll
-          for (int d = 0; d < AT_DH; d++) oacc[d] = (oacc[d] + ov[d]) * alpha;
+          for (int d = 0; d < OC; d++) oacc[d] = (oacc[d] + ov[d]) * alpha;
         }
       }
       {
-        float ov[AT_DH];
+        float ov[OC];
         mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u);
         tc_fence_after();
-        tmem_ld32(tO0 + 32 * ((tc - 1) & 1) + lane_off, ov);
+        if (SW == 8) tmem_ld16(tO0 + 32 * ((tc - 1) & 1) + 16 * half + lane_off, ov);
+        else tmem_ld32(tO0 + 32 * ((tc - 1) & 1) + lane_off, ov);
         tmem_ld_wait();
         tc_fence_before();
+        // the 32 output rows of this lane quarter leave through shared memory and one TMA store (a thread owns a 64-byte row: direct
+        // stores would be 32 half-used sectors per instruction); rows beyond T are clipped by the tensor map
+        uint8_t* const stg = base_gen + AttnFwdSmem::STG + (grp * 4 + quarter) * 2048;
+        const bool issuer = SW == 4 || half == 0;
         if (ONES) {                                                        // the ones column of V: row sum of the bf16 probabilities
-          l = oacc[AF_PAD0] + ov[AF_PAD0];
-          oacc[AF_PAD0] = oacc[AF_PAD0 + 1] = 0.f;
-          ov[AF_PAD0] = ov[AF_PAD0 + 1] = 0.f;
+          constexpr int PC = AF_PAD0 % OC;                                 // (column 26 sits in the second half's 16 columns)
+          if (SW == 4 || half == 1) {
+            l = oacc[PC] + ov[PC];
+            oacc[PC] = oacc[PC + 1] = 0.f;
+            ov[PC] = ov[PC + 1] = 0.f;
+            if (SW == 8) xsum[rr] = l;
+          }
         }
+        if (issuer) {
+          if (elect_one()) bulk_wait_read<0>();                            // the previous item's store has read the slice
+          __syncwarp();
+        }
+        pair_sync();                                                       // SW = 8: row sum visible to the first half; staging slice free
+        if (SW == 8 && half == 0) l = xsum[rr];
         const float inv_l = (DROP ? dc.inv_keep : 1.f) / l;
 #pragma unroll
-        for (int d = 0; d < AT_DH; d++) oacc[d] = (oacc[d] + ov[d]) * inv_l;
-      }
-      {
-        // the 32 output rows of this warp leave through shared memory and one TMA store (a thread owns a 64-byte row: direct stores
-        // would be 32 half-used sectors per instruction); rows beyond T are clipped by the tensor map
-        uint8_t* const stg = base_gen + AttnFwdSmem::STG + (grp * 4 + (gw - 2)) * 2048;
-        if (elect_one()) bulk_wait_read<0>();                              // the previous item's store has read the slice
-        __syncwarp();
+        for (int d = 0; d < OC; d++) oacc[d] = (oacc[d] + ov[d]) * inv_l;
 #pragma unroll
-        for (int u = 0; u < AT_DH / 8; u++) {
+        for (int u = 0; u < OC / 8; u++) {
           uint4 w;
           w.x = pack_bf16x2(oacc[u * 8 + 0], oacc[u * 8 + 1]); w.y = pack_bf16x2(oacc[u * 8 + 2], oacc[u * 8 + 3]);
           w.z = pack_bf16x2(oacc[u * 8 + 4], oacc[u * 8 + 5]); w.w = pack_bf16x2(oacc[u * 8 + 6], oacc[u * 8 + 7]);
-          *(uint4*)(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = w;
+          const int uu = (SW == 8 ? 2 * half : 0) + u;                     // 16-byte unit of the 64-byte row
+          *(uint4*)(stg + lane * 64 + ((uu ^ ((lane >> 1) & 3)) << 4)) = w;
         }
         fence_async_smem();
+        pair_sync();                                                       // SW = 8: both halves of the rows are staged
         __syncwarp();
-        if (elect_one()) {
-          tma_store_3d(&tmO, base + AttnFwdSmem::STG + (grp * 4 + (gw - 2)) * 2048, h * AT_DH, q0 + quarter * 32, b);
-          bulk_commit();
+        if (issuer) {
+          if (elect_one()) {
+            tma_store_3d(&tmO, base + AttnFwdSmem::STG + (grp * 4 + quarter) * 2048, h * AT_DH, q0 + quarter * 32, b);
+            bulk_commit();
+          }
+          __syncwarp();
+          if (qi < T) lse[(int64_t)bh * T + qi] = (m + log2f(l)) * LN2_F;
         }
-        __syncwarp();
-        if (qi < T) lse[(int64_t)bh * T + qi] = (m + log2f(l)) * LN2_F;
       }
     }
     if (elect_one()) bulk_wait_read<0>();                                 // the staging slice must outlive the last TMA store's read
@@ -412,18 +446,21 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   size_t smem = AttnFwdSmem::TOTAL + 1024;
   // 0: no dropout, row sums through a ones column of V (needs two free padding columns);  1: dropout;  2: no dropout, no ones column
   const int dm = a->drop.p > 0.f ? 1 : ((a->dh <= AF_PAD0 && !(bpm_debug_get(1) & 8192)) ? 0 : 2);
-  auto kern = dm == 1 ? attn_fwd_tc_kernel<true, false> : (dm == 0 ? attn_fwd_tc_kernel<false, true> : attn_fwd_tc_kernel<false, false>);
+  const int sw = (dm == 0 && !(bpm_debug_get(1) & 32768)) ? 8 : 4;
+  auto kern = dm == 1 ? attn_fwd_tc_kernel<true, false, 4>
+                      : (dm == 0 ? (sw == 8 ? attn_fwd_tc_kernel<false, true, 8> : attn_fwd_tc_kernel<false, true, 4>) : attn_fwd_tc_kernel<false, false, 4>);
   CUtensorMap to;
   if ((rc = make_qkv_map(&to, out, a->B, a->T, HP, 32))) return rc;                      // output: {32 columns, 32 rows} store boxes
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[dm]) {
+  static bool attr_set[4] = {false, false, false, false};
+  const int ki = (dm == 0 && sw == 4) ? 3 : dm;
+  if (!attr_set[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bpm_set_error("xattn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
-    attr_set[dm] = true;
+    attr_set[ki] = true;
   }
   const int n_items = a->B * a->H * bpm_cdiv(a->T, AT_BM);
   const int ctas = min(bpm_num_sms(), bpm_cdiv(n_items, AF_GROUPS));
-  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AF_THREADS), smem, stream, tq, tk, tv, to, lse, a->B, a->T, a->S, a->H,
+  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AF_THREADS(sw)), smem, stream, tq, tk, tv, to, lse, a->B, a->T, a->S, a->H,
                               a->mask_off, a->drop, a->drop_bits);
   if (le != cudaSuccess) { bpm_set_error("xattn_fwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
