@@ -205,6 +205,8 @@ ATTN_CASES = [  # B, T, S, H, dh, dhp, mask_off, p
     (2, 130, 200, 12, 25, 32, 70, 0.1), (1, 256, 256, 12, 25, 32, 0, 0.0), (1, 200, 512, 6, 128, 128, -1, 0.1), (2, 512, 512, 2, 25, 32, 0, 0.2),
     # head dims without two free padding columns: the instantiations that do NOT fold lse / delta / row sums into the MMAs
     (2, 140, 140, 3, 30, 32, 0, 0.0), (1, 64, 200, 2, 32, 32, -1, 0.0),
+    # ragged lengths / offset-causal masks on the folded no-dropout instantiations (T != S as in the 4-modality model)
+    (2, 200, 512, 12, 25, 32, 312, 0.0), (2, 512, 200, 12, 25, 32, 312, 0.0), (3, 384, 384, 5, 25, 32, 0, 0.0), (1, 76, 333, 3, 25, 32, -1, 0.0),
 ]
 
 
