@@ -559,11 +559,11 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
 //   FOLD (no dropout only): -lse and -delta already sit inside the MMA results (two padding columns of the head dimension carry them
 //         as bf16 hi + lo parts against ones in K / V, see the S^T issuer), so sv = S^T - lse and dpv = dP^T - delta on entry:
 //         per element one multiply, one ex2, one multiply, and no shared-memory operands.
-template <int DROP, bool MASKED, int NC, bool FOLD>
+template <int DROP, bool MASKED, int NC, int FOLD>
 __device__ __forceinline__ void bwd_chunk_math(float* sv, float* dpv, const float* __restrict__ lse_c, const float* __restrict__ del_c, int c_lo, int cmin,
                                                bool key_oob, bool diag, const DropCtx& dc, const uint32_t* __restrict__ bits_c, uint32_t mw, int lane,
                                                uint64_t e_row, int q_lo, int T, int S) {
-  if (FOLD) {
+  if (FOLD == 1) {
 #pragma unroll
     for (int c = 0; c < NC; c += 2) {
       float t0 = sv[c], t1 = sv[c + 1];
@@ -577,12 +577,12 @@ __device__ __forceinline__ void bwd_chunk_math(float* sv, float* dpv, const floa
   }
 #pragma unroll
   for (int c = 0; c < NC; c += 4) {
-    const float4 l4 = *(const float4*)(lse_c + c);
+    const float4 l4 = FOLD == 2 ? make_float4(0.f, 0.f, 0.f, 0.f) : *(const float4*)(lse_c + c);
     const float4 d4 = *(const float4*)(del_c + c);
     const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      float p = ex2f(fmaf(sv[c + e], LOG2E_F, -ls[e]));
+      float p = FOLD == 2 ? ex2f(sv[c + e] * LOG2E_F) : ex2f(fmaf(sv[c + e], LOG2E_F, -ls[e]));     // FOLD 2: -lse is inside S^T already
       if (MASKED) p = (c + e < cmin) ? 0.f : p;                    // cmin: first visible column of this key row, relative to the chunk
       if (DROP == 0) {
         sv[c + e] = p;
@@ -772,7 +772,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float l2 = lse_s[qi];                                 // lse * log2e, +inf beyond T
             const bool live = qi < T && l2 < 1e30f;
             *pad_word(qt, row) = live ? hi_lo(-l2 * LN2_F) : 0x0000C6EAu;   // (-30000, 0): exp2 underflows to 0 for dead query rows
-            *pad_word(qt + 8192, row) = live ? hi_lo(-del_s[qi]) : 0u;
+            if (DM == 0) *pad_word(qt + 8192, row) = live ? hi_lo(-del_s[qi]) : 0u;     // (with dropout, delta stays outside: dS = P (mask dP - delta))
           }
           fence_async_smem();                                          // generic-proxy writes -> visible to the MMAs' operand reads
           __syncwarp();
@@ -999,8 +999,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               const int cm = key_oob ? 0x40000000 : (diag ? cmin - cs : -0x40000000);
 #define BWD_MATH(DROP)                                                                                                                        \
   do {                                                                                                                                        \
-    if (need_mask) bwd_chunk_math<DROP, true, 16, FOLD && DROP == 0>(sv, dpv, lse_c, del_c, cs, cm, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S); \
-    else bwd_chunk_math<DROP, false, 16, FOLD && DROP == 0>(sv, dpv, lse_c, del_c, cs, cmin, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S);       \
+    if (need_mask) bwd_chunk_math<DROP, true, 16, FOLD ? (DROP == 0 ? 1 : 2) : 0>(sv, dpv, lse_c, del_c, cs, cm, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S); \
+    else bwd_chunk_math<DROP, false, 16, FOLD ? (DROP == 0 ? 1 : 2) : 0>(sv, dpv, lse_c, del_c, cs, cmin, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S);       \
   } while (0)
               if (drop_mode == 0) BWD_MATH(0);
               else if (drop_mode == 1) BWD_MATH(1);
@@ -1110,10 +1110,11 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   // 0: no dropout, -lse / -delta folded into the MMAs (needs two free padding columns);  1: dropout;  2: no dropout, no fold
   const int dm = a->drop.p > 0.f ? 1 : ((a->dh <= AB_PAD0 && !(bpm_debug_get(1) & 2048)) ? 0 : 2);
   const int cw = (dm == 0 && !(bpm_debug_get(1) & 4096)) ? 16 : 8;
+  const bool fold1 = dm == 1 && a->dh <= AB_PAD0 && !(bpm_debug_get(1) & 2048);     // dropout: lse still folds into S^T
   auto kern = dm == 0 ? (cw == 16 ? attn_bwd_tc_kernel<0, true, 16> : attn_bwd_tc_kernel<0, true, 8>)
-                      : (dm == 1 ? attn_bwd_tc_kernel<1, false, 8> : attn_bwd_tc_kernel<0, false, 8>);
-  static bool attr_set[4] = {false, false, false, false};
-  const int ki = dm == 0 && cw == 8 ? 3 : dm;
+                      : (dm == 1 ? (fold1 ? attn_bwd_tc_kernel<1, true, 8> : attn_bwd_tc_kernel<1, false, 8>) : attn_bwd_tc_kernel<0, false, 8>);
+  static bool attr_set[5] = {false, false, false, false, false};
+  const int ki = dm == 0 && cw == 8 ? 3 : (dm == 1 && fold1 ? 4 : dm);
   if (!attr_set[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { bpm_set_error("xattn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
