@@ -77,3 +77,35 @@ def test_optimizer_state_round_trip_resumes_bit_exactly():
     lb = [b.step(*batch) for _ in range(2)]
     assert la == lb
     assert torch.equal(a.flat_p, b.flat_p)
+
+
+def test_trainer_drives_the_4_modality_model():
+    """mmtrvapt through the Trainer's host logic (5-tensor batch, flat buffers incl. the time-axis linears and the poster projection)"""
+    import bpmult_b200.modules as M
+    from emu_ops import EmuOps
+    from bpmult_b200.trainer import Trainer
+    o = EmuOps()
+    M._ops_for = lambda device: o
+    cfg = synth.tiny_cfg(layers=1, n_classes=13, orig_d_p=48)
+
+    def mk():
+        m = M.MultiprojectionMMTransformerGMUClf(Namespace(**vars(cfg)), precision="fp32")
+        m.load_state_dict(synth.make_state_dict(synth.mmtrvapt_shapes(cfg), 5), strict=False)
+        return m.train()
+    txt, img, audio, poster, tgt = synth.mmtrvapt_inputs(cfg, 2, 20, 30, 25)
+    a, b = mk(), mk()
+    opt = torch.optim.Adam([p for p in a.parameters()], lr=1e-3)
+    tr = Trainer(b, lr=1e-3, use_graph=False)
+    for _ in range(2):
+        opt.zero_grad()
+        loss = torch.nn.BCEWithLogitsLoss()(a(txt, None, None, img, audio, poster), tgt)
+        loss.backward()
+        opt.step()
+        lb = tr.step(txt, img, audio, poster, tgt)
+        assert abs(float(loss) - lb) < 1e-5
+    names = [bk[0] for bk in tr.buckets]
+    assert names[-1] == "misc" and len(names) == 13
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    num = sum(float((pb[n].detach() - pa[n].detach()).double().pow(2).sum()) for n in pa)
+    den = sum(float(pa[n].detach().double().pow(2).sum()) for n in pa)
+    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
