@@ -49,3 +49,11 @@ t = timeit(lambda i: ops.layernorm_bwd(dy[i], x[i], mean, rstd, g, d.D, dx[i], T
 print("ln bwd (bf16 dy, fp32 x, dx += , bf16 cast):   %6.1f us  %5.2f TB/s" % (t, M * d.Dp * (2 + 4 + 8 + 2) / t / 1e6))
 t = timeit(lambda i: ops.layernorm_bwd(dy[i], x[i], mean, rstd, g, d.D, dx[i], True, dg, db))
 print("ln bwd (bf16 dy, fp32 x, dx += ):              %6.1f us  %5.2f TB/s" % (t, M * d.Dp * (2 + 4 + 8) / t / 1e6))
+# calibration: plain device copies of the same size / larger (what the memory system gives a trivially parallel stream)
+xs = [torch.randn(M, d.Dp, device=dev) for _ in range(NS)]
+t = timeit(lambda i: xs[i].copy_(x[i]))
+print("torch copy fp32 [rows, 320] (42 MB -> 42 MB):  %6.1f us  %5.2f TB/s" % (t, M * d.Dp * 8 / t / 1e6))
+big_a = [torch.empty(64 << 20, device=dev) for _ in range(2)]
+big_b = [torch.empty(64 << 20, device=dev) for _ in range(2)]
+t = timeit(lambda i: big_b[i % 2].copy_(big_a[i % 2]), iters=8)
+print("torch copy fp32 256 MB -> 256 MB:              %6.1f us  %5.2f TB/s" % (t, (64 << 20) * 8 / t / 1e6))
