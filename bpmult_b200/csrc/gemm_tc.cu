@@ -564,9 +564,10 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   const int fixed = 2048 + 8 * (2 * TC_MAX_STAGES + 4 + TC_EPI_WARPS * TC_MAX_NB) + 16 + 1024;      // ones tile, barriers, alignment slack
   const int budget = 227 * 1024 - fixed;
   // staging buffers per epilogue warp: with a residual / gate tile prefetched through them 3 (two chunks ahead) when the operand
-  // ring still gets 3 stages, else 2
+  // ring still gets 3 stages AND the main loop is short (K <= 512: epilogue-bound, out-proj 28.1 -> 27.3 us); with a long K the
+  // shared memory is worth more as a fourth ring stage (fc2, K = 1216: 42.3 -> 38.9 us with 2), else 2
   p.nb = 2;
-  if (p.in_mode && (budget - TC_EPI_WARPS * 3 * eb) / stage_bytes >= 3) p.nb = 3;
+  if (p.in_mode && g->K <= 512 && (budget - TC_EPI_WARPS * 3 * eb) / stage_bytes >= 3) p.nb = 3;
   if (bpm_debug_get(3) >= 2 && bpm_debug_get(3) <= TC_MAX_NB) p.nb = bpm_debug_get(3);
   p.stages = max(2, min(TC_MAX_STAGES, (budget - TC_EPI_WARPS * p.nb * eb) / stage_bytes));
   p.ring_bytes = p.stages * stage_bytes;
