@@ -17,7 +17,7 @@
 #define AT_BM 128
 #define AT_BN 128
 #define AT_DH 32
-#define AT_KV_STAGES 3
+#define AT_KV_STAGES 4
 #define AF_GROUPS 2
 #define AF_THREADS(SW) (32 * AF_GROUPS * (2 + (SW)))     // per group: 1 producer, 1 MMA issuer, SW softmax warps (4, or 8 = two per TMEM lane quarter)
 #define LOG2E_F 1.4426950408889634f
