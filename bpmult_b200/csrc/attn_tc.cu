@@ -545,10 +545,6 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
   }
 }
 
-__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
-               : "memory");
-}
 
 
 // One NC-column chunk of a (128 keys x 128 queries) pair for key row `key`: sv (S^T) -> P~^T, dpv (dP^T) -> dS^T, in place.

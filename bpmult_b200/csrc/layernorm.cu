@@ -3,6 +3,7 @@
 // Reference: nn.LayerNorm(embed_dim) eps 1e-5, models/transformer.py:197-202,227-229.
 // Algorithmic bytes: rows*D*(e_in + e_out) fwd; rows*D*(e_dy + e_x + 4 [+4 accumulate read]) bwd.
 #include "bpm_common.cuh"
+#include "tc_common.cuh"
 
 #define LN_WARPS 4
 
@@ -179,6 +180,154 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 4) ln_bwd_kernel(const TG* __re
   }
 }
 
+#define LN_PF 3                                  // rows in flight per warp in the prefetching backward
+template <typename TG, typename TX, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, 4) ln_bwd_pf_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in, const float* __restrict__ gamma, int rows, int D,
+                                                               int Dp, float* __restrict__ dx, int accumulate, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, void* __restrict__ cast_out, int cast_dtype,
+                                                               bpm_dropout_t cast_drop) {
+  // Same math as ln_bwd_kernel; the rows are PREFETCHED: lane 0 of every warp keeps LN_PF bulk copies (dy, x, dx rows) in flight
+  // into a per-warp shared-memory ring, so the memory latency of row k + LN_PF overlaps the arithmetic of row k without holding the
+  // rows in registers (the register version waits on its own loads half of the time: ncu long-scoreboard 49 %).
+  extern __shared__ float sm[];  // [LN_WARPS][2][Dp] column sums | rings [LN_WARPS][LN_PF][dy row | x row | dx row] | barriers
+  pdl_trigger();
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t row_g = (uint32_t)Dp * sizeof(TG), row_x = (uint32_t)Dp * sizeof(TX), row_d = (uint32_t)Dp * 4u;
+  const uint32_t stb = row_g + row_x + row_d;
+  uint8_t* const ring_gen = (uint8_t*)sm + (size_t)LN_WARPS * 2 * Dp * 4 + (size_t)warp * LN_PF * stb;
+  const uint32_t ring_s = smem_u32(ring_gen);
+  const uint32_t bars = smem_u32((uint8_t*)sm + (size_t)LN_WARPS * 2 * Dp * 4 + (size_t)LN_WARPS * LN_PF * stb) + (uint32_t)warp * LN_PF * 8u;
+  if (lane == 0) {
+    for (int s2 = 0; s2 < LN_PF; s2++) mbar_init(bars + 8u * s2, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  pdl_wait();
+  const int row0 = blockIdx.x * LN_WARPS + warp, rstride = gridDim.x * LN_WARPS;
+  auto issue = [&](int k) {                       // lane 0: row k of this warp -> stage k % LN_PF
+    const int64_t row = row0 + (int64_t)k * rstride;
+    if (row >= rows) return;
+    const int s2 = k % LN_PF;
+    const uint32_t dst = ring_s + (uint32_t)s2 * stb, bar = bars + 8u * s2;
+    mbar_expect_tx(bar, row_g + row_x + (accumulate ? row_d : 0u));
+    bulk_load_1d(dst, dy + row * Dp, row_g, bar);
+    bulk_load_1d(dst + row_g, x + row * Dp, row_x, bar);
+    if (accumulate) bulk_load_1d(dst + row_g + row_x, dx + row * Dp, row_d, bar);
+  };
+  if (lane == 0) {
+    for (int k = 0; k < LN_PF; k++) issue(k);
+  }
+  int kk = 0;
+  int nvec = Dp >> 3;
+  float invD = 1.f / (float)D;
+  float ag[NV][8], ab[NV][8];
+  Vec8<float> gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    int c = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { ag[i][j] = 0.f; ab[i][j] = 0.f; gm[i].v[j] = 0.f; }
+    if (c < nvec) gm[i].load(gamma + c * 8);
+  }
+  const DropCtx dc = make_drop(cast_drop);
+  for (int row = row0; row < rows; row += rstride, kk++) {
+    const int st = kk % LN_PF;
+    const TG* gr = (const TG*)(ring_gen + (size_t)st * stb);
+    const TX* xr = (const TX*)(ring_gen + (size_t)st * stb + row_g);
+    const float* dri = (const float*)(ring_gen + (size_t)st * stb + row_g + row_x);
+    float* dr = dx + (int64_t)row * Dp;
+    float mean = mean_in[row], rstd = rstd_in[row];
+    mbar_wait(bars + 8u * st, (uint32_t)(kk / LN_PF) & 1u);
+    Vec8<TG> g[NV];
+    Vec8<TX> xv[NV];
+    Vec8<float> o[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {                          // every load of the row is issued before anything is consumed
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        g[i].load(gr + c * 8);
+        xv[i].load(xr + c * 8);
+        if (accumulate) o[i].load(dri + c * 8);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[i].v[j] = 0.f;
+        }
+      }
+    }
+    __syncwarp();                                           // every lane holds its part of the row: the stage may be refilled
+    if (lane == 0) issue(kk + LN_PF);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        // dy pads are zero (they come from GEMMs against zero-padded weights) and gamma pads are zero, so only x-hat needs care:
+        // x-hat_pad = -mean * rstd is finite and always multiplied by a zero gradient.
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float xh = (xv[i].v[j] - mean) * rstd;
+          float gy = g[i].v[j];
+          float gh = gy * gm[i].v[j];
+          xv[i].v[j] = xh; g[i].v[j] = gh;
+          s1 += gh; s2 = fmaf(gh, xh, s2);
+          ag[i][j] = fmaf(gy, xh, ag[i][j]); ab[i][j] += gy;
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      int c = lane + 32 * i;
+      if (c < nvec) {
+        if (c * 8 + 8 <= D) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[i].v[j] += rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2);
+        } else {                                              // the chunk that straddles D (and pure pad chunks): keep pads at zero
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[i].v[j] += (c * 8 + j < D) ? rstd * (g[i].v[j] - s1 - xv[i].v[j] * s2) : 0.f;
+        }
+        o[i].store(dr + c * 8);
+        if (cast_out != nullptr) {
+          float m[8];
+          drop_mult8(dc, (uint64_t)row * (uint64_t)Dp + (uint64_t)(c * 8), m);
+          if (cast_dtype == BPM_BF16) {
+            Vec8<bf16> t;
+#pragma unroll
+            for (int j = 0; j < 8; j++) t.v[j] = o[i].v[j] * m[j];
+            t.store((bf16*)cast_out + (int64_t)row * Dp + c * 8);
+          } else {
+            Vec8<float> t;
+#pragma unroll
+            for (int j = 0; j < 8; j++) t.v[j] = o[i].v[j] * m[j];
+            t.store((float*)cast_out + (int64_t)row * Dp + c * 8);
+          }
+        }
+      }
+    }
+  }
+  // block-level reduction of the parameter gradients, then one atomic per column per block
+  float* sg = sm + (size_t)warp * 2 * Dp;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    int c = lane + 32 * i;
+    if (c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) { sg[c * 8 + j] = ag[i][j]; sg[Dp + c * 8 + j] = ab[i][j]; }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * Dp; c += blockDim.x) {
+    int col = c % Dp;
+    if (col >= D) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; w++) s += sm[(size_t)w * 2 * Dp + c];
+    atomicAdd((c < Dp ? dgamma : dbeta) + col, s);
+  }
+}
+
 template <typename TI, typename TO>
 static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, int rows, int D, int Dp, float eps, void* y, float* mean, float* rstd,
                          cudaStream_t s) {
@@ -217,9 +366,20 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
   int nv = bpm_cdiv(Dp / 8, 32);
   int grid = min(bpm_cdiv(rows, LN_WARPS), bpm_num_sms() * 4);
   size_t smem = (size_t)LN_WARPS * 2 * Dp * sizeof(float);
+  const size_t ring = (size_t)LN_WARPS * LN_PF * Dp * (sizeof(TG) + sizeof(TX) + 4) + LN_WARPS * LN_PF * 8;
+  const bool pf = smem + ring <= 52 * 1024 && !(bpm_debug_get(0) & 1024);          // 4 CTAs per SM must still fit
 #define LNB(NV) \
-  (void)bpm_launch(ln_bwd_kernel<TG, TX, NV>, dim3(grid), dim3(LN_WARPS * 32), smem, s, (const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, Dp, dx, \
-                   accumulate, dgamma, dbeta, cast_out, cast_dtype, cast_drop)
+  do { \
+    if (pf) { \
+      static bool attr = false; \
+      if (!attr) { cudaFuncSetAttribute(ln_bwd_pf_kernel<TG, TX, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024); attr = true; } \
+      (void)bpm_launch(ln_bwd_pf_kernel<TG, TX, NV>, dim3(grid), dim3(LN_WARPS * 32), smem + ring, s, (const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, \
+                       Dp, dx, accumulate, dgamma, dbeta, cast_out, cast_dtype, cast_drop); \
+    } else { \
+      (void)bpm_launch(ln_bwd_kernel<TG, TX, NV>, dim3(grid), dim3(LN_WARPS * 32), smem, s, (const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, Dp, dx, \
+                       accumulate, dgamma, dbeta, cast_out, cast_dtype, cast_drop); \
+    } \
+  } while (0)
   switch (nv) {
     case 1: LNB(1); break;
     case 2: LNB(2); break;

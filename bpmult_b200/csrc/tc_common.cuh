@@ -68,6 +68,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
                : "memory");
 }
 
+// 1-D bulk copy global -> shared memory (16-byte aligned address and size), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 // shared memory -> global through the TMA unit (bulk async group of the issuing thread); rows / columns outside the tensor are clipped
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)m), "r"(smem_src), "r"(c0), "r"(c1),

@@ -53,5 +53,15 @@ elif which == "ln_fwd":
     mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
     for _ in range(iters):
         ops.layernorm_fwd(x, g, b, d.D, y, mean, rstd)
+elif which == "ln_bwd":
+    x = torch.randn(M, d.Dp, device=dev)
+    dy = torch.randn(M, d.Dp, device=dev).to(bf)
+    dx = torch.randn(M, d.Dp, device=dev)
+    co = torch.empty(M, d.Dp, device=dev, dtype=bf)
+    g = torch.ones(d.Dp, device=dev)
+    mean, rstd = torch.zeros(M, device=dev), torch.ones(M, device=dev)
+    dg, db = torch.zeros(d.Dp, device=dev), torch.zeros(d.Dp, device=dev)
+    for _ in range(iters):
+        ops.layernorm_bwd(dy, x, mean, rstd, g, d.D, dx, True, dg, db, co, None)
 torch.cuda.synchronize()
 print("ok", which)
