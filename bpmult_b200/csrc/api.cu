@@ -1,7 +1,24 @@
 // C-ABI dispatch: picks the tensor-core (bf16) or exact-fp32 kernel for GEMM and attention.
 // There is no CPU path: every entry point launches CUDA kernels on the caller's stream.
 #include <stdlib.h>
+#include <mutex>
+#include <set>
+#include <utility>
 #include "bpm_common.cuh"
+
+int bpm_func_smem(const void* func, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); bpm_set_error("%s: cudaGetDevice failed", what); return BPM_ELAUNCH; }
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_pair(func, dev);
+  if (done.count(key)) return BPM_OK;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { bpm_set_error("%s: cudaFuncSetAttribute(%d B): %s", what, bytes, cudaGetErrorString(e)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
+  done.insert(key);
+  return BPM_OK;
+}
 
 int bpm_gemm_simt(const bpm_gemm_t* g, cudaStream_t stream);
 int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream);

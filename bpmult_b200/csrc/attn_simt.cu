@@ -187,8 +187,8 @@ template <typename K>
 static int set_smem(K kern, size_t bytes) {
   if (bytes > 48 * 1024) {
     BPM_REQUIRE(bytes <= 227 * 1024, "xattn(simt): sequence too long for the fp32 precision-mode kernel (%zu B smem)", bytes);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) { bpm_set_error("xattn(simt): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
+    // the requirement grows with S: always raise the limit to the maximum once per (kernel, device)
+    if (int rc = bpm_func_smem((const void*)kern, 227 * 1024, "xattn(simt)")) return rc;
   }
   return BPM_OK;
 }

@@ -451,13 +451,7 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
                       : (dm == 0 ? (sw == 8 ? attn_fwd_tc_kernel<false, true, 8> : attn_fwd_tc_kernel<false, true, 4>) : attn_fwd_tc_kernel<false, false, 4>);
   CUtensorMap to;
   if ((rc = make_qkv_map(&to, out, a->B, a->T, HP, 32))) return rc;                      // output: {32 columns, 32 rows} store boxes
-  static bool attr_set[4] = {false, false, false, false};
-  const int ki = (dm == 0 && sw == 4) ? 3 : dm;
-  if (!attr_set[ki]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { bpm_set_error("xattn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
-    attr_set[ki] = true;
-  }
+  if (int rc2 = bpm_func_smem((const void*)kern, (int)smem, "xattn_fwd_tc")) return rc2;
   const int n_items = a->B * a->H * bpm_cdiv(a->T, AT_BM);
   const int ctas = min(bpm_num_sms(), bpm_cdiv(n_items, AF_GROUPS));
   cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AF_THREADS(sw)), smem, stream, tq, tk, tv, to, lse, a->B, a->T, a->S, a->H,
@@ -1109,13 +1103,7 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   const bool fold1 = dm == 1 && a->dh <= AB_PAD0 && !(bpm_debug_get(1) & 2048);     // dropout: lse still folds into S^T
   auto kern = dm == 0 ? (cw == 16 ? attn_bwd_tc_kernel<0, true, 16> : attn_bwd_tc_kernel<0, true, 8>)
                       : (dm == 1 ? (fold1 ? attn_bwd_tc_kernel<1, true, 8> : attn_bwd_tc_kernel<1, false, 8>) : attn_bwd_tc_kernel<0, false, 8>);
-  static bool attr_set[5] = {false, false, false, false, false};
-  const int ki = dm == 0 && cw == 8 ? 3 : (dm == 1 && fold1 ? 4 : dm);
-  if (!attr_set[ki]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { bpm_set_error("xattn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
-    attr_set[ki] = true;
-  }
+  if (int rc2 = bpm_func_smem((const void*)kern, (int)smem, "xattn_bwd_tc")) return rc2;
   const int ctas = min(a->B * a->H, bpm_num_sms());
   cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AB_THREADS(cw)), smem, stream, tq, tk, tv, tg, tb, tdq, tdk, tdv, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
                                                          a->mask_off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr());

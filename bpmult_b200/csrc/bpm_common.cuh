@@ -29,6 +29,9 @@ void bpm_set_error(const char* fmt, ...);
 
 static inline int bpm_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 int bpm_num_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-(function, device) setting: remembered per device, so a second GPU used
+// from the same process gets it too (api.cu)
+int bpm_func_smem(const void* func, int bytes, const char* what);
 int bpm_debug_get(int slot);   // diagnostic knobs (api.cu)
 void* bpm_debug_get_ptr();     // optional device buffer for kernel event traces
 

@@ -511,12 +511,7 @@ static int pick_bn(int N, int max_bn) {
 template <int ELEM, int CB, int CG, int EPI>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmI, const TcGemmParams& p, int ctas,
                      size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ELEM, CB, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e != cudaSuccess) { bpm_set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return BPM_ELAUNCH; }
-    attr_set = true;
-  }
+  if (int rc = bpm_func_smem((const void*)gemm_tc_kernel<ELEM, CB, CG, EPI>, 227 * 1024, "gemm_tc")) return rc;
   cudaError_t le = bpm_launch_cluster(CG, gemm_tc_kernel<ELEM, CB, CG, EPI>, dim3(ctas), dim3(TC_THREADS), smem, stream, tmA, tmB, tmC, tmI, p);
   if (le != cudaSuccess) { bpm_set_error("gemm_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;

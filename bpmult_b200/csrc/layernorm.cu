@@ -371,8 +371,7 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
 #define LNB(NV) \
   do { \
     if (pf) { \
-      static bool attr = false; \
-      if (!attr) { cudaFuncSetAttribute(ln_bwd_pf_kernel<TG, TX, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024); attr = true; } \
+      if (int rc = bpm_func_smem((const void*)ln_bwd_pf_kernel<TG, TX, NV>, 56 * 1024, "layernorm_bwd")) return rc; \
       (void)bpm_launch(ln_bwd_pf_kernel<TG, TX, NV>, dim3(grid), dim3(LN_WARPS * 32), smem + ring, s, (const TG*)dy, (const TX*)x, mean, rstd, gamma, rows, D, \
                        Dp, dx, accumulate, dgamma, dbeta, cast_out, cast_dtype, cast_drop); \
     } else { \

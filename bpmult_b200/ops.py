@@ -47,7 +47,8 @@ class CudaOps:
         self.launches = 0
         self._depth = 0
         self._batch = None          # (mode, key, [descriptor tuples]) while pack / unpack calls are being collected
-        self._tables = {}           # (mode, key) -> (signature, device table)
+        self._tables = {}           # descriptor-list signature -> [device table, pinned by a captured graph]  (see _table)
+        self.max_tables = 256
 
     # ------------------------------------------------------------------ batched pack / unpack (one launch per table)
     def batch_begin(self, mode, key):
@@ -65,21 +66,38 @@ class CudaOps:
         self._batch = None
         if not items:
             return
-        sig = (mode,) + tuple(items)
-        tab = self._tables.get(sig)                 # keyed by the full descriptor list: alternating engines never rebuild (and never
-        if tab is None:                             # trigger a host->device copy inside a CUDA-graph capture)
+        def build():
             dt = np.dtype([("src", "u8"), ("dst", "u8")] + [(n, "i4") for n in ("rows", "cols", "ld_src", "ld_dst", "rows_p", "cols_p", "row_dh",
                           "row_dhp", "col_dh", "col_dhp", "dst_dtype", "accumulate")] + [("scale", "f4"), ("pad", "i4")], align=True)
             assert dt.itemsize == 72
             arr = np.zeros(len(items), dtype=dt)
             for i, it in enumerate(items):
                 arr[i] = it + (0,)
-            tab = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
-            if len(self._tables) > 256:
-                self._tables.clear()
-            self._tables[sig] = tab
-        ent = (sig, tab)
-        self._ck(self.lib.bpm_remap_batch(ent[1].data_ptr(), len(items), 0 if mode == "pack" else 1, self._s()), "remap_batch")
+            return arr
+        tab = self._table((mode,) + tuple(items), build)
+        self._ck(self.lib.bpm_remap_batch(tab.data_ptr(), len(items), 0 if mode == "pack" else 1, self._s()), "remap_batch")
+
+    def _table(self, sig, build):
+        """Device descriptor table for a batched launch, cached by the full descriptor list (alternating engines never rebuild, and
+        a CUDA-graph capture never sees a host->device copy: the eager warm-up steps have created every table it uses).
+        A table that has been used while the stream was capturing is baked into that graph's kernel arguments, so it is PINNED:
+        it is never evicted (its memory must not return to the allocator while the graph can still be replayed).  Only unpinned
+        tables -- the eager autograd path, whose gradient tensors may have new addresses every call -- are evicted, oldest first."""
+        ent = self._tables.get(sig)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if ent is None:
+            if capturing:
+                raise _lib.BpmError("bpmult_b200: a descriptor table is missing during CUDA-graph capture (run the step eagerly once first)")
+            ent = [torch.from_numpy(build().view("uint8").copy()).to(self.device), False]
+            self._tables[sig] = ent
+            if len(self._tables) > self.max_tables:
+                for k in [k for k, e in self._tables.items() if not e[1]][:len(self._tables) - self.max_tables]:
+                    del self._tables[k]
+        else:
+            self._tables[sig] = self._tables.pop(sig)       # most recently used last
+        if capturing:
+            ent[1] = True
+        return ent[0]
 
     # ------------------------------------------------------------------ helpers
     def _s(self):
@@ -166,17 +184,15 @@ class CudaOps:
         self._fold = None
         if not items:
             return
-        sig = ("fold", mode) + tuple(items)
-        tab = self._tables.get(sig)
-        if tab is None:
+        def build():
             dt = np.dtype([(n, "u8") for n in ("W", "bias", "gamma", "beta", "Wp", "bp", "gWf", "gbf", "gW", "gb", "dgamma", "dbeta")] +
                           [(n, "i4") for n in ("rows", "cols", "ldw", "ldp", "ldf", "ldg", "row_dh", "row_dhp", "wp_dtype", "pad")], align=True)
             assert dt.itemsize == 136
             arr = np.zeros(len(items), dtype=dt)
             for i, it in enumerate(items):
                 arr[i] = it
-            tab = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
-            self._tables[sig] = tab
+            return arr
+        tab = self._table(("fold", mode) + tuple(items), build)
         self._ck(self.lib.bpm_ln_fold_batch(tab.data_ptr(), len(items), max(it[12] for it in items), 0 if mode == "fwd" else 1, self._s()),
                  "ln_fold_batch")
 

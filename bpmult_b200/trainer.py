@@ -97,6 +97,19 @@ class Trainer:
             if n in pmap:
                 self.params[n] = pmap[n].data
         self.n_params = total
+        self.order = order                                  # flat-buffer layout: parameter names in bucket order
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """Data parallelism only all-reduces GRADIENTS, so the replicas must start identical: rank 0's parameters and optimizer state
+        are broadcast to every rank (one call each: the buffers are flat).  nn.DataParallel (train.py:354-356) has a single parameter
+        copy and DDP broadcasts at construction; ranks built under different RNG state, or a checkpoint loaded on rank 0 only, would
+        otherwise silently train different models."""
+        if self.world > 1:
+            for t in (self.flat_p, self.flat_m, self.flat_v, self.flat_g):
+                dist.broadcast(t, 0)
+            if hasattr(self, "step_t"):
+                dist.broadcast(self.step_t, 0)
 
     # ---------------------------------------------------------------- one step (enqueue only)
     def _enqueue(self, *batch, apply=True):
@@ -155,17 +168,124 @@ class Trainer:
         return self.lr
 
     def optimizer_state_dict(self):
+        """native (flat) format; `names` pins the flat layout so an engine change cannot silently re-map a saved state"""
         return dict(step=int(self.step_t.item()), lr=self.lr, betas=self.betas, eps=self.eps, exp_avg=self.flat_m.clone(),
-                    exp_avg_sq=self.flat_v.clone(), seed=int(self.seed_t.item()), micro=self.micro, grad=self.flat_g.clone())
+                    exp_avg_sq=self.flat_v.clone(), seed=int(self.seed_t.item()), rank=self.rank, micro=self.micro, grad=self.flat_g.clone(),
+                    names=list(self.order))
 
     def load_optimizer_state_dict(self, sd):
+        """accepts the native flat format or torch.optim.Adam's state_dict (the reference checkpoint's "optimizer" entry)"""
+        if "param_groups" in sd:
+            return self.load_torch_optimizer_state_dict(sd)
+        if "names" in sd and list(sd["names"]) != list(self.order):
+            raise ValueError("optimizer state was saved with a different flat parameter layout (%d vs %d tensors)" % (len(sd["names"]), len(self.order)))
         self.step_t.fill_(sd["step"])
-        self.seed_t.fill_(sd["seed"])
+        self.seed_t.fill_(sd["seed"] + 7919 * (self.rank - sd.get("rank", 0)))          # the seed stream stays per-rank
         self.flat_m.copy_(sd["exp_avg"])
         self.flat_v.copy_(sd["exp_avg_sq"])
         self.flat_g.copy_(sd["grad"])
         self.micro = sd["micro"]
         self.set_lr(sd["lr"])
+        self.sync_replicas()
+
+    # torch.optim.Adam layout (train.py:123-125 `optim.Adam(model.parameters(), lr)`, saved at train.py:422, loaded at :378):
+    #   {"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [{"lr", "betas", "eps", "weight_decay", "amsgrad", ..., "params": [0..]}]}
+    # with i = position in model.parameters(); parameters that never received a gradient have no state entry.
+    def _param_index(self):
+        return {n: i for i, (n, _) in enumerate(self.model.named_parameters())}
+
+    def torch_optimizer_state_dict(self):
+        idx = self._param_index()
+        step = float(self.step_t.item())
+        state = {}
+        off = 0
+        for n in self.order:
+            k = self.params[n].numel()
+            if step > 0:
+                state[idx[n]] = {"step": torch.tensor(step), "exp_avg": self.flat_m[off:off + k].view_as(self.params[n]).clone(),
+                                 "exp_avg_sq": self.flat_v[off:off + k].view_as(self.params[n]).clone()}
+            off += k
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(idx)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_torch_optimizer_state_dict(self, sd):
+        names = [n for n, _ in self.model.named_parameters()]
+        g = sd["param_groups"][0]
+        assert len(sd["param_groups"]) == 1 and len(g["params"]) == len(names), "optimizer state does not match model.parameters()"
+        assert not g.get("amsgrad", False) and not g.get("weight_decay", 0), "the fused Adam has no amsgrad / weight decay (train.py:124 uses neither)"
+        pos = {n: i for i, n in enumerate(names)}
+        self.flat_m.zero_()
+        self.flat_v.zero_()
+        step, off = 0, 0
+        for n in self.order:
+            k = self.params[n].numel()
+            st = sd["state"].get(g["params"][pos[n]])
+            if st is not None:
+                self.flat_m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.flat_v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                step = max(step, int(float(st["step"])))
+            off += k
+        self.step_t.fill_(step)
+        self.betas, self.eps = tuple(g["betas"]), g["eps"]
+        if self.graphs:                                      # betas / eps are baked into a captured step
+            self.graphs = {}
+            self.warm = 0
+        self.set_lr(g["lr"])
+        self.sync_replicas()
+
+    @property
+    def param_groups(self):
+        """lets torch.optim.lr_scheduler.ReduceLROnPlateau-style code (train.py:128-136, 408) read and write `param_groups[0]["lr"]`"""
+        tr = self
+
+        class _Group(dict):
+            def __setitem__(self, k, v):
+                dict.__setitem__(self, k, v)
+                if k == "lr":
+                    tr.set_lr(v)
+        return [_Group(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=0)]
+
+    # ---------------------------------------------------------------- reference checkpoint format (utils/utils.py:21-30, train.py:372-379,419-430)
+    def checkpoint(self, epoch=0, scheduler=None, n_no_improve=0, best_metric=float("-inf")):
+        """the dict train.py:419-430 hands to save_checkpoint: loadable by the reference (`model.load_state_dict(ck["state_dict"])`,
+        `optim.Adam.load_state_dict(ck["optimizer"])`)"""
+        sd = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        return {"epoch": epoch, "state_dict": sd, "optimizer": self.torch_optimizer_state_dict(),
+                "scheduler": scheduler.state_dict() if scheduler is not None else {}, "n_no_improve": n_no_improve, "best_metric": best_metric}
+
+    def load_checkpoint(self, ck, strict=False):
+        """`ck`: a reference-format checkpoint dict (or a path to one).  Keys saved under nn.DataParallel carry a "module." prefix
+        (train.py:354-356,422); parameters of modules outside the trunk (enc.bert.*, audio_enc.*) are ignored unless strict."""
+        if isinstance(ck, (str, bytes, os.PathLike)):
+            ck = torch.load(ck, map_location="cpu", weights_only=False)
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ck["state_dict"].items()}
+        own = self.model.state_dict()
+        missing = [k for k in own if k not in sd and not k.endswith(("_float_tensor", "version"))]
+        unexpected = [k for k in sd if k not in own]
+        if strict and (missing or unexpected):
+            raise KeyError("checkpoint mismatch: missing %s unexpected %s" % (missing[:4], unexpected[:4]))
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k in own and not k.endswith("_float_tensor"):
+                    own[k].copy_(v)                      # parameters are views into the flat buffer: copy in place, never re-point
+        if ck.get("optimizer"):
+            self.load_optimizer_state_dict(ck["optimizer"])
+        else:
+            self.sync_replicas()
+        return dict(epoch=ck.get("epoch", 0), n_no_improve=ck.get("n_no_improve", 0), best_metric=ck.get("best_metric"), missing=missing,
+                    unexpected=unexpected)
+
+    def close(self):
+        """Drops the captured graphs (they hold the NCCL kernels of the gradient all-reduces) and drains the device, so that the
+        process group can be destroyed afterwards.  Call before dist.destroy_process_group()."""
+        if self.on_gpu:
+            torch.cuda.synchronize(self.device)
+        self.graphs = {}
+        self.warm = 0
+        if self.on_gpu:
+            torch.cuda.synchronize(self.device)
 
     # ---------------------------------------------------------------- public API
     def _ensure_static(self, *batch):

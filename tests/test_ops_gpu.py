@@ -241,15 +241,49 @@ def test_xattn_fwd_bwd(ops, dtype, case):
         assert max_rel(cw, ew) < 2e-5
 
 
-def test_xattn_key_padding_mask(ops):
-    B, T, S, H, dh, dhp = 2, 8, 10, 2, 16, 32
-    q, k, v = rnd((B * T, H * dhp), 50), rnd((B * S, H * dhp), 51), rnd((B * S, H * dhp), 52)
+# head dim 64 / 128 on the tensor-core kernels of attn_tc128.cu (the 4-modality model: hidden 768 / 6 heads, README.md:30,36)
+ATTN_CASES_WIDE = [  # B, T, S, H, dh, dhp, mask_off, p
+    (1, 128, 128, 1, 128, 128, -1, 0.0), (2, 256, 256, 2, 128, 128, 0, 0.0), (1, 512, 512, 6, 128, 128, 0, 0.0),
+    (2, 200, 512, 6, 128, 128, 312, 0.0), (2, 512, 200, 6, 128, 128, 312, 0.0), (3, 200, 200, 6, 128, 128, 0, 0.1),
+    (1, 76, 333, 3, 128, 128, -1, 0.2), (1, 1024, 640, 2, 128, 128, 384, 0.0), (2, 130, 70, 2, 100, 128, 60, 0.0),
+    (1, 384, 384, 2, 64, 64, 0, 0.0), (2, 200, 512, 3, 64, 64, -1, 0.1), (1, 300, 150, 2, 50, 64, 150, 0.0),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES_WIDE)
+def test_xattn_fwd_bwd_wide_heads(ops, case):
+    test_xattn_fwd_bwd(ops, BF16, case)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("dims", [(2, 8, 10, 2, 16, 32, -1), (2, 140, 200, 3, 25, 32, 60), (2, 200, 333, 2, 128, 128, -1), (1, 256, 256, 2, 128, 128, 0)])
+def test_xattn_key_padding_mask(ops, dtype, dims):
+    """north star (2): key-padding mask (superset feature -- the reference has none, multihead_attention.py:52), forward AND backward.
+    Padded keys get probability 0 and zero dK / dV; every query keeps at least one visible key."""
+    B, T, S, H, dh, dhp, off = dims
+    HP = H * dhp
+
+    def mk(rows, seed, scale):
+        t = torch.zeros(rows, H, dhp)
+        t[:, :, :dh] = rnd((rows, H, dh), seed) * scale
+        return t.view(rows, HP).to(dtype)
+    q, k, v, do = mk(B * T, 50, dh ** -0.25), mk(B * S, 51, dh ** -0.25), mk(B * S, 52, 1.0), mk(B * T, 53, 1.0)
     kp = torch.zeros(B, S, dtype=torch.uint8)
-    kp[0, 7:] = 1
-    kp[1, 3] = 1
-    e, c = both(ops, lambda o, q, k, v, kp, out, lse: o.xattn_fwd(q, k, v, out, lse, B, T, S, H, dh, dhp, -1, kp, None), [q, k, v, kp],
-                [torch.zeros(B * T, H * dhp), torch.zeros(B * H * T)])
-    assert max_rel(c[0], e[0]) < 2e-5
+    kp[0, S - S // 3:] = 1                         # a padded tail
+    kp[B - 1, 3] = 1                               # and a hole
+    kp[B - 1, S // 2:S // 2 + 5] = 1
+    e, c = both(ops, lambda o, q, k, v, kp, out, lse: o.xattn_fwd(q, k, v, out, lse, B, T, S, H, dh, dhp, off, kp, None), [q, k, v, kp],
+                [torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * H * T)])
+    assert max_rel(c[0], e[0]) < tol(dtype)
+    assert max_rel(c[1], e[1]) < (1e-5 if dtype == F32 else 2e-3)
+    outs = [torch.zeros(2 * B * H * T), torch.zeros(B * T, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype), torch.zeros(B * S, HP, dtype=dtype)]
+    e2, c2 = both(ops, lambda o, q, k, v, kp, out, do, lse, dl, dq, dk, dv: o.xattn_bwd(q, k, v, out, do, lse, dl, dq, 0.2, dk, dv, B, T, S, H, dh, dhp, off,
+                                                                                       kp, None), [q, k, v, kp, e[0], do, e[1]], outs)
+    t = 2e-5 if dtype == F32 else 1.5e-2
+    for a, b, nm in zip(c2[1:], e2[1:], ["dq", "dk", "dv"]):
+        assert max_rel(a, b) < t, nm
+    padded = kp.bool().view(B * S)
+    assert float(c2[2].float()[padded].abs().max()) == 0.0 and float(c2[3].float()[padded].abs().max()) == 0.0
 
 
 # ------------------------------------------------------------------------------------------------ GMU / pooling / head pieces / loss / adam

@@ -109,3 +109,95 @@ def test_trainer_drives_the_4_modality_model():
     num = sum(float((pb[n].detach() - pa[n].detach()).double().pow(2).sum()) for n in pa)
     den = sum(float(pa[n].detach().double().pow(2).sum()) for n in pa)
     assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+
+
+def test_reference_format_checkpoint_round_trip_with_torch_adam():
+    """SURVEY 8 f3 (utils/utils.py:21-30, train.py:372-379,419-430): a checkpoint written the way the reference writes it -- model
+    state_dict with the nn.DataParallel `module.` prefix, `optim.Adam(model.parameters()).state_dict()` -- loads into model + Trainer
+    and training continues exactly as torch's Adam would; the Trainer's own checkpoint loads back into torch's Adam."""
+    from bpmult_b200.trainer import Trainer
+    cfg = synth.tiny_cfg(layers=1)
+    batch = synth.mmtrvat_inputs(cfg, 2, 8, 12, 10)
+    txt, img, audio, tgt = batch
+    crit = torch.nn.BCEWithLogitsLoss()
+
+    def torch_steps(model, opt, n):
+        out = []
+        for _ in range(n):
+            opt.zero_grad()
+            loss = crit(model(txt, None, None, img, audio), tgt)
+            loss.backward()
+            opt.step()
+            out.append(float(loss))
+        return out
+    # "reference side": the drop-in module driven by torch's own Adam, checkpointed like train.py:419-430 under DataParallel
+    a = _build(cfg)
+    opt_a = torch.optim.Adam(a.parameters(), lr=1e-2)
+    torch_steps(a, opt_a, 2)
+    ck = {"epoch": 3, "state_dict": {"module." + k: v.clone() for k, v in a.state_dict().items()}, "optimizer": opt_a.state_dict(),
+          "scheduler": {}, "n_no_improve": 1, "best_metric": 0.5}
+    ck = {k: (v if k != "optimizer" else torch.load(_roundtrip(v), weights_only=False)) for k, v in ck.items()}
+    la = torch_steps(a, opt_a, 2)
+    # Trainer side: fresh model with other weights, resume from the checkpoint
+    b = _build(cfg)
+    with torch.no_grad():
+        for p in b.parameters():
+            p.add_(0.25)
+    tr = Trainer(b, lr=123.0, use_graph=False)
+    info = tr.load_checkpoint(ck)
+    assert info["epoch"] == 3 and info["n_no_improve"] == 1 and not info["unexpected"] and not info["missing"]
+    assert abs(tr.get_lr() - 1e-2) < 1e-12 and int(tr.step_t) == 2
+    lb = [tr.step(*batch) for _ in range(2)]
+    assert max(abs(x - y) for x, y in zip(la, lb)) < 1e-5, (la, lb)
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    num = sum(float((pb[n].detach() - pa[n].detach()).double().pow(2).sum()) for n in pa)
+    den = sum(float(pa[n].detach().double().pow(2).sum()) for n in pa)
+    assert (num / den) ** 0.5 < 1e-3
+    # and back: the Trainer's checkpoint resumes under torch's Adam on a reference-layout model
+    ck2 = tr.checkpoint(epoch=4)
+    c = _build(cfg)
+    c.load_state_dict(ck2["state_dict"], strict=False)
+    opt_c = torch.optim.Adam(c.parameters(), lr=1.0)
+    opt_c.load_state_dict(ck2["optimizer"])
+    assert opt_c.param_groups[0]["lr"] == 1e-2
+    lc = torch_steps(c, opt_c, 1)
+    ld = [tr.step(*batch)]
+    assert abs(lc[0] - ld[0]) < 1e-5
+    # ReduceLROnPlateau-style code can drive the rate through param_groups
+    tr.param_groups[0]["lr"] = 5e-3
+    assert tr.get_lr() == 5e-3
+
+
+def _roundtrip(obj):
+    import io
+    buf = io.BytesIO()
+    torch.save(obj, buf)
+    buf.seek(0)
+    return buf
+
+
+def test_reference_checkpoint_loads_into_the_live_reference_when_available():
+    """a Trainer checkpoint's state_dict loads into the UNMODIFIED reference model (shimmed import) and gives the same logits"""
+    import pytest
+    from oracle.ref_shim import load_reference, zero_dropout
+    ref = load_reference()
+    if ref is None:
+        pytest.skip("reference tree not present")
+    from bpmult_b200.trainer import Trainer
+    cfg = synth.tiny_cfg(layers=1)
+    batch = synth.mmtrvat_inputs(cfg, 2, 8, 12, 10)
+    tr = Trainer(_build(cfg), lr=1e-2, use_graph=False)
+    tr.step(*batch)
+    ck = tr.checkpoint(epoch=1)
+    rm = ref.mmtr.MultiprojectionMMTransformer3DGMUClf(zero_dropout(Namespace(**vars(cfg))))
+    missing, unexpected = rm.load_state_dict(ck["state_dict"], strict=False)
+    assert not unexpected and all(k.endswith("_float_tensor") or k.endswith("version") for k in missing), (missing, unexpected)
+    rm.eval()
+    tr.model.eval()
+    with torch.no_grad():
+        lr_ = rm(batch[0], None, None, batch[1], batch[2])
+        lo = tr.model(batch[0], None, None, batch[1], batch[2])
+    assert float((lr_ - lo).abs().max()) < 1e-5
+    opt = torch.optim.Adam(rm.parameters(), lr=1.0)
+    opt.load_state_dict(ck["optimizer"])                       # same parameter order as the reference's model.parameters()
+    assert opt.param_groups[0]["lr"] == 1e-2
