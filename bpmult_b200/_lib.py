@@ -57,6 +57,7 @@ SIGNATURES = {
     "bpm_colsum": [_P, _I, _I, _I, _I, _P, _P],
     "bpm_xattn_fwd": [C.POINTER(Attn), _P, _P, _P, _P, _P, _P],
     "bpm_xattn_bwd": [C.POINTER(Attn), _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P],
+    "bpm_xattn_bwd_workspace": [C.POINTER(Attn)],
     "bpm_xattn_weights": [C.POINTER(Attn), _P, _P, _P, _P, _P],
     "bpm_gmu_fwd": [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P],
     "bpm_gmu_bwd": [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P],
@@ -72,7 +73,7 @@ SIGNATURES = {
     "bpm_timelin_bwd": [_I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "bpm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P, _P, _P],
 }
-_RESTYPE = {"bpm_last_error": C.c_char_p}
+_RESTYPE = {"bpm_last_error": C.c_char_p, "bpm_xattn_bwd_workspace": C.c_int64}
 
 _lib = None
 

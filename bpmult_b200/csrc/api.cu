@@ -29,6 +29,12 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
 int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                      float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t s);
 int bpm_xattn_tc_supported(const bpm_attn_t* a);
+// head dim 64 / 128 (attn_tc128.cu)
+int bpm_xattn128_supported(const bpm_attn_t* a, int backward);
+int64_t bpm_xattn128_ws_floats(const bpm_attn_t* a);
+int bpm_xattn_fwd_tc128(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, cudaStream_t s);
+int bpm_xattn_bwd_tc128(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                        float* ws, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t s);
 extern "C" int bpm_colsum(const void* X, int dtype, int M, int N, int ld, float* out, void* stream);
 
 // diagnostic knobs for kernel bring-up / profiling (scripts/ only; the product never sets them): slot 0 = GEMM, 1 = attention
@@ -70,14 +76,27 @@ extern "C" int bpm_gemm(const bpm_gemm_t* g, void* stream) {
 
 extern "C" int bpm_xattn_fwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, void* stream) {
   BPM_REQUIRE(a && q && k && v && out && lse, "xattn_fwd: null pointer");
-  if (a->dtype == BPM_BF16 && !debug_ffma() && bpm_xattn_tc_supported(a)) return bpm_xattn_fwd_tc(a, q, k, v, out, lse, (cudaStream_t)stream);
+  if (a->dtype == BPM_BF16 && !debug_ffma()) {
+    if (bpm_xattn_tc_supported(a)) return bpm_xattn_fwd_tc(a, q, k, v, out, lse, (cudaStream_t)stream);
+    if (bpm_xattn128_supported(a, 0) && !(bpm_debug_get(1) & 65536)) return bpm_xattn_fwd_tc128(a, q, k, v, out, lse, (cudaStream_t)stream);
+  }
   return bpm_xattn_fwd_simt(a, q, k, v, out, lse, (cudaStream_t)stream);
 }
 
 extern "C" int bpm_xattn_bwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                              float* delta, void* dq, float dq_scale, void* dk, void* dv, void* stream) {
   BPM_REQUIRE(a && q && k && v && out && dout && lse && delta && dq && dk && dv, "xattn_bwd: null pointer");
-  if (a->dtype == BPM_BF16 && !debug_ffma() && bpm_xattn_tc_supported(a))
-    return bpm_xattn_bwd_tc(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, (cudaStream_t)stream);
+  if (a->dtype == BPM_BF16 && !debug_ffma()) {
+    if (bpm_xattn_tc_supported(a)) return bpm_xattn_bwd_tc(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, (cudaStream_t)stream);
+    if (bpm_xattn128_supported(a, 1) && !(bpm_debug_get(1) & 131072))
+      return bpm_xattn_bwd_tc128(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, (cudaStream_t)stream);
+  }
   return bpm_xattn_bwd_simt(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, (cudaStream_t)stream);
+}
+
+extern "C" int64_t bpm_xattn_bwd_workspace(const bpm_attn_t* a) {
+  if (!a) return 0;
+  const int64_t base = 2 * (int64_t)a->B * a->H * a->T;
+  if (a->dtype == BPM_BF16 && !debug_ffma() && !bpm_xattn_tc_supported(a) && bpm_xattn128_supported(a, 1)) return bpm_xattn128_ws_floats(a);
+  return base;
 }

@@ -13,6 +13,7 @@
 //   With dh = 32 the kernel is bound by exponentials (128x128 ex2 per tile on the 16/clk/SM MUFU = 1024 clk vs ~410 MMA clk).
 //   V is consumed directly from its [keys, dh] tile as an MN-major B operand (no transpose).  Fully masked KV tiles are skipped.
 #include "tc_common.cuh"
+#include "attn_math.cuh"
 
 #define AT_BM 128
 #define AT_BN 128
@@ -20,34 +21,6 @@
 #define AT_KV_STAGES 4
 #define AF_GROUPS 2
 #define AF_THREADS(SW) (32 * AF_GROUPS * (2 + (SW)))     // per group: 1 producer, 1 MMA issuer, SW softmax warps (4, or 8 = two per TMEM lane quarter)
-#define LOG2E_F 1.4426950408889634f
-#define LN2_F 0.6931471805599453f
-
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of work
-__device__ __forceinline__ void ffma2(float& a0, float& a1, float b, float c) {
-  asm("{.reg .b64 x, y, z;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %2};\n mov.b64 z, {%3, %3};\n fma.rn.f32x2 x, x, y, z;\n mov.b64 {%0, %1}, x;}"
-      : "+f"(a0), "+f"(a1) : "f"(b), "f"(c));
-}
-__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
-  asm("{.reg .b64 x, y;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %3};\n add.rn.f32x2 x, x, y;\n mov.b64 {%0, %1}, x;}"
-      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ void fmul2(float& a0, float& a1, float b) {
-  asm("{.reg .b64 x, y;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %2};\n mul.rn.f32x2 x, x, y;\n mov.b64 {%0, %1}, x;}" : "+f"(a0), "+f"(a1) : "f"(b));
-}
-__device__ __forceinline__ void fmul2v(float& a0, float& a1, float b0, float b1) {
-  asm("{.reg .b64 x, y;\n mov.b64 x, {%0, %1};\n mov.b64 y, {%2, %3};\n mul.rn.f32x2 x, x, y;\n mov.b64 {%0, %1}, x;}" : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *(uint32_t*)&v;
-}
-
 struct AttnFwdSmem {
   // per group, offsets from the group's 1024-aligned base
   static constexpr int Q = 0;                                   // 2 x (128 x 64 B)

@@ -493,6 +493,11 @@ int bpm_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
   return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz);
 }
 
+int bpm_make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMapSwizzle swz) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swz);
+}
+
 // [rows, cols] row-major map for the epilogue (C / residual / gate): box {chunk columns, 32 rows}
 static int make_epi_map(CUtensorMap* out, const void* base, int rows, int cols, int ld, int elem, int chunk_bytes) {
   uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows}, str[1] = {(uint64_t)ld * elem};

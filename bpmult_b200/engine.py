@@ -318,7 +318,8 @@ class EncoderEngine:
         else:
             dk = Sh.get("dk", (Ms, d.HP), self.T_)
             dv = Sh.get("dv", (Ms, d.HP), self.T_)
-        delta = Sh.get("delta", (2 * B * d.H * T,), torch.float32)      # [0] rowsum(dO*O), [1] lse*log2e
+        # [0] rowsum(dO*O), [1] lse*log2e (+ the fp32 dQ accumulator of the head-dim-128 tensor-core backward)
+        delta = Sh.get("delta", (o.xattn_bwd_workspace(self.T_, B, T, S, d.H, d.dh, d.dhp),), torch.float32)
         o.xattn_bwd(sv["q"], sv["k"], sv["v"], sv["a"], da, sv["lse"], delta, dq, d.scaling, dk, dv, B, T, S, d.H, d.dh, d.dhp,
                     mask_off=self._mask_off(T, S), drop=self._drop(self.p_attn, l, 10 + (blk == "x")), drop_bits=sv["bits"])
         # dq already carries the dh^-0.5 factor => it is the gradient wrt (x Wq^T + bq)

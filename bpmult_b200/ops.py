@@ -257,9 +257,16 @@ class CudaOps:
         a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, drop_bits, k=k, v=v)
         self._ck(self.lib.bpm_xattn_fwd(C.byref(a), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), self._s()), "xattn_fwd")
 
+    def xattn_bwd_workspace(self, dtype, B, T, S, H, dh, dhp):
+        """floats the backward needs at `delta` (2*B*H*T, plus the fp32 dQ accumulator of the head-dim-128 tensor-core kernel)"""
+        a = Attn()
+        a.dtype, a.B, a.T, a.S, a.H, a.dh, a.dhp = (_lib.BPM_BF16 if dtype == torch.bfloat16 else _lib.BPM_F32), B, T, S, H, dh, dhp
+        return int(self.lib.bpm_xattn_bwd_workspace(C.byref(a)))
+
     def xattn_bwd(self, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None,
                   drop_bits=None):
         a = self._attn(q, B, T, S, H, dh, dhp, mask_off, key_pad, drop, drop_bits, k=k, v=v, dk=dk, dv=dv)
+        assert delta.numel() >= self.lib.bpm_xattn_bwd_workspace(C.byref(a)), "xattn_bwd: workspace too small (see xattn_bwd_workspace)"
         self._ck(self.lib.bpm_xattn_bwd(C.byref(a), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                         delta.data_ptr(), dq.data_ptr(), float(dq_scale), dk.data_ptr(), dv.data_ptr(), self._s()), "xattn_bwd")
 

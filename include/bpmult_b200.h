@@ -154,8 +154,13 @@ int bpm_colsum(const void* X, int dtype, int M, int N, int ld, float* out, void*
 /* ---- crossmodal attention: models/multihead_attention.py:95-127 + mask models/transformer.py:209-216 ----------
  * q [B,T,H*dhp] (already scaled by dh^-0.5), k, v [B,S,H*dhp] in T; out [B,T,H*dhp]; lse fp32 [B,H,T].
  * mask_off >= 0: key j visible to query i iff j <= i + mask_off (reference: mask_off = |S - T|); mask_off < 0: no mask.
- * key_pad (uint8 [B,S], 1 = padded key, may be NULL): superset feature, default off (the reference has none).
- * bwd writes dq * dq_scale, dk, dv (T) and needs a workspace `delta` fp32 [2,B,H,T]: on return [0] = rowsum(dO*O), [1] = lse*log2e. */
+ * key_pad (uint8 [B,S], 1 = padded key, may be NULL): superset feature, default off (the reference has none,
+ * multihead_attention.py:52); a padded key gets probability 0 and zero dk / dv.  Every query must keep one visible key.
+ * bwd writes dq * dq_scale, dk, dv (T) and needs a workspace `delta` of bpm_xattn_bwd_workspace(a) floats, 128-byte aligned: on return
+ * [0 .. B*H*T) = rowsum(dO*O), [B*H*T .. 2*B*H*T) = lse*log2e; the tensor-core kernels for head dim 128 keep their fp32 dQ accumulator
+ * (TMA reduce-add target, [B, T, H*dhp]) behind that.
+ * Kernels: dhp = 32 -> attn_tc.cu, dhp = 64 (forward) / 128 -> attn_tc128.cu (tcgen05 + TMEM + TMA); fp32 storage or any other head
+ * dim -> exact-fp32 kernels (attn_simt.cu). */
 typedef struct {
   int dtype, B, T, S, H, dh, dhp, mask_off;
   const uint8_t* key_pad;
@@ -168,6 +173,8 @@ typedef struct {
 int bpm_xattn_fwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, void* stream);
 int bpm_xattn_bwd(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout,
                   const float* lse, float* delta, void* dq, float dq_scale, void* dk, void* dv, void* stream);
+/* number of floats bpm_xattn_bwd needs at `delta` for this problem (always >= 2*B*H*T) */
+int64_t bpm_xattn_bwd_workspace(const bpm_attn_t* a);
 /* head-averaged probabilities (multihead_attention.py:133-135), only on request: w fp32 [B,T,S] */
 int bpm_xattn_weights(const bpm_attn_t* a, const void* q, const void* k, const float* lse, float* w, void* stream);
 

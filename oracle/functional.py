@@ -19,6 +19,9 @@ import torch
 import torch.nn.functional as F
 
 
+PROBE = None        # optional dict filled with intermediate activations by the functions below (test diagnostics only)
+
+
 # ----------------------------------------------------------------------------- positional embedding
 def sinusoid_table(num_pos, dim, dtype=torch.float32):
     """models/position_embedding.py:44-60 (get_embedding): halves concatenated [sin | cos], row 0 zeroed,
@@ -113,7 +116,10 @@ def encoder_layer(sd, pfx, x, x_k, x_v, num_heads, attn_mask, biprojection=False
         ffn_ln = 1
     residual = x                                                           # :181-190
     h = _ln(sd, pfx + "layer_norms.%d." % ffn_ln, x)
-    h = F.relu(F.linear(h, sd[pfx + "fc1.weight"], sd[pfx + "fc1.bias"]))
+    pre = F.linear(h, sd[pfx + "fc1.weight"], sd[pfx + "fc1.bias"])
+    if PROBE is not None:                                                  # tests: FFN pre-activations (ReLU ties, see tests/test_fullshape_gpu.py)
+        PROBE[pfx + "fc1_pre"] = pre.detach()
+    h = F.relu(pre)
     h = F.linear(h, sd[pfx + "fc2.weight"], sd[pfx + "fc2.bias"])
     return residual + h
 

@@ -231,6 +231,9 @@ class EmuOps:
         out.copy_(o.to(out.dtype))
         lse.copy_(L.reshape(-1))
 
+    def xattn_bwd_workspace(self, dtype, B, T, S, H, dh, dhp):
+        return 2 * B * H * T
+
     def xattn_bwd(self, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, B, T, S, H, dh, dhp, mask_off=-1, key_pad=None, drop=None, drop_bits=None):
         s = self._probs(q, k, B, T, S, H, dhp, mask_off, key_pad)
         p = torch.exp(s - lse.view(B, H, T, 1))
@@ -248,7 +251,7 @@ class EmuOps:
         dk_ = ds.transpose(-1, -2) @ qh
         n = B * H * T
         delta[:n].copy_(dl.reshape(-1))
-        delta[n:].copy_((lse.float() * 1.4426950408889634).reshape(-1))      # workspace [1]: lse * log2e
+        delta[n:2 * n].copy_((lse.float() * 1.4426950408889634).reshape(-1))      # workspace [1]: lse * log2e
         dq.copy_(dq_.permute(0, 2, 1, 3).reshape(B * T, H * dhp).to(dq.dtype))
         dk.copy_(dk_.permute(0, 2, 1, 3).reshape(B * S, H * dhp).to(dk.dtype))
         dv.copy_(dv_.permute(0, 2, 1, 3).reshape(B * S, H * dhp).to(dv.dtype))

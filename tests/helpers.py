@@ -51,12 +51,13 @@ def run_encoder_engine(ops, sd, x, k, g, H, L, mask, biproj, self_only, dtype=to
     return out_tbd, dx, dkk, {n: v.cpu() for n, v in grads.items()}, eng
 
 
-def run_model_engine(ops, rec, dtype=torch.float32, full=True):
+def run_model_engine(ops, rec, dtype=torch.float32, full=True, sd=None):
     from argparse import Namespace
     from bpmult_b200.model_engine import MMTrVatEngine
     cfg = Namespace(**rec["cfg"])
     B, T_l, T_a, T_v = rec["dims"]
-    sd = synth.make_state_dict(synth.mmtrvat_shapes(cfg), rec["seed"])
+    if sd is None:
+        sd = synth.make_state_dict(synth.mmtrvat_shapes(cfg), rec["seed"])
     txt, img, audio, tgt = synth.mmtrvat_inputs(cfg, B, T_l, T_a, T_v)
     eng = MMTrVatEngine(ops, cfg, dtype=dtype)
     dev = ops.device
@@ -91,13 +92,14 @@ def check_fingerprints(grads, fps, tol):
     return worst
 
 
-def run_model4_engine(ops, rec, dtype=torch.float32):
+def run_model4_engine(ops, rec, dtype=torch.float32, sd=None):
     """MMTrVaptEngine on a golden record: returns logits, z, loss, dtxt, reference-layout parameter gradients"""
     from argparse import Namespace
     from bpmult_b200.model_engine4 import MMTrVaptEngine
     cfg = Namespace(**rec["cfg"])
     B, T_l, T_a, T_v = rec["dims"]
-    sd = synth.make_state_dict(synth.mmtrvapt_shapes(cfg), rec["seed"])
+    if sd is None:
+        sd = synth.make_state_dict(synth.mmtrvapt_shapes(cfg), rec["seed"])
     txt, img, audio, poster, tgt = synth.mmtrvapt_inputs(cfg, B, T_l, T_a, T_v)
     eng = MMTrVaptEngine(ops, cfg, dtype=dtype)
     dev = ops.device
