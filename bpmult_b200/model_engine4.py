@@ -6,11 +6,14 @@ explicit forward / backward schedule over the same engines as mmtrvat.  Differen
     (transfm_a2l, transfm_v2l : 200 -> 512;  transfm_l2a, transfm_l2v : 512 -> 200; :375-378, 507-508, 530, 553);
   * the poster vector joins at the head: proj_poster (Linear 4096 -> D, no bias, :310,486) and a 4-input TextShifting4Layer (:369,574).
 BERT and the AudioEncoder sit upstream of this path (out of scope): text and audio arrive as feature sequences.
-hybrid = True is not supported (broken in the reference).  Single stream (this model is a "next" row, not the benchmark)."""
+hybrid = True is not supported (broken in the reference).  Independent encoders of a wave run on side streams ("lanes",
+see model_engine.Lanes): at B = 8 per GPU (README.md:30) a kernel has 1600 .. 4096 rows and fills a fraction of the 148 SMs."""
+import os
+
 import torch
 
 from .engine import Arena, Dims, EncoderEngine, HeadEngine, SeqGmuEngine, round_up
-from .model_engine import ENC_NAMES, HEAD_ORDER, TARGETS, WAVE1, attn_dropout_for
+from .model_engine import ENC_NAMES, HEAD_ORDER, TARGETS, WAVE1, Lanes, attn_dropout_for
 from .ops import Drop
 
 BIPROJ = ("l_with_v2a", "l_with_a2v", "v_with_l2a", "v_with_a2l", "a_with_v2l", "a_with_l2v")
@@ -33,17 +36,26 @@ class MMTrVaptEngine:
         self.orig = {"l": args.orig_d_l, "a": args.orig_d_a, "v": args.orig_d_v}
         self.Kp = {m: (self.d.Dp if self.orig[m] == D else round_up(self.orig[m], 64)) for m in "lav"}
         self.Kpp = round_up(args.orig_d_p, 64)
-        self.shared = Arena(ops)
+        self.lanes = Lanes(ops.device, int(os.environ.get("BPM_LANES", "6")))
+        self.lane_shared = [Arena(ops) for _ in range(self.lanes.n)]
+        self.shared = self.lane_shared[0]
         self.arena = Arena(ops)
+        # lane of each encoder: wave 1 alternates, the two wave-2 encoders of a target modality sit on different lanes
+        self.lane_of = {n: i % self.lanes.n for i, n in enumerate(WAVE1)}
+        for i, m in enumerate(HEAD_ORDER):
+            u, w, pn, qn = TARGETS[m]
+            self.lane_of[pn], self.lane_of[qn] = (2 * i) % self.lanes.n, (2 * i + 1) % self.lanes.n
+        self.mod_lane = {m: i % self.lanes.n for i, m in enumerate(HEAD_ORDER)}      # lane of a modality's staging / gated units
         self.enc = {}
         for i, n in enumerate(ENC_NAMES):
             self.enc[n] = EncoderEngine(ops, D, H, L, attn_dropout=attn_dropout_for(n, args), relu_dropout=args.relu_dropout,
                                         res_dropout=args.res_dropout, embed_dropout=args.embed_dropout, attn_mask=args.attn_mask,
-                                        biprojection=n in BIPROJ, dtype=dtype, uid=i + 1, shared=self.shared)
+                                        biprojection=n in BIPROJ, dtype=dtype, uid=i + 1, shared=self.lane_shared[self.lane_of[n]])
         self.gmu = {}
         for m in "lav":
-            self.gmu[m + "_m"] = SeqGmuEngine(ops, D, dtype, True, self.shared, "gmu_%s_m" % m)
-            self.gmu[m] = SeqGmuEngine(ops, D, dtype, True, self.shared, "gmu_%s" % m)
+            sh = self.lane_shared[self.mod_lane[m]]
+            self.gmu[m + "_m"] = SeqGmuEngine(ops, D, dtype, True, sh, "gmu_%s_m" % m)
+            self.gmu[m] = SeqGmuEngine(ops, D, dtype, True, sh, "gmu_%s" % m)
         self.head = HeadEngine(ops, D, 4, args.n_classes, out_dropout=args.out_dropout)
         z = ops.zeros
         self.Wproj = {m: (z((self.d.Dp, self.Kp[m]), dtype) if self.orig[m] != D else None) for m in "lav"}
@@ -153,42 +165,56 @@ class MMTrVaptEngine:
         self.in_shapes = {m: tuple(feats[m].shape) for m in "lav"}
         P = {}
         self.X = {}
+        ln = self.lanes
+        ln.fork()
         for m in "lav":
             drop = Drop(self.args.embed_dropout, seed, seed_ptr, 7) if (m == "l" and training and self.args.embed_dropout > 0) else None
             X = A.get("X_" + m, (B * NV[m], self.Kp[m]), self.T_)
-            o.stage_rows(feats[m], X, NV[m], drop)                              # transpose / embed-dropout / zero-pad to num_vectors_m
-            self.X[m] = X
-            if self.Wproj[m] is not None:
-                P[m] = A.get("P_" + m, (B * NV[m], d.Dp), self.T_)
-                o.gemm(X, self.Wproj[m], P[m], B * NV[m], d.Dp, self.Kp[m])
-            else:
-                P[m] = X
+            with ln.on(self.mod_lane[m]):
+                o.stage_rows(feats[m], X, NV[m], drop)                          # transpose / embed-dropout / zero-pad to num_vectors_m
+                self.X[m] = X
+                if self.Wproj[m] is not None:
+                    P[m] = A.get("P_" + m, (B * NV[m], d.Dp), self.T_)
+                    o.gemm(X, self.Wproj[m], P[m], B * NV[m], d.Dp, self.Kp[m])
+                else:
+                    P[m] = X
         self.P = P
         h = {}
+        ln.barrier()
         for n, (qm, km) in WAVE1.items():
-            h[n] = self.enc[n].forward(P[qm], B, NV[qm], src_k=P[km], S=NV[km], training=training, seed=seed, seed_ptr=seed_ptr)
+            with ln.on(self.lane_of[n]):
+                h[n] = self.enc[n].forward(P[qm], B, NV[qm], src_k=P[km], S=NV[km], training=training, seed=seed, seed_ptr=seed_ptr)
+        ln.barrier()                                                            # wave 2 reads wave-1 outputs of either lane
+        for m in HEAD_ORDER:
+            u, w, pn, qn = TARGETS[m]
+            su, sw = NV[_mod_of(u)], NV[_mod_of(w)]
+            with ln.on(self.lane_of[pn]):
+                h[pn] = self.enc[pn].forward(P[m], B, NV[m], src_k=h[u], S=su, training=training, seed=seed, seed_ptr=seed_ptr)
+            with ln.on(self.lane_of[qn]):
+                h[qn] = self.enc[qn].forward(P[m], B, NV[m], src_k=h[w], S=sw, training=training, seed=seed, seed_ptr=seed_ptr)
+        ln.barrier()
         cat = self.head.cat_buf(B)
         self.tsrc = {}
-        for ci, m in enumerate(HEAD_ORDER):
+        for ci, m in enumerate(HEAD_ORDER):                                      # the three targets' gated units: one lane each
             u, w, pn, qn = TARGETS[m]
             Mm = B * NV[m]
             su, sw = NV[_mod_of(u)], NV[_mod_of(w)]
-            hp = self.enc[pn].forward(P[m], B, NV[m], src_k=h[u], S=su, training=training, seed=seed, seed_ptr=seed_ptr)
-            hq = self.enc[qn].forward(P[m], B, NV[m], src_k=h[w], S=sw, training=training, seed=seed, seed_ptr=seed_ptr)
-            h[pn], h[qn] = hp, hq
-            # wave-1 outputs at this target's length: through the time-axis linear when the lengths differ (:507-508,530,553)
-            tname_u = "%s2%s" % (_mod_of(u), m) if su != NV[m] else None
-            tname_w = "%s2%s" % (_mod_of(w), m) if sw != NV[m] else None
-            tu = self._time_linear(tname_u, h[u], B) if tname_u else h[u]
-            tw = self._time_linear(tname_w, h[w], B) if tname_w else h[w]
-            self.tsrc[m] = (tname_u, tname_w, tu, tw)
-            mid = self.gmu[m + "_m"].forward(tu, tw, Mm)                          # "GMU middle"
-            a1 = A.get("a1_" + m, (Mm, d.Dp), self.T_)
-            a2 = A.get("a2_" + m, (Mm, d.Dp), self.T_)
-            o.add(hp, tu, a1)                                                    # residual level 1 -> 2
-            o.add(hq, tw, a2)
-            top = self.gmu[m].forward(a1, a2, Mm, addend=mid)                    # "GMU top" + residual level 1 -> 3
-            o.pool_fwd(top, B, NV[m], cat, ci * d.Dp)                            # h[0] + h[-1]
+            hp, hq = h[pn], h[qn]
+            with ln.on(self.mod_lane[m]):
+                # wave-1 outputs at this target's length: through the time-axis linear when the lengths differ (:507-508,530,553)
+                tname_u = "%s2%s" % (_mod_of(u), m) if su != NV[m] else None
+                tname_w = "%s2%s" % (_mod_of(w), m) if sw != NV[m] else None
+                tu = self._time_linear(tname_u, h[u], B) if tname_u else h[u]
+                tw = self._time_linear(tname_w, h[w], B) if tname_w else h[w]
+                self.tsrc[m] = (tname_u, tname_w, tu, tw)
+                mid = self.gmu[m + "_m"].forward(tu, tw, Mm)                      # "GMU middle"
+                a1 = A.get("a1_" + m, (Mm, d.Dp), self.T_)
+                a2 = A.get("a2_" + m, (Mm, d.Dp), self.T_)
+                o.add(hp, tu, a1)                                                # residual level 1 -> 2
+                o.add(hq, tw, a2)
+                top = self.gmu[m].forward(a1, a2, Mm, addend=mid)                # "GMU top" + residual level 1 -> 3
+                o.pool_fwd(top, B, NV[m], cat, ci * d.Dp)                        # h[0] + h[-1]
+        ln.join()
         # poster: Linear(orig_d_p -> D, no bias) straight into the 4th block of the head's input
         Xp = A.get("X_p", (B, self.Kpp), self.T_)
         o.stage_rows(poster.view(B, 1, -1), Xp, 1, None)
@@ -220,51 +246,70 @@ class MMTrVaptEngine:
         gpo = A.get("dpost", (B, d.Dp), self.T_)
         gpo.copy_(dcat[:, 3 * d.Dp:])                                            # (strided slice + cast: a torch copy, off the hot path)
         o.gemm(gpo, self.Xp, self.Gpost, d.Dp, self.Kpp, B, ta=1, tb=1, accumulate=True)
-        dP = {m: A.get("dP_" + m, (B * NV[m], d.Dp), f32) for m in "lav"}
+        ln = self.lanes
+        # every lane accumulates the projection-output gradients in its own buffers (two encoders of different lanes share a query
+        # stream); they are summed once at the end
+        dPl = [{m: A.get("dP%d_%s" % (k, m), (B * NV[m], d.Dp), f32) for m in "lav"} for k in range(ln.n)]
+        dP = dPl[0]
         dh = {n: A.get("dh_" + n, (B * NV[_mod_of(n)], d.Dp), f32) for n in WAVE1}
-        for t in list(dP.values()) + list(dh.values()):
+        for t in [t for k in range(ln.n) for t in dPl[k].values()] + list(dh.values()):
             o.zero_(t)
-        for ci, m in reversed(list(enumerate(HEAD_ORDER))):
+        da = {}
+        ln.fork()
+        for ci, m in reversed(list(enumerate(HEAD_ORDER))):                      # gated fusion units of the three targets: one lane each
             u, w, pn, qn = TARGETS[m]
             Mm = B * NV[m]
             tname_u, tname_w, tu, tw = self.tsrc[m]
-            dtop = A.get("dtop_" + m, (Mm, d.Dp), f32)
-            da1 = A.get("da1_" + m, (Mm, d.Dp), f32)
-            da2 = A.get("da2_" + m, (Mm, d.Dp), f32)
-            dtu = A.get("dtu_" + m, (Mm, d.Dp), f32) if tname_u else dh[u]       # gradient wrt the (time-mapped) wave-1 outputs
-            dtw = A.get("dtw_" + m, (Mm, d.Dp), f32) if tname_w else dh[w]
-            for t in [dtop, da1, da2] + ([dtu] if tname_u else []) + ([dtw] if tname_w else []):
-                o.zero_(t)
-            o.pool_bwd(dcat, ci * d.Dp, B, NV[m], dtop)
-            self.gmu[m].backward(dtop, da1, da2)                                 # d(p + tu), d(q + tw)
-            self.gmu[m + "_m"].backward(dtop, dtu, dtw)
-            o.axpy_f32(da1, dtu, True)
-            o.axpy_f32(da2, dtw, True)
-            if tname_u:
-                self._time_linear_bwd(tname_u, dtu, h[u], dh[u], B)
-            if tname_w:
-                self._time_linear_bwd(tname_w, dtw, h[w], dh[w], B)
-            self.enc[qn].backward(da2, dP[m], dh[w])
-            if on_done:
-                on_done(qn)
-            self.enc[pn].backward(da1, dP[m], dh[u])
-            if on_done:
-                on_done(pn)
+            with ln.on(self.mod_lane[m]):
+                dtop = A.get("dtop_" + m, (Mm, d.Dp), f32)
+                da1 = A.get("da1_" + m, (Mm, d.Dp), f32)
+                da2 = A.get("da2_" + m, (Mm, d.Dp), f32)
+                dtu = A.get("dtu_" + m, (Mm, d.Dp), f32) if tname_u else dh[u]   # gradient wrt the (time-mapped) wave-1 outputs
+                dtw = A.get("dtw_" + m, (Mm, d.Dp), f32) if tname_w else dh[w]
+                for t in [dtop, da1, da2] + ([dtu] if tname_u else []) + ([dtw] if tname_w else []):
+                    o.zero_(t)
+                o.pool_bwd(dcat, ci * d.Dp, B, NV[m], dtop)
+                self.gmu[m].backward(dtop, da1, da2)                             # d(p + tu), d(q + tw)
+                self.gmu[m + "_m"].backward(dtop, dtu, dtw)
+                o.axpy_f32(da1, dtu, True)
+                o.axpy_f32(da2, dtw, True)
+                if tname_u:
+                    self._time_linear_bwd(tname_u, dtu, h[u], dh[u], B)
+                if tname_w:
+                    self._time_linear_bwd(tname_w, dtw, h[w], dh[w], B)
+                da[m] = (da1, da2)
+        ln.barrier()
+        for m in reversed(HEAD_ORDER):
+            u, w, pn, qn = TARGETS[m]
+            for n, g_, dsrc in ((qn, da[m][1], dh[w]), (pn, da[m][0], dh[u])):
+                with ln.on(self.lane_of[n]):
+                    self.enc[n].backward(g_, dPl[self.lane_of[n]][m], dsrc)
+                    if on_done:
+                        on_done(n)
+        ln.barrier()                                                            # wave 1 consumes dh written on either lane
         for n, (qm, km) in reversed(list(WAVE1.items())):
-            self.enc[n].backward(dh[n], dP[qm], dP[km])
-            if on_done:
-                on_done(n)
-        for m in "lav":
-            if self.Wproj[m] is not None:
-                g = self.shared.get("dPc_" + m, (B * NV[m], d.Dp), self.T_)
-                o.cast_drop(dP[m], g, None)
-                o.gemm(g, self.X[m], self.Gproj[m], d.Dp, self.Kp[m], B * NV[m], ta=1, tb=1, accumulate=True)     # dW = dP^T X
-                if d_inputs is not None and m in d_inputs:
-                    dX = self.shared.get("dX_" + m, (B * NV[m], self.Kp[m]), f32)
-                    o.gemm(g, self.Wproj[m], dX, B * NV[m], self.Kp[m], d.Dp, tb=1)
-                    self._unstage(m, dX, d_inputs[m])
-            elif d_inputs is not None and m in d_inputs:
-                self._unstage(m, dP[m], d_inputs[m])
+            k = self.lane_of[n]
+            with ln.on(k):
+                self.enc[n].backward(dh[n], dPl[k][qm], dPl[k][km])
+                if on_done:
+                    on_done(n)
+        ln.barrier()
+        for m in "lav":                                                          # input projections: one lane per modality
+            with ln.on(self.mod_lane[m]):
+                for k in range(1, ln.n):
+                    o.axpy_f32(dPl[k][m], dP[m], True)
+                sh = self.lane_shared[self.mod_lane[m]]
+                if self.Wproj[m] is not None:
+                    g = sh.get("dPc_" + m, (B * NV[m], d.Dp), self.T_)
+                    o.cast_drop(dP[m], g, None)
+                    o.gemm(g, self.X[m], self.Gproj[m], d.Dp, self.Kp[m], B * NV[m], ta=1, tb=1, accumulate=True)     # dW = dP^T X
+                    if d_inputs is not None and m in d_inputs:
+                        dX = sh.get("dX_" + m, (B * NV[m], self.Kp[m]), f32)
+                        o.gemm(g, self.Wproj[m], dX, B * NV[m], self.Kp[m], d.Dp, tb=1)
+                        self._unstage(m, dX, d_inputs[m])
+                elif d_inputs is not None and m in d_inputs:
+                    self._unstage(m, dP[m], d_inputs[m])
+        ln.join()
 
     def _unstage(self, m, g, dst):
         drop = Drop(self.args.embed_dropout, self.seed, self.seed_ptr, 7) if (m == "l" and self.training and self.args.embed_dropout > 0) else None

@@ -1,4 +1,6 @@
-"""Times the crossmodal attention kernels at the cfg-2 shape (CUDA-graph captured iterations, CUDA events)."""
+"""Times the crossmodal attention kernels (CUDA-graph captured iterations, CUDA events).
+    python scripts/bench_attn.py [more]           cfg-2 shape: hidden 300 / 12 heads (head dim 25 -> 32)
+    python scripts/bench_attn.py wide [B]         cfg-3 shape: hidden 768 / 6 heads (head dim 128), the lengths of the 4-modality model"""
 import sys
 
 import torch
@@ -9,7 +11,8 @@ from bpmult_b200.ops import CudaOps, Drop
 
 ops = CudaOps()
 dev = ops.device
-d = Dims(300, 12)
+WIDE = len(sys.argv) > 1 and sys.argv[1] == "wide"
+d = Dims(768, 6) if WIDE else Dims(300, 12)
 bf = torch.bfloat16
 
 
@@ -45,7 +48,7 @@ def run(B, T, S, mask_off, p):
     do = torch.randn(M, d.HP, device=dev).to(bf)
     dq = torch.empty(M, d.HP, device=dev, dtype=bf)
     dk, dv = [torch.empty(Ms, d.HP, device=dev, dtype=bf) for _ in range(2)]
-    delta = torch.empty(2 * B * d.H * T, device=dev)
+    delta = torch.empty(ops.xattn_bwd_workspace(bf, B, T, S, d.H, d.dh, d.dhp), device=dev)
     tf = timeit(lambda: ops.xattn_fwd(q, k, v, o, lse, B, T, S, d.H, d.dh, d.dhp, mask_off=mask_off, drop=drop, drop_bits=bits))
     tb = timeit(lambda: ops.xattn_bwd(q, k, v, o, do, lse, delta, dq, d.scaling, dk, dv, B, T, S, d.H, d.dh, d.dhp, mask_off=mask_off, drop=drop,
                                       drop_bits=bits))
@@ -59,6 +62,13 @@ def run(B, T, S, mask_off, p):
         B, T, S, mask_off, p, tf, fl / tf * 1e-6, tb, 2.5 * fl / tb * 1e-6), flush=True)
 
 
+if WIDE:
+    Bw = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    for (T, S, off, p) in ((512, 512, 0, 0.0), (512, 512, 0, 0.1), (512, 200, 312, 0.0), (200, 512, 312, 0.0), (200, 200, 0, 0.0), (512, 512, -1, 0.0)):
+        run(Bw, T, S, off, p)
+    run(64, 512, 512, 0, 0.0)
+    run(16, 2048, 2048, 0, 0.0)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1].startswith("dbg="):
     for kv in sys.argv[1][4:].split(","):
         ops.lib.bpm_debug_set(1, int(kv))
