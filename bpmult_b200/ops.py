@@ -49,6 +49,7 @@ class CudaOps:
         self._batch = None          # (mode, key, [descriptor tuples]) while pack / unpack calls are being collected
         self._tables = {}           # descriptor-list signature -> [device table, pinned by a captured graph]  (see _table)
         self.max_tables = 256
+        self.capture_owner = "anonymous"
 
     # ------------------------------------------------------------------ batched pack / unpack (one launch per table)
     def batch_begin(self, mode, key):
@@ -80,24 +81,30 @@ class CudaOps:
     def _table(self, sig, build):
         """Device descriptor table for a batched launch, cached by the full descriptor list (alternating engines never rebuild, and
         a CUDA-graph capture never sees a host->device copy: the eager warm-up steps have created every table it uses).
-        A table that has been used while the stream was capturing is baked into that graph's kernel arguments, so it is PINNED:
-        it is never evicted (its memory must not return to the allocator while the graph can still be replayed).  Only unpinned
-        tables -- the eager autograd path, whose gradient tensors may have new addresses every call -- are evicted, oldest first."""
+        A table that is used while the stream is capturing is baked into that graph's kernel arguments, so it is PINNED by the
+        capturing owner (`capture_owner`, set by the Trainer): it is never evicted -- its memory must not return to the allocator while
+        the graph can still be replayed -- until the owner calls release_tables().  Only unpinned tables (the eager autograd path,
+        whose gradient tensors may have new addresses every call) are evicted, oldest first, beyond `max_tables`."""
         ent = self._tables.get(sig)
         capturing = torch.cuda.is_current_stream_capturing()
         if ent is None:
             if capturing:
                 raise _lib.BpmError("bpmult_b200: a descriptor table is missing during CUDA-graph capture (run the step eagerly once first)")
-            ent = [torch.from_numpy(build().view("uint8").copy()).to(self.device), False]
+            ent = [torch.from_numpy(build().view("uint8").copy()).to(self.device), set()]
             self._tables[sig] = ent
-            if len(self._tables) > self.max_tables:
-                for k in [k for k, e in self._tables.items() if not e[1]][:len(self._tables) - self.max_tables]:
-                    del self._tables[k]
+            unpinned = [k for k, e in self._tables.items() if not e[1]]
+            for k in unpinned[:max(0, len(unpinned) - self.max_tables)]:
+                del self._tables[k]
         else:
             self._tables[sig] = self._tables.pop(sig)       # most recently used last
         if capturing:
-            ent[1] = True
+            ent[1].add(self.capture_owner)
         return ent[0]
+
+    def release_tables(self, owner):
+        """the graphs captured by `owner` are gone: their descriptor tables may be evicted again"""
+        for e in self._tables.values():
+            e[1].discard(owner)
 
     # ------------------------------------------------------------------ helpers
     def _s(self):

@@ -230,8 +230,7 @@ class Trainer:
         self.step_t.fill_(step)
         self.betas, self.eps = tuple(g["betas"]), g["eps"]
         if self.graphs:                                      # betas / eps are baked into a captured step
-            self.graphs = {}
-            self.warm = 0
+            self.close()
         self.set_lr(g["lr"])
         self.sync_replicas()
 
@@ -286,6 +285,14 @@ class Trainer:
         self.warm = 0
         if self.on_gpu:
             torch.cuda.synchronize(self.device)
+            self.ops.release_tables(id(self))
+
+    def __del__(self):
+        try:
+            if self.on_gpu and self.graphs:
+                self.ops.release_tables(id(self))
+        except Exception:
+            pass
 
     # ---------------------------------------------------------------- public API
     def _ensure_static(self, *batch):
@@ -353,6 +360,7 @@ class Trainer:
                 return
             torch.cuda.synchronize(self.device)
             self.ops.launches = 0
+            self.ops.capture_owner = id(self)               # descriptor tables used by this capture stay alive until close()
             g = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):

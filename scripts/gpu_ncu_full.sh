@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for K in ${KERNELS:-attn_fwd attn_bwd gemm_q gemm_fc1 gemm_fc2 ln_fwd}; do
   python scripts/prof_kernel.py $K 3 > gpurun_out/plain_$K.log 2>&1 || { echo "plain $K failed"; tail -5 gpurun_out/plain_$K.log; continue; }
-  case $K in attn_fwd*) RX=attn_fwd_tc_kernel;; attn_bwd*) RX=attn_bwd_tc_kernel;; gemm*) RX=gemm_tc_kernel;; ln_fwd) RX=ln_fwd_kernel;; ln_bwd) RX=ln_bwd_kernel;; esac
+  case $K in attn128_fwd*) RX=attn128_fwd_kernel;; attn128_bwd*) RX=attn128_bwd_kernel;; attn_fwd*) RX=attn_fwd_tc_kernel;; attn_bwd*) RX=attn_bwd_tc_kernel;; gemm*|wgrad*) RX=gemm_tc_kernel;; ln_fwd) RX=ln_fwd_kernel;; ln_bwd) RX=ln_bwd;; esac
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$RX -s 1 -c 1 -f -o gpurun_out/full_$K python scripts/prof_kernel.py $K 3 > gpurun_out/ncu_$K.log 2>&1
   echo "$K ncu rc=$?"; ls -la gpurun_out/full_$K.ncu-rep 2>/dev/null | awk '{print $5}'
 done

@@ -11,11 +11,12 @@ which = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ops = CudaOps()
 dev = ops.device
-d = Dims(300, 12)
-B, T = 64, 512
+WIDE = which.startswith("attn128")                     # head dim 128 kernels (attn_tc128.cu): hidden 768 / 6 heads
+d = Dims(768, 6) if WIDE else Dims(300, 12)
+B, T = int(sys.argv[3]) if len(sys.argv) > 3 else 64, 512
 M = B * T
 bf = torch.bfloat16
-if which in ("attn_fwd", "attn_bwd", "attn_fwd_drop", "attn_bwd_drop"):
+if which in ("attn_fwd", "attn_bwd", "attn_fwd_drop", "attn_bwd_drop", "attn128_fwd", "attn128_bwd", "attn128_fwd_drop", "attn128_bwd_drop"):
     q = torch.randn(M, d.HP, device=dev).to(bf) * 0.3
     k = torch.randn(M, d.HP, device=dev).to(bf) * 0.3
     v = torch.randn(M, d.HP, device=dev).to(bf)
@@ -28,7 +29,7 @@ if which in ("attn_fwd", "attn_bwd", "attn_fwd_drop", "attn_bwd_drop"):
     if "bwd" in which:
         do = torch.randn(M, d.HP, device=dev).to(bf)
         dq, dk, dv = [torch.empty(M, d.HP, device=dev, dtype=bf) for _ in range(3)]
-        delta = torch.empty(2 * B * d.H * T, device=dev)
+        delta = torch.empty(ops.xattn_bwd_workspace(bf, B, T, T, d.H, d.dh, d.dhp), device=dev)
         for _ in range(iters):
             ops.xattn_bwd(q, k, v, o, do, lse, delta, dq, d.scaling, dk, dv, B, T, T, d.H, d.dh, d.dhp, mask_off=0, drop=drop, drop_bits=bits)
 elif which.startswith("gemm"):
@@ -46,6 +47,16 @@ elif which.startswith("gemm"):
         C = torch.empty(Mm, N, device=dev, dtype=bf)
         for _ in range(iters):
             ops.gemm(A, W, C, Mm, N, K, bias=bias, act=1 if which == "gemm_fc1" else 0, drop=Drop(0.1, 1, None, 3) if which == "gemm_fc1" else None)
+elif which.startswith("wgrad"):
+    # weight gradients dW = dY^T X (+ bias gradient): [N_out, M rows] x [M rows, K_in], split-K over the M = 32768 rows
+    shapes = {"wgrad_q": (d.HP, d.Dp), "wgrad_o": (d.Dp, d.HP), "wgrad_fc1": (d.FP, d.Dp), "wgrad_fc2": (d.Dp, d.FP), "wgrad_kv": (8 * d.HP, d.Dp)}
+    No, Ki = shapes[which]
+    dY = torch.randn(M, No, device=dev).to(bf)
+    X = torch.randn(M, Ki, device=dev).to(bf)
+    G = torch.zeros(No, Ki, device=dev)
+    gb = torch.zeros(No, device=dev)
+    for _ in range(iters):
+        ops.gemm(dY, X, G, No, Ki, M, ta=1, tb=1, accumulate=True, colsum=gb)
 elif which == "ln_fwd":
     x = torch.randn(M, d.Dp, device=dev)
     y = torch.empty(M, d.Dp, device=dev, dtype=bf)
