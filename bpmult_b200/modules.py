@@ -16,8 +16,11 @@ model_engine.py; torch only owns the tensors.  `precision="bf16"` (default: bf16
 tensor cores) or `"fp32"` (exact-fp32 kernels).  The reference's feature extractors (BERT, AudioEncoder) are bypassed:
 `txt` is a float feature sequence (B, L, orig_d_l)."""
 import math
+import weakref
+from typing import List, Optional, Tuple
 
 import torch
+from torch import Tensor
 import torch.nn.functional as F
 from torch import nn
 from torch.nn import Parameter
@@ -39,6 +42,51 @@ def _ops_for(device):
         _OPS[key] = CudaOps(torch.device("cuda", key))
     return _OPS[key]
 
+
+# ---- torch custom-op plumbing -------------------------------------------------------------------------------------
+# Every module forward is ONE registered torch op `bpmult_b200::<name>` (torch.library.custom_op) with a fake (meta) kernel for
+# shape inference -- so the modules trace under torch.compile(fullgraph=True) / torch.export -- and a registered autograd formula
+# whose backward is itself a registered op.  The op bodies run the explicit kernel schedules of engine.py / model_engine*.py over
+# the C ABI; a module is passed to its op as an integer handle (ops take tensors and plain scalars only).
+_HANDLES = weakref.WeakValueDictionary()
+_NEXT_HANDLE = [1]
+
+
+def _handle(mod):
+    h = getattr(mod, "_bpm_handle", None)
+    if h is None:
+        h = mod._bpm_handle = _NEXT_HANDLE[0]
+        _NEXT_HANDLE[0] += 1
+    _HANDLES[h] = mod
+    return h
+
+
+def _mod(handle):
+    m = _HANDLES.get(handle)
+    if m is None:
+        raise RuntimeError("bpmult_b200: stale module handle %d" % handle)
+    return m
+
+
+def _stamp(eng):
+    """forward generation of an engine: its saved activations belong to the LAST forward only (the buffers are reused)"""
+    eng._fwd_gen = getattr(eng, "_fwd_gen", 0) + 1
+    return eng._fwd_gen
+
+
+def _check_gen(eng, gen, what):
+    if getattr(eng, "_fwd_gen", None) != gen:
+        raise RuntimeError("bpmult_b200.%s: backward() of a forward whose saved activations have been overwritten by a later forward of "
+                           "the same module (the engine keeps ONE set of activation buffers: run backward before the next forward, "
+                           "or use a second module instance)" % what)
+
+
+def _opt(t):
+    """Tensor[] results cannot hold None: an empty tensor stands for 'no gradient'"""
+    return None if (t is None or t.numel() == 0) else t
+
+
+_NONE = lambda ref: ref.new_empty((0,))
 
 _SEED = [0x5EED]
 
@@ -142,58 +190,83 @@ class MultiheadAttention(nn.Module):
                 if not torch.equal(attn_mask, buffered_future_mask(query, key).to(attn_mask.dtype)):
                     raise NotImplementedError("bpmult_b200 attention supports the reference's future mask "
                                               "(transformer.py:209-216) or no mask; arbitrary additive masks are not implemented")
-        return _MHAFn.apply(self, query, key, value, mask_off, need_weights, self.in_proj_weight, self.in_proj_bias,
-                            self.out_proj.weight, self.out_proj.bias)
+        attn, w = torch.ops.bpmult_b200.multihead_attention(_handle(self), self.training, query, key, value, mask_off, need_weights,
+                                                            self.in_proj_weight, self.in_proj_bias, self.out_proj.weight, self.out_proj.bias)
+        return attn, (w if need_weights else None)
 
 
-class _MHAFn(torch.autograd.Function):
+@torch.library.custom_op("bpmult_b200::multihead_attention", mutates_args=())
+def _mha_op(handle: int, training: bool, query: Tensor, key: Tensor, value: Tensor, mask_off: int, need_weights: bool, ipw: Tensor, ipb: Tensor,
+            ow: Tensor, ob: Tensor) -> Tuple[Tensor, Tensor]:
     """standalone attention block: one-layer EncoderEngine pieces without LayerNorm / residual / FFN"""
+    mod = _mod(handle)
+    T, B, D = query.shape
+    S = key.shape[0]
+    ops = _ops_for(query.device)
+    dt = _DT[mod.precision]
+    if mod._eng is None or mod._eng.T_ != dt or mod._eng.ops is not ops:
+        mod._eng = E.EncoderEngine(ops, D, mod.num_heads, 1, attn_dropout=mod.attn_dropout, attn_mask=True, dtype=dt, uid=900)
+    eng = mod._eng
+    d = eng.d
+    eng.pack_attention(0, ipw.detach(), ipb.detach(), ow.detach(), ob.detach())
+    eng.training, eng.seed, eng.seed_ptr = training, _next_seed(), None
+    eng._mask_override = mask_off
+    xs = []
+    for t, n in ((query, T), (key, S), (value, S)):
+        r = ops.empty((B * n, d.Dp), dt)
+        ops.stage_rows(t.detach().float().permute(1, 0, 2), r, n)
+        xs.append(r)
+    zero = eng.arena.get("mha.zero", (B * T, d.Dp), torch.float32, zero=True)
+    out = eng.arena.get("mha.out", (B * T, d.Dp), torch.float32)
+    mod._bpm_sv = eng._attn_fwd(0, "x", xs[0], xs[1], xs[2], B, T, S, zero, out, res_drop=False)
+    mod._bpm_gen = _stamp(eng)
+    if need_weights:
+        w = ops.empty((B, T, S), torch.float32)
+        ops.xattn_weights(mod._bpm_sv["q"], mod._bpm_sv["k"], mod._bpm_sv["lse"], w, B, T, S, d.H, d.dh, d.dhp, mask_off=mask_off,
+                          drop=eng._drop(eng.p_attn, 0, 11))
+    else:
+        w = query.new_empty((0,), dtype=torch.float32)
+    return out.view(B, T, d.Dp)[:, :, :D].permute(1, 0, 2).clone(), w
 
-    @staticmethod
-    def forward(ctx, mod, query, key, value, mask_off, need_weights, ipw, ipb, ow, ob):
-        T, B, D = query.shape
-        S = key.shape[0]
-        ops = _ops_for(query.device)
-        dt = _DT[mod.precision]
-        if mod._eng is None or mod._eng.T_ != dt or mod._eng.ops is not ops:
-            mod._eng = E.EncoderEngine(ops, D, mod.num_heads, 1, attn_dropout=mod.attn_dropout, attn_mask=True, dtype=dt, uid=900)
-        eng = mod._eng
-        d = eng.d
-        eng.pack_attention(0, ipw.detach(), ipb.detach(), ow.detach(), ob.detach())
-        eng.training, eng.seed, eng.seed_ptr = mod.training, _next_seed(), None
-        eng._mask_override = mask_off
-        xs = []
-        for t, n in ((query, T), (key, S), (value, S)):
-            r = ops.empty((B * n, d.Dp), dt)
-            ops.stage_rows(t.detach().float().permute(1, 0, 2), r, n)
-            xs.append(r)
-        zero = eng.arena.get("mha.zero", (B * T, d.Dp), torch.float32, zero=True)
-        out = eng.arena.get("mha.out", (B * T, d.Dp), torch.float32)
-        sv = eng._attn_fwd(0, "x", xs[0], xs[1], xs[2], B, T, S, zero, out, res_drop=False)
-        ctx.mod, ctx.sv, ctx.dims = mod, sv, (T, B, S, D)
-        w = None
-        if need_weights:
-            w = ops.empty((B, T, S), torch.float32)
-            ops.xattn_weights(sv["q"], sv["k"], sv["lse"], w, B, T, S, d.H, d.dh, d.dhp, mask_off=mask_off,
-                              drop=eng._drop(eng.p_attn, 0, 11))
-        ctx.mark_non_differentiable(*([w] if w is not None else []))
-        return out.view(B, T, d.Dp)[:, :, :D].permute(1, 0, 2).clone(), w
 
-    @staticmethod
-    def backward(ctx, g, _gw):
-        mod, sv = ctx.mod, ctx.sv
-        T, B, S, D = ctx.dims
-        eng = mod._eng
-        ops, d = eng.ops, eng.d
-        eng.zero_grads()
-        gx = ops.empty((B * T, d.Dp), torch.float32)
-        ops.stage_rows(g.float().permute(1, 0, 2), gx, T)
-        dq_in, dk_in, dv_in = eng._attn_bwd(0, "x", sv, B, T, gx, res_drop=False)
-        outs = []
-        for t, n in ((dq_in, T), (dk_in, S), (dv_in, S)):
-            outs.append(t.float().view(B, n, d.Dp)[:, :, :D].permute(1, 0, 2).clone())
-        gr = eng.unpack_attention_grads(0)
-        return (None, outs[0], outs[1], outs[2], None, None) + gr
+@_mha_op.register_fake
+def _(handle, training, query, key, value, mask_off, need_weights, ipw, ipb, ow, ob):
+    T, B, D = query.shape
+    return query.new_empty((T, B, D), dtype=torch.float32), query.new_empty((B, T, key.shape[0]) if need_weights else (0,), dtype=torch.float32)
+
+
+@torch.library.custom_op("bpmult_b200::multihead_attention_bwd", mutates_args=())
+def _mha_bwd_op(handle: int, gen: int, g: Tensor, S: int) -> List[Tensor]:
+    mod = _mod(handle)
+    eng, sv = mod._eng, mod._bpm_sv
+    _check_gen(eng, gen, "MultiheadAttention")
+    T, B, D = g.shape
+    ops, d = eng.ops, eng.d
+    eng.zero_grads()
+    gx = ops.empty((B * T, d.Dp), torch.float32)
+    ops.stage_rows(g.float().permute(1, 0, 2), gx, T)
+    dq_in, dk_in, dv_in = eng._attn_bwd(0, "x", sv, B, T, gx, res_drop=False)
+    outs = [t.float().view(B, n, d.Dp)[:, :, :D].permute(1, 0, 2).clone() for t, n in ((dq_in, T), (dk_in, S), (dv_in, S))]
+    return outs + list(eng.unpack_attention_grads(0))
+
+
+@_mha_bwd_op.register_fake
+def _(handle, gen, g, S):
+    T, B, D = g.shape
+    e = lambda *shp: g.new_empty(shp, dtype=torch.float32)
+    return [e(T, B, D), e(S, B, D), e(S, B, D), e(3 * D, D), e(3 * D), e(D, D), e(D)]
+
+
+def _mha_setup(ctx, inputs, output):
+    ctx.handle, ctx.gen, ctx.S = inputs[0], _mod(inputs[0])._bpm_gen, inputs[3].shape[0]
+
+
+def _mha_backward(ctx, g, _gw):
+    r = torch.ops.bpmult_b200.multihead_attention_bwd(ctx.handle, ctx.gen, g.contiguous(), ctx.S)
+    return (None, None, r[0], r[1], r[2], None, None, r[3], r[4], r[5], r[6])
+
+
+_mha_op.register_autograd(_mha_backward, setup_context=_mha_setup)
 
 
 class TransformerEncoderLayer(nn.Module):
@@ -252,9 +325,11 @@ class TransformerEncoder(nn.Module):
         return self._eng
 
     def forward(self, x_in, x_in_k=None, x_in_v=None):
-        names = [n for n, _ in self.named_parameters()]
-        params = [p for _, p in self.named_parameters()]
-        return _EncoderFn.apply(self, names, x_in, x_in_k, x_in_v, *params)
+        if (x_in_k is None) != (x_in_v is None):                   # transformer.py:73: K and V are given together or not at all
+            x_in_k = x_in_v = None
+        same_kv = x_in_v is x_in_k
+        return torch.ops.bpmult_b200.transformer_encoder(_handle(self), self.training, x_in, x_in_k, None if same_kv else x_in_v,
+                                                         [p for _, p in self.named_parameters()])
 
     def max_positions(self):
         return self.embed_positions.max_positions()
@@ -282,48 +357,79 @@ class _LayerRunner:
         return self.enc(x, x_k, x_v)
 
 
-class _EncoderFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, mod, names, x_in, x_in_k, x_in_v, *params):
-        eng = mod._engine(x_in.device)
-        ops, d, dt = eng.ops, eng.d, eng.T_
-        T, B, D = x_in.shape
-        eng.pack({n: p.detach() for n, p in zip(names, params)})
-        xq = ops.empty((B * T, d.Dp), dt)
-        ops.stage_rows(x_in.detach().float().permute(1, 0, 2), xq, T)
-        xk = xv = None
-        S = None
-        if x_in_k is not None and x_in_v is not None:
-            S = x_in_k.shape[0]
-            xk = ops.empty((B * S, d.Dp), dt)
-            ops.stage_rows(x_in_k.detach().float().permute(1, 0, 2), xk, S)
-            if x_in_v is not x_in_k:
-                xv = ops.empty((B * S, d.Dp), dt)
-                ops.stage_rows(x_in_v.detach().float().permute(1, 0, 2), xv, S)
-        out = eng.forward(xq, B, T, src_k=xk, S=S, src_v=xv, training=mod.training, seed=_next_seed())
-        ctx.mod, ctx.names, ctx.dims, ctx.kv = mod, names, (T, B, S, D), (x_in_k is not None, x_in_v is not x_in_k)
-        return out.float().view(B, T, d.Dp)[:, :, :D].permute(1, 0, 2).clone()
+@torch.library.custom_op("bpmult_b200::transformer_encoder", mutates_args=())
+def _encoder_op(handle: int, training: bool, x_in: Tensor, x_in_k: Optional[Tensor], x_in_v: Optional[Tensor], params: List[Tensor]) -> Tensor:
+    """x_in_v = None with x_in_k given: K and V inputs are the same tensor (what the trunk always passes, mmtr.py:779-786)"""
+    mod = _mod(handle)
+    eng = mod._engine(x_in.device)
+    ops, d, dt = eng.ops, eng.d, eng.T_
+    T, B, D = x_in.shape
+    names = [n for n, _ in mod.named_parameters()]
+    eng.pack({n: p.detach() for n, p in zip(names, params)})
+    xq = ops.empty((B * T, d.Dp), dt)
+    ops.stage_rows(x_in.detach().float().permute(1, 0, 2), xq, T)
+    xk = xv = None
+    S = None
+    if x_in_k is not None:
+        S = x_in_k.shape[0]
+        xk = ops.empty((B * S, d.Dp), dt)
+        ops.stage_rows(x_in_k.detach().float().permute(1, 0, 2), xk, S)
+        if x_in_v is not None:
+            xv = ops.empty((B * S, d.Dp), dt)
+            ops.stage_rows(x_in_v.detach().float().permute(1, 0, 2), xv, S)
+    out = eng.forward(xq, B, T, src_k=xk, S=S, src_v=xv, training=training, seed=_next_seed())
+    mod._bpm_gen = _stamp(eng)
+    return out.float().view(B, T, d.Dp)[:, :, :D].permute(1, 0, 2).clone()
 
-    @staticmethod
-    def backward(ctx, g):
-        mod, names = ctx.mod, ctx.names
-        T, B, S, D = ctx.dims
-        has_kv, v_distinct = ctx.kv
-        eng = mod._eng
-        ops, d = eng.ops, eng.d
-        eng.zero_grads()
-        dout = ops.empty((B * T, d.Dp), torch.float32)
-        ops.stage_rows(g.float().permute(1, 0, 2), dout, T)
-        dq = ops.zeros((B * T, d.Dp), torch.float32)
-        dk = ops.zeros((B * S, d.Dp), torch.float32) if has_kv else None
-        dv = ops.zeros((B * S, d.Dp), torch.float32) if (has_kv and v_distinct) else None
-        eng.backward(dout, dq, dk, dv)
-        grads = {n: torch.zeros_like(p) for n, p in zip(names, [p for _, p in mod.named_parameters()])}
-        eng.unpack_grads(grads)
-        un = lambda t, n: t.view(B, n, d.Dp)[:, :, :D].permute(1, 0, 2).clone()
-        gk = un(dk, S) if has_kv else None
-        gv = (un(dv, S) if v_distinct else None) if has_kv else None
-        return (None, None, un(dq, T), gk, gv) + tuple(grads[n] for n in names)
+
+@_encoder_op.register_fake
+def _(handle, training, x_in, x_in_k, x_in_v, params):
+    return x_in.new_empty(tuple(x_in.shape), dtype=torch.float32)
+
+
+@torch.library.custom_op("bpmult_b200::transformer_encoder_bwd", mutates_args=())
+def _encoder_bwd_op(handle: int, gen: int, g: Tensor, S: int, v_distinct: bool) -> List[Tensor]:
+    """[dx_in, dx_in_k, dx_in_v] (empty when absent) + parameter gradients in named_parameters() order"""
+    mod = _mod(handle)
+    eng = mod._eng
+    _check_gen(eng, gen, "TransformerEncoder")
+    T, B, D = g.shape
+    ops, d = eng.ops, eng.d
+    has_kv = S > 0
+    eng.zero_grads()
+    dout = ops.empty((B * T, d.Dp), torch.float32)
+    ops.stage_rows(g.float().permute(1, 0, 2), dout, T)
+    dq = ops.zeros((B * T, d.Dp), torch.float32)
+    dk = ops.zeros((B * S, d.Dp), torch.float32) if has_kv else None
+    dv = ops.zeros((B * S, d.Dp), torch.float32) if (has_kv and v_distinct) else None
+    eng.backward(dout, dq, dk, dv)
+    named = list(mod.named_parameters())
+    grads = {n: torch.zeros_like(p) for n, p in named}
+    eng.unpack_grads(grads)
+    un = lambda t, n: t.view(B, n, d.Dp)[:, :, :D].permute(1, 0, 2).clone()
+    return [un(dq, T), un(dk, S) if has_kv else _NONE(g), un(dv, S) if (has_kv and v_distinct) else _NONE(g)] + [grads[n] for n, _ in named]
+
+
+@_encoder_bwd_op.register_fake
+def _(handle, gen, g, S, v_distinct):
+    T, B, D = g.shape
+    e = lambda *shp: g.new_empty(shp, dtype=torch.float32)
+    return [e(T, B, D), e(S, B, D) if S > 0 else e(0), e(S, B, D) if (S > 0 and v_distinct) else e(0)] + \
+           [e(*p.shape) for _, p in _mod(handle).named_parameters()]
+
+
+def _encoder_setup(ctx, inputs, output):
+    handle, training, x_in, x_in_k, x_in_v, params = inputs
+    ctx.handle, ctx.gen = handle, _mod(handle)._bpm_gen
+    ctx.S, ctx.v_distinct = (0 if x_in_k is None else x_in_k.shape[0]), x_in_v is not None
+
+
+def _encoder_backward(ctx, g):
+    r = torch.ops.bpmult_b200.transformer_encoder_bwd(ctx.handle, ctx.gen, g.contiguous(), ctx.S, ctx.v_distinct)
+    return (None, None, r[0], _opt(r[1]), _opt(r[2]), list(r[3:]))
+
+
+_encoder_op.register_autograd(_encoder_backward, setup_context=_encoder_setup)
 
 
 # ============================================================================================== GMUs
@@ -341,7 +447,7 @@ class _SeqGmuBase(nn.Module):
 
     def forward(self, xs):
         assert self.size_in1 == self.size_in2 == self.size_out, "the fused GMU kernel needs size_in1 == size_in2 == size_out"
-        return _SeqGmuFn.apply(self, xs[0], xs[1], self.hidden1.weight, self.hidden2.weight, self.x_gate.weight)
+        return torch.ops.bpmult_b200.seq_gmu(_handle(self), xs[0], xs[1], self.hidden1.weight, self.hidden2.weight, self.x_gate.weight)
 
 
 class GatedMultimodalLayer(_SeqGmuBase):                               # mmtr.py:161-177
@@ -352,45 +458,70 @@ class GatedMultimodalLayerFeatures(_SeqGmuBase):                       # mmtr.py
     FEATURES = True
 
 
-class _SeqGmuFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, mod, x1, x2, w1, w2, wz):
-        ops = _ops_for(x1.device)
-        dt = _DT[mod.precision]
-        D = mod.size_out
-        if mod._eng is None or mod._eng.T_ != dt or mod._eng.ops is not ops:
-            mod._eng = E.SeqGmuEngine(ops, D, dt, mod.FEATURES)
-        eng = mod._eng
-        eng.pack({"hidden1.weight": w1.detach(), "hidden2.weight": w2.detach(), "x_gate.weight": wz.detach()})
-        shape = x1.shape
-        rows = x1.numel() // D
-        a = []
-        for x in (x1, x2):
-            r = ops.empty((rows, eng.Dp), dt)
-            ops.stage_rows(x.detach().float().reshape(1, rows, D), r, rows)
-            a.append(r)
-        y = eng.forward(a[0], a[1], rows, want_gate=True)
-        ctx.mod, ctx.shape, ctx.rows = mod, shape, rows
-        z = eng.sv["z"].float()[:, :D].reshape(shape)
-        ctx.mark_non_differentiable(z)
-        out = y.float()[:, :D].reshape(shape)
-        return out, torch.cat((z, 1 - z), dim=-1)
+@torch.library.custom_op("bpmult_b200::seq_gmu", mutates_args=())
+def _seq_gmu_op(handle: int, x1: Tensor, x2: Tensor, w1: Tensor, w2: Tensor, wz: Tensor) -> Tuple[Tensor, Tensor]:
+    mod = _mod(handle)
+    ops = _ops_for(x1.device)
+    dt = _DT[mod.precision]
+    D = mod.size_out
+    if mod._eng is None or mod._eng.T_ != dt or mod._eng.ops is not ops:
+        mod._eng = E.SeqGmuEngine(ops, D, dt, mod.FEATURES)
+    eng = mod._eng
+    eng.pack({"hidden1.weight": w1.detach(), "hidden2.weight": w2.detach(), "x_gate.weight": wz.detach()})
+    shape = x1.shape
+    rows = x1.numel() // D
+    a = []
+    for x in (x1, x2):
+        r = ops.empty((rows, eng.Dp), dt)
+        ops.stage_rows(x.detach().float().reshape(1, rows, D), r, rows)
+        a.append(r)
+    y = eng.forward(a[0], a[1], rows, want_gate=True)
+    mod._bpm_gen = _stamp(eng)
+    z = eng.sv["z"].float()[:, :D].reshape(shape)
+    return y.float()[:, :D].reshape(shape).clone(), torch.cat((z, 1 - z), dim=-1)
 
-    @staticmethod
-    def backward(ctx, g, _gz):
-        mod, shape, rows = ctx.mod, ctx.shape, ctx.rows
-        eng = mod._eng
-        ops, D = eng.ops, eng.D
-        eng.zero_grads()
-        dy = ops.empty((rows, eng.Dp), torch.float32)
-        ops.stage_rows(g.float().reshape(1, rows, D), dy, rows)
-        da1, da2 = ops.zeros((rows, eng.Dp), torch.float32), ops.zeros((rows, eng.Dp), torch.float32)
-        eng.backward(dy, da1, da2)
-        grads = {"hidden1.weight": torch.zeros_like(mod.hidden1.weight), "hidden2.weight": torch.zeros_like(mod.hidden2.weight),
-                 "x_gate.weight": torch.zeros_like(mod.x_gate.weight)}
-        eng.unpack_grads(grads)
-        return (None, da1[:, :D].reshape(shape), da2[:, :D].reshape(shape), grads["hidden1.weight"], grads["hidden2.weight"],
-                grads["x_gate.weight"])
+
+@_seq_gmu_op.register_fake
+def _(handle, x1, x2, w1, w2, wz):
+    return x1.new_empty(tuple(x1.shape), dtype=torch.float32), x1.new_empty(tuple(x1.shape[:-1]) + (2 * x1.shape[-1],), dtype=torch.float32)
+
+
+@torch.library.custom_op("bpmult_b200::seq_gmu_bwd", mutates_args=())
+def _seq_gmu_bwd_op(handle: int, gen: int, g: Tensor) -> List[Tensor]:
+    mod = _mod(handle)
+    eng = mod._eng
+    _check_gen(eng, gen, type(mod).__name__)
+    ops, D = eng.ops, eng.D
+    shape = g.shape
+    rows = g.numel() // D
+    eng.zero_grads()
+    dy = ops.empty((rows, eng.Dp), torch.float32)
+    ops.stage_rows(g.float().reshape(1, rows, D), dy, rows)
+    da1, da2 = ops.zeros((rows, eng.Dp), torch.float32), ops.zeros((rows, eng.Dp), torch.float32)
+    eng.backward(dy, da1, da2)
+    grads = {"hidden1.weight": torch.zeros_like(mod.hidden1.weight), "hidden2.weight": torch.zeros_like(mod.hidden2.weight),
+             "x_gate.weight": torch.zeros_like(mod.x_gate.weight)}
+    eng.unpack_grads(grads)
+    return [da1[:, :D].reshape(shape).clone(), da2[:, :D].reshape(shape).clone(), grads["hidden1.weight"], grads["hidden2.weight"], grads["x_gate.weight"]]
+
+
+@_seq_gmu_bwd_op.register_fake
+def _(handle, gen, g):
+    mod = _mod(handle)
+    e = lambda t: g.new_empty(tuple(t.shape), dtype=torch.float32)
+    return [e(g), e(g), e(mod.hidden1.weight), e(mod.hidden2.weight), e(mod.x_gate.weight)]
+
+
+def _seq_gmu_setup(ctx, inputs, output):
+    ctx.handle, ctx.gen = inputs[0], _mod(inputs[0])._bpm_gen
+
+
+def _seq_gmu_backward(ctx, g, _gz):
+    r = torch.ops.bpmult_b200.seq_gmu_bwd(ctx.handle, ctx.gen, g.contiguous())
+    return (None, r[0], r[1], r[2], r[3], r[4])
+
+
+_seq_gmu_op.register_autograd(_seq_gmu_backward, setup_context=_seq_gmu_setup)
 
 
 class _TextShiftingBase(nn.Module):
@@ -409,7 +540,7 @@ class _TextShiftingBase(nn.Module):
     def forward(self, xs):
         n = self.N_IN
         ws = [getattr(self, "hidden%d" % (i + 1)).weight for i in range(n)] + [getattr(self, "x%d_gate" % (i + 1)).weight for i in range(n)]
-        return _TextShiftingFn.apply(self, n, *list(xs[:n]), *ws)
+        return torch.ops.bpmult_b200.text_shifting(_handle(self), list(xs[:n]), ws)
 
 
 class TextShifting3Layer(_TextShiftingBase):
@@ -452,54 +583,80 @@ class TextShiftingNLayer(nn.Module):                                  # mmtr.py:
         n = len(self.sizes_in)
         assert len(xs) == n, "TextShiftingNLayer: expected %d inputs" % n
         ws = [h.weight for h in self.hiddens] + [g.weight for g in self.x_gates]
-        return _TextShiftingFn.apply(self, n, *xs, *ws)
+        return torch.ops.bpmult_b200.text_shifting(_handle(self), list(xs), ws)
 
 
-class _TextShiftingFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, mod, n, *args):
-        xs, ws = args[:n], args[n:]
-        ops = _ops_for(xs[0].device)
-        D = mod.size_out
-        if mod._eng is None or mod._eng.ops is not ops:
-            mod._eng = E.HeadEngine(ops, D, n, 8)
-        eng = mod._eng
-        B = xs[0].shape[0]
-        Dp = eng.Dp
-        for i in range(n):
-            ops.pack_matrix(ws[i].detach(), eng.W["h"][i])
-            ops.pack_matrix(ws[n + i].detach(), eng.W["zg"][i], col_map=(D, Dp))
-        cat = eng.cat_buf(B)
-        cat.zero_()
-        for i in range(n):
-            cat[:, i * Dp:i * Dp + D] = xs[i].detach().float()
-        fused, z = eng.gate_forward(B)
-        ctx.mod, ctx.n, ctx.B = mod, n, B
-        ctx.wshapes = [tuple(w.shape) for w in ws]
-        zz = z.view(B, n, Dp)[:, :, :D].reshape(B, n * D).clone()
-        ctx.mark_non_differentiable(zz)
-        return fused[:, :D].clone(), zz
+@torch.library.custom_op("bpmult_b200::text_shifting", mutates_args=())
+def _text_shifting_op(handle: int, xs: List[Tensor], ws: List[Tensor]) -> Tuple[Tensor, Tensor]:
+    """ws = the n hidden weights followed by the n gate weights"""
+    mod = _mod(handle)
+    n = len(xs)
+    ops = _ops_for(xs[0].device)
+    D = mod.size_out
+    if mod._eng is None or mod._eng.ops is not ops or mod._eng.n_in != n:
+        mod._eng = E.HeadEngine(ops, D, n, 8)
+    eng = mod._eng
+    B = xs[0].shape[0]
+    Dp = eng.Dp
+    for i in range(n):
+        ops.pack_matrix(ws[i].detach(), eng.W["h"][i])
+        ops.pack_matrix(ws[n + i].detach(), eng.W["zg"][i], col_map=(D, Dp))
+    cat = eng.cat_buf(B)
+    cat.zero_()
+    for i in range(n):
+        cat[:, i * Dp:i * Dp + D] = xs[i].detach().float()
+    fused, z = eng.gate_forward(B)
+    mod._bpm_gen = _stamp(eng)
+    return fused[:, :D].clone(), z.view(B, n, Dp)[:, :, :D].reshape(B, n * D).clone()
 
-    @staticmethod
-    def backward(ctx, g, _gz):
-        mod, n, B = ctx.mod, ctx.n, ctx.B
-        eng = mod._eng
-        ops, D, Dp = eng.ops, eng.D, eng.Dp
-        eng.zero_grads()
-        df = ops.zeros((B, Dp), torch.float32)
-        df[:, :D] = g.float()
-        dcat = eng.gate_backward(df)
-        gx = tuple(dcat[:, i * Dp:i * Dp + D].clone() for i in range(n))
-        gw = []
-        for i in range(n):
-            t = torch.zeros(ctx.wshapes[i], dtype=torch.float32, device=g.device)
+
+@_text_shifting_op.register_fake
+def _(handle, xs, ws):
+    B, D = xs[0].shape
+    return xs[0].new_empty((B, D), dtype=torch.float32), xs[0].new_empty((B, len(xs) * D), dtype=torch.float32)
+
+
+@torch.library.custom_op("bpmult_b200::text_shifting_bwd", mutates_args=())
+def _text_shifting_bwd_op(handle: int, gen: int, g: Tensor, n: int, wshapes: List[int]) -> List[Tensor]:
+    """n input gradients followed by the 2n weight gradients (wshapes: their (rows, cols) pairs, flattened)"""
+    mod = _mod(handle)
+    eng = mod._eng
+    _check_gen(eng, gen, type(mod).__name__)
+    ops, D, Dp = eng.ops, eng.D, eng.Dp
+    B = g.shape[0]
+    eng.zero_grads()
+    df = ops.zeros((B, Dp), torch.float32)
+    df[:, :D] = g.float()
+    dcat = eng.gate_backward(df)
+    out = [dcat[:, i * Dp:i * Dp + D].clone() for i in range(n)]
+    for i in range(2 * n):
+        t = torch.zeros((wshapes[2 * i], wshapes[2 * i + 1]), dtype=torch.float32, device=g.device)
+        if i < n:
             ops.unpack_matrix(eng.G["h"][i], t)
-            gw.append(t)
-        for i in range(n):
-            t = torch.zeros(ctx.wshapes[n + i], dtype=torch.float32, device=g.device)
-            ops.unpack_matrix(eng.G["zg"][i], t, col_map=(D, Dp))
-            gw.append(t)
-        return (None, None) + gx + tuple(gw)
+        else:
+            ops.unpack_matrix(eng.G["zg"][i - n], t, col_map=(D, Dp))
+        out.append(t)
+    return out
+
+
+@_text_shifting_bwd_op.register_fake
+def _(handle, gen, g, n, wshapes):
+    return [g.new_empty(tuple(g.shape), dtype=torch.float32) for _ in range(n)] + \
+           [g.new_empty((wshapes[2 * i], wshapes[2 * i + 1]), dtype=torch.float32) for i in range(2 * n)]
+
+
+def _text_shifting_setup(ctx, inputs, output):
+    handle, xs, ws = inputs
+    ctx.handle, ctx.gen, ctx.n = handle, _mod(handle)._bpm_gen, len(xs)
+    ctx.wshapes = [int(x) for w in ws for x in w.shape]
+
+
+def _text_shifting_backward(ctx, g, _gz):
+    r = torch.ops.bpmult_b200.text_shifting_bwd(ctx.handle, ctx.gen, g.contiguous(), ctx.n, ctx.wshapes)
+    return (None, list(r[:ctx.n]), list(r[ctx.n:]))
+
+
+_text_shifting_op.register_autograd(_text_shifting_backward, setup_context=_text_shifting_setup)
 
 
 # ============================================================================================== the model
@@ -572,45 +729,87 @@ class MultiprojectionMMTransformer3DGMUClf(nn.Module):
 
     def forward(self, txt, mask, segment, img, audio, output_gate=False):
         x_l = self.enc(txt, mask, segment)
-        named = self.trunk_named_parameters()
-        names = [n for n, _ in named]
-        logits, z = _MMTrVatFn.apply(self, names, x_l, img, audio, *[p for _, p in named])
+        logits, z = torch.ops.bpmult_b200.mmtrvat(_handle(self), self.training, x_l, img, audio, [p for _, p in self.trunk_named_parameters()])
         return (logits, z) if output_gate else logits
 
 
-class _MMTrVatFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, mod, names, txt, img, audio, *params):
-        eng = mod.engine(txt.device)
-        for nm, t, dim in (("text", txt, mod.orig_d_l), ("img", img, mod.orig_d_v), ("audio", audio, mod.orig_d_a)):
-            assert t.dim() == 3 and t.shape[2] == dim, "%s features must be (B, T, %d)" % (nm, dim)
-        eng.pack({n: p.detach() for n, p in zip(names, params)})
-        logits, z = eng.forward(txt.detach().float(), img.detach().float(), audio.detach().float(), training=mod.training, seed=_next_seed())
-        B, C, D, Dp = txt.shape[0], mod.args.n_classes, mod.args.hidden_sz, eng.d.Dp
-        ctx.mod, ctx.names, ctx.shapes = mod, names, (txt.shape, img.shape, audio.shape)
-        ctx.need_in = (txt.requires_grad, img.requires_grad, audio.requires_grad)
-        zz = z.view(B, 3, Dp)[:, :, :D].reshape(B, 3 * D).clone()
-        ctx.mark_non_differentiable(zz)
-        return logits[:, :C].clone(), zz
+def _model_fwd(mod, training, feats, params, n_gate):
+    eng = mod.engine(feats[0].device)
+    names = [n for n, _ in mod.trunk_named_parameters()]
+    dims = (("text", mod.orig_d_l), ("img", mod.orig_d_v), ("audio", mod.orig_d_a))
+    for (nm, dim), t in zip(dims, feats):
+        assert t.dim() == 3 and t.shape[2] == dim, "%s features must be (B, T, %d)" % (nm, dim)
+    eng.pack({n: p.detach() for n, p in zip(names, params)})
+    logits, z = eng.forward(*[t.detach().float() for t in feats], training=training, seed=_next_seed())
+    mod._bpm_gen = _stamp(eng)
+    B, C, D, Dp = feats[0].shape[0], mod.args.n_classes, mod.args.hidden_sz, eng.d.Dp
+    return logits[:, :C].clone(), z.view(B, n_gate, Dp)[:, :, :D].reshape(B, n_gate * D).clone()
 
-    @staticmethod
-    def backward(ctx, g, _gz):
-        mod, names = ctx.mod, ctx.names
-        eng = mod._eng
-        ops = eng.ops
-        B, C = g.shape
-        dl = ops.zeros((B, eng.head.Cp), torch.float32)
-        dl[:, :C] = g.float()
-        eng.zero_grads()
-        d_in = {}
-        for m, need, shp in zip("lva", ctx.need_in, ctx.shapes):
-            if need:
-                d_in[m] = ops.zeros(tuple(shp), torch.float32)
-        eng.backward(dl, d_in)
-        pmap = dict(mod.trunk_named_parameters())
-        grads = {n: torch.zeros_like(pmap[n]) for n in eng.param_shapes()}
-        eng.unpack_grads(grads)
-        return (None, None, d_in.get("l"), d_in.get("v"), d_in.get("a")) + tuple(grads.get(n) for n in names)
+
+def _model_bwd(mod, gen, g, need, shapes):
+    """returns [d txt, d img, d audio] (empty when not needed) + parameter gradients in trunk_named_parameters() order"""
+    eng = mod._eng
+    _check_gen(eng, gen, type(mod).__name__)
+    ops = eng.ops
+    B, C = g.shape
+    dl = ops.zeros((B, eng.head.Cp), torch.float32)
+    dl[:, :C] = g.float()
+    eng.zero_grads()
+    d_in = {}
+    for i, (m, nd) in enumerate(zip("lva", need)):
+        if nd:
+            d_in[m] = ops.zeros(tuple(shapes[3 * i:3 * i + 3]), torch.float32)       # (shapes: the three (B, T, C) triples, flattened)
+    eng.backward(dl, d_in)
+    named = mod.trunk_named_parameters()
+    grads = {n: torch.zeros_like(p) for n, p in named if n in eng.param_shapes()}
+    eng.unpack_grads(grads)
+    return [d_in.get(m, _NONE(g)) for m in "lva"] + [grads.get(n, _NONE(g)) for n, _ in named]
+
+
+@torch.library.custom_op("bpmult_b200::mmtrvat", mutates_args=())
+def _mmtrvat_op(handle: int, training: bool, txt: Tensor, img: Tensor, audio: Tensor, params: List[Tensor]) -> Tuple[Tensor, Tensor]:
+    return _model_fwd(_mod(handle), training, (txt, img, audio), params, 3)
+
+
+@_mmtrvat_op.register_fake
+def _(handle, training, txt, img, audio, params):
+    a = _mod(handle).args
+    return txt.new_empty((txt.shape[0], a.n_classes), dtype=torch.float32), txt.new_empty((txt.shape[0], 3 * a.hidden_sz), dtype=torch.float32)
+
+
+@torch.library.custom_op("bpmult_b200::mmtrvat_bwd", mutates_args=())
+def _mmtrvat_bwd_op(handle: int, gen: int, g: Tensor, need: List[bool], shapes: List[int]) -> List[Tensor]:
+    return _model_bwd(_mod(handle), gen, g, need, shapes)
+
+
+def _model_bwd_fake(handle, g, need, shapes):
+    mod = _mod(handle)
+    out = [g.new_empty(tuple(shapes[3 * i:3 * i + 3]) if nd else (0,), dtype=torch.float32) for i, nd in enumerate(need)]
+    shapes_p = mod.engine(g.device).param_shapes()              # (parameters the forward never touches get no gradient)
+    for n, p in mod.trunk_named_parameters():
+        out.append(g.new_empty(tuple(p.shape) if n in shapes_p else (0,), dtype=torch.float32))
+    return out
+
+
+@_mmtrvat_bwd_op.register_fake
+def _(handle, gen, g, need, shapes):
+    return _model_bwd_fake(handle, g, need, shapes)
+
+
+def _model_setup(ctx, inputs, output):
+    handle, training, *feats = inputs[:-1]
+    ctx.handle, ctx.gen = handle, _mod(handle)._bpm_gen
+    ctx.need = [bool(t.requires_grad) for t in feats[:3]]
+    ctx.shapes = [int(x) for t in feats[:3] for x in t.shape]
+    ctx.n_feats = len(feats)
+
+
+def _mmtrvat_backward(ctx, g, _gz):
+    r = torch.ops.bpmult_b200.mmtrvat_bwd(ctx.handle, ctx.gen, g.contiguous(), ctx.need, ctx.shapes)
+    return (None, None, _opt(r[0]), _opt(r[1]), _opt(r[2]), [_opt(t) for t in r[3:]])
+
+
+_mmtrvat_op.register_autograd(_mmtrvat_backward, setup_context=_model_setup)
 
 
 class AudioFeatures(nn.Module):
@@ -684,49 +883,42 @@ class MultiprojectionMMTransformerGMUClf(nn.Module):
     def forward(self, txt, mask, segment, img, audio, poster, output_gate=False):
         x_l = self.enc(txt, mask, segment)
         x_a = self.audio_enc(audio)
-        named = self.trunk_named_parameters()
-        names = [n for n, _ in named]
-        logits, z = _MMTrVaptFn.apply(self, names, x_l, img, x_a, poster, *[p for _, p in named])
+        logits, z = torch.ops.bpmult_b200.mmtrvapt(_handle(self), self.training, x_l, img, x_a, poster,
+                                                   [p for _, p in self.trunk_named_parameters()])
         return (logits, z) if output_gate else logits
 
 
-class _MMTrVaptFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, mod, names, txt, img, audio, poster, *params):
-        eng = mod.engine(txt.device)
-        for nm, t, dim in (("text", txt, mod.orig_d_l), ("img", img, mod.orig_d_v), ("audio", audio, mod.orig_d_a)):
-            assert t.dim() == 3 and t.shape[2] == dim, "%s features must be (B, T, %d)" % (nm, dim)
-        assert poster.dim() == 2 and poster.shape[1] == mod.orig_d_p, "poster must be (B, %d)" % mod.orig_d_p
-        assert txt.shape[1] <= mod.num_vectors_l and audio.shape[1] <= mod.num_vectors_a and img.shape[1] <= mod.num_vectors_v, \
-            "a sequence exceeds its fixed length (the reference raises on a negative pad size, mmtr.py:431-441)"
-        eng.pack({n: p.detach() for n, p in zip(names, params)})
-        logits, z = eng.forward(txt.detach().float(), img.detach().float(), audio.detach().float(), poster.detach().float(),
-                                training=mod.training, seed=_next_seed())
-        B, C, D, Dp = txt.shape[0], mod.args.n_classes, mod.args.hidden_sz, eng.d.Dp
-        ctx.mod, ctx.names, ctx.shapes = mod, names, (txt.shape, img.shape, audio.shape)
-        ctx.need_in = (txt.requires_grad, img.requires_grad, audio.requires_grad)
-        zz = z.view(B, 4, Dp)[:, :, :D].reshape(B, 4 * D).clone()
-        ctx.mark_non_differentiable(zz)
-        return logits[:, :C].clone(), zz
+@torch.library.custom_op("bpmult_b200::mmtrvapt", mutates_args=())
+def _mmtrvapt_op(handle: int, training: bool, txt: Tensor, img: Tensor, audio: Tensor, poster: Tensor, params: List[Tensor]) -> Tuple[Tensor, Tensor]:
+    mod = _mod(handle)
+    assert poster.dim() == 2 and poster.shape[1] == mod.orig_d_p, "poster must be (B, %d)" % mod.orig_d_p
+    assert txt.shape[1] <= mod.num_vectors_l and audio.shape[1] <= mod.num_vectors_a and img.shape[1] <= mod.num_vectors_v, \
+        "a sequence exceeds its fixed length (the reference raises on a negative pad size, mmtr.py:431-441)"
+    return _model_fwd(mod, training, (txt, img, audio, poster), params, 4)
 
-    @staticmethod
-    def backward(ctx, g, _gz):
-        mod, names = ctx.mod, ctx.names
-        eng = mod._eng
-        ops = eng.ops
-        B, C = g.shape
-        dl = ops.zeros((B, eng.head.Cp), torch.float32)
-        dl[:, :C] = g.float()
-        eng.zero_grads()
-        d_in = {}
-        for m, need, shp in zip("lva", ctx.need_in, ctx.shapes):
-            if need:
-                d_in[m] = ops.zeros(tuple(shp), torch.float32)
-        eng.backward(dl, d_in)
-        pmap = dict(mod.trunk_named_parameters())
-        grads = {n: torch.zeros_like(pmap[n]) for n in eng.param_shapes()}
-        eng.unpack_grads(grads)
-        return (None, None, d_in.get("l"), d_in.get("v"), d_in.get("a"), None) + tuple(grads.get(n) for n in names)     # (no poster input gradient)
+
+@_mmtrvapt_op.register_fake
+def _(handle, training, txt, img, audio, poster, params):
+    a = _mod(handle).args
+    return txt.new_empty((txt.shape[0], a.n_classes), dtype=torch.float32), txt.new_empty((txt.shape[0], 4 * a.hidden_sz), dtype=torch.float32)
+
+
+@torch.library.custom_op("bpmult_b200::mmtrvapt_bwd", mutates_args=())
+def _mmtrvapt_bwd_op(handle: int, gen: int, g: Tensor, need: List[bool], shapes: List[int]) -> List[Tensor]:
+    return _model_bwd(_mod(handle), gen, g, need, shapes)
+
+
+@_mmtrvapt_bwd_op.register_fake
+def _(handle, gen, g, need, shapes):
+    return _model_bwd_fake(handle, g, need, shapes)
+
+
+def _mmtrvapt_backward(ctx, g, _gz):
+    r = torch.ops.bpmult_b200.mmtrvapt_bwd(ctx.handle, ctx.gen, g.contiguous(), ctx.need, ctx.shapes)
+    return (None, None, _opt(r[0]), _opt(r[1]), _opt(r[2]), None, [_opt(t) for t in r[3:]])       # (no poster input gradient)
+
+
+_mmtrvapt_op.register_autograd(_mmtrvapt_backward, setup_context=_model_setup)
 
 
 MODELS = {"mmtrvat": MultiprojectionMMTransformer3DGMUClf, "mmtrvapt": MultiprojectionMMTransformerGMUClf}    # models/__init__.py:6-9

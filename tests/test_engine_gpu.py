@@ -174,3 +174,29 @@ def test_mmtrvat_vs_reference_golden(ops, gold, dtype):
     assert Fn.rel_l2(dtxt, dtxt32) < max(2e-2, 2.0 * Fn.rel_l2(dtxtac, dtxt32))
     for e, eac, n in report:
         assert e < max(2e-2, 2.0 * ac_worst), (n, e, eac, ac_worst)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_mmtrvapt_bimodal_imdb_widths(ops, dtype):
+    """BASELINE configs[3] (README.md:36): mmtrvapt with orig_d_v = 300 (GloVe plot as the video stream) and orig_d_a = 1 (bag of words as
+    a one-channel audio stream), against the oracle restatement evaluated on this GPU in true fp32"""
+    from argparse import Namespace
+    from helpers import run_model4_engine
+    cfg = synth.tiny_cfg(hidden_sz=64, num_heads=2, layers=1, orig_d_l=64, orig_d_v=300, orig_d_a=1, orig_d_p=48, n_classes=23)
+    rec = dict(cfg=vars(cfg), dims=(2, 40, 30, 25), seed=31, pos_weight=torch.ones(23))
+    logits, z, loss, dtxt, grads, eng = run_model4_engine(ops, rec, dtype=dtype)
+    torch.cuda.synchronize()
+    sd = synth.make_state_dict(synth.mmtrvapt_shapes(cfg), rec["seed"])
+    ins = [t.cuda() for t in synth.mmtrvapt_inputs(cfg, 2, 40, 30, 25)]
+    sdo = {k: v.cuda().requires_grad_() for k, v in sd.items()}
+    ins[0].requires_grad_()
+    lo, zo = Fn.mmtrvapt_forward(sdo, Namespace(**vars(cfg)), *ins[:-1])
+    Fn.bce_with_logits(lo, ins[-1], rec["pos_weight"].cuda()).backward()
+    fp32 = dtype == torch.float32
+    assert Fn.max_rel(logits, lo.detach().cpu()) < (1e-4 if fp32 else 2e-2)
+    assert Fn.max_rel(z, zo.detach().cpu()) < (1e-4 if fp32 else 2e-2)
+    assert Fn.rel_l2(dtxt, ins[0].grad.cpu()) < (2e-4 if fp32 else 1e-1)
+    worst = max((Fn.rel_l2(grads[n], v.grad.cpu()), n) for n, v in sdo.items() if v.grad is not None)
+    print("mmtrvapt bimodal widths %s: worst param grad rel-l2 %.3e %s" % ("fp32" if fp32 else "bf16", worst[0], worst[1]))
+    assert worst[0] < (2e-4 if fp32 else 2.5e-1), worst
+    assert Fn.rel_l2(grads["proj_a.weight"], sdo["proj_a.weight"].grad.cpu()) < (2e-4 if fp32 else 5e-2)      # the 1-channel projection

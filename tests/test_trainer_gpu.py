@@ -179,3 +179,63 @@ def test_no_cpu_fallback():
     m = TransformerEncoder(40, 4, 1)
     with pytest.raises(RuntimeError):
         m(torch.randn(5, 2, 40))
+
+
+def test_reference_format_checkpoint_round_trip_on_gpu(tmp_path):
+    """SURVEY 8 f3 on the CUDA path (utils/utils.py:21-30, train.py:372-379,419-430): a `checkpoint.pt` written the way the reference
+    writes it (nn.DataParallel `module.` prefix, torch Adam state) resumes in model + Trainer under CUDA-graph replay exactly as torch's
+    Adam would continue; the Trainer's own checkpoint loads back into torch Adam and, when the reference tree is on the box
+    (baseline/_ref), into the UNMODIFIED reference model with identical logits."""
+    from bpmult_b200 import Trainer
+    cfg = synth.tiny_cfg()
+    txt, img, audio, tgt = [t.cuda() for t in synth.mmtrvat_inputs(cfg, 2, 10, 30, 25)]
+    crit = torch.nn.BCEWithLogitsLoss()
+
+    def torch_steps(model, opt, n):
+        out = []
+        for _ in range(n):
+            opt.zero_grad()
+            loss = crit(model(txt, None, None, img, audio), tgt)
+            loss.backward()
+            opt.step()
+            out.append(float(loss.detach()))
+        return out
+    a = _model(cfg, "fp32")
+    opt_a = torch.optim.Adam(a.parameters(), lr=1e-3)
+    torch_steps(a, opt_a, 2)
+    path = str(tmp_path / "checkpoint.pt")
+    torch.save({"epoch": 3, "state_dict": {"module." + k: v for k, v in a.state_dict().items()}, "optimizer": opt_a.state_dict(),
+                "scheduler": {}, "n_no_improve": 1, "best_metric": 0.5}, path)
+    la = torch_steps(a, opt_a, 4)
+    b = _model(cfg, "fp32", seed=99)                               # other weights: everything must come from the checkpoint
+    tr = Trainer(b, lr=0.5)
+    info = tr.load_checkpoint(path)
+    assert info["epoch"] == 3 and not info["missing"] and not info["unexpected"] and int(tr.step_t) == 2
+    lb = [float(tr.step_device(txt, img, audio, tgt)[0]) for _ in range(4)]          # 2 eager steps, capture, replay
+    assert tr.graph is not None
+    assert max(abs(x - y) for x, y in zip(la, lb)) < 2e-5, (la, lb)
+    ck2 = tr.checkpoint(epoch=4)
+    c = _model(cfg, "fp32", seed=7)
+    c.load_state_dict(ck2["state_dict"], strict=False)
+    opt_c = torch.optim.Adam(c.parameters(), lr=1.0)
+    opt_c.load_state_dict(ck2["optimizer"])
+    lc = torch_steps(c, opt_c, 1)
+    ld = float(tr.step_device(txt, img, audio, tgt)[0])
+    assert abs(lc[0] - ld) < 2e-5
+    tr.close()
+    from oracle.ref_shim import load_reference, zero_dropout
+    ref = load_reference()
+    if ref is not None:
+        rm = ref.mmtr.MultiprojectionMMTransformer3DGMUClf(zero_dropout(Namespace(**vars(cfg))))
+        missing, unexpected = rm.load_state_dict({k: v.cpu() for k, v in ck2["state_dict"].items()}, strict=False)
+        assert not unexpected
+        rm.eval()
+        pad = lambda t: torch.cat([t.cpu(), torch.zeros(t.shape[0], 512 - t.shape[1], t.shape[2])], 1)     # (the reference's own padding calls .cuda())
+        with torch.no_grad():
+            lr_ = rm(pad(txt), None, None, pad(img), pad(audio))
+        b2 = _model(cfg, "fp32", seed=3)
+        b2.load_state_dict(ck2["state_dict"], strict=False)
+        b2.eval()
+        with torch.no_grad():
+            lo = b2(txt, None, None, img, audio).cpu()
+        assert float((lr_ - lo).abs().max()) < 2e-5
