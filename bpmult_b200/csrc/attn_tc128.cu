@@ -252,21 +252,30 @@ attn128_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(s_full(g), (uint32_t)tc & 1u);
         tc_fence_after();
-        // ---- pass 1: row maximum
+        // ---- pass 1: row maximum (two 32-column chunks in flight per wait)
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int ci = 0; ci < nvis; ci++) {
-          const int c = ci * 32;
-          float sv[32];
-          tmem_ld32(tS + c, sv);
-          tmem_ld_wait();
-          if (k0 + c + 31 > vis_all || padm[ci]) a8_mask32(sv, row_lim - (k0 + c), padm[ci]);
-          float m4[4] = {sv[0], sv[1], sv[2], sv[3]};
+        {
+          float sa[32], sb[32];
+          auto chunk_max = [&](float* sv, int ci) {
+            const int c = ci * 32;
+            if (k0 + c + 31 > vis_all || padm[ci]) a8_mask32(sv, row_lim - (k0 + c), padm[ci]);
+            float m4[4] = {sv[0], sv[1], sv[2], sv[3]};
 #pragma unroll
-          for (int e = 4; e < 32; e += 4) {
-            m4[0] = fmaxf(m4[0], sv[e]); m4[1] = fmaxf(m4[1], sv[e + 1]); m4[2] = fmaxf(m4[2], sv[e + 2]); m4[3] = fmaxf(m4[3], sv[e + 3]);
+            for (int e = 4; e < 32; e += 4) {
+              m4[0] = fmaxf(m4[0], sv[e]); m4[1] = fmaxf(m4[1], sv[e + 1]); m4[2] = fmaxf(m4[2], sv[e + 2]); m4[3] = fmaxf(m4[3], sv[e + 3]);
+            }
+            mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          };
+#pragma unroll
+          for (int cp = 0; cp < 2; cp++) {
+            if (2 * cp < nvis) {
+              tmem_ld32(tS + 64 * cp, sa);
+              if (2 * cp + 1 < nvis) tmem_ld32(tS + 64 * cp + 32, sb);
+              tmem_ld_wait();
+              chunk_max(sa, 2 * cp);
+              if (2 * cp + 1 < nvis) chunk_max(sb, 2 * cp + 1);
+            }
           }
-          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
         }
         // ---- lazy rescale: only when the row maximum has outgrown the reference by more than 2^8
         const float cand = mx * LOG2E_F;
@@ -293,7 +302,7 @@ attn128_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // ---- pass 2: P = exp2(S log2e - m_used), row sum, dropout, packed bf16 over the consumed score columns
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll 1
-        for (int ci = 0; ci < 4; ci++) {
+        for (int ci = 0; ci < 4; ci++) {                                   // (not unrolled / prefetched: measured 10 % slower, the loop outgrows the instruction cache)
           const int c = ci * 32;
           uint32_t pk[16];
           if (ci >= nvis) {
@@ -403,22 +412,26 @@ attn128_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //              that half's lse * log2e and delta rows (1-D bulk copies)
 //   warp 1     issues S^T and dP^T (two TMEM generations: X_0 | X_1 and Y_0 | Y_1, 64 columns each)
 //   warp 2     issues dV += P~^T dO_h (A = P~^T from TMEM), dK += dS^T Q_h, dQ_h^T = K_j^T dS_h (into the Y generation dP^T came from)
-//   warps 3-10 compute: two warps per TMEM lane quarter (32 of the 64 query columns each); thread = key row.  They also drain dQ_h^T
-//              of the PREVIOUS half tile (thread = head dim, TMA reduce-add of a [32 query][32 dim] fp32 block per warp) and, at the end
-//              of an item, dK_j (column half 0) / dV_j (column half 1) through the same 4 KB staging block per warp.
+//   warps 3-10 compute: two warps per TMEM lane quarter (32 of the 64 query columns each); thread = key row; both tiles' 32 columns are
+//              loaded up front (64 values in flight), so the exponentials of a row have 32-way instruction-level parallelism
+//   warps 11-14 drain: one per lane quarter.  dQ_h^T of every half tile (thread = head dim) goes through two alternating 4 KB staging
+//              slices as [32 query][32 dim] fp32 blocks into TMA reduce-adds; at the end of an item dK_j and dV_j leave the same way
+//              (bf16, TMA stores).  The compute warps never wait for a drain or a store (measured before the split: 27 % of their time
+//              waiting for the next S^T / dP^T, which could not be issued before they had drained dQ^T, 10 % for staging reads).
 // TMEM: X_0 64 | X_1 64 | Y_0 64 | Y_1 64 | dK 128 | dV 128 = 512 columns.
 // P~^T is packed over the S^T columns its own warp has consumed: queries [0,32) -> X columns [0,16), queries [32,64) -> [32,48).
 // =====================================================================================================================
-#define B8_CW 8
-#define B8_THREADS (96 + 32 * B8_CW)
+#define B8_CW 8                         // compute warps (3 .. 10)
+#define B8_DW 4                         // drain warps (11 .. 14), one per TMEM lane quarter
+#define B8_THREADS (96 + 32 * (B8_CW + B8_DW))
 #define B8_QS 3
 
 struct B8Smem {
   static constexpr int KV = 0;                                   // K_j 32 KB (2 sub-tiles of 128 rows x 128 B), V_j 32 KB
   static constexpr int QD = KV + 2 * 32768;                      // stages x (Q_h 16 KB: 2 sub-tiles of 64 rows x 128 B | dO_h 16 KB)
   static constexpr int DST = QD + B8_QS * 32768;                 // dS^T: 2 buffers x (128 keys x 64 queries bf16, 128-byte rows)
-  static constexpr int STG = DST + 2 * 16384;                    // per compute warp 4 KB: dQ^T block / dK, dV slices on their way out
-  static constexpr int LD = STG + B8_CW * 4096;                  // stages x (64 floats lse*log2e | 64 floats delta)
+  static constexpr int STG = DST + 2 * 16384;                    // per drain warp 2 slices of 4 KB: dQ^T blocks / dK, dV slices on their way out
+  static constexpr int LD = STG + B8_DW * 8192;                  // stages x (64 floats lse*log2e | 64 floats delta)
   static constexpr int BAR = LD + B8_QS * 512;
   static constexpr int NBAR = 2 + 2 * B8_QS + 14;
   static constexpr int TOTAL = BAR + 8 * NBAR + 16;
@@ -514,10 +527,10 @@ attn128_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int s = 0; s < B8_QS; s++) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
     for (int b = 0; b < 2; b++) {
-      mbar_init(st_full(b), 1); mbar_init(x_free(b), 1); mbar_init(y_free(b), B8_CW); mbar_init(pt_full(b), B8_CW);
+      mbar_init(st_full(b), 1); mbar_init(x_free(b), 1); mbar_init(y_free(b), B8_DW); mbar_init(pt_full(b), B8_CW);
       mbar_init(ds_free(b), 1); mbar_init(dq_full(b), 1);
     }
-    mbar_init(dkv_full, 1); mbar_init(dkv_free, B8_CW);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, B8_DW);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, 512);
@@ -642,44 +655,18 @@ attn128_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       ic++;
     }
-  } else {
+  } else if (warp < 3 + B8_CW) {
     // ===================== compute warps =====================
     const int cw = warp - 3;
     const int quarter = warp & 3, colh = cw >> 2;                          // TMEM lane quarter; query-column half [32 colh, +32) of the half tile
-    const int r = quarter * 32 + lane;                                     // key row of the tile == TMEM lane (== head dim when draining dQ^T)
+    const int r = quarter * 32 + lane;                                     // key row of the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const DropCtx dc = make_drop(drop);
     const int W = (S + 31) >> 5;
     const int drop_mode = !DROP ? 0 : (!dc.on ? 0 : (drop_bits != nullptr ? 2 : 3));
     // dS^T row r: 128-byte rows, 8-row groups of 1024 B, 16-byte unit u at u ^ (r & 7)
     const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-    uint8_t* const stg = base_gen + L::STG + cw * 4096;
-    const uint32_t stg_s = base + L::STG + cw * 4096;
-    uint32_t n = 0, ic = 0;
-    int pend = -1, pend_q0 = 0, pend_b = 0, pend_h = 0;                    // half tile whose dQ^T still sits in TMEM
-    auto drain_dq = [&]() {
-      const int pb = pend & 1;
-      mbar_wait(dq_full(pb), ((uint32_t)pend >> 1) & 1u);
-      tc_fence_after();
-      float acc[32];
-      tmem_ld32(tY(pb) + lane_off + 32 * colh, acc);                       // lane = head dim r, columns = this warp's 32 queries
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(y_free(pb));
-      if (elect_one()) bulk_wait_read<0>();                                // the previous store has read the staging block
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < 32; c++) *(float*)(stg + c * 128 + lane * 4) = acc[c];      // [query][dim]: a warp writes 128 contiguous bytes
-      fence_async_smem();
-      __syncwarp();
-      if (elect_one()) {
-        tma_reduce_add_3d(&tmDQ, stg_s, pend_h * DH + 32 * quarter, pend_q0 + 32 * colh, pend_b);
-        bulk_commit();
-      }
-      __syncwarp();
-      pend = -1;
-    };
+    uint32_t n = 0;
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
       const int j = idx / nbh, bh = idx % nbh, b = bh / H, h = bh % H;
       const int ih0 = ih_min_of(j);
@@ -711,81 +698,115 @@ attn128_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(st_full(pb), (n >> 1) & 1u);
         tc_fence_after();
+        float sv[32], dpv[32];                                             // both tiles' columns of this warp in flight at once
+        tmem_ld32(tX(pb) + lane_off + 32 * colh, sv);
+        tmem_ld32(tY(pb) + lane_off + 32 * colh, dpv);
         mbar_wait(ds_free(pb), ((n >> 1) & 1u) ^ 1u);                      // the MMAs of two half tiles ago have read this dS^T buffer
         uint8_t* const dtile = base_gen + L::DST + pb * 16384 + row_off;
+        tmem_ld_wait();
 #pragma unroll
-        for (int s2 = 0; s2 < 2; s2++) {                                   // 16-column sub-chunks keep the live register set small
-          const int cs = 16 * s2;
-          float sv[16], dpv[16];
-          tmem_ld16(tX(pb) + lane_off + 32 * colh + cs, sv);
-          tmem_ld16(tY(pb) + lane_off + 32 * colh + cs, dpv);
-          tmem_ld_wait();
+        for (int c = 0; c < 32; c += 4) {
+          const float4 l4 = *(const float4*)(lse_s + c);
+          const float4 d4 = *(const float4*)(del_s + c);
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) {
-            const float4 l4 = *(const float4*)(lse_s + cs + c);
-            const float4 d4 = *(const float4*)(del_s + cs + c);
-            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int cc = cs + c + e;
-              float p = ex2f(fmaf(sv[c + e], LOG2E_F, -ls[e]));
-              float ds;
-              if (!DROP || drop_mode == 0) {
-                ds = p * (dpv[c + e] - dl[e]);
-              } else {
-                float mult;
-                if (drop_mode == 2) mult = ((__shfl_sync(0xffffffffu, mw, cc) >> lane) & 1u) ? dc.inv_keep : 0.f;
-                else mult = drop_mult1(dc, ((uint64_t)min(qc + cc, T - 1)) * (uint64_t)S + e_row);
-                ds = p * fmaf(dpv[c + e], mult, -dl[e]);                   // dS^T
-                p *= mult;                                                 // P~^T
-              }
-              // (the lse / delta rows of query columns beyond T are not loaded: their products may be anything, the selects discard them)
-              const bool dead = need_mask && (row_dead || cc < cmin || cc >= cmax);
-              sv[c + e] = dead ? 0.f : p;
-              dpv[c + e] = dead ? 0.f : ds;
+          for (int e = 0; e < 4; e++) {
+            const int cc = c + e;
+            float p = ex2f(fmaf(sv[cc], LOG2E_F, -ls[e]));
+            float ds;
+            if (!DROP || drop_mode == 0) {
+              ds = p * (dpv[cc] - dl[e]);
+            } else {
+              float mult;
+              if (drop_mode == 2) mult = ((__shfl_sync(0xffffffffu, mw, cc) >> lane) & 1u) ? dc.inv_keep : 0.f;
+              else mult = drop_mult1(dc, ((uint64_t)min(qc + cc, T - 1)) * (uint64_t)S + e_row);
+              ds = p * fmaf(dpv[cc], mult, -dl[e]);                        // dS^T
+              p *= mult;                                                   // P~^T
             }
+            // (the lse / delta rows of query columns beyond T are not loaded: their products may be anything, the selects discard them)
+            const bool dead = need_mask && (row_dead || cc < cmin || cc >= cmax);
+            sv[cc] = dead ? 0.f : p;
+            dpv[cc] = dead ? 0.f : ds;
           }
-          uint32_t pk[8];
+        }
+        uint32_t pk[16];
 #pragma unroll
-          for (int u = 0; u < 8; u++) pk[u] = pack_bf16x2(sv[2 * u], sv[2 * u + 1]);
-          tmem_st8(tX(pb) + lane_off + (uint32_t)(32 * colh + 8 * s2), pk);                 // queries [32 colh + 16 s2, +16) of the half tile
+        for (int u = 0; u < 16; u++) pk[u] = pack_bf16x2(sv[2 * u], sv[2 * u + 1]);
+        tmem_st16(tX(pb) + lane_off + (uint32_t)(32 * colh), pk);          // queries [32 colh, +32) of the half tile -> 16 packed columns
 #pragma unroll
-          for (int uu = 0; uu < 2; uu++) {
-            const int u = colh * 4 + s2 * 2 + uu;                          // 16-byte unit of the 128-byte dS^T row
-            *(uint4*)(dtile + ((u ^ (r & 7)) << 4)) =
-                make_uint4(pack_bf16x2(dpv[uu * 8], dpv[uu * 8 + 1]), pack_bf16x2(dpv[uu * 8 + 2], dpv[uu * 8 + 3]),
-                           pack_bf16x2(dpv[uu * 8 + 4], dpv[uu * 8 + 5]), pack_bf16x2(dpv[uu * 8 + 6], dpv[uu * 8 + 7]));
-          }
+        for (int uu = 0; uu < 4; uu++) {
+          const int u = colh * 4 + uu;                                     // 16-byte unit of the 128-byte dS^T row
+          *(uint4*)(dtile + ((u ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16x2(dpv[uu * 8], dpv[uu * 8 + 1]), pack_bf16x2(dpv[uu * 8 + 2], dpv[uu * 8 + 3]),
+                         pack_bf16x2(dpv[uu * 8 + 4], dpv[uu * 8 + 5]), pack_bf16x2(dpv[uu * 8 + 6], dpv[uu * 8 + 7]));
         }
         tmem_st_wait();
         tc_fence_before();
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(pt_full(pb));
-        if (pend >= 0) drain_dq();                                         // the previous half tile's dQ^T: its MMAs ran while this one was computed
-        pend = (int)n; pend_q0 = q0; pend_b = b; pend_h = h;
       }
-      // ---- end of the item: the last dQ^T, then dK_j (column half 0) / dV_j (column half 1): 4 x (32 rows x 64 columns) slices per warp
-      drain_dq();
+    }
+  } else {
+    // ===================== drain warps: dQ_h^T of every half tile (TMA reduce-add), dK_j / dV_j at the end of an item =====================
+    const int dw = warp - (3 + B8_CW);
+    const int quarter = warp & 3;                                          // lanes = head dims [32 quarter, +32) of dQ^T / key rows of dK, dV
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    uint8_t* const stg = base_gen + L::STG + dw * 8192;                    // two 4 KB slices, used alternately
+    const uint32_t stg_s = base + L::STG + dw * 8192;
+    uint32_t n = 0, ic = 0, sl = 0;
+    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+      const int j = idx / nbh, bh = idx % nbh, b = bh / H, h = bh % H;
+      const int ih0 = ih_min_of(j);
+      if (ih0 >= nqh) continue;
+      for (int ih = ih0; ih < nqh; ih++, n++) {
+        const int pb = n & 1;
+        mbar_wait(dq_full(pb), (n >> 1) & 1u);
+        tc_fence_after();
+        float acc[64];                                                     // lane = head dim, columns = the 64 queries of the half tile
+        tmem_ld32(tY(pb) + lane_off, acc);
+        tmem_ld32(tY(pb) + lane_off + 32, acc + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(y_free(pb));
+#pragma unroll
+        for (int hq = 0; hq < 2; hq++, sl ^= 1u) {                         // 32 queries per slice: [query][dim] fp32, a warp writes 128 contiguous bytes
+          if (elect_one()) bulk_wait_read<1>();                            // the store that last used this slice (two stores ago) has read it
+          __syncwarp();
+          uint8_t* const sp = stg + sl * 4096;
+#pragma unroll
+          for (int c = 0; c < 32; c++) *(float*)(sp + c * 128 + lane * 4) = acc[hq * 32 + c];
+          fence_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_reduce_add_3d(&tmDQ, stg_s + sl * 4096, h * DH + 32 * quarter, ih * 64 + 32 * hq, b);
+            bulk_commit();
+          }
+          __syncwarp();
+        }
+      }
+      // ---- end of the item: dK_j then dV_j of this lane quarter's 32 key rows, 2 x (32 rows x 64 columns bf16) slices each
       mbar_wait(dkv_full, ic & 1u);
       tc_fence_after();
       ic++;
 #pragma unroll 1
-      for (int sub = 0; sub < 2; sub++) {
-        if (elect_one()) bulk_wait_read<0>();
+      for (int part = 0; part < 4; part++, sl ^= 1u) {                     // dK columns [0,64), [64,128), dV columns [0,64), [64,128)
+        if (elect_one()) bulk_wait_read<1>();
         __syncwarp();
+        uint8_t* const sp = stg + sl * 4096;
 #pragma unroll
         for (int c2 = 0; c2 < 2; c2++) {
           float acc[32];
-          tmem_ld32((colh ? tDV : tDK) + lane_off + 64 * sub + 32 * c2, acc);
+          tmem_ld32(((part >> 1) ? tDV : tDK) + lane_off + 64 * (part & 1) + 32 * c2, acc);
           tmem_ld_wait();
 #pragma unroll
           for (int u = 0; u < 4; u++)
-            *(uint4*)(stg + lane * 128 + (((c2 * 4 + u) ^ (lane & 7)) << 4)) =
+            *(uint4*)(sp + lane * 128 + (((c2 * 4 + u) ^ (lane & 7)) << 4)) =
                 make_uint4(pack_bf16x2(acc[u * 8], acc[u * 8 + 1]), pack_bf16x2(acc[u * 8 + 2], acc[u * 8 + 3]),
                            pack_bf16x2(acc[u * 8 + 4], acc[u * 8 + 5]), pack_bf16x2(acc[u * 8 + 6], acc[u * 8 + 7]));
         }
-        if (sub == 1) {
+        if (part == 3) {                                                   // both accumulators are out of TMEM: the next item may start
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(dkv_free);
@@ -793,7 +814,7 @@ attn128_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         fence_async_smem();
         __syncwarp();
         if (elect_one()) {
-          tma_store_3d(colh ? &tmDV : &tmDK, stg_s, h * DH + 64 * sub, j * 128 + quarter * 32, b);
+          tma_store_3d((part >> 1) ? &tmDV : &tmDK, stg_s + sl * 4096, h * DH + 64 * (part & 1), j * 128 + quarter * 32, b);
           bulk_commit();
         }
         __syncwarp();
