@@ -10,7 +10,7 @@ __version__ = "0.1.0"
 _PUBLIC = {
     "modules": ["MultiprojectionMMTransformer3DGMUClf", "MultiprojectionMMTransformerGMUClf", "TransformerEncoder", "TransformerEncoderLayer", "MultiheadAttention",
                 "SinusoidalPositionalEmbedding", "GatedMultimodalLayer", "GatedMultimodalLayerFeatures", "TextShifting3Layer",
-                "TextShifting4Layer", "TextShiftingNLayer", "buffered_future_mask", "get_model", "MODELS", "manual_seed"],
+                "TextShifting4Layer", "TextShiftingNLayer", "AudioEncoder", "buffered_future_mask", "get_model", "MODELS", "manual_seed"],
     "trainer": ["Trainer"],
 }
 

@@ -71,6 +71,12 @@ SIGNATURES = {
     "bpm_bce_fwd_bwd": [_P, _I, _P, _P, _I, _I, _F, _P, _P, _P],
     "bpm_timelin_fwd": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "bpm_timelin_bwd": [_I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
+    "bpm_conv1d_im2col": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P],
+    "bpm_conv1d_col2im": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P],
+    "bpm_conv1d_pack_weight": [_P, _I, _I, _I, _P, _I, _P],
+    "bpm_conv1d_unpack_wgrad": [_P, _I, _I, _I, _P, _I, _P],
+    "bpm_adaptive_pool_fwd": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
+    "bpm_adaptive_pool_bwd": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
     "bpm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P, _P, _P],
 }
 _RESTYPE = {"bpm_last_error": C.c_char_p, "bpm_xattn_bwd_workspace": C.c_int64}

@@ -40,6 +40,11 @@ __device__ __forceinline__ void fwd_mask32(float* sv, int lim) {
 #pragma unroll
   for (int c = 0; c < 32; c++) sv[c] = (c <= lim) ? sv[c] : -INFINITY;
 }
+// ... and the chunk's key-padding bits (bit c set = key c of the chunk is padded)
+__device__ __forceinline__ void fwd_mask32_pad(float* sv, int lim, uint32_t padm) {
+#pragma unroll
+  for (int c = 0; c < 32; c++) sv[c] = (c <= lim && !((padm >> c) & 1u)) ? sv[c] : -INFINITY;
+}
 
 // ONES (no dropout, head dim <= 26 of 32): the MMA warp writes ones into two padding columns of every V tile in shared memory, so
 // column AF_PAD0 of the P V accumulator is the row sum of P -- rescaled with the other columns, summed by the tensor core from the
@@ -48,11 +53,13 @@ __device__ __forceinline__ void fwd_mask32(float* sv, int lim) {
 // SW = 8 (with ONES): two softmax warps per TMEM lane quarter, 64 of the tile's 128 key columns and 16 of the 32 output columns
 // each; the pair shares the row maximum through shared memory (one 64-thread named barrier per tile).  The kernel is bound by the
 // serial latency of a tile's softmax, not by a pipe (35 % issue slots, 41 % MUFU with SW = 4): halving the columns per warp shortens it.
-template <bool DROP, bool ONES, int SW>
+// KP: key-padding mask (uint8 [B, S], 1 = padded key; north star (2) -- the reference has none, multihead_attention.py:52): a separate
+// instantiation, so the hot ones carry no code for it.
+template <bool DROP, bool ONES, int SW, bool KP = false>
 __global__ void __launch_bounds__(AF_THREADS(SW), 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int B, int T, int S, int H, int mask_off, bpm_dropout_t drop,
-                   uint32_t* __restrict__ drop_bits) {
+                   uint32_t* __restrict__ drop_bits, const uint8_t* __restrict__ key_pad = nullptr) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -231,7 +238,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           float sv[32];
           tmem_ld32(tS + lane_off + c, sv);
           tmem_ld_wait();
-          if (k0 + c + 31 > vis_all) fwd_mask32(sv, row_lim - (k0 + c));
+          if (KP) {
+            const int key = k0 + c + lane;
+            const uint32_t padm = __ballot_sync(0xffffffffu, key < S && key_pad[(int64_t)b * S + key] != 0);
+            if (k0 + c + 31 > vis_all || padm) fwd_mask32_pad(sv, row_lim - (k0 + c), padm);
+          } else if (k0 + c + 31 > vis_all) fwd_mask32(sv, row_lim - (k0 + c));
           float m4[4] = {sv[0], sv[1], sv[2], sv[3]};
 #pragma unroll
           for (int e = 4; e < 32; e += 4) {
@@ -246,7 +257,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mx = fmaxf(mx, xm[(half ^ 1) * AT_BM + rr]);
         }
         const float m_new = fmaxf(m, mx * LOG2E_F);
-        const float alpha = ex2f(m - m_new);
+        const float alpha = (KP && m_new == -INFINITY) ? 1.f : ex2f(m - m_new);
         // P (single TMEM buffer) is free once the previous tile's PV has been issued AND completed; its result O_{j-1} is then ready too
         if (tc > 0) { mbar_wait(o_full((tc - 1) & 1), (uint32_t)((tc - 1) >> 1) & 1u); tc_fence_after(); }
         // ---- pass 2: P = exp2(S log2e - m_new), row sum, dropout, packed bf16 back to TMEM
@@ -274,9 +285,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(s_free);
           }
-          if (k0 + c + 31 > vis_all) fwd_mask32(sv, row_lim - (k0 + c));
+          if (KP) {
+            const int key = k0 + c + lane;
+            const uint32_t padm = __ballot_sync(0xffffffffu, key < S && key_pad[(int64_t)b * S + key] != 0);
+            if (k0 + c + 31 > vis_all || padm) fwd_mask32_pad(sv, row_lim - (k0 + c), padm);
+          } else if (k0 + c + 31 > vis_all) fwd_mask32(sv, row_lim - (k0 + c));
           float r4[4] = {0.f, 0.f, 0.f, 0.f};
-          const float neg_m = -m_new;
+          const float neg_m = (KP && m_new == -INFINITY) ? 0.f : -m_new;     // (a row whose keys so far are all padded: exp2(-inf - 0) = 0)
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             ffma2(sv[e], sv[e + 1], LOG2E_F, neg_m);
@@ -404,7 +419,7 @@ static int make_qkv_map(CUtensorMap* m, const void* p, int B, int rows, int HP, 
 }
 
 int bpm_xattn_tc_supported(const bpm_attn_t* a) {
-  return a->dtype == BPM_BF16 && a->dhp == AT_DH && a->key_pad == nullptr;
+  return a->dtype == BPM_BF16 && a->dhp == AT_DH;
 }
 
 int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const void* v, void* out, float* lse, cudaStream_t stream) {
@@ -418,17 +433,19 @@ int bpm_xattn_fwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, AT_BN, a->ld_kv))) return rc;
   size_t smem = AttnFwdSmem::TOTAL + 1024;
   // 0: no dropout, row sums through a ones column of V (needs two free padding columns);  1: dropout;  2: no dropout, no ones column
-  const int dm = a->drop.p > 0.f ? 1 : ((a->dh <= AF_PAD0 && !(bpm_debug_get(1) & 8192)) ? 0 : 2);
+  const bool kp = a->key_pad != nullptr;
+  const int dm = a->drop.p > 0.f ? 1 : ((!kp && a->dh <= AF_PAD0 && !(bpm_debug_get(1) & 8192)) ? 0 : 2);
   const int sw = (dm == 0 && !(bpm_debug_get(1) & 32768)) ? 8 : 4;
-  auto kern = dm == 1 ? attn_fwd_tc_kernel<true, false, 4>
-                      : (dm == 0 ? (sw == 8 ? attn_fwd_tc_kernel<false, true, 8> : attn_fwd_tc_kernel<false, true, 4>) : attn_fwd_tc_kernel<false, false, 4>);
+  auto kern = kp ? (dm == 1 ? attn_fwd_tc_kernel<true, false, 4, true> : attn_fwd_tc_kernel<false, false, 4, true>)
+                 : (dm == 1 ? attn_fwd_tc_kernel<true, false, 4>
+                            : (dm == 0 ? (sw == 8 ? attn_fwd_tc_kernel<false, true, 8> : attn_fwd_tc_kernel<false, true, 4>) : attn_fwd_tc_kernel<false, false, 4>));
   CUtensorMap to;
   if ((rc = make_qkv_map(&to, out, a->B, a->T, HP, 32))) return rc;                      // output: {32 columns, 32 rows} store boxes
   if (int rc2 = bpm_func_smem((const void*)kern, (int)smem, "xattn_fwd_tc")) return rc2;
   const int n_items = a->B * a->H * bpm_cdiv(a->T, AT_BM);
   const int ctas = min(bpm_num_sms(), bpm_cdiv(n_items, AF_GROUPS));
   cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AF_THREADS(sw)), smem, stream, tq, tk, tv, to, lse, a->B, a->T, a->S, a->H,
-                              a->mask_off, a->drop, a->drop_bits);
+                              a->mask_off, a->drop, a->drop_bits, a->key_pad);
   if (le != cudaSuccess) { bpm_set_error("xattn_fwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
 }
@@ -577,7 +594,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const int bits_tma,
                    const float* __restrict__ ws, bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T,
                    int S, int H, int mask_off, bpm_dropout_t drop, const uint32_t* __restrict__ drop_bits, const int ld_dkv, const int dbg,
-                   unsigned long long* __restrict__ trace) {
+                   unsigned long long* __restrict__ trace, const uint8_t* __restrict__ key_pad) {
   int tr_n = 0;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -906,18 +923,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           continue;
         }
-        const bool key_oob = key >= S;
+        // a padded key behaves like a key beyond S: probability 0, dS = 0, so dK = dV = 0 for its row
+        const bool key_oob = key >= S || (key_pad != nullptr && key_pad[(int64_t)b * S + key] != 0);
+        const bool any_pad = key_pad != nullptr && __any_sync(0xffffffffu, key_oob);
         // element index of (query q, key) in the [B*H, T, S] probability tensor = (bh*T + q)*S + key
         const uint64_t e_row = (uint64_t)bh * (uint64_t)T * (uint64_t)S + (uint64_t)min(key, S - 1);
         for (int i = imin; i < nq; i++, pc++) {
           const int q0 = i * 128;
           const int pb = pc & 1, qs = pc % AB_QD_STAGES;
           const bool diag = (mask_off >= 0) && (j * 128 + 127 > q0 + mask_off);
-          const bool masked = diag || (j * 128 + 127 >= S);
+          const bool masked = diag || (j * 128 + 127 >= S) || any_pad;
           const int cmin = key - mask_off - q0;               // columns < cmin are masked for this key row (diag tiles only)
           // warp-uniform view: 16-query sub-chunks starting at or beyond cmin_hi (the last key row's cmin) need no mask arithmetic
           const int cmin_hi = j * 128 + quarter * 32 + 31 - mask_off - q0;
-          const bool warp_oob = j * 128 + quarter * 32 + 31 >= S;
+          const bool warp_oob = j * 128 + quarter * 32 + 31 >= S || any_pad;
           uint8_t* const dtile = base_gen + AttnBwdSmem::DST + pb * 32768 + row_off;
           // keep bits written by the forward: word (query, 32-key group).  Fast path: the TMA producer staged the 128 x 4-word tile of
           // this pair next to Q / dO (one broadcast LDS per column); otherwise each lane fetches the words of its columns (32 per word).
@@ -1079,7 +1098,7 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
   if (int rc2 = bpm_func_smem((const void*)kern, (int)smem, "xattn_bwd_tc")) return rc2;
   const int ctas = min(a->B * a->H, bpm_num_sms());
   cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AB_THREADS(cw)), smem, stream, tq, tk, tv, tg, tb, tdq, tdk, tdv, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
-                                                         a->mask_off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr());
+                                                         a->mask_off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr(), a->key_pad);
   if (le != cudaSuccess) { bpm_set_error("xattn_bwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   return BPM_OK;
 }

@@ -793,3 +793,79 @@ class HeadEngine:
             o.gemm(dhpre[i], W["h"][i], dcat[:, i * Dp:(i + 1) * Dp], B, Dp, Dp, tb=1, residual=dcat[:, i * Dp:(i + 1) * Dp])
             o.gemm(dzpre[i], W["zg"][i], dcat, B, n * Dp, Dp, tb=1, residual=dcat)
         return dcat
+
+
+# ============================================================================================== audio encoder (mmtr.py:93-108)
+class AudioEncoderEngine:
+    """AudioEncoder of the 4-modality model: Conv1d(C, C, k=128, stride=2) x 2 + AdaptiveAvgPool1d(Tp) on a raw spectrogram (B, C, T_raw).
+    Each strided convolution is an implicit GEMM with K = 128 * C (im2col rows -> the tensor-core GEMM); activations are time-major rows
+    [B*T, C].  forward() writes the pooled features straight into the caller's staged input rows (pitch = that buffer's)."""
+    KW, STRIDE = 128, 2
+
+    def __init__(self, ops, C=96, Tp=200, dtype=torch.bfloat16):
+        self.ops, self.C, self.Tp, self.T_ = ops, C, Tp, dtype
+        z = ops.zeros
+        K = self.KW * C
+        self.W = [dict(w=z((C, K), dtype), b=z((C,), torch.float32)) for _ in range(2)]
+        self.G = [dict(w=z((C, K), torch.float32), b=z((C,), torch.float32)) for _ in range(2)]
+        self.arena = Arena(ops)
+
+    def param_shapes(self):
+        C = self.C
+        return {"conv_layers.0.weight": (C, C, self.KW), "conv_layers.0.bias": (C,), "conv_layers.1.weight": (C, C, self.KW), "conv_layers.1.bias": (C,)}
+
+    def pack(self, params, pfx=""):
+        for i in range(2):
+            self.ops.conv1d_pack_weight(params["%sconv_layers.%d.weight" % (pfx, i)], self.W[i]["w"])
+            self.W[i]["b"].copy_(params["%sconv_layers.%d.bias" % (pfx, i)])
+
+    def zero_grads(self):
+        for g in self.G:
+            self.ops.zero_(g["w"])
+            self.ops.zero_(g["b"])
+
+    def unpack_grads(self, grads, pfx="", accumulate=False):
+        for i in range(2):
+            self.ops.conv1d_unpack_wgrad(self.G[i]["w"], grads["%sconv_layers.%d.weight" % (pfx, i)], accumulate)
+            gb = grads["%sconv_layers.%d.bias" % (pfx, i)]
+            gb.copy_(gb + self.G[i]["b"] if accumulate else self.G[i]["b"])
+
+    def out_len(self, T):
+        return (T - self.KW) // self.STRIDE + 1
+
+    def forward(self, audio, out_rows):
+        """audio fp32 (B, C, T_raw) (channel-major, as the reference's Conv1d takes it); out_rows [B*Tp, ld >= C] receives the features"""
+        o, A, C = self.ops, self.arena, self.C
+        B, Cc, T0 = audio.shape
+        assert Cc == C and T0 >= 3 * self.KW + 2, "AudioEncoder: (B, %d, T >= %d) expected" % (C, 3 * self.KW + 2)
+        T1 = self.out_len(T0)
+        T2 = self.out_len(T1)
+        x0 = A.get("x0", (B * T0, C), self.T_)
+        o.stage_rows(audio.permute(0, 2, 1), x0, T0)                            # (B, C, T) -> time-major rows [B*T, C]
+        col1 = A.get("col1", (B * T1, self.KW * C), self.T_)
+        o.conv1d_im2col(x0, B, T0, C, self.KW, self.STRIDE, col1, T1)
+        y1 = A.get("y1", (B * T1, C), self.T_)
+        o.gemm(col1, self.W[0]["w"], y1, B * T1, C, self.KW * C, bias=self.W[0]["b"])
+        col2 = A.get("col2", (B * T2, self.KW * C), self.T_)
+        o.conv1d_im2col(y1, B, T1, C, self.KW, self.STRIDE, col2, T2)
+        y2 = A.get("y2", (B * T2, C), self.T_)
+        o.gemm(col2, self.W[1]["w"], y2, B * T2, C, self.KW * C, bias=self.W[1]["b"])
+        o.adaptive_pool_fwd(y2, B, T2, C, self.Tp, out_rows)
+        self.sv = dict(B=B, T1=T1, T2=T2, col1=col1, col2=col2)
+
+    def backward(self, dout):
+        """dout fp32 [B*Tp, ld >= C]: gradient of the pooled features.  Accumulates the weight / bias gradients (the spectrogram gets none)."""
+        o, A, C, sv = self.ops, self.arena, self.C, self.sv
+        B, T1, T2, K = sv["B"], sv["T1"], sv["T2"], self.KW * C
+        dy2 = A.get("dy2", (B * T2, C), torch.float32)
+        o.adaptive_pool_bwd(dout, B, T2, C, self.Tp, dy2)
+        g2 = A.get("g2", (B * T2, C), self.T_)
+        o.cast_drop(dy2, g2, None)
+        o.gemm(g2, sv["col2"], self.G[1]["w"], C, K, B * T2, ta=1, tb=1, accumulate=True, colsum=self.G[1]["b"])     # dW2 = dY2^T col2
+        dcol2 = A.get("dcol2", (B * T2, K), self.T_)
+        o.gemm(g2, self.W[1]["w"], dcol2, B * T2, K, C, tb=1)                                                       # dcol2 = dY2 W2
+        dy1 = A.get("dy1", (B * T1, C), torch.float32)
+        o.conv1d_col2im(dcol2, B, T1, C, self.KW, self.STRIDE, T2, dy1)
+        g1 = A.get("g1", (B * T1, C), self.T_)
+        o.cast_drop(dy1, g1, None)
+        o.gemm(g1, sv["col1"], self.G[0]["w"], C, K, B * T1, ta=1, tb=1, accumulate=True, colsum=self.G[0]["b"])     # dW1 = dY1^T col1

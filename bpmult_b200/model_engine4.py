@@ -12,7 +12,7 @@ import os
 
 import torch
 
-from .engine import Arena, Dims, EncoderEngine, HeadEngine, SeqGmuEngine, round_up
+from .engine import Arena, AudioEncoderEngine, Dims, EncoderEngine, HeadEngine, SeqGmuEngine, round_up
 from .model_engine import ENC_NAMES, HEAD_ORDER, TARGETS, WAVE1, Lanes, attn_dropout_for
 from .ops import Drop
 
@@ -57,6 +57,8 @@ class MMTrVaptEngine:
             self.gmu[m + "_m"] = SeqGmuEngine(ops, D, dtype, True, sh, "gmu_%s_m" % m)
             self.gmu[m] = SeqGmuEngine(ops, D, dtype, True, sh, "gmu_%s" % m)
         self.head = HeadEngine(ops, D, 4, args.n_classes, out_dropout=args.out_dropout)
+        # mmtr.py:307,452: the AudioEncoder (raw spectrogram (B, orig_d_a, T_raw) -> (B, orig_d_a, 200)); off = audio arrives as features
+        self.audio = AudioEncoderEngine(ops, C=args.orig_d_a, Tp=NV["a"], dtype=dtype) if getattr(args, "audio_encoder", False) else None
         z = ops.zeros
         self.Wproj = {m: (z((self.d.Dp, self.Kp[m]), dtype) if self.orig[m] != D else None) for m in "lav"}
         self.Gproj = {m: (z((self.d.Dp, self.Kp[m]), torch.float32) if self.orig[m] != D else None) for m in "lav"}
@@ -82,6 +84,9 @@ class MMTrVaptEngine:
         for n, (ti, to) in TRANSFM.items():
             s["transfm_%s.weight" % n] = (NV[to], NV[ti])
             s["transfm_%s.bias" % n] = (NV[to],)
+        if self.audio is not None:
+            for k, v in self.audio.param_shapes().items():
+                s["audio_enc." + k] = v
         return s
 
     def unused_params(self):
@@ -101,6 +106,8 @@ class MMTrVaptEngine:
                 o.pack_matrix(w.view(w.shape[0], w.shape[1]), self.Wproj[m])
         o.pack_matrix(params["proj_poster.weight"], self.Wpost)
         o.batch_end()
+        if self.audio is not None:
+            self.audio.pack(params, "audio_enc.")
         for n in TRANSFM:
             self.Wt[n][0].copy_(params["transfm_%s.weight" % n])
             self.Wt[n][1].copy_(params["transfm_%s.bias" % n])
@@ -115,6 +122,8 @@ class MMTrVaptEngine:
             if self.Gproj[m] is not None:
                 self.ops.zero_(self.Gproj[m])
         self.ops.zero_(self.Gpost)
+        if self.audio is not None:
+            self.audio.zero_grads()
         for gw, gb in self.Gt.values():
             self.ops.zero_(gw)
             self.ops.zero_(gb)
@@ -137,6 +146,8 @@ class MMTrVaptEngine:
                 o.unpack_matrix(self.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=accumulate)
         o.unpack_matrix(self.Gpost, grads["proj_poster.weight"], accumulate=accumulate)
         o.batch_end()
+        if self.audio is not None:
+            self.audio.unpack_grads(grads, "audio_enc.", accumulate)
         for n in TRANSFM:
             for src, key in ((self.Gt[n][0], "weight"), (self.Gt[n][1], "bias")):
                 dst = grads["transfm_%s.%s" % (n, key)]
@@ -169,9 +180,12 @@ class MMTrVaptEngine:
         ln.fork()
         for m in "lav":
             drop = Drop(self.args.embed_dropout, seed, seed_ptr, 7) if (m == "l" and training and self.args.embed_dropout > 0) else None
-            X = A.get("X_" + m, (B * NV[m], self.Kp[m]), self.T_)
+            X = A.get("X_" + m, (B * NV[m], self.Kp[m]), self.T_, zero=True)
             with ln.on(self.mod_lane[m]):
-                o.stage_rows(feats[m], X, NV[m], drop)                          # transpose / embed-dropout / zero-pad to num_vectors_m
+                if m == "a" and self.audio is not None:
+                    self.audio.forward(feats[m], X)                             # raw spectrogram (B, C, T_raw) -> 200 feature rows (mmtr.py:452)
+                else:
+                    o.stage_rows(feats[m], X, NV[m], drop)                      # transpose / embed-dropout / zero-pad to num_vectors_m
                 self.X[m] = X
                 if self.Wproj[m] is not None:
                     P[m] = A.get("P_" + m, (B * NV[m], d.Dp), self.T_)
@@ -303,10 +317,16 @@ class MMTrVaptEngine:
                     g = sh.get("dPc_" + m, (B * NV[m], d.Dp), self.T_)
                     o.cast_drop(dP[m], g, None)
                     o.gemm(g, self.X[m], self.Gproj[m], d.Dp, self.Kp[m], B * NV[m], ta=1, tb=1, accumulate=True)     # dW = dP^T X
-                    if d_inputs is not None and m in d_inputs:
+                    enc_a = m == "a" and self.audio is not None               # the audio encoder sits upstream of this projection
+                    if enc_a or (d_inputs is not None and m in d_inputs):
                         dX = sh.get("dX_" + m, (B * NV[m], self.Kp[m]), f32)
                         o.gemm(g, self.Wproj[m], dX, B * NV[m], self.Kp[m], d.Dp, tb=1)
-                        self._unstage(m, dX, d_inputs[m])
+                        if enc_a:
+                            self.audio.backward(dX)
+                        else:
+                            self._unstage(m, dX, d_inputs[m])
+                elif m == "a" and self.audio is not None:
+                    self.audio.backward(dP[m])
                 elif d_inputs is not None and m in d_inputs:
                     self._unstage(m, dP[m], d_inputs[m])
         ln.join()

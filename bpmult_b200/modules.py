@@ -738,7 +738,10 @@ def _model_fwd(mod, training, feats, params, n_gate):
     names = [n for n, _ in mod.trunk_named_parameters()]
     dims = (("text", mod.orig_d_l), ("img", mod.orig_d_v), ("audio", mod.orig_d_a))
     for (nm, dim), t in zip(dims, feats):
-        assert t.dim() == 3 and t.shape[2] == dim, "%s features must be (B, T, %d)" % (nm, dim)
+        if nm == "audio" and getattr(mod, "with_audio_enc", False):
+            assert t.dim() == 3 and t.shape[1] == dim, "raw audio must be (B, %d, T_raw)" % dim
+        else:
+            assert t.dim() == 3 and t.shape[2] == dim, "%s features must be (B, T, %d)" % (nm, dim)
     eng.pack({n: p.detach() for n, p in zip(names, params)})
     logits, z = eng.forward(*[t.detach().float() for t in feats], training=training, seed=_next_seed())
     mod._bpm_gen = _stamp(eng)
@@ -812,6 +815,81 @@ def _mmtrvat_backward(ctx, g, _gz):
 _mmtrvat_op.register_autograd(_mmtrvat_backward, setup_context=_model_setup)
 
 
+class AudioEncoder(nn.Module):
+    """mmtr.py:93-108: Conv1d(96, 96, 128, stride=2) x 2 + AdaptiveAvgPool1d(200) on a raw spectrogram (B, 96, T_raw) -> (B, 96, 200).
+    Same parameter names (`conv_layers.{0,1}.{weight,bias}`) and initialisation as the reference.  Inside the 4-modality model
+    (`audio_encoder=True`) it runs as part of the trunk's schedule (engine.AudioEncoderEngine: im2col rows + tensor-core GEMMs);
+    the standalone forward is a registered op of its own."""
+
+    def __init__(self, args=None, channels=96, out_len=200):
+        super().__init__()
+        self.args = args
+        c = getattr(args, "orig_d_a", channels) if args is not None else channels
+        self.conv_layers = nn.ModuleList([nn.Conv1d(c, c, 128, stride=2), nn.Conv1d(c, c, 128, stride=2), nn.AdaptiveAvgPool1d(out_len)])
+        self.channels, self.out_len = c, out_len
+        self.precision = "bf16"
+        self._eng = None
+
+    def forward(self, x):
+        return torch.ops.bpmult_b200.audio_encoder(_handle(self), x, [p for _, p in self.named_parameters()])
+
+
+def _audio_engine(mod, device):
+    ops = _ops_for(device)
+    dt = _DT[mod.precision]
+    if mod._eng is None or mod._eng.T_ != dt or mod._eng.ops is not ops:
+        mod._eng = E.AudioEncoderEngine(ops, C=mod.channels, Tp=mod.out_len, dtype=dt)
+    return mod._eng
+
+
+@torch.library.custom_op("bpmult_b200::audio_encoder", mutates_args=())
+def _audio_op(handle: int, x: Tensor, params: List[Tensor]) -> Tensor:
+    mod = _mod(handle)
+    eng = _audio_engine(mod, x.device)
+    eng.pack({n: p.detach() for (n, _), p in zip(mod.named_parameters(), params)})
+    B = x.shape[0]
+    out = eng.ops.zeros((B * mod.out_len, mod.channels), torch.float32)
+    eng.forward(x.detach().float(), out)
+    mod._bpm_gen = _stamp(eng)
+    return out.view(B, mod.out_len, mod.channels).permute(0, 2, 1).clone()
+
+
+@_audio_op.register_fake
+def _(handle, x, params):
+    mod = _mod(handle)
+    return x.new_empty((x.shape[0], mod.channels, mod.out_len), dtype=torch.float32)
+
+
+@torch.library.custom_op("bpmult_b200::audio_encoder_bwd", mutates_args=())
+def _audio_bwd_op(handle: int, gen: int, g: Tensor) -> List[Tensor]:
+    mod = _mod(handle)
+    eng = mod._eng
+    _check_gen(eng, gen, "AudioEncoder")
+    B = g.shape[0]
+    eng.zero_grads()
+    dout = g.float().permute(0, 2, 1).contiguous().view(B * mod.out_len, mod.channels)
+    eng.backward(dout)
+    grads = {n: torch.zeros_like(p) for n, p in mod.named_parameters()}
+    eng.unpack_grads(grads)
+    return [grads[n] for n, _ in mod.named_parameters()]
+
+
+@_audio_bwd_op.register_fake
+def _(handle, gen, g):
+    return [g.new_empty(tuple(p.shape), dtype=torch.float32) for _, p in _mod(handle).named_parameters()]
+
+
+def _audio_setup(ctx, inputs, output):
+    ctx.handle, ctx.gen = inputs[0], _mod(inputs[0])._bpm_gen
+
+
+def _audio_backward(ctx, g):
+    return (None, None, list(torch.ops.bpmult_b200.audio_encoder_bwd(ctx.handle, ctx.gen, g.contiguous())))     # (no gradient for the spectrogram)
+
+
+_audio_op.register_autograd(_audio_backward, setup_context=_audio_setup)
+
+
 class AudioFeatures(nn.Module):
     """stands in for mmtr.AudioEncoder (mmtr.py:452): the audio arrives as post-encoder features (B, T_a, orig_d_a)."""
 
@@ -827,9 +905,13 @@ class MultiprojectionMMTransformerGMUClf(nn.Module):
     txt (B, L <= 512, orig_d_l) float, img (B, T_v <= 200, orig_d_v), audio (B, T_a <= 200, orig_d_a) post-encoder features,
     poster (B, orig_d_p).  Sequences are zero-padded to 512 / 200 / 200 inside (mmtr.py:371-373, 461-466)."""
 
-    def __init__(self, args, precision="bf16"):
+    def __init__(self, args, precision="bf16", audio_encoder=None):
+        """audio_encoder (default: `args.audio_encoder`, else False): True = the reference's AudioEncoder is part of the model and `audio`
+        is a raw spectrogram (B, orig_d_a, T_raw) as at mmtr.py:452; False = `audio` arrives as post-encoder features (B, T_a, orig_d_a)."""
         super().__init__()
         from .model_engine4 import BIPROJ, NV, TRANSFM
+        if audio_encoder is not None:
+            args = type(args)(**dict(vars(args), audio_encoder=bool(audio_encoder)))
         self.args = args
         self.orig_d_l, self.orig_d_v, self.orig_d_a, self.orig_d_p = args.orig_d_l, args.orig_d_v, args.orig_d_a, args.orig_d_p
         self.d_l = self.d_a = self.d_v = D = args.hidden_sz
@@ -840,7 +922,8 @@ class MultiprojectionMMTransformerGMUClf(nn.Module):
             raise NotImplementedError("hybrid=True is broken in the reference (list-vs-varargs call sites, mmtr.py:572); not implemented")
         self.precision = precision
         self.enc = FeatureEncoder(args)
-        self.audio_enc = AudioFeatures(args)
+        self.with_audio_enc = bool(getattr(args, "audio_encoder", False))
+        self.audio_enc = AudioEncoder(args) if self.with_audio_enc else AudioFeatures(args)         # mmtr.py:307
         self.proj_poster = nn.Linear(self.orig_d_p, D, bias=False)             # construction order = reference (mmtr.py:310-378)
         mk = lambda: GatedMultimodalLayerFeatures(D, D, D)
         self.gmu_l_m, self.gmu_v_m, self.gmu_a_m = mk(), mk(), mk()
@@ -882,7 +965,7 @@ class MultiprojectionMMTransformerGMUClf(nn.Module):
 
     def forward(self, txt, mask, segment, img, audio, poster, output_gate=False):
         x_l = self.enc(txt, mask, segment)
-        x_a = self.audio_enc(audio)
+        x_a = audio if self.with_audio_enc else self.audio_enc(audio)        # (the encoder runs inside the trunk's schedule)
         logits, z = torch.ops.bpmult_b200.mmtrvapt(_handle(self), self.training, x_l, img, x_a, poster,
                                                    [p for _, p in self.trunk_named_parameters()])
         return (logits, z) if output_gate else logits
@@ -892,7 +975,7 @@ class MultiprojectionMMTransformerGMUClf(nn.Module):
 def _mmtrvapt_op(handle: int, training: bool, txt: Tensor, img: Tensor, audio: Tensor, poster: Tensor, params: List[Tensor]) -> Tuple[Tensor, Tensor]:
     mod = _mod(handle)
     assert poster.dim() == 2 and poster.shape[1] == mod.orig_d_p, "poster must be (B, %d)" % mod.orig_d_p
-    assert txt.shape[1] <= mod.num_vectors_l and audio.shape[1] <= mod.num_vectors_a and img.shape[1] <= mod.num_vectors_v, \
+    assert txt.shape[1] <= mod.num_vectors_l and (mod.with_audio_enc or audio.shape[1] <= mod.num_vectors_a) and img.shape[1] <= mod.num_vectors_v, \
         "a sequence exceeds its fixed length (the reference raises on a negative pad size, mmtr.py:431-441)"
     return _model_fwd(mod, training, (txt, img, audio, poster), params, 4)
 

@@ -327,6 +327,34 @@ class CudaOps:
                                           0 if dW is None else dW.data_ptr(), 0 if db is None else db.data_ptr(), B, Tin, Tout, D, x.shape[1],
                                           self._s()), "timelin_bwd")
 
+    # ------------------------------------------------------------------ AudioEncoder layout kernels (mmtr.py:93-108)
+    def conv1d_im2col(self, x, B, Tin, C, KW, stride, col, Tout):
+        """x [B*Tin, ldx] rows -> col [B*Tout, KW*C] (tap-major K)"""
+        assert x.dtype == col.dtype and col.shape[1] == KW * C and col.is_contiguous()
+        self._ck(self.lib.bpm_conv1d_im2col(x.data_ptr(), _dt(x), B, Tin, C, x.stride(0), KW, stride, col.data_ptr(), Tout, self._s()), "conv1d_im2col")
+
+    def conv1d_col2im(self, dcol, B, Tin, C, KW, stride, Tout, dx):
+        assert dx.dtype == torch.float32 and dcol.is_contiguous()
+        self._ck(self.lib.bpm_conv1d_col2im(dcol.data_ptr(), _dt(dcol), B, Tin, C, KW, stride, Tout, dx.data_ptr(), dx.stride(0), self._s()), "conv1d_col2im")
+
+    def conv1d_pack_weight(self, W, Wp):
+        """W fp32 (Cout, Cin, KW) -> Wp (Cout, KW*Cin), K tap-major"""
+        Cout, Cin, KW = W.shape
+        assert W.dtype == torch.float32 and W.is_contiguous() and Wp.is_contiguous()
+        self._ck(self.lib.bpm_conv1d_pack_weight(W.data_ptr(), Cout, Cin, KW, Wp.data_ptr(), _dt(Wp), self._s()), "conv1d_pack_weight")
+
+    def conv1d_unpack_wgrad(self, gWp, gW, accumulate=False):
+        Cout, Cin, KW = gW.shape
+        assert gWp.dtype == torch.float32 and gW.dtype == torch.float32 and gW.is_contiguous() and gWp.is_contiguous()
+        self._ck(self.lib.bpm_conv1d_unpack_wgrad(gWp.data_ptr(), Cout, Cin, KW, gW.data_ptr(), int(accumulate), self._s()), "conv1d_unpack_wgrad")
+
+    def adaptive_pool_fwd(self, x, B, T, C, Tp, y):
+        self._ck(self.lib.bpm_adaptive_pool_fwd(x.data_ptr(), _dt(x), B, T, C, x.stride(0), Tp, y.data_ptr(), _dt(y), y.stride(0), self._s()), "adaptive_pool_fwd")
+
+    def adaptive_pool_bwd(self, dy, B, T, C, Tp, dx):
+        assert dy.dtype == torch.float32 and dx.dtype == torch.float32
+        self._ck(self.lib.bpm_adaptive_pool_bwd(dy.data_ptr(), B, T, C, Tp, dy.stride(0), dx.data_ptr(), dx.stride(0), self._s()), "adaptive_pool_bwd")
+
     def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t, lr_t=None):
         self._ck(self.lib.bpm_adam_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(), float(lr), float(beta1),
                                         float(beta2), float(eps), float(grad_scale), step_t.data_ptr(),

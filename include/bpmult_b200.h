@@ -213,6 +213,20 @@ int bpm_timelin_fwd(int dtype, const void* x, const float* W, const float* bias,
 int bpm_timelin_bwd(int x_dtype, const float* dy, const void* x, const float* W, float* dx, int accumulate_dx, float* dW, float* db,
                     int B, int Tin, int Tout, int D, int ld, void* stream);
 
+/* ---- AudioEncoder of the 4-modality model: mmtr.py:93-108  Conv1d(C, C, k=KW, stride) x 2 + AdaptiveAvgPool1d(Tp) --------------------
+ * The strided convolution is an implicit GEMM (K = KW*C, run by bpm_gemm on tensor cores); these are the layout kernels around it,
+ * on time-major rows [B*T, C] (C % 8 == 0):
+ *   im2col   col[(b*Tout + t), k*C + c] = x[(b*Tin + stride*t + k), c],  Tout = (Tin - KW)/stride + 1  (col has x's dtype, pitch KW*C)
+ *   col2im   dx[(b*Tin + u), c] = sum_{k: (u-k) % stride == 0} dcol[(b*Tout + (u-k)/stride), k*C + c]  (fp32 out, a gather: no atomics)
+ *   weights  Wp[co, k*Cin + ci] = W[co, ci, k] (nn.Conv1d layout, fp32 -> dst dtype) and the inverse for the weight gradient
+ *   pooling  y[(b*Tp + i), c] = mean_{t in [floor(i*T/Tp), ceil((i+1)*T/Tp))} x[(b*T + t), c]  (torch AdaptiveAvgPool1d) and its backward */
+int bpm_conv1d_im2col(const void* x, int dtype, int B, int Tin, int C, int ldx, int KW, int stride, void* col, int Tout, void* stream);
+int bpm_conv1d_col2im(const void* dcol, int dtype, int B, int Tin, int C, int KW, int stride, int Tout, float* dx, int lddx, void* stream);
+int bpm_conv1d_pack_weight(const float* W, int Cout, int Cin, int KW, void* Wp, int dst_dtype, void* stream);
+int bpm_conv1d_unpack_wgrad(const float* gWp, int Cout, int Cin, int KW, float* gW, int accumulate, void* stream);
+int bpm_adaptive_pool_fwd(const void* x, int x_dtype, int B, int T, int C, int ldx, int Tp, void* y, int y_dtype, int ldy, void* stream);
+int bpm_adaptive_pool_bwd(const float* dy, int B, int T, int C, int Tp, int lddy, float* dx, int lddx, void* stream);
+
 /* ---- loss: train.py:99-106,333 nn.BCEWithLogitsLoss(pos_weight), mean over (B, C) -----------------------------
  * loss (fp32 scalar, overwritten) and dlogits = dloss/dlogits * grad_scale (fp32 [B, ldl]) in one launch. */
 int bpm_bce_fwd_bwd(const float* logits, int ldl, const float* targets, const float* pos_weight, int B, int C,

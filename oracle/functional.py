@@ -251,6 +251,13 @@ def time_linear(sd, name, h):
     return F.linear(h.permute(2, 1, 0), sd["transfm_%s.weight" % name], sd["transfm_%s.bias" % name]).permute(2, 1, 0)
 
 
+def audio_encoder(sd, pfx, x, out_len=200):
+    """models/mmtr.py:93-108 AudioEncoder: Conv1d(96, 96, 128, stride=2) x 2 + AdaptiveAvgPool1d(200); x (B, 96, T_raw) -> (B, 96, 200)."""
+    x = F.conv1d(x, sd[pfx + "conv_layers.0.weight"], sd[pfx + "conv_layers.0.bias"], stride=2)
+    x = F.conv1d(x, sd[pfx + "conv_layers.1.weight"], sd[pfx + "conv_layers.1.bias"], stride=2)
+    return F.adaptive_avg_pool1d(x, out_len)
+
+
 def mmtrvapt_forward(sd, cfg, txt, img, audio, poster, nv=(512, 200, 200)):
     """models/mmtr.py:444-583 MultiprojectionMMTransformerGMUClf.forward, hybrid = False, dropout = 0, BERT and AudioEncoder bypassed
     (txt float (B, T_l, orig_d_l); audio float (B, T_a, orig_d_a) post-encoder); wave-2 encoders are biprojection layers (:342-353)."""
@@ -264,6 +271,8 @@ def mmtrvapt_forward(sd, cfg, txt, img, audio, poster, nv=(512, 200, 200)):
         return _pad_time(x.permute(2, 0, 1), n)
 
     p_l = proj(txt, "proj_l.weight", cfg.orig_d_l, nl)
+    if "audio_enc.conv_layers.0.weight" in sd:                             # :452 x_a = self.audio_enc(audio): raw (B, 96, T_raw) -> (B, 96, 200)
+        audio = audio_encoder(sd, "audio_enc.", audio).transpose(1, 2)
     p_a = proj(audio, "proj_a.weight", cfg.orig_d_a, na)
     p_v = proj(img, "proj_v.weight", cfg.orig_d_v, nvv)
     post = F.linear(poster, sd["proj_poster.weight"])                      # :486

@@ -81,9 +81,10 @@ def load_reference(patch_cuda=True):
 
         def forward(self, audio):
             return audio.transpose(1, 2)
+    audio_real = mmtr.AudioEncoder                                               # the unmodified class, for the AudioEncoder goldens
     mmtr.AudioEncoder = AudioFeat
 
-    _LOADED = Namespace(root=root, pe=pe, mha=mha, mmtr=mmtr, tr=tr)
+    _LOADED = Namespace(root=root, pe=pe, mha=mha, mmtr=mmtr, tr=tr, AudioEncoderReal=audio_real)
     return _LOADED
 
 

@@ -87,6 +87,11 @@ def mmtrvapt_shapes(cfg):
     return s
 
 
+def audio_encoder_shapes(C=96, pfx=""):
+    return {pfx + "conv_layers.0.weight": (C, C, 128), pfx + "conv_layers.0.bias": (C,),
+            pfx + "conv_layers.1.weight": (C, C, 128), pfx + "conv_layers.1.bias": (C,)}
+
+
 def mmtrvapt_inputs(cfg, B, T_l, T_a, T_v, seed=2024):
     """text (B, T_l, orig_d_l), video (B, T_v, orig_d_v), audio (B, T_a, orig_d_a) post-encoder features, poster (B, orig_d_p), targets"""
     g = torch.Generator().manual_seed(seed)
@@ -106,7 +111,9 @@ def make_state_dict(shapes, seed, dtype=torch.float32, gain=1.0):
     sd = {}
     for k, shp in shapes.items():
         if len(shp) >= 2:
-            fan_in = shp[1]
+            fan_in = 1
+            for x in shp[1:]:                                      # (conv weights: in_channels * kernel_size; k = 1 for the projections)
+                fan_in *= x
             t = torch.randn(shp, generator=g) * (gain / fan_in ** 0.5)
         elif "layer_norm" in k and k.endswith("weight"):
             t = 1.0 + 0.1 * torch.randn(shp, generator=g)

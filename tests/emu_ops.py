@@ -346,6 +346,39 @@ class EmuOps:
         if db is not None:
             db += g.sum(dim=(0, 2))
 
+    # ------------------------------------------------------------------ AudioEncoder layout kernels
+    def conv1d_im2col(self, x, B, Tin, C, KW, stride, col, Tout):
+        xv = x.view(B, Tin, x.shape[1])[:, :, :C]
+        for t in range(Tout):
+            col.view(B, Tout, KW, C)[:, t] = xv[:, stride * t:stride * t + KW]
+
+    def conv1d_col2im(self, dcol, B, Tin, C, KW, stride, Tout, dx):
+        d = dcol.float().view(B, Tout, KW, C)
+        out = torch.zeros(B, Tin, C)
+        for t in range(Tout):
+            out[:, stride * t:stride * t + KW] += d[:, t]
+        dx.view(B, Tin, dx.shape[1])[:, :, :C] = out
+
+    def conv1d_pack_weight(self, W, Wp):
+        Wp.copy_(W.permute(0, 2, 1).reshape(W.shape[0], -1).to(Wp.dtype))
+
+    def conv1d_unpack_wgrad(self, gWp, gW, accumulate=False):
+        Cout, Cin, KW = gW.shape
+        g = gWp.view(Cout, KW, Cin).permute(0, 2, 1)
+        gW.copy_(gW + g if accumulate else g)
+
+    def adaptive_pool_fwd(self, x, B, T, C, Tp, y):
+        xv = x.float().view(B, T, x.shape[1])[:, :, :C].permute(0, 2, 1)
+        y.view(B, Tp, y.shape[1])[:, :, :C] = torch.nn.functional.adaptive_avg_pool1d(xv, Tp).permute(0, 2, 1).to(y.dtype)
+
+    def adaptive_pool_bwd(self, dy, B, T, C, Tp, dx):
+        d = dy.view(B, Tp, dy.shape[1])[:, :, :C]
+        out = torch.zeros(B, T, C)
+        for i in range(Tp):                                    # torch's AdaptiveAvgPool1d windows: [floor(i*T/Tp), ceil((i+1)*T/Tp))
+            t0, t1 = (i * T) // Tp, -((-(i + 1) * T) // Tp)
+            out[:, t0:t1] += d[:, i:i + 1] / (t1 - t0)
+        dx.view(B, T, dx.shape[1])[:, :, :C] = out
+
     def adam_step(self, param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_t, lr_t=None):
         step = float(step_t.item())
         if lr_t is not None:

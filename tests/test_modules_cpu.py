@@ -233,3 +233,44 @@ def test_mmtrvat_module_autograd_matches_reference_golden():
     assert sorted(n for n, p in m.named_parameters() if p.grad is None) == sorted(rec["nograd"])
     with pytest.raises(Exception):
         m(torch.randn(1, 600, cfg.orig_d_l), None, None, img[:1], audio[:1])        # longer than the fixed 512 steps (mmtr.py:722-732)
+
+
+def test_audio_encoder_module_matches_reference_golden():
+    """mmtr.py:93-108: parameter names, forward and parameter gradients of the standalone module (host logic on the emulation)"""
+    from helpers import check_fingerprints
+    g = load_gold("audio_encoder.pt")["audio_encoder"]
+    m = M.AudioEncoder()
+    m.precision = "fp32"
+    sd = synth.make_state_dict(synth.audio_encoder_shapes(96), g["seed"])
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd)
+    x = synth.randn((2, 96, 900), g["seed"] + 1)
+    y = m(x)
+    (y * synth.randn((2, 96, 200), g["seed"] + 2)).sum().backward()
+    assert Fn.max_rel(y, g["out"]) < 2e-5
+    check_fingerprints({n: p.grad for n, p in m.named_parameters()}, g["pgrad_fp"], 1e-4)
+
+
+def test_mmtrvapt_with_audio_encoder_matches_reference_golden():
+    """the 4-modality model as the reference ships it: raw spectrogram through audio_enc (mmtr.py:307,452) into the trunk"""
+    from helpers import check_fingerprints
+    rec = load_gold("audio_encoder.pt")["mmtrvapt_audio"]
+    cfg = Namespace(**rec["cfg"])
+    m = M.MultiprojectionMMTransformerGMUClf(cfg, precision="fp32")
+    assert m.with_audio_enc
+    shapes = synth.mmtrvapt_shapes(cfg)
+    shapes.update(synth.audio_encoder_shapes(96, "audio_enc."))
+    keys = {k for k in m.state_dict().keys() if not (k.endswith(".version") or k.endswith("_float_tensor"))}
+    assert keys == set(shapes.keys()), sorted(keys ^ set(shapes.keys()))[:8]
+    m.load_state_dict(synth.make_state_dict(shapes, rec["seed"]), strict=False)
+    m.train()
+    B, T_l, T_raw, T_v = rec["dims"]
+    txt, img, _, poster, tgt = synth.mmtrvapt_inputs(cfg, B, T_l, 30, T_v)
+    audio = synth.randn((B, 96, T_raw), rec["seed"] + 5)
+    txt.requires_grad_()
+    logits, z = m(txt, None, None, img, audio, poster, output_gate=True)
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=rec["pos_weight"])(logits, tgt)
+    loss.backward()
+    assert Fn.max_rel(logits, rec["logits"]) < 2e-5 and Fn.max_rel(z, rec["z"]) < 2e-5
+    assert Fn.max_rel(txt.grad, rec["dtxt"]) < 1e-4
+    check_fingerprints({n: p.grad for n, p in m.named_parameters()}, rec["pgrad_fp"], 2e-4)

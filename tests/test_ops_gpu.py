@@ -411,3 +411,29 @@ def test_gemm_bf16_tails_are_clipped(ops, cdt):
     e, c = both(ops, lambda o, A, Bm, big: o.gemm(A, Bm, big[:M, :N], M, N, K), [A, Bm], [big])
     assert max_rel(c[0][:M, :N], e[0][:M, :N]) < tol(cdt)
     assert (c[0][M:] == 7.0).all() and (c[0][:, N:] == 7.0).all()
+
+
+# ------------------------------------------------------------------------------------------------ AudioEncoder layout kernels (mmtr.py:93-108)
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_conv1d_im2col_col2im_pool(ops, dtype):
+    B, Tin, C, KW, st = 2, 300, 96, 128, 2
+    Tout = (Tin - KW) // st + 1
+    x = rnd((B * Tin, C), 90, dtype)
+    (e,), (c,) = both(ops, lambda o, x, col: o.conv1d_im2col(x, B, Tin, C, KW, st, col, Tout), [x], [torch.zeros(B * Tout, KW * C, dtype=dtype)])
+    assert torch.equal(e, c)
+    dcol = rnd((B * Tout, KW * C), 91, dtype)
+    (e,), (c,) = both(ops, lambda o, d, dx: o.conv1d_col2im(d, B, Tin, C, KW, st, Tout, dx), [dcol], [torch.zeros(B * Tin, C)])
+    assert max_rel(c, e) < 1e-5
+    W = rnd((C, C, KW), 92)
+    (e,), (c,) = both(ops, lambda o, W, Wp: o.conv1d_pack_weight(W, Wp), [W], [torch.zeros(C, KW * C, dtype=dtype)])
+    assert torch.equal(e, c)
+    gWp = rnd((C, KW * C), 93)
+    (e,), (c,) = both(ops, lambda o, g, gW: o.conv1d_unpack_wgrad(g, gW, True), [gWp], [rnd((C, C, KW), 94)])
+    assert torch.allclose(e, c, rtol=1e-6, atol=1e-6)
+    for T, Tp in ((255, 200), (80, 200), (400, 200)):                  # down-sampling, up-sampling, exact halving
+        xs = rnd((B * T, C), 95, dtype)
+        (e,), (c,) = both(ops, lambda o, xs, y: o.adaptive_pool_fwd(xs, B, T, C, Tp, y), [xs], [torch.zeros(B * Tp, 128, dtype=dtype)])
+        assert max_rel(c, e) < (1e-6 if dtype == F32 else 8e-3)
+        dy = rnd((B * Tp, 128), 96)
+        (e,), (c,) = both(ops, lambda o, dy, dx: o.adaptive_pool_bwd(dy, B, T, C, Tp, dx), [dy], [torch.zeros(B * T, C)])
+        assert max_rel(c, e) < 1e-5
