@@ -53,11 +53,13 @@ _NEXT_HANDLE = [1]
 
 
 def _handle(mod):
-    h = getattr(mod, "_bpm_handle", None)
-    if h is None:
+    if torch.compiler.is_compiling():                   # traced code reads the handle the constructor (or an earlier eager call) registered
+        return mod._bpm_handle
+    h = mod.__dict__.get("_bpm_handle")
+    if h is None or _HANDLES.get(h) is not mod:         # (a deep copy carries its original's number: it gets its own)
         h = mod._bpm_handle = _NEXT_HANDLE[0]
         _NEXT_HANDLE[0] += 1
-    _HANDLES[h] = mod
+        _HANDLES[h] = mod
     return h
 
 
@@ -74,8 +76,15 @@ def _stamp(eng):
     return eng._fwd_gen
 
 
+def _gen_of(handle, out):
+    """forward generation to remember in an autograd context; -1 (= unchecked) while torch.compile traces with fake tensors, where
+    the number read here would be the trace-time one"""
+    t = out[0] if isinstance(out, (tuple, list)) else out
+    return -1 if torch._subclasses.fake_tensor.is_fake(t) else _mod(handle)._bpm_gen
+
+
 def _check_gen(eng, gen, what):
-    if getattr(eng, "_fwd_gen", None) != gen:
+    if gen >= 0 and getattr(eng, "_fwd_gen", None) != gen:
         raise RuntimeError("bpmult_b200.%s: backward() of a forward whose saved activations have been overwritten by a later forward of "
                            "the same module (the engine keeps ONE set of activation buffers: run backward before the next forward, "
                            "or use a second module instance)" % what)
@@ -170,6 +179,7 @@ class MultiheadAttention(nn.Module):
         self.precision = "bf16"
         self._eng = None
         self.reset_parameters()
+        _handle(self)
 
     def reset_parameters(self):
         nn.init.xavier_uniform_(self.in_proj_weight)
@@ -258,7 +268,7 @@ def _(handle, gen, g, S):
 
 
 def _mha_setup(ctx, inputs, output):
-    ctx.handle, ctx.gen, ctx.S = inputs[0], _mod(inputs[0])._bpm_gen, inputs[3].shape[0]
+    ctx.handle, ctx.gen, ctx.S = inputs[0], _gen_of(inputs[0], output), inputs[3].shape[0]
 
 
 def _mha_backward(ctx, g, _gw):
@@ -313,6 +323,7 @@ class TransformerEncoder(nn.Module):
         self.precision = precision
         self._eng = None
         self.with_embed, self.with_final_ln = True, True
+        _handle(self)
 
     def _engine(self, device):
         ops = _ops_for(device)
@@ -349,6 +360,7 @@ class _LayerRunner:
         enc.precision = layer.precision
         enc._eng = None
         enc.with_embed, enc.with_final_ln = False, False
+        _handle(enc)
         self.enc = enc
 
     def __call__(self, x, x_k, x_v):
@@ -420,7 +432,7 @@ def _(handle, gen, g, S, v_distinct):
 
 def _encoder_setup(ctx, inputs, output):
     handle, training, x_in, x_in_k, x_in_v, params = inputs
-    ctx.handle, ctx.gen = handle, _mod(handle)._bpm_gen
+    ctx.handle, ctx.gen = handle, _gen_of(handle, output)
     ctx.S, ctx.v_distinct = (0 if x_in_k is None else x_in_k.shape[0]), x_in_v is not None
 
 
@@ -444,6 +456,7 @@ class _SeqGmuBase(nn.Module):
         self.x_gate = nn.Linear(size_in1 + size_in2, size_out, bias=False)
         self.precision = "bf16"
         self._eng = None
+        _handle(self)
 
     def forward(self, xs):
         assert self.size_in1 == self.size_in2 == self.size_out, "the fused GMU kernel needs size_in1 == size_in2 == size_out"
@@ -513,7 +526,7 @@ def _(handle, gen, g):
 
 
 def _seq_gmu_setup(ctx, inputs, output):
-    ctx.handle, ctx.gen = inputs[0], _mod(inputs[0])._bpm_gen
+    ctx.handle, ctx.gen = inputs[0], _gen_of(inputs[0], output)
 
 
 def _seq_gmu_backward(ctx, g, _gz):
@@ -536,6 +549,7 @@ class _TextShiftingBase(nn.Module):
             setattr(self, "x%d_gate" % (i + 1), nn.Linear(tot, size_out, bias=False))
         self.size_out = size_out
         self._eng = None
+        _handle(self)
 
     def forward(self, xs):
         n = self.N_IN
@@ -578,6 +592,7 @@ class TextShiftingNLayer(nn.Module):                                  # mmtr.py:
         self.hiddens = nn.ModuleList([nn.Linear(s, size_out, bias=False) for s in self.sizes_in])
         self.x_gates = nn.ModuleList([nn.Linear(sum(self.sizes_in), size_out, bias=False) for _ in self.sizes_in])
         self._eng = None
+        _handle(self)
 
     def forward(self, *xs):
         n = len(self.sizes_in)
@@ -647,7 +662,7 @@ def _(handle, gen, g, n, wshapes):
 
 def _text_shifting_setup(ctx, inputs, output):
     handle, xs, ws = inputs
-    ctx.handle, ctx.gen, ctx.n = handle, _mod(handle)._bpm_gen, len(xs)
+    ctx.handle, ctx.gen, ctx.n = handle, _gen_of(handle, output), len(xs)
     ctx.wshapes = [int(x) for w in ws for x in w.shape]
 
 
@@ -707,6 +722,7 @@ class MultiprojectionMMTransformer3DGMUClf(nn.Module):
         self.transfm_l2a = nn.Linear(512, 512)
         self.transfm_l2v = nn.Linear(512, 512)
         self._eng = None
+        _handle(self)
 
     def get_network(self, name):
         a = self.args
@@ -801,7 +817,7 @@ def _(handle, gen, g, need, shapes):
 
 def _model_setup(ctx, inputs, output):
     handle, training, *feats = inputs[:-1]
-    ctx.handle, ctx.gen = handle, _mod(handle)._bpm_gen
+    ctx.handle, ctx.gen = handle, _gen_of(handle, output)
     ctx.need = [bool(t.requires_grad) for t in feats[:3]]
     ctx.shapes = [int(x) for t in feats[:3] for x in t.shape]
     ctx.n_feats = len(feats)
@@ -829,6 +845,7 @@ class AudioEncoder(nn.Module):
         self.channels, self.out_len = c, out_len
         self.precision = "bf16"
         self._eng = None
+        _handle(self)
 
     def forward(self, x):
         return torch.ops.bpmult_b200.audio_encoder(_handle(self), x, [p for _, p in self.named_parameters()])
@@ -880,7 +897,7 @@ def _(handle, gen, g):
 
 
 def _audio_setup(ctx, inputs, output):
-    ctx.handle, ctx.gen = inputs[0], _mod(inputs[0])._bpm_gen
+    ctx.handle, ctx.gen = inputs[0], _gen_of(inputs[0], output)
 
 
 def _audio_backward(ctx, g):
@@ -943,6 +960,7 @@ class MultiprojectionMMTransformerGMUClf(nn.Module):
             ti, to = TRANSFM[n]
             setattr(self, "transfm_" + n, nn.Linear(NV[ti], NV[to]))
         self._eng = None
+        _handle(self)
 
     def get_network(self, name, biprojection=False):
         a = self.args

@@ -78,6 +78,18 @@ def run_model_engine(ops, rec, dtype=torch.float32, full=True, sd=None):
 
 
 
+def fingerprint_errors(grads, fps):
+    """per-tensor error of gradients against stored fingerprints (max of the strided-sample rel-L2 and the norm error)"""
+    out = {}
+    for n, fp in fps.items():
+        g = grads[n].detach().reshape(-1).double().cpu()
+        ref = fp["val"].double()
+        e = float((g[fp["idx"]] - ref).norm() / ref.norm().clamp_min(1e-30))
+        en = abs(float(g.norm()) - fp["norm"]) / max(fp["norm"], 1e-30)
+        out[n] = max(e, en)
+    return out
+
+
 def check_fingerprints(grads, fps, tol):
     """gradients against the stored fingerprints (norm + strided sample, oracle/synth.py:summarize) of the reference's"""
     worst = (0.0, "")
