@@ -410,10 +410,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ---------------------------------------------------------------- host
-static int make_qkv_map(CUtensorMap* m, const void* p, int B, int rows, int HP, int box_rows, int pitch = 0) {
+static int make_qkv_map(CUtensorMap* m, const void* p, int B, int rows, int HP, int box_rows, int pitch = 0, int batch_rows = 0) {
   if (pitch == 0) pitch = HP;                         // row pitch in elements (k / v may be column slices of a wider buffer)
+  if (batch_rows == 0) batch_rows = rows;             // rows between two batch entries (a query chunk is a row range of every batch entry)
   uint64_t dims[3] = {(uint64_t)HP, (uint64_t)rows, (uint64_t)B};
-  uint64_t str[2] = {(uint64_t)pitch * 2, (uint64_t)rows * pitch * 2};
+  uint64_t str[2] = {(uint64_t)pitch * 2, (uint64_t)batch_rows * pitch * 2};
   uint32_t box[3] = {AT_DH, (uint32_t)box_rows, 1};
   return bpm_make_tmap_bf16(m, p, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
@@ -594,7 +595,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const int bits_tma,
                    const float* __restrict__ ws, bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv, float dq_scale, int B, int T,
                    int S, int H, int mask_off, bpm_dropout_t drop, const uint32_t* __restrict__ drop_bits, const int ld_dkv, const int dbg,
-                   unsigned long long* __restrict__ trace, const uint8_t* __restrict__ key_pad) {
+                   unsigned long long* __restrict__ trace, const uint8_t* __restrict__ key_pad, const int q_base, const int T_full,
+                   const int kv_add) {
+  // Query chunking (T_full > 512): the host launches this kernel once per chunk of <= 512 queries.  T is the chunk length (tiling, TMEM),
+  // q_base its first query and T_full the whole sequence (lse / delta rows, dropout element indices); the tensor maps of Q / dO / dQ
+  // already start at the chunk, mask_off already includes q_base.  Chunks after the first ADD their dK / dV to what is there (kv_add:
+  // TMA reduce-add instead of store).
   int tr_n = 0;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -621,7 +627,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nbh = B * H;
-  const int64_t nrow = (int64_t)nbh * T;
+  const int64_t nrow = (int64_t)nbh * T_full;
   const int nq = (T + 127) / 128, nkv = (S + 127) / 128;
   // first query tile that can see key tile j (visible iff key <= q + off)
   auto i_min_of = [&](int j) { int qlo = j * 128 - mask_off; return (mask_off < 0 || qlo <= 0) ? 0 : qlo / 128; };
@@ -677,8 +683,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mbar_wait(ld_empty(s), ((uint32_t)(bc >> 1) & 1u) ^ 1u);
           if (elect_one()) {
             mbar_expect_tx(ld_full(s), 2u * (uint32_t)T * 4u);
-            bulk_load_1d(base + AttnBwdSmem::LD + s * 4096, ws + nrow + (int64_t)bh * T, (uint32_t)T * 4u, ld_full(s));
-            bulk_load_1d(base + AttnBwdSmem::LD + s * 4096 + 2048, ws + (int64_t)bh * T, (uint32_t)T * 4u, ld_full(s));
+            bulk_load_1d(base + AttnBwdSmem::LD + s * 4096, ws + nrow + (int64_t)bh * T_full + q_base, (uint32_t)T * 4u, ld_full(s));
+            bulk_load_1d(base + AttnBwdSmem::LD + s * 4096 + 2048, ws + (int64_t)bh * T_full + q_base, (uint32_t)T * 4u, ld_full(s));
           }
           __syncwarp();
         }
@@ -701,7 +707,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               mbar_expect_tx(q_full(qs), 2 * 128 * 64 + (bits_tma ? 2048 : 0));
               tma_load_3d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE, &tmQ, q_full(qs), h * AT_DH, i * 128, b);
               tma_load_3d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 8192, &tmdO, q_full(qs), h * AT_DH, i * 128, b);
-              if (bits_tma) tma_load_2d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 16384, &tmBits, q_full(qs), j * 4, bh * T + i * 128);
+              if (bits_tma) tma_load_2d(base + AttnBwdSmem::QD + qs * AttnBwdSmem::QD_STAGE + 16384, &tmBits, q_full(qs), j * 4, bh * T_full + q_base + i * 128);
             }
             __syncwarp();
           }
@@ -858,7 +864,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint8_t* const stg_gen = base_gen + AttnBwdSmem::STG + cw * NSL * 2048;
     const uint32_t stg_s = base + AttnBwdSmem::STG + cw * NSL * 2048;
     int stg_n = 0;                                            // staging slices used so far (slice = stg_n % NSL)
-    auto stage_store = [&](const float* acc, float scale, const CUtensorMap* map, int c0, int row0, int bidx) {
+    auto stage_store = [&](const float* acc, float scale, const CUtensorMap* map, int c0, int row0, int bidx, bool add = false) {
       const int sl = stg_n % NSL;
       stg_n++;
       if (elect_one()) bulk_wait_read<NSL - 1>();             // the store that last used this slice has read it
@@ -871,7 +877,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_async_smem();
       __syncwarp();
       if (elect_one()) {
-        tma_store_3d(map, stg_s + sl * 2048, c0, row0, bidx);
+        if (add) tma_reduce_add_3d(map, stg_s + sl * 2048, c0, row0, bidx);
+        else tma_store_3d(map, stg_s + sl * 2048, c0, row0, bidx);
         bulk_commit();
       }
       __syncwarp();
@@ -904,7 +911,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(dkv_free);
       if (FOLD) acc[AB_PAD0] = acc[AB_PAD0 + 1] = 0.f;
-      stage_store(acc, 1.f, drain_dv ? &tmDV : &tmDK, pend_h * AT_DH, pend_key - lane, pend_b);
+      stage_store(acc, 1.f, drain_dv ? &tmDV : &tmDK, pend_h * AT_DH, pend_key - lane, pend_b, kv_add != 0);
       pend_jc = -1;
     };
     for (int bh = blockIdx.x; bh < nbh; bh += gridDim.x, bc++) {
@@ -916,7 +923,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int key = j * 128 + r;
         const int imin = i_min_of(j);
         if (imin >= nq) {                                     // no query sees this key tile: dK = dV = 0
-          if (key < S && drains_kv) {
+          if (key < S && drains_kv && !kv_add) {
             bf16* dst = (drain_dv ? dv : dk) + ((int64_t)b * S + key) * ld_dkv + h * AT_DH + dcol0;
 #pragma unroll
             for (int u = 0; u < DCOL / 8; u++) *(uint4*)(dst + u * 8) = make_uint4(0, 0, 0, 0);
@@ -927,7 +934,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const bool key_oob = key >= S || (key_pad != nullptr && key_pad[(int64_t)b * S + key] != 0);
         const bool any_pad = key_pad != nullptr && __any_sync(0xffffffffu, key_oob);
         // element index of (query q, key) in the [B*H, T, S] probability tensor = (bh*T + q)*S + key
-        const uint64_t e_row = (uint64_t)bh * (uint64_t)T * (uint64_t)S + (uint64_t)min(key, S - 1);
+        const uint64_t e_row = (uint64_t)bh * (uint64_t)T_full * (uint64_t)S + (uint64_t)min(key, S - 1);
         for (int i = imin; i < nq; i++, pc++) {
           const int q0 = i * 128;
           const int pb = pc & 1, qs = pc % AB_QD_STAGES;
@@ -947,7 +954,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mw[g] = 0xFFFFFFFFu;
             if (drop_mode == 2) {
               const int qq = q0 + c0 + g * 32 + lane;
-              mw[g] = (qq < T && j * 4 + quarter < W) ? drop_bits[((int64_t)bh * T + qq) * W + j * 4 + quarter] : 0u;
+              mw[g] = (qq < T && j * 4 + quarter < W) ? drop_bits[((int64_t)bh * T_full + q_base + qq) * W + j * 4 + quarter] : 0u;
             }
           }
           TRACE(3 + (colq & 1), 20);
@@ -981,8 +988,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               const int cm = key_oob ? 0x40000000 : (diag ? cmin - cs : -0x40000000);
 #define BWD_MATH(DROP)                                                                                                                        \
   do {                                                                                                                                        \
-    if (need_mask) bwd_chunk_math<DROP, true, 16, FOLD ? (DROP == 0 ? 1 : 2) : 0>(sv, dpv, lse_c, del_c, cs, cm, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S); \
-    else bwd_chunk_math<DROP, false, 16, FOLD ? (DROP == 0 ? 1 : 2) : 0>(sv, dpv, lse_c, del_c, cs, cmin, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q0 + cs, T, S);       \
+    if (need_mask) bwd_chunk_math<DROP, true, 16, FOLD ? (DROP == 0 ? 1 : 2) : 0>(sv, dpv, lse_c, del_c, cs, cm, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q_base + q0 + cs, T_full, S); \
+    else bwd_chunk_math<DROP, false, 16, FOLD ? (DROP == 0 ? 1 : 2) : 0>(sv, dpv, lse_c, del_c, cs, cmin, key_oob, diag, dc, bits_s + cs * 4, mws, lane, e_row, q_base + q0 + cs, T_full, S);       \
   } while (0)
               if (drop_mode == 0) BWD_MATH(0);
               else if (drop_mode == 1) BWD_MATH(1);
@@ -1054,9 +1061,10 @@ int bpm_xattn_bwd_simt(const bpm_attn_t* a, const void* q, const void* k, const 
 
 int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                      float* delta, void* dq, float dq_scale, void* dk, void* dv, cudaStream_t stream) {
-  // dQ accumulators of all query tiles must fit in TMEM and the per-(b,h) lse / delta vectors travel as 16-byte bulk copies;
-  // other shapes use the fp32-math kernel
-  if (a->T > 128 * AB_MAXQT || a->T % 4 != 0) return bpm_xattn_bwd_simt(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, stream);
+  // The per-(b,h) lse / delta vectors travel as 16-byte bulk copies (T % 4); other shapes use the fp32-math kernel.  The dQ accumulators
+  // of a (b,h) live in TMEM (4 query tiles): longer sequences run as chunks of 512 queries, one launch each, every chunk producing its
+  // own dQ rows and ADDING its share of dK / dV (TMA reduce-add in the storage type) to the first chunk's.
+  if (a->T % 4 != 0) return bpm_xattn_bwd_simt(a, q, k, v, out, dout, lse, delta, dq, dq_scale, dk, dv, stream);
   BPM_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv |
                (uintptr_t)delta) % 16 == 0, "xattn_bwd: pointers must be 16-byte aligned");
   const int HP = a->H * a->dhp;
@@ -1066,18 +1074,15 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
     cudaError_t le = bpm_launch(attn_delta_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)out, (const bf16*)dout, lse, delta, a->B, a->T, a->H);
     if (le != cudaSuccess) { bpm_set_error("xattn_delta: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   }
-  CUtensorMap tq, tk, tv, tg, tdq, tdk, tdv;
-  int rc;
-  if ((rc = make_qkv_map(&tq, q, a->B, a->T, HP, 128))) return rc;
   BPM_REQUIRE(a->ld_kv % 8 == 0 && a->ld_dkv % 8 == 0, "xattn_bwd: ld_kv / ld_dkv must be multiples of 8 elements");
-  if ((rc = make_qkv_map(&tdq, dq, a->B, a->T, HP, 32))) return rc;                       // outputs: {32 columns, 32 rows} store boxes
-  if ((rc = make_qkv_map(&tdk, dk, a->B, a->S, HP, 32, a->ld_dkv))) return rc;
+  CUtensorMap tk, tv, tdk, tdv;
+  int rc;
+  if ((rc = make_qkv_map(&tdk, dk, a->B, a->S, HP, 32, a->ld_dkv))) return rc;            // outputs: {32 columns, 32 rows} store boxes
   if ((rc = make_qkv_map(&tdv, dv, a->B, a->S, HP, 32, a->ld_dkv))) return rc;
   if ((rc = make_qkv_map(&tk, k, a->B, a->S, HP, 128, a->ld_kv))) return rc;
   if ((rc = make_qkv_map(&tv, v, a->B, a->S, HP, 128, a->ld_kv))) return rc;
-  if ((rc = make_qkv_map(&tg, dout, a->B, a->T, HP, 128))) return rc;
   // dropout keep bits as a [B*H*T, W] uint32 tensor, box {4 words, 128 queries}; needs a 16-byte pitch (S % 128 == 0)
-  CUtensorMap tb = tq;
+  CUtensorMap tb = tk;
   const int W = (a->S + 31) / 32;
   const int bits_tma = (a->drop.p > 0.f && a->drop_bits != nullptr && a->S % 128 == 0) ? 1 : 0;
   if (bits_tma) {
@@ -1097,8 +1102,19 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
                       : (dm == 1 ? (fold1 ? attn_bwd_tc_kernel<1, true, 8> : attn_bwd_tc_kernel<1, false, 8>) : attn_bwd_tc_kernel<0, false, 8>);
   if (int rc2 = bpm_func_smem((const void*)kern, (int)smem, "xattn_bwd_tc")) return rc2;
   const int ctas = min(a->B * a->H, bpm_num_sms());
-  cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AB_THREADS(cw)), smem, stream, tq, tk, tv, tg, tb, tdq, tdk, tdv, bits_tma, delta, (bf16*)dq, (bf16*)dk, (bf16*)dv, dq_scale, a->B, a->T, a->S, a->H,
-                                                         a->mask_off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1), (unsigned long long*)bpm_debug_get_ptr(), a->key_pad);
-  if (le != cudaSuccess) { bpm_set_error("xattn_bwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
+  const int TC = 128 * AB_MAXQT;
+  for (int q_base = 0; q_base < a->T; q_base += TC) {
+    const int Tc = min(TC, a->T - q_base);
+    const int64_t row_off = (int64_t)q_base * HP;                                         // element offset of the chunk inside a batch entry
+    CUtensorMap tq, tg, tdq;
+    if ((rc = make_qkv_map(&tq, (const bf16*)q + row_off, a->B, Tc, HP, 128, 0, a->T))) return rc;
+    if ((rc = make_qkv_map(&tg, (const bf16*)dout + row_off, a->B, Tc, HP, 128, 0, a->T))) return rc;
+    if ((rc = make_qkv_map(&tdq, (bf16*)dq + row_off, a->B, Tc, HP, 32, 0, a->T))) return rc;
+    const int off = a->mask_off >= 0 ? a->mask_off + q_base : a->mask_off;
+    cudaError_t le = bpm_launch(kern, dim3(ctas), dim3(AB_THREADS(cw)), smem, stream, tq, tk, tv, tg, tb, tdq, tdk, tdv, bits_tma, delta, (bf16*)dq, (bf16*)dk,
+                                (bf16*)dv, dq_scale, a->B, Tc, a->S, a->H, off, a->drop, a->drop_bits, a->ld_dkv ? a->ld_dkv : HP, bpm_debug_get(1),
+                                (unsigned long long*)bpm_debug_get_ptr(), a->key_pad, q_base, a->T, q_base > 0 ? 1 : 0);
+    if (le != cudaSuccess) { bpm_set_error("xattn_bwd_tc: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
+  }
   return BPM_OK;
 }

@@ -207,6 +207,8 @@ ATTN_CASES = [  # B, T, S, H, dh, dhp, mask_off, p
     (2, 140, 140, 3, 30, 32, 0, 0.0), (1, 64, 200, 2, 32, 32, -1, 0.0),
     # ragged lengths / offset-causal masks on the folded no-dropout instantiations (T != S as in the 4-modality model)
     (2, 200, 512, 12, 25, 32, 312, 0.0), (2, 512, 200, 12, 25, 32, 312, 0.0), (3, 384, 384, 5, 25, 32, 0, 0.0), (1, 76, 333, 3, 25, 32, -1, 0.0),
+    # more than 512 queries at head dim 32: the backward runs as chunks of 512 queries whose dK / dV shares are added by TMA reduce
+    (1, 1024, 640, 2, 25, 32, 384, 0.0), (1, 700, 700, 3, 25, 32, 0, 0.1), (2, 1100, 300, 2, 25, 32, -1, 0.0), (1, 2048, 2048, 1, 30, 32, 0, 0.0),
 ]
 
 
