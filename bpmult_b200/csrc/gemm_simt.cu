@@ -66,8 +66,73 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(int ta, int tb, int M, i
   }
 }
 
+// Skinny problems (M <= 64 rows: the [B, D] head of the model -- final GMU, residual MLP, out_layer and their input gradients).  The 64x64
+// tiles above give such a problem N/64 CTAs (5 of 148 SMs for N = 320) and a K loop of 20..80 barrier-separated steps: ~30 us a launch,
+// 0.8 ms of the cfg-2 step over the head's 27 GEMMs.  Here a CTA owns 8 output columns and ALL rows, K is split 4 ways inside the CTA
+// (thread = (row, k-slice)) and reduced through shared memory: N/8 CTAs, 64-deep K steps.
+#define SK_BN 8
+#define SK_BK 64
+template <int TB>
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                          EpiParams ep) {
+  __shared__ float As[SK_BK][64 + 1];        // [k][m]
+  __shared__ float Bs[SK_BN][SK_BK + 1];     // [n][k]
+  __shared__ float red[3][64][SK_BN];
+  const int t = threadIdx.x, m = t & 63, ks = t >> 6;
+  const int n0 = blockIdx.x * SK_BN;
+  float acc[SK_BN];
+#pragma unroll
+  for (int j = 0; j < SK_BN; j++) acc[j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += SK_BK) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int idx = t + 256 * i, k = idx & 63, mm = idx >> 6;
+      As[k][mm] = (mm < M && k0 + k < K) ? A[(int64_t)mm * lda + k0 + k] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int idx = t + 256 * i;
+      int k, n;
+      if (TB == 0) { k = idx & 63; n = idx >> 6; }
+      else { n = idx & 7; k = idx >> 3; }
+      float v = 0.f;
+      if (n0 + n < N && k0 + k < K) v = TB == 0 ? B[(int64_t)(n0 + n) * ldb + k0 + k] : B[(int64_t)(k0 + k) * ldb + n0 + n];
+      Bs[n][k] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+      const int k = ks * 16 + kk;
+      const float a = As[k][m];
+#pragma unroll
+      for (int j = 0; j < SK_BN; j++) acc[j] = fmaf(a, Bs[j][k], acc[j]);
+    }
+    __syncthreads();
+  }
+  if (ks > 0) {
+#pragma unroll
+    for (int j = 0; j < SK_BN; j++) red[ks - 1][m][j] = acc[j];
+  }
+  __syncthreads();
+  if (ks == 0 && m < M) {
+    const DropCtx dc = make_drop(ep.drop);
+#pragma unroll
+    for (int j = 0; j < SK_BN; j++) {
+      const float v = acc[j] + red[0][m][j] + red[1][m][j] + red[2][m][j];
+      if (n0 + j < N) epi_store1(ep, dc, m, n0 + j, v);
+    }
+  }
+}
+
 int bpm_gemm_simt(const bpm_gemm_t* g, cudaStream_t stream) {
   EpiParams ep = make_epi(g);
+  if (g->ab_dtype == BPM_F32 && g->ta == 0 && g->M <= 64 && g->K >= 64) {
+    dim3 grid(bpm_cdiv(g->N, SK_BN));
+    if (g->tb == 0) gemm_skinny_kernel<0><<<grid, 256, 0, stream>>>(g->M, g->N, g->K, (const float*)g->A, g->lda, (const float*)g->B, g->ldb, ep);
+    else gemm_skinny_kernel<1><<<grid, 256, 0, stream>>>(g->M, g->N, g->K, (const float*)g->A, g->lda, (const float*)g->B, g->ldb, ep);
+    BPM_CHECK_LAUNCH("gemm_skinny");
+    return BPM_OK;
+  }
   int gx = bpm_cdiv(g->N, SG_BN), gy = bpm_cdiv(g->M, SG_BM);
   int split = 1;
   if (g->accumulate) {

@@ -88,7 +88,7 @@ def attn_case(d, B, T, S, causal, p):
     fl = 4.0 * B * d.H * vis * d.dh
     iters = 3 if fl > 2e12 else 6
     tf = timeit(lambda: ops.xattn_fwd(q, k, v, o, lse, B, T, S, d.H, d.dh, d.dhp, mask_off=off, drop=drop, drop_bits=bits), iters)
-    tc_bwd = d.dhp == 128 or T <= 512                        # head dim 32: all dQ tiles of a (b, h) live in TMEM (T <= 512); else exact-fp32 kernel
+    tc_bwd = T % 4 == 0                                      # (lse / delta rows travel as 16-byte bulk copies; other lengths: exact-fp32 kernel)
     if tc_bwd or fl < 3e11:
         tb = timeit(lambda: ops.xattn_bwd(q, k, v, o, do, lse, delta, dq, d.scaling, dk, dv, B, T, S, d.H, d.dh, d.dhp, mask_off=off, drop=drop,
                                           drop_bits=bits), iters)

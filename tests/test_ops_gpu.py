@@ -439,3 +439,13 @@ def test_conv1d_im2col_col2im_pool(ops, dtype):
         dy = rnd((B * Tp, 128), 96)
         (e,), (c,) = both(ops, lambda o, dy, dx: o.adaptive_pool_bwd(dy, B, T, C, Tp, dx), [dy], [torch.zeros(B * T, C)])
         assert max_rel(c, e) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 320, 320), (64, 320, 960), (8, 8, 320), (64, 3072, 768), (33, 45, 100)])
+def test_gemm_skinny_rows(ops, M, N, K):
+    """the [B, D] head's GEMMs (M <= 64 rows, exact fp32): the skinny kernel with every epilogue the head uses"""
+    assert _gemm_case(ops, F32, M, N, K, 0, 0) < 2e-5
+    assert _gemm_case(ops, F32, M, N, K, 0, 0, bias=True, act=1, drop=DROP) < 2e-5
+    assert _gemm_case(ops, F32, M, N, K, 0, 0, bias=True, residual=F32) < 2e-5
+    assert _gemm_case(ops, F32, M, N, K, 0, 1, gate=True, gate_scale=1.25) < 2e-5
+    assert _gemm_case(ops, F32, M, N, K, 0, 1, residual=F32) < 2e-5
