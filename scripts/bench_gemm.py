@@ -13,7 +13,8 @@ dev = ops.device
 d = Dims(300, 12)
 M = 64 * 512
 bf = torch.bfloat16
-NSET = 3
+import os
+NSET = int(os.environ.get("NSET", "3"))
 
 
 def mk(shape, dtype=bf):
