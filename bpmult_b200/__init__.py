@@ -12,6 +12,7 @@ _PUBLIC = {
                 "SinusoidalPositionalEmbedding", "GatedMultimodalLayer", "GatedMultimodalLayerFeatures", "TextShifting3Layer",
                 "TextShifting4Layer", "TextShiftingNLayer", "AudioEncoder", "buffered_future_mask", "get_model", "MODELS", "manual_seed"],
     "trainer": ["Trainer"],
+    "evaluate": ["model_eval", "multilabel_metrics", "weighted_acc"],
 }
 
 

@@ -345,6 +345,27 @@ class Trainer:
             ev.record(torch.cuda.current_stream(self.device))
         return _Loss(self.loss_slots[slot], ev)
 
+    def evaluate(self, *batch, output_gates=False):
+        """model_forward + the device half of model_eval (train.py:165-186, 283-338) for one batch, on the Trainer's own engine and
+        weights: forward in eval mode (no dropout, nothing saved for a backward), BCEWithLogits with this Trainer's pos_weight,
+        sigmoid, 0.5 threshold.  batch = (features..., targets), host or device tensors.  Returns a dict of HOST tensors:
+        loss (python float), logits, probs, preds (bool), targets [, gates: the final GMU's z, mmtr.py:863-866]."""
+        dev = self.device
+        *feats, tgt = [t.to(dev, torch.float32, non_blocking=True) for t in batch]
+        if self.on_gpu:
+            torch.cuda.current_stream(dev).synchronize()        # a captured training step may still be replaying into the same arenas
+        self.eng.pack(self.params)
+        logits, z = self.eng.forward(*feats, training=False, seed=0)
+        loss, _ = self.eng.loss(logits, tgt, self.pos_weight, 1.0)
+        B, C, D, Dp = tgt.shape[0], tgt.shape[1], self.model.args.hidden_sz, self.eng.d.Dp          # engine buffers are padded: cut to (B, C) / (B, n*D)
+        logits = logits[:, :C]
+        probs = torch.sigmoid(logits)
+        out = {"logits": logits.detach().cpu(), "probs": probs.cpu(), "preds": (probs > 0.5).cpu(), "targets": tgt.cpu(), "loss": float(loss)}
+        if output_gates:
+            n_gate = z.numel() // (B * Dp)
+            out["gates"] = z.view(B, n_gate, Dp)[:, :, :D].reshape(B, n_gate * D).cpu()
+        return out
+
     def _run(self):
         apply = (self.micro + 1) % self.grad_accum == 0     # train.py:395-398: optimizer step every grad_accum micro-batches
         self.micro = (self.micro + 1) % self.grad_accum

@@ -239,3 +239,33 @@ def test_reference_format_checkpoint_round_trip_on_gpu(tmp_path):
         with torch.no_grad():
             lo = b2(txt, None, None, img, audio).cpu()
         assert float((lr_ - lo).abs().max()) < 2e-5
+
+
+def test_evaluate_between_graph_replays_matches_eval_mode_forward_and_the_oracle():
+    """train.py:165-186 / 283-338: the eval pass runs on the Trainer's engine between captured training steps (dropout sites off),
+    returns what the module forward returns in eval mode, and leaves the training trajectory untouched"""
+    from bpmult_b200 import Trainer, model_eval
+    cfg = synth.tiny_cfg(attn_dropout=0.1, relu_dropout=0.1, res_dropout=0.1, embed_dropout=0.25, out_dropout=0.1)
+    batch = synth.mmtrvat_inputs(cfg, 2, 10, 30, 25)
+    pw = torch.tensor([1.0, 2.0, 0.5, 3.0, 1.0, 1.5])
+    a, b = Trainer(_model(cfg, "fp32"), lr=1e-3, pos_weight=pw), Trainer(_model(cfg, "fp32"), lr=1e-3, pos_weight=pw)
+    for i in range(5):
+        la = a.step(*batch)
+        if i == 3:
+            metrics, arrays = model_eval([batch, batch], b, "cmu-mosei", output_gates=True)
+        lb = b.step(*batch)
+        assert la == lb, (i, la, lb)                           # same seeds, same dropout masks: evaluate() changed nothing
+    assert torch.equal(a.flat_p, b.flat_p) and b.graph is not None
+    m = b.model.eval()
+    with torch.no_grad():
+        logits, z = m(batch[0].cuda(), None, None, batch[1].cuda(), batch[2].cuda(), True)
+    r = b.evaluate(*batch, output_gates=True)
+    assert torch.equal(r["logits"], logits.cpu()) and torch.equal(r["gates"], z.cpu())
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    cfg0 = synth.tiny_cfg()
+    lo, zo = Fn.mmtrvat_forward(sd, cfg0, *batch[:3])
+    assert Fn.max_rel(r["logits"], lo) < 1e-4 and Fn.max_rel(r["gates"], zo) < 1e-4
+    assert abs(r["loss"] - float(Fn.bce_with_logits(lo, batch[3], pw))) < 1e-5
+    assert arrays["preds"].shape == (4, 6) and arrays["gates"].shape == (4, 3 * cfg.hidden_sz) and "wacc_emo6" in metrics
+    a.close()
+    b.close()
