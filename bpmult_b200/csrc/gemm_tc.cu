@@ -26,7 +26,7 @@
 #define TC_BK 64
 #define TC_EPI_WARPS 8
 #define TC_THREADS (64 + 32 * TC_EPI_WARPS)
-#define TC_MAX_STAGES 6
+#define TC_MAX_STAGES 8
 #define TC_MAX_NB 4
 
 struct TcGemmParams {
@@ -36,6 +36,7 @@ struct TcGemmParams {
   int stages;
   int a_bytes, b_bytes;   // per-stage bytes (multiples of 1024)
   int ring_bytes;
+  int ebuf_off, misc_off;  // byte offsets of the staging buffers and of the ones tile / barriers behind the 1024-aligned base
   int kb_per_split;
   int gx, gy, split;
   int tmem_cols;
@@ -45,6 +46,7 @@ struct TcGemmParams {
   int in_mode;            // 0 none, 1 residual (added), 2 gate (relu-backward mask from a saved activation)
   int reduce_add;
   float* colsum;          // fused bias gradient (wgrad only), or null
+  unsigned long long* trace;   // BPM_GEMM_TRACE builds only: per-role event log of CTA 0 (scripts/trace_gemm.py)
   int dbg;                // diagnostic knobs (bpm_debug_set slot 0): 1 no TMA loads, 2 no MMAs, 4 no epilogue math, 8 no staging/store, 16 no tcgen05.ld, 32 MMA issuer skips the full-barrier wait, 64 no empty-barrier traffic, 128 never pair CTAs
   const float* bias; float alpha; int act; float gate_scale; int ldc;
   bpm_dropout_t drop;
@@ -74,6 +76,19 @@ template <int CB> __device__ __forceinline__ uint32_t swz_off(int r, int u) {
 // needs (a shorter instruction stream per chunk; the epilogue warps are instruction-fetch sensitive):
 //   1 plain / bias / bias + relu     2 + dropout (fc1)     3 relu-backward gate tile (dgrad into fc1)
 //   4 dropout + residual tile, fp32 out (out-proj, fc2)     5 fp32 reduce-add with fused column sums (wgrad)
+#ifdef BPM_GEMM_TRACE
+#define GT_N 1024
+#define GT(role, id)                                                                                         \
+  do {                                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && gt_n < GT_N) {                                 \
+      p.trace[(role) * GT_N + gt_n] = ((unsigned long long)clock64() << 8) | (unsigned long long)(id);      \
+      gt_n++;                                                                                                \
+    }                                                                                                        \
+  } while (0)
+#else
+#define GT(role, id) do {} while (0)
+#endif
+
 template <int ELEM, int CB, int CG, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
@@ -87,9 +102,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* const base_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  // layout: [operand ring | staging buffers: 8 warps x nb x EB | ones tile 2 KB | barriers]
-  const int ebuf_base = p.ring_bytes;
-  const int misc = ebuf_base + TC_EPI_WARPS * p.nb * EB;
+  // layout: [operand ring | staging buffers: 8 warps x nb x EB | ones tile 2 KB | barriers]; split-K wgrads whose CTAs own ONE tile each
+  // put the staging buffers ON the ring (it is idle by the time the only epilogue starts): the 64 KB go to ring stages instead
+  const int ebuf_base = p.ebuf_off;
+  const int misc = p.misc_off;
   const uint32_t ones_addr = smem_base + misc;
   const uint32_t bar_base = smem_base + misc + 2048;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -103,6 +119,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef BPM_GEMM_TRACE
+  int gt_n = 0;
+#endif
   const int num_kb_total = (p.K + TC_BK - 1) / TC_BK;
   const int tiles_mn = p.gx * p.gy;                  // p.gy counts (CG * 128)-row tiles
   const int total_tiles = tiles_mn * p.split;
@@ -150,6 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = z * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; kb++) {
           if (!(p.dbg & 64)) mbar_wait(empty_bar(s), ph ^ 1u);
+          GT(0, 1);
           const uint32_t sa = smem_base + s * stage_bytes, sb = sa + p.a_bytes;
           const uint32_t fb = full_bar(s);
           if (elect_one()) {
@@ -218,6 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
           }
+          GT(1, 2);
           const uint32_t sa = smem_base + s * stage_bytes;
           uint64_t da = da_t | (uint64_t)((sa & 0x3FFFFu) >> 4), db = db_t | (uint64_t)(((sa + p.a_bytes) & 0x3FFFFu) >> 4);
           if (elect_one()) {
@@ -240,6 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           __syncwarp();
+          GT(1, 3);
           accum = 1;
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -301,6 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = half; chunk_ok(t, c); c += 2) last_c = c;
       mbar_wait(tmem_full(a), (uint32_t)(tc >> 1) & 1u);
       tc_fence_after();
+      if (ew == 0) GT(2, 4);
       if (last_c < 0) {                                                    // nothing for this warp in this tile
         if (do_colsum) {
           float cs[16];
@@ -323,6 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else tmem_ld16(acc + (uint32_t)col0, v);
           tmem_ld_wait();
         }
+        if (ew == 0) GT(2, 6);
         if (c == last_c) {
           float cs0 = 0.f;
           if (do_colsum) {
@@ -377,6 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (ew == 0) GT(2, 7);
         if (skip_store) continue;
         uint8_t* const st = ebuf_gen + b * EB;
         if (in_mode_) {
@@ -421,6 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (elect_one()) bulk_wait_read_n(nb - 1);                        // the store that last used this buffer has read it
           __syncwarp();
         }
+        if (ew == 0) GT(2, 8);
         // ---- stage the chunk (swizzled, in place over the residual / gate tile) and hand it to the TMA unit
 #pragma unroll
         for (int u = 0; u < CB / 16; u++) {
@@ -442,10 +468,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bulk_commit();
         }
         __syncwarp();
+        if (ew == 0) GT(2, 9);
       }
     }
     if (elect_one()) bulk_wait_read<0>();                                   // smem must outlive the last TMA store's read
     __syncwarp();
+    if (ew == 0) GT(2, 5);
   }
   tc_fence_before();
   __syncthreads();
@@ -542,6 +570,7 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   p.M = g->M; p.N = g->N; p.K = g->K;
   p.colsum = g->colsum_out;
   p.dbg = bpm_debug_get(0);
+  p.trace = (unsigned long long*)bpm_debug_get_ptr();
   int max_bn = p.colsum ? 224 : 256;               // 2 x (224 + 16) TMEM columns still fit in 512
   if (bpm_debug_get(2) >= 32) max_bn = min(max_bn, bpm_debug_get(2));
   p.BN = pick_bn(g->N, max_bn);
@@ -569,8 +598,6 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   p.nb = 2;
   if (p.in_mode && g->K <= 512 && (budget - TC_EPI_WARPS * 3 * eb) / stage_bytes >= 3) p.nb = 3;
   if (bpm_debug_get(3) >= 2 && bpm_debug_get(3) <= TC_MAX_NB) p.nb = bpm_debug_get(3);
-  p.stages = max(2, min(TC_MAX_STAGES, (budget - TC_EPI_WARPS * p.nb * eb) / stage_bytes));
-  p.ring_bytes = p.stages * stage_bytes;
   // two accumulators (one per in-flight tile); each BN (+16 for the fused column sum) columns wide
   p.tmem_cols = 64;
   while (p.tmem_cols < 2 * (p.BN + (p.colsum ? 16 : 0))) p.tmem_cols *= 2;
@@ -599,6 +626,14 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
   p.kb_per_split = bpm_cdiv(num_kb, split);
   split = bpm_cdiv(num_kb, p.kb_per_split);
   p.gx = gx; p.gy = gy; p.split = split;
+  // A DRAM-streaming main loop runs at (bytes in flight) / (loaded DRAM latency, ~3000 clk) per SM (measured: 5 stages x 32 KB give 38 B/clk):
+  // when no CTA sees a second tile the epilogue's staging buffers can live on the drained ring, and its 64 KB become ring stages.
+  const bool alias = g->accumulate && gx * gy * split <= bpm_num_sms() / cg && !(p.dbg & 32768);
+  const int stage_area = TC_EPI_WARPS * p.nb * eb;
+  p.stages = max(2, min(TC_MAX_STAGES, (budget - (alias ? 0 : stage_area)) / stage_bytes));
+  p.ring_bytes = p.stages * stage_bytes;
+  p.ebuf_off = alias ? 0 : p.ring_bytes;
+  p.misc_off = alias ? max(p.ring_bytes, stage_area) : p.ring_bytes + stage_area;
 
   CUtensorMap tmA, tmB, tmC, tmI;
   {
@@ -620,7 +655,7 @@ int bpm_gemm_tc(const bpm_gemm_t* g, cudaStream_t stream) {
     if (g->residual && (rc = make_epi_map(&tmI, g->residual, g->M, g->N, g->ldr, elem, cb))) return rc;
     if (g->gate && (rc = make_epi_map(&tmI, g->gate, g->M, g->N, g->ldg, elem, cb))) return rc;
   }
-  size_t smem = (size_t)p.ring_bytes + TC_EPI_WARPS * p.nb * eb + fixed;
+  size_t smem = (size_t)p.misc_off + fixed;
   BPM_REQUIRE(smem <= 227 * 1024 && p.tmem_cols <= 512, "gemm_tc: smem %zu / tmem %d too large", smem, p.tmem_cols);
   int total_tiles = gx * gy * split;
   int ctas = cg * min(total_tiles, bpm_num_sms() / cg);
