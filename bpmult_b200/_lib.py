@@ -43,6 +43,7 @@ SIGNATURES = {
     "bpm_pack_matrix": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpm_unpack_matrix": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "bpm_remap_batch": [_P, _I, _I, _P],
+    "bpm_remap_units": [_P, _P, _I, _I, _P],
     "bpm_stage_rows": [_P, _I, _I, _I, _L, _L, _L, _P, _I, _I, _I, Dropout, _P],
     "bpm_unstage_rows": [_P, _I, _I, _I, _I, _I, _P, _L, _L, _L, _I, Dropout, _P],
     "bpm_embed_fwd": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _I, Dropout, _P],

@@ -74,9 +74,16 @@ class CudaOps:
             arr = np.zeros(len(items), dtype=dt)
             for i, it in enumerate(items):
                 arr[i] = it + (0,)
-            return arr
-        tab = self._table((mode,) + tuple(items), build)
-        self._ck(self.lib.bpm_remap_batch(tab.data_ptr(), len(items), 0 if mode == "pack" else 1, self._s()), "remap_batch")
+            # work units: runs of destination rows worth ~16 K elements each (padded rows when packing, reference rows when unpacking)
+            units = []
+            for i, it in enumerate(items):
+                rows, cols = (it[6], it[7]) if mode == "pack" else (it[2], it[3])
+                step = max(1, 16384 // max(1, cols))
+                units += [(i, r0, min(step, rows - r0), 0) for r0 in range(0, rows, step)]
+            return np.concatenate([arr.view("uint8"), np.asarray(units, dtype=np.int32).reshape(-1).view("uint8")]), len(units)
+        tab, n_units = self._table((mode,) + tuple(items), build)
+        self._ck(self.lib.bpm_remap_units(tab.data_ptr(), tab.data_ptr() + 72 * len(items), n_units, 0 if mode == "pack" else 1, self._s()),
+                 "remap_units")
 
     def _table(self, sig, build):
         """Device descriptor table for a batched launch, cached by the full descriptor list (alternating engines never rebuild, and
@@ -90,7 +97,10 @@ class CudaOps:
         if ent is None:
             if capturing:
                 raise _lib.BpmError("bpmult_b200: a descriptor table is missing during CUDA-graph capture (run the step eagerly once first)")
-            ent = [torch.from_numpy(build().view("uint8").copy()).to(self.device), set()]
+            built, meta = build(), None
+            if isinstance(built, tuple):                    # (table bytes, host-side metadata kept with the entry)
+                built, meta = built
+            ent = [torch.from_numpy(built.view("uint8").copy()).to(self.device), set(), meta]
             self._tables[sig] = ent
             unpinned = [k for k, e in self._tables.items() if not e[1]]
             for k in unpinned[:max(0, len(unpinned) - self.max_tables)]:
@@ -99,7 +109,7 @@ class CudaOps:
             self._tables[sig] = self._tables.pop(sig)       # most recently used last
         if capturing:
             ent[1].add(self.capture_owner)
-        return ent[0]
+        return ent[0] if ent[2] is None else (ent[0], ent[2])
 
     def release_tables(self, owner):
         """the graphs captured by `owner` are gone: their descriptor tables may be evicted again"""

@@ -71,6 +71,11 @@ typedef struct {
   float scale; int32_t pad_;
 } bpm_remap_desc_t;
 int bpm_remap_batch(const bpm_remap_desc_t* descs_dev, int n, int mode, void* stream);
+/* the same with an explicit work list: unit = rows [row0, row0 + nrows) of descriptor `desc`, counted in DESTINATION rows (padded rows
+ * when packing, reference rows when unpacking); one thread block per unit.  The caller sizes units by element count (~16 K per unit)
+ * so that tensors of very different sizes share the machine evenly. */
+typedef struct { int32_t desc, row0, nrows, pad_; } bpm_remap_unit_t;
+int bpm_remap_units(const bpm_remap_desc_t* descs_dev, const bpm_remap_unit_t* units_dev, int n_units, int mode, void* stream);
 
 /* ---- input staging: models/mmtr.py:741-761 (transpose, embed dropout on text, zero-pad time to n_vec) ----------
  * src fp32 element (b, t, c) at src[b*sb + t*st + c*sc]; dst T rows b*Tp + t, pitch Cp, zero for t >= T or c >= C. */

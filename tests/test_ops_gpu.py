@@ -71,6 +71,42 @@ def test_pack_unpack(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", [F32, BF16])
+def test_batched_pack_unpack_equals_single_calls(ops, dtype):
+    """one launch over tensors of very different sizes (work units by element count; vector path where both sides are 16-byte aligned,
+    scalar path for head remaps in the columns, odd widths and misaligned sources) == the per-tensor kernels, bit for bit"""
+    dev = ops.device
+    flat = rnd((1 << 20,), 7).to(dev)                                    # parameters live at arbitrary offsets of one flat buffer
+    specs = [  # (rows, cols, offset in flat, padded rows, padded cols, row_map, col_map)
+        (900, 300, 0, 1152, 320, (25, 32), (0, 0)), (300, 300, 270000, 320, 384, (0, 0), (25, 32)), (1200, 300, 360000, 1216, 320, (0, 0), (0, 0)),
+        (1, 300, 720000, 1, 320, (0, 0), (0, 0)), (6, 300, 720301, 8, 320, (0, 0), (0, 0)), (300, 35, 722200, 320, 64, (0, 0), (0, 0)),
+        (1, 6, 732706, 1, 8, (0, 0), (0, 0)), (768, 200, 733000, 768, 256, (0, 0), (0, 0))]
+    srcs = [flat[o:o + r * c].view(r, c) for r, c, o, *_ in specs]
+    single = [torch.full((rp, cp), 3.0, dtype=dtype, device=dev) for _, _, _, rp, cp, *_ in specs]
+    batched = [t.clone() for t in single]
+    for s_, d_, (_, _, _, _, _, rm, cm) in zip(srcs, single, specs):
+        ops.pack_matrix(s_, d_, row_map=rm, col_map=cm)
+    ops.batch_begin("pack", "t")
+    for s_, d_, (_, _, _, _, _, rm, cm) in zip(srcs, batched, specs):
+        ops.pack_matrix(s_, d_, row_map=rm, col_map=cm)
+    ops.batch_end()
+    for a, b in zip(single, batched):
+        assert torch.equal(a, b)
+    # unpack (fp32 padded accumulators -> reference layout), accumulate and scale, into views of a flat gradient buffer
+    accs = [rnd((rp, cp), 20 + i).to(dev) for i, (_, _, _, rp, cp, *_) in enumerate(specs)]
+    g1, g2 = rnd((1 << 20,), 9).to(dev), None
+    g2 = g1.clone()
+    for g, use_batch in ((g1, False), (g2, True)):
+        outs = [g[o:o + r * c].view(r, c) for r, c, o, *_ in specs]
+        if use_batch:
+            ops.batch_begin("unpack", "t")
+        for i, (a_, o_, (_, _, _, _, _, rm, cm)) in enumerate(zip(accs, outs, specs)):
+            ops.unpack_matrix(a_, o_, row_map=rm, col_map=cm, accumulate=(i % 2 == 0), scale=0.5 if i % 3 == 0 else 1.0)
+        if use_batch:
+            ops.batch_end()
+    assert torch.equal(g1, g2)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
 def test_ln_fold(ops, dtype):
     """LayerNorm affine folded into the K / V projection: packed operands and the gradient unfold"""
     D, H, dh, dhp, Dp = 300, 12, 25, 32, 320

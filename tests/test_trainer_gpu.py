@@ -254,8 +254,10 @@ def test_evaluate_between_graph_replays_matches_eval_mode_forward_and_the_oracle
         if i == 3:
             metrics, arrays = model_eval([batch, batch], b, "cmu-mosei", output_gates=True)
         lb = b.step(*batch)
-        assert la == lb, (i, la, lb)                           # same seeds, same dropout masks: evaluate() changed nothing
-    assert torch.equal(a.flat_p, b.flat_p) and b.graph is not None
+        # same seeds, same dropout masks: evaluate() changed nothing (two runs differ by the order of atomic / split-K additions only)
+        assert abs(la - lb) < 2e-6 * max(1.0, abs(la)), (i, la, lb)
+    rel = ((a.flat_p - b.flat_p).double().norm() / a.flat_p.double().norm()).item()
+    assert rel < 1e-5 and b.graph is not None, rel
     m = b.model.eval()
     with torch.no_grad():
         logits, z = m(batch[0].cuda(), None, None, batch[1].cuda(), batch[2].cuda(), True)
