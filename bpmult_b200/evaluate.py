@@ -11,7 +11,8 @@ import numpy as np
 
 
 def weighted_acc(preds, truths):
-    """train.py:140-163 for one label column: weighted accuracy (tp * n / p + tn) / (2 n) and the eps-smoothed F1"""
+    """train.py:140-163 for one label column: weighted accuracy (tp * n / p + tn) / (2 n) and the eps-smoothed F1.  Like the reference it
+    raises ZeroDivisionError for a column without positives (or without negatives): evaluate on a set that has both."""
     preds, truths = np.asarray(preds).reshape(-1).astype(bool), np.asarray(truths).reshape(-1)
     pos, neg = truths == 1, truths == 0
     p, n = int(pos.sum()), int(neg.sum())

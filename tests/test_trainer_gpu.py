@@ -252,12 +252,12 @@ def test_evaluate_between_graph_replays_matches_eval_mode_forward_and_the_oracle
     for i in range(5):
         la = a.step(*batch)
         if i == 3:
-            metrics, arrays = model_eval([batch, batch], b, "cmu-mosei", output_gates=True)
+            metrics, arrays = model_eval([batch, batch], b, "moviescope", output_gates=True)
         lb = b.step(*batch)
         # same seeds, same dropout masks: evaluate() changed nothing (two runs differ by the order of atomic / split-K additions only)
         assert abs(la - lb) < 2e-6 * max(1.0, abs(la)), (i, la, lb)
     rel = ((a.flat_p - b.flat_p).double().norm() / a.flat_p.double().norm()).item()
-    assert rel < 1e-5 and b.graph is not None, rel
+    assert rel < 2e-4 and b.graph is not None, rel      # (Adam turns rounding noise on near-zero gradients into +-lr moves)
     m = b.model.eval()
     with torch.no_grad():
         logits, z = m(batch[0].cuda(), None, None, batch[1].cuda(), batch[2].cuda(), True)
@@ -268,6 +268,6 @@ def test_evaluate_between_graph_replays_matches_eval_mode_forward_and_the_oracle
     lo, zo = Fn.mmtrvat_forward(sd, cfg0, *batch[:3])
     assert Fn.max_rel(r["logits"], lo) < 1e-4 and Fn.max_rel(r["gates"], zo) < 1e-4
     assert abs(r["loss"] - float(Fn.bce_with_logits(lo, batch[3], pw))) < 1e-5
-    assert arrays["preds"].shape == (4, 6) and arrays["gates"].shape == (4, 3 * cfg.hidden_sz) and "wacc_emo6" in metrics
+    assert arrays["preds"].shape == (4, 6) and arrays["gates"].shape == (4, 3 * cfg.hidden_sz) and "auc_pr_samples" in metrics
     a.close()
     b.close()
