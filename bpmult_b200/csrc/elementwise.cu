@@ -567,6 +567,25 @@ __global__ void timelin_wgrad_kernel(const float* __restrict__ dy, const T* __re
   }
 }
 
+// db[t2] += sum_{b, d < D} dy[b, t2, d] alone (the weight gradient then comes from tensor-core GEMMs): one block per output step
+__global__ void timelin_db_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int Tout, int D, int ld) {
+  const int t2 = blockIdx.x;
+  float acc = 0.f;
+  for (int b = 0; b < B; b++) {
+    const float* r = dy + ((int64_t)b * Tout + t2) * ld;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) acc += r[d];
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w];
+    db[t2] += v;
+  }
+}
+
 extern "C" int bpm_timelin_fwd(int dtype, const void* x, const float* W, const float* bias, void* y, int B, int Tin, int Tout, int D, int ld,
                                void* stream) {
   BPM_REQUIRE(x && W && y && B > 0 && Tin > 0 && Tout > 0 && D > 0 && ld >= D && ld % 8 == 0, "timelin_fwd: bad args");
@@ -589,6 +608,10 @@ extern "C" int bpm_timelin_bwd(int x_dtype, const float* dy, const void* x, cons
     timelin_kernel<float, true><<<grid, 128, (size_t)Tout * sizeof(float), (cudaStream_t)stream>>>(dy, W, nullptr, dx, Tout, Tin, D, ld, Tin,
                                                                                                     accumulate_dx);
     BPM_CHECK_LAUNCH("timelin_bwd(dx)");
+  }
+  if (dW == nullptr && db != nullptr) {
+    timelin_db_kernel<<<Tout, 256, 0, (cudaStream_t)stream>>>(dy, db, B, Tout, D, ld);
+    BPM_CHECK_LAUNCH("timelin_bwd(db)");
   }
   if (dW != nullptr) {
     dim3 grid(Tout, bpm_cdiv(Tin, 8));

@@ -64,9 +64,15 @@ class MMTrVaptEngine:
         self.Gproj = {m: (z((self.d.Dp, self.Kp[m]), torch.float32) if self.orig[m] != D else None) for m in "lav"}
         self.Wpost = z((self.d.Dp, self.Kpp), dtype)
         self.Gpost = z((self.d.Dp, self.Kpp), torch.float32)
-        # time-axis linears stay fp32 in the reference layout [T_out, T_in] (small, SIMT kernel)
+        # time-axis linears: fp32 in the reference layout [T_out, T_in] (exact SIMT kernels = precision mode).  With bf16 storage the three
+        # products run on tensor cores as per-sample GEMMs (y_b = W x_b + bias tile, dW += dy_b x_b^T, dx_b += W^T dy_b): W also as bf16,
+        # the bias as a [T_out, Dp] bf16 tile the GEMM epilogue adds as its residual input (zero in the pad columns).
         self.Wt = {n: (z((NV[to], NV[ti]), torch.float32), z((NV[to],), torch.float32)) for n, (ti, to) in TRANSFM.items()}
         self.Gt = {n: (z((NV[to], NV[ti]), torch.float32), z((NV[to],), torch.float32)) for n, (ti, to) in TRANSFM.items()}
+        self.tc_time = dtype == torch.bfloat16
+        if self.tc_time:
+            self.Wt_bf = {n: z((NV[to], NV[ti]), dtype) for n, (ti, to) in TRANSFM.items()}
+            self.Bt = {n: z((NV[to], self.d.Dp), dtype) for n, (ti, to) in TRANSFM.items()}
 
     # ---------------------------------------------------------------- parameters
     def param_shapes(self):
@@ -105,12 +111,17 @@ class MMTrVaptEngine:
                 w = params["proj_%s.weight" % m]
                 o.pack_matrix(w.view(w.shape[0], w.shape[1]), self.Wproj[m])
         o.pack_matrix(params["proj_poster.weight"], self.Wpost)
+        if self.tc_time:
+            for n in TRANSFM:
+                o.pack_matrix(params["transfm_%s.weight" % n], self.Wt_bf[n])
         o.batch_end()
         if self.audio is not None:
             self.audio.pack(params, "audio_enc.")
         for n in TRANSFM:
             self.Wt[n][0].copy_(params["transfm_%s.weight" % n])
             self.Wt[n][1].copy_(params["transfm_%s.bias" % n])
+            if self.tc_time:
+                self.Bt[n][:, :self.d.D].copy_(params["transfm_%s.bias" % n].view(-1, 1).expand(-1, self.d.D))
 
     def zero_grads(self):
         for e in self.enc.values():
@@ -156,14 +167,30 @@ class MMTrVaptEngine:
     # ---------------------------------------------------------------- pieces
     def _time_linear(self, name, h, B):
         ti, to = TRANSFM[name]
-        y = self.arena.get("t_" + name, (B * NV[to], self.d.Dp), self.T_)
-        self.ops.timelin_fwd(h, self.Wt[name][0], self.Wt[name][1], y, B, NV[ti], NV[to], self.d.D)
+        Tin, Tout, Dp = NV[ti], NV[to], self.d.Dp
+        y = self.arena.get("t_" + name, (B * Tout, Dp), self.T_)
+        if self.tc_time:
+            for b in range(B):                                   # A = W [T_out, T_in]; B operand = x_b stored [K = T_in, N = Dp]
+                self.ops.gemm(self.Wt_bf[name], h[b * Tin:(b + 1) * Tin], y[b * Tout:(b + 1) * Tout], Tout, Dp, Tin, tb=1, residual=self.Bt[name])
+        else:
+            self.ops.timelin_fwd(h, self.Wt[name][0], self.Wt[name][1], y, B, Tin, Tout, self.d.D)
         return y
 
     def _time_linear_bwd(self, name, dy, h, dh, B):
         """dy fp32 [B*T_out, Dp] -> dh fp32 [B*T_in, Dp] += ; weight / bias gradients accumulate"""
         ti, to = TRANSFM[name]
-        self.ops.timelin_bwd(dy, h, self.Wt[name][0], dh, True, self.Gt[name][0], self.Gt[name][1], B, NV[ti], NV[to], self.d.D)
+        Tin, Tout, D, Dp, o = NV[ti], NV[to], self.d.D, self.d.Dp, self.ops
+        if not self.tc_time:
+            o.timelin_bwd(dy, h, self.Wt[name][0], dh, True, self.Gt[name][0], self.Gt[name][1], B, Tin, Tout, D)
+            return
+        dyb = self.arena.get("t_dy_" + name, (B * Tout, Dp), self.T_)
+        o.cast_drop(dy, dyb)
+        o.timelin_bwd(dy, h, self.Wt[name][0], None, False, None, self.Gt[name][1], B, Tin, Tout, D)      # bias gradient only
+        for b in range(B):
+            g, x = dyb[b * Tout:(b + 1) * Tout], h[b * Tin:(b + 1) * Tin]
+            o.gemm(g, x, self.Gt[name][0], Tout, Tin, Dp, accumulate=True)                               # dW += dy_b x_b^T   (K = Dp)
+            # dx_b += W^T dy_b: A = W stored [K = T_out, M = T_in], B operand = dy_b stored [K, N]; N = D keeps the pad columns untouched
+            o.gemm(self.Wt_bf[name], g, dh[b * Tin:(b + 1) * Tin], Tin, D, Tout, ta=1, tb=1, accumulate=True)
 
     # ---------------------------------------------------------------- forward
     def forward(self, txt, img, audio, poster, training=True, seed=0, seed_ptr=None):

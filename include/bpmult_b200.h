@@ -212,7 +212,9 @@ int bpm_tsgate_bwd(const float* hpre, const float* zpre, const float* dfused, in
 
 /* ---- time-axis Linear of the 4-modality model: mmtr.py:507-508,530,553  transfm_x2y(h.permute(2,1,0)).permute(2,1,0) ------
  * y[b, t2, d] = bias[t2] + sum_t W[t2, t] x[b, t, d] on batch-major [B, T, ld] rows (W = the nn.Linear weight [Tout, Tin], fp32;
- * columns D..ld are written as zeros).  Backward: dy fp32 -> dx fp32 (+= when accumulate_dx), dW += , db += (NULL pointers skip). */
+ * columns D..ld are written as zeros).  Backward: dy fp32 -> dx fp32 (+= when accumulate_dx), dW += , db += (NULL pointers skip;
+ * dW == NULL with db != NULL computes the bias gradient alone).  These are the exact-fp32 kernels; with bf16 storage the engine runs the
+ * three products as per-sample bpm_gemm calls on tensor cores (y_b = W x_b, dW += dy_b x_b^T, dx_b += W^T dy_b) and takes only db here. */
 int bpm_timelin_fwd(int dtype, const void* x, const float* W, const float* bias, void* y, int B, int Tin, int Tout, int D, int ld,
                     void* stream);
 int bpm_timelin_bwd(int x_dtype, const float* dy, const void* x, const float* W, float* dx, int accumulate_dx, float* dW, float* db,
