@@ -897,23 +897,37 @@ extern "C" int bpm_bce_fwd_bwd(const float* logits, int ldl, const float* target
 
 // ---------------------------------------------------------------- Adam
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
-                            float b1, float b2, float eps, float gs, const int64_t* __restrict__ step_ptr, const float* __restrict__ lr_ptr) {
+                            float b1, float b2, float eps, float gs, const int64_t* __restrict__ step_ptr, const float* __restrict__ lr_ptr, int vec) {
   float step = (float)(*step_ptr);
   if (lr_ptr) lr = *lr_ptr;
   float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
   float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i] * gs;
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gs;
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  };
+  // 28 bytes of traffic per parameter and nothing else: 16-byte accesses (the four buffers are 16-byte aligned: checked by the caller)
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pi = ((float4*)p)[i], mi = ((float4*)m)[i], vi = ((float4*)v)[i];
+    const float4 gi = __ldg((const float4*)g + i);
+    upd(pi.x, gi.x, mi.x, vi.x); upd(pi.y, gi.y, mi.y, vi.y); upd(pi.z, gi.z, mi.z, vi.z); upd(pi.w, gi.w, mi.w, vi.w);
+    ((float4*)m)[i] = mi; ((float4*)v)[i] = vi; ((float4*)p)[i] = pi;
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
   }
 }
 extern "C" int bpm_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                              float grad_scale, const int64_t* step_ptr, const float* lr_ptr, void* stream) {
   BPM_REQUIRE(param && grad && m && v && step_ptr && n > 0, "adam: bad args");
-  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, grad_scale, step_ptr, lr_ptr);
+  const int vec = ((((uintptr_t)param) | ((uintptr_t)grad) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+  adam_kernel<<<grid_for(vec ? (n + 3) / 4 : n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, grad_scale, step_ptr,
+                                                                                      lr_ptr, vec);
   BPM_CHECK_LAUNCH("adam");
   return BPM_OK;
 }

@@ -134,6 +134,13 @@ class MMTrVatEngine:
         o.batch_end()
 
     def zero_grads(self):
+        self.ops.zero_begin()
+        try:
+            self._zero_grads()
+        finally:
+            self.ops.zero_end()
+
+    def _zero_grads(self):
         for e in self.enc.values():
             e.zero_grads()
         for g in self.gmu.values():

@@ -124,6 +124,13 @@ class MMTrVaptEngine:
                 self.Bt[n][:, :self.d.D].copy_(params["transfm_%s.bias" % n].view(-1, 1).expand(-1, self.d.D))
 
     def zero_grads(self):
+        self.ops.zero_begin()
+        try:
+            self._zero_grads()
+        finally:
+            self.ops.zero_end()
+
+    def _zero_grads(self):
         for e in self.enc.values():
             e.zero_grads()
         for g in self.gmu.values():

@@ -65,6 +65,7 @@ class CudaOps:
             return
         mode, key, items = self._batch
         self._batch = None
+        self._zlist, self._zdepth = None, 0
         if not items:
             return
         def build():
@@ -371,5 +372,21 @@ class CudaOps:
                                         0 if lr_t is None else lr_t.data_ptr(), self._s()), "adam_step")
 
     def zero_(self, t):
-        """memset on the current stream (cudaMemsetAsync through torch; capturable)."""
-        t.zero_()
+        """memset on the current stream (cudaMemsetAsync through torch; capturable); inside zero_begin() / zero_end() the tensors are
+        collected and cleared by ONE multi-tensor launch (the ~100 gradient accumulators of a model: 0.6 ms of 6 us fills per step)."""
+        if self._zlist is not None:
+            self._zlist.append(t)
+        else:
+            t.zero_()
+
+    def zero_begin(self):
+        self._zdepth += 1
+        if self._zlist is None:
+            self._zlist = []
+
+    def zero_end(self):
+        self._zdepth -= 1
+        if self._zdepth == 0:
+            lst, self._zlist = self._zlist, None
+            if lst:
+                torch._foreach_zero_(lst)

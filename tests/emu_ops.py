@@ -71,6 +71,12 @@ class EmuOps:
     def zero_(self, t):
         t.zero_()
 
+    def zero_begin(self):
+        pass
+
+    def zero_end(self):
+        pass
+
     def batch_begin(self, mode, key):
         pass
 

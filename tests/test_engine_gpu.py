@@ -127,7 +127,55 @@ def test_mmtrvapt_vs_reference_golden(ops, dtype):
         # (the bars that mean something are at the benchmarked width, against torch's own bf16 autocast: tests/test_fullshape_gpu.py --
         # there d txt is 2.3e-2 with 1.8e-2 for autocast.  Measured here: 1.02e-1 with the time-axis linears on tensor cores, 0.9e-1 before)
         assert Fn.rel_l2(dtxt, rec["dtxt"]) < 1.5e-1
-        check_fingerprints(grads, rec["pgrad_fp"], 2.5e-1)
+        # the head's proj1 has B * D = 80 ReLU units here: bf16 noise on its input moves one of them across zero and its bias gradient
+        # (40 numbers) by 0.44; every other tensor stays under the sanity bar
+        from helpers import fingerprint_errors
+        errs = fingerprint_errors(grads, rec["pgrad_fp"])
+        head = {n: e for n, e in errs.items() if n.startswith("proj1.")}
+        rest = {n: e for n, e in errs.items() if not n.startswith("proj1.")}
+        assert max(rest.values()) < 2.5e-1, max(rest.items(), key=lambda kv: kv[1])
+        assert max(head.values()) < 6e-1, head
+
+
+def rnd_(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("D", [40, 128])
+def test_time_axis_linears_on_tensor_cores_match_the_definition(ops, D):
+    """mmtr.py:507-508,530,553 with bf16 storage: per-sample GEMMs (y_b = W x_b + bias, dW += dy_b x_b^T, dx_b += W^T dy_b) against the
+    einsum definition on bf16-representable operands, so that only the bf16 rounding of the outputs / of dy is left: pad columns
+    (D = 40 -> Dp = 64) stay zero in y and untouched in dx; D = 128 has none."""
+    from argparse import Namespace
+    from emu_ops import EmuOps
+    from bpmult_b200.model_engine4 import MMTrVaptEngine, NV, TRANSFM
+    cfg = synth.tiny_cfg(layers=1, hidden_sz=D, num_heads=4)
+    eng = MMTrVaptEngine(ops, Namespace(**vars(cfg)), dtype=torch.bfloat16)
+    assert eng.tc_time
+    dev, B, Dp, emu = ops.device, 3, eng.d.Dp, EmuOps()
+    bfr = lambda t: t.to(torch.bfloat16).float()
+    for name, (ti, to) in TRANSFM.items():
+        Tin, Tout = NV[ti], NV[to]
+        W, bias = bfr(rnd_((Tout, Tin), 1) * 0.1), bfr(rnd_((Tout,), 2))
+        x = torch.zeros(B * Tin, Dp)
+        x[:, :D] = bfr(rnd_((B * Tin, D), 3))
+        dy = torch.zeros(B * Tout, Dp)
+        dy[:, :D] = bfr(rnd_((B * Tout, D), 4))
+        dx0 = rnd_((B * Tin, Dp), 5)
+        eng.Wt[name][0].copy_(W); eng.Wt[name][1].copy_(bias)
+        eng.Wt_bf[name].copy_(W); eng.Bt[name].zero_(); eng.Bt[name][:, :D].copy_(bias.view(-1, 1).expand(-1, D))
+        eng.Gt[name][0].zero_(); eng.Gt[name][1].zero_()
+        xg, dxg = x.to(dev, torch.bfloat16), dx0.to(dev)
+        y = eng._time_linear(name, xg, B)
+        eng._time_linear_bwd(name, dy.to(dev), xg, dxg, B)
+        torch.cuda.synchronize()
+        y_e, dx_e, dW_e, db_e = torch.zeros(B * Tout, Dp), dx0.clone(), torch.zeros(Tout, Tin), torch.zeros(Tout)
+        emu.timelin_fwd(x, W, bias, y_e, B, Tin, Tout, D)
+        emu.timelin_bwd(dy, x, W, dx_e, True, dW_e, db_e, B, Tin, Tout, D)
+        assert Fn.max_rel(y.float().cpu(), y_e) < 6e-3, name                         # bf16 output rounding
+        assert float(y[:, D:].float().abs().max()) == 0.0 if Dp > D else True
+        assert Fn.max_rel(dxg.cpu(), dx_e) < 1e-5 and torch.equal(dxg.cpu()[:, D:], dx0[:, D:]), name
+        assert Fn.max_rel(eng.Gt[name][0].cpu(), dW_e) < 1e-5 and Fn.max_rel(eng.Gt[name][1].cpu(), db_e) < 1e-5, name
 
 
 @pytest.mark.parametrize("lanes", ["1", "3"])
