@@ -57,7 +57,8 @@ class Trainer:
         if self.device.type == "cuda":
             self.loss_slots = [t.pin_memory() for t in self.loss_slots]
         self.loss_host = self.loss_slots[0]
-        self._h2d_done = None
+        self._h2d_done = self._taken = None
+        self._copy_stream = None
         self.steps_done = 0
 
     # ---------------------------------------------------------------- flat parameter / gradient buffers
@@ -301,9 +302,12 @@ class Trainer:
             dev = self.device
             self.static = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
             self.pinned = [torch.zeros(s, dtype=torch.float32).pin_memory() if self.on_gpu else torch.zeros(s) for s in shapes]
+            # device-side landing buffers of step_async: the H2D of step k + 1 runs on a copy stream while step k computes
+            self.stage_dev = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes] if self.on_gpu else None
             self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
             self.shapes, self.graphs = shapes, {}
             self.warm = 0
+            self._h2d_done = self._landed = self._taken = None
 
     def step_device(self, *batch):
         """batch = (txt, img, audio, targets) for mmtrvat, (txt, img, audio, poster, targets) for mmtrvapt, already resident on the
@@ -325,18 +329,35 @@ class Trainer:
         (enqueue step k+1, then `item()` of step k) keeps the GPU busy while the host prepares the next launch.  Pinned inputs are
         read by DMA straight from the caller's tensors: keep them unchanged until the handle has been read."""
         self._ensure_static(*batch)
-        if self.on_gpu and self._h2d_done is not None:
-            self._h2d_done.synchronize()                    # the previous step's copies out of the staging buffers have finished
-        for pbuf, s, t in zip(self.pinned, self.static, batch):
-            if self.on_gpu and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous():
-                s.copy_(t, non_blocking=True)               # e.g. DataLoader(pin_memory=True): DMA straight from the caller's buffer
-            else:
-                pbuf.copy_(t)                               # pageable input: staged through this trainer's pinned buffers
-                s.copy_(pbuf, non_blocking=True)
+        if not self.on_gpu:
+            for s, t in zip(self.static, batch):
+                s.copy_(t)
+        else:
+            # copy stream: pinned host -> landing buffers (waits only for the previous step's D2D out of them, which is the first thing
+            # that step did); compute stream: landing -> static inputs (D2D, microseconds), then the captured step
+            main = torch.cuda.current_stream(self.device)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            cs = self._copy_stream
+            if self._h2d_done is not None:
+                self._h2d_done.synchronize()                # the previous copies out of this trainer's pinned staging have finished
+            if self._taken is not None:
+                cs.wait_event(self._taken)
+            with torch.cuda.stream(cs):
+                for pbuf, sd, t in zip(self.pinned, self.stage_dev, batch):
+                    if t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous():
+                        sd.copy_(t, non_blocking=True)      # e.g. DataLoader(pin_memory=True): DMA straight from the caller's buffer
+                    else:
+                        pbuf.copy_(t)                       # pageable input: staged through this trainer's pinned buffers
+                        sd.copy_(pbuf, non_blocking=True)
+                self._h2d_done = torch.cuda.Event()
+                self._h2d_done.record(cs)
+            main.wait_event(self._h2d_done)
+            for s, sd in zip(self.static, self.stage_dev):
+                s.copy_(sd, non_blocking=True)
+            self._taken = torch.cuda.Event()
+            self._taken.record(main)
         slot = self._loss_slot = (getattr(self, "_loss_slot", 1) + 1) & 1
-        if self.on_gpu:
-            self._h2d_done = torch.cuda.Event()
-            self._h2d_done.record(torch.cuda.current_stream(self.device))
         self._run()
         self.loss_slots[slot].copy_(self.loss_dev, non_blocking=True)
         ev = None
