@@ -47,6 +47,7 @@ class CudaOps:
         self.launches = 0
         self._depth = 0
         self._batch = None          # (mode, key, [descriptor tuples]) while pack / unpack calls are being collected
+        self._zlist, self._zdepth = None, 0     # tensors collected between zero_begin() and zero_end()
         self._tables = {}           # descriptor-list signature -> [device table, pinned by a captured graph]  (see _table)
         self.max_tables = 256
         self.capture_owner = "anonymous"
@@ -65,7 +66,6 @@ class CudaOps:
             return
         mode, key, items = self._batch
         self._batch = None
-        self._zlist, self._zdepth = None, 0
         if not items:
             return
         def build():

@@ -175,6 +175,31 @@ def test_layernorm(ops, D, Dp, xd, yd):
         assert max_rel(a, b) < 2e-5
 
 
+@pytest.mark.parametrize("D,Dp", [(300, 320), (40, 64), (100, 128), (768, 768), (380, 384)])
+@pytest.mark.parametrize("cd", [F32, BF16])
+@pytest.mark.parametrize("rows", [77, 1, 512])
+def test_layernorm_bwd_with_fused_cast_and_dropout(ops, D, Dp, cd, rows):
+    """the backward's fused epilogue (next block's GEMM operand = dropout mask * dx_new, bit-exact mask) in overwrite mode, for the
+    half-warp-per-row mapping (Dp = 64 * n, odd row counts, a single row) and the warp-per-row one (Dp = 768)"""
+    x = torch.zeros(rows, Dp)
+    x[:, :D] = rnd((rows, D), 31) * 2 - 0.5
+    gam = torch.zeros(Dp)
+    gam[:D] = 1 + 0.1 * rnd((D,), 32)
+    mean = x[:, :D].mean(1)
+    rstd = (x[:, :D].var(1, unbiased=False) + 1e-5).rsqrt()
+    dy = torch.zeros(rows, Dp)
+    dy[:, :D] = rnd((rows, D), 33)
+    dy = dy.to(BF16)
+    outs = [rnd((rows, Dp), 34), torch.zeros(Dp), torch.zeros(Dp), torch.full((rows, Dp), 7.0, dtype=cd)]
+    e, c = both(ops, lambda o, dy, x, m, r, g, dx, dg, db, co: o.layernorm_bwd(dy, x, m, r, g, D, dx, False, dg, db, cast_out=co, cast_drop=DROP),
+                [dy, x, mean, rstd, gam], outs)
+    for a, b in zip(c[:3], e[:3]):
+        assert max_rel(a, b) < 2e-5
+    assert torch.equal(c[3] == 0, e[3] == 0)                              # the same elements dropped
+    assert max_rel(c[3].float(), e[3].float()) < tol(cd)
+    assert (c[0][:, D:] == 0).all() and (c[3][:, D:] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------------ GEMM (FFMA fp32 + tcgen05 bf16)
 GEMM_SHAPES = [(128, 320, 320), (256, 384, 320), (40, 320, 384), (200, 1216, 320), (300, 320, 1216), (128, 64, 64), (130, 48, 72), (1024, 320, 320)]
 
