@@ -63,6 +63,78 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TI* __restr
   }
 }
 
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) { const float4 a = *(const float4*)p; v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+  __device__ __forceinline__ void store(float* p) const { *(float4*)p = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec4<bf16> {
+  float v[4];
+  __device__ __forceinline__ void load(const bf16* p) {
+    const uint2 r = *(const uint2*)p;
+    const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&r.x), b = __bfloat1622float2(*(const __nv_bfloat162*)&r.y);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  __device__ __forceinline__ void store(bf16* p) const {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 r;
+    r.x = *(const uint32_t*)&a; r.y = *(const uint32_t*)&b;
+    *(uint2*)p = r;
+  }
+};
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// forward with half a warp per row (two rows per warp, 4-element vectors): for Dp = 64 * n every lane is busy and a warp has two rows
+// of loads in flight (the warp-per-row kernel is latency-bound: ncu long-scoreboard 50 %, and fills 40 of 64 lane slots at Dp = 320)
+template <typename TI, typename TO, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_hw_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  int rows, int D, int Dp, float eps, TO* __restrict__ y, float* __restrict__ mean_out,
+                                                                  float* __restrict__ rstd_out) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+  const float invD = 1.f / (float)D, npad = (float)(Dp - D);
+  Vec4<float> g[NV], b[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) { g[i].load(gamma + (hl + 16 * i) * 4); b[i].load(beta + (hl + 16 * i) * 4); }
+  for (int64_t pr = blockIdx.x * LN_WARPS + warp; 2 * pr < rows; pr += gridDim.x * LN_WARPS) {
+    const int64_t row = 2 * pr + half;
+    const bool valid = row < rows;
+    const TI* xr = x + row * Dp;
+    Vec4<TI> v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      if (valid) v[i].load(xr + (hl + 16 * i) * 4);
+      else v[i].v[0] = v[i].v[1] = v[i].v[2] = v[i].v[3] = 0.f;
+      s += (v[i].v[0] + v[i].v[1]) + (v[i].v[2] + v[i].v[3]);
+    }
+    const float mean = half_warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const float d = v[i].v[j] - mean; v[i].v[j] = d; q = fmaf(d, d, q); }
+    }
+    const float rstd = rsqrtf((half_warp_sum(q) - npad * mean * mean) * invD + eps);
+    if (!valid) continue;
+    if (hl == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    TO* yr = y + row * Dp;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      Vec4<TO> o;
+#pragma unroll
+      for (int j = 0; j < 4; j++) o.v[j] = fmaf(v[i].v[j] * rstd, g[i].v[j], b[i].v[j]);
+      o.store(yr + (hl + 16 * i) * 4);
+    }
+  }
+}
+
 // backward: persistent grid, each warp walks rows; dgamma/dbeta partials stay in registers until the end.
 // Optional fused epilogue: cast_out (bf16 / fp32, pitch Dp) = dropmask * dx_new, i.e. the GEMM operand the NEXT backward block would
 // otherwise produce with a separate pass over dx (bpm_cast_drop); element index of the mask = row * Dp + column.
@@ -334,32 +406,6 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 4) ln_bwd_pf_kernel(const TG* _
 // warp takes TWO consecutive rows, 16 lanes each, 4-element vectors: Dp = 64 * NV fills every lane (320 = 16 x 5 x 4).  Same prefetch
 // scheme (one bulk copy brings both rows of a stage: consecutive rows are contiguous), same arithmetic and summation order per row.
 #define LN_HPF 2                                 // stages (row pairs) in flight per warp
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
-  float v[4];
-  __device__ __forceinline__ void load(const float* p) { const float4 a = *(const float4*)p; v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
-  __device__ __forceinline__ void store(float* p) const { *(float4*)p = make_float4(v[0], v[1], v[2], v[3]); }
-};
-template <> struct Vec4<bf16> {
-  float v[4];
-  __device__ __forceinline__ void load(const bf16* p) {
-    const uint2 r = *(const uint2*)p;
-    const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&r.x), b = __bfloat1622float2(*(const __nv_bfloat162*)&r.y);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-  }
-  __device__ __forceinline__ void store(bf16* p) const {
-    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 r;
-    r.x = *(const uint32_t*)&a; r.y = *(const uint32_t*)&b;
-    *(uint2*)p = r;
-  }
-};
-__device__ __forceinline__ float half_warp_sum(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 template <typename TG, typename TX, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_bwd_hw_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean_in,
                                                                const float* __restrict__ rstd_in, const float* __restrict__ gamma, int rows, int D,
@@ -526,6 +572,19 @@ static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, i
                          cudaStream_t s) {
   int nv = bpm_cdiv(Dp / 8, 32);
   int grid = min(bpm_cdiv(rows, LN_WARPS), bpm_num_sms() * 16);
+  if (Dp % 64 == 0 && Dp / 64 <= 6 && Dp % 256 != 0 && !(bpm_debug_get(0) & 2048)) {
+    const int hgrid = min(bpm_cdiv(bpm_cdiv(rows, 2), LN_WARPS), bpm_num_sms() * 16);
+#define LNFH(NV) (void)bpm_launch(ln_fwd_hw_kernel<TI, TO, NV>, dim3(hgrid), dim3(LN_WARPS * 32), 0, s, (const TI*)x, gamma, beta, rows, D, Dp, eps, (TO*)y, mean, rstd)
+    switch (Dp / 64) {
+      case 1: LNFH(1); break;
+      case 2: LNFH(2); break;
+      case 3: LNFH(3); break;
+      case 5: LNFH(5); break;
+      default: LNFH(6); break;
+    }
+#undef LNFH
+    return BPM_OK;
+  }
 #define LNF(NV) (void)bpm_launch(ln_fwd_kernel<TI, TO, NV>, dim3(grid), dim3(LN_WARPS * 32), 0, s, (const TI*)x, gamma, beta, rows, D, Dp, eps, (TO*)y, mean, rstd)
   switch (nv) {
     case 1: LNF(1); break;
