@@ -505,18 +505,24 @@ struct AttnBwdSmem {
 static_assert(AttnBwdSmem::DST % 1024 == 0 && AttnBwdSmem::STG % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 static_assert(AttnBwdSmem::TOTAL + 1024 <= 227 * 1024, "shared memory budget");
 
-__global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ ws,
-                                  int B, int T, int H) {
-  // ws[0][b, h, t] = delta = sum_d dO * O   (one thread per (row, head): 2 x 64 B);   ws[1][b, h, t] = lse * log2e
+#define AD_TT 32                                  // rows (time steps) per block of the delta kernel
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                                                         float* __restrict__ ws, int B, int T, int H) {
+  // ws[0][b, h, t] = delta = sum_d dO * O;   ws[1][b, h, t] = lse * log2e.  A block takes AD_TT consecutive rows of one sample: the dot
+  // products run head-fastest (a warp reads 2 KB contiguous of O and dO), land in shared memory as [h][t] and leave time-fastest, so
+  // that both sides are coalesced (thread-per-(row, head) wrote 4-byte words T * 4 bytes apart: 14.8 us for 50 MB).
+  __shared__ float d_s[32 * (AD_TT + 1)];
   pdl_trigger();
   pdl_wait();
-  int64_t n = (int64_t)B * T * H;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-    int h = (int)(idx % H);
-    int64_t row = idx / H;
-    int t = (int)(row % T), b = (int)(row / T);
-    const bf16* o = out + row * (H * AT_DH) + h * AT_DH;
-    const bf16* g = dout + row * (H * AT_DH) + h * AT_DH;
+  const int tiles = (T + AD_TT - 1) / AD_TT;
+  const int b = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * AD_TT;
+  const int nt = min(AD_TT, T - t0), HP = H * AT_DH;
+  const int64_t n = (int64_t)B * T * H;
+  for (int i = threadIdx.x; i < nt * H; i += blockDim.x) {
+    const int tl = i / H, h = i - tl * H;
+    const int64_t row = (int64_t)b * T + t0 + tl;
+    const bf16* o = out + row * HP + h * AT_DH;
+    const bf16* g = dout + row * HP + h * AT_DH;
     float acc = 0.f;
 #pragma unroll
     for (int u = 0; u < AT_DH / 8; u++) {
@@ -524,13 +530,18 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
 #pragma unroll
       for (int j = 0; j < 8; j++) acc = fmaf(a.v[j], c.v[j], acc);
     }
-    const int64_t o_idx = ((int64_t)b * H + h) * T + t;
-    ws[o_idx] = acc;
-    ws[n + o_idx] = lse[o_idx] * LOG2E_F;
+    d_s[h * (AD_TT + 1) + tl] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < AD_TT * H; i += blockDim.x) {
+    const int h = i / AD_TT, tl = i - h * AD_TT;
+    if (tl < nt) {
+      const int64_t o_idx = ((int64_t)b * H + h) * T + t0 + tl;
+      ws[o_idx] = d_s[h * (AD_TT + 1) + tl];
+      ws[n + o_idx] = lse[o_idx] * LOG2E_F;
+    }
   }
 }
-
-
 
 // One NC-column chunk of a (128 keys x 128 queries) pair for key row `key`: sv (S^T) -> P~^T, dpv (dP^T) -> dS^T, in place.
 //   MASKED: columns [0, cmin) of the chunk are invisible to this key row (cmin >= NC: all of them, e.g. a key beyond S).
@@ -1069,8 +1080,8 @@ int bpm_xattn_bwd_tc(const bpm_attn_t* a, const void* q, const void* k, const vo
                (uintptr_t)delta) % 16 == 0, "xattn_bwd: pointers must be 16-byte aligned");
   const int HP = a->H * a->dhp;
   {
-    int64_t n = (int64_t)a->B * a->T * a->H;
-    int grid = (int)((n + 255) / 256 < (int64_t)bpm_num_sms() * 8 ? (n + 255) / 256 : (int64_t)bpm_num_sms() * 8);
+    BPM_REQUIRE(a->H <= 32, "xattn_bwd: more than 32 heads");
+    const int grid = a->B * ((a->T + AD_TT - 1) / AD_TT);
     cudaError_t le = bpm_launch(attn_delta_kernel, dim3(grid), dim3(256), 0, stream, (const bf16*)out, (const bf16*)dout, lse, delta, a->B, a->T, a->H);
     if (le != cudaSuccess) { bpm_set_error("xattn_delta: launch failed: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return BPM_ELAUNCH; }
   }
