@@ -7,10 +7,13 @@ sys.path.insert(0, ".")
 from bpmult_b200.engine import Dims
 from bpmult_b200.ops import CudaOps
 
+import os
 ops = CudaOps()
 dev = ops.device
-d = Dims(300, 12)
-M = 64 * 512
+d = Dims(int(os.environ.get("LN_D", "300")), 12 if os.environ.get("LN_D", "300") == "300" else 6)
+M = int(os.environ.get("LN_ROWS", str(64 * 512)))
+if os.environ.get("LN_RPW"):
+    ops.lib.bpm_debug_set(2, int(os.environ["LN_RPW"]))
 NS = 4
 bf = torch.bfloat16
 x = [torch.randn(M, d.Dp, device=dev) for _ in range(NS)]
