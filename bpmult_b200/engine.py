@@ -671,34 +671,47 @@ class HeadEngine:
     """pooling (mmtr.py:808,830,852) -> TextShiftingN (mmtr.py:197-247) -> residual MLP (:860-861) -> out_layer (:866)
     -> BCEWithLogits (train.py:104,333).  B rows only: runs entirely in fp32 on the FFMA GEMM + small fused kernels."""
 
-    def __init__(self, ops, D, n_in, n_classes, out_dropout=0.0, uid=4095):
+    def __init__(self, ops, D, n_in, n_classes, out_dropout=0.0, uid=4095, prefix="gmu.", list_names=False, gate_only=False):
+        """prefix / list_names: parameter names of the gate -- `<prefix>hidden{i+1}.weight`, `<prefix>x{i+1}_gate.weight` (TextShifting3/4Layer)
+        or `<prefix>hiddens.{i}.weight`, `<prefix>x_gates.{i}.weight` (TextShiftingNLayer, an nn.ModuleList).  gate_only: the gate alone
+        (gate_forward / gate_backward), without the residual MLP and the classifier -- the hybrid branch's gmu_early (mmtr.py:631,775)."""
         self.ops, self.D, self.Dp, self.n_in, self.C = ops, D, round_up(D, 64), n_in, n_classes
         self.Cp = round_up(n_classes, 8)
         self.p_out, self.uid = out_dropout, uid
+        self.prefix, self.list_names, self.gate_only = prefix, list_names, gate_only
         z, f32, Dp, n = ops.zeros, torch.float32, self.Dp, n_in
-        self.W = dict(h=[z((Dp, Dp), f32) for _ in range(n)], zg=[z((Dp, n * Dp), f32) for _ in range(n)],
-                      p1=z((Dp, Dp), f32), p1b=z((Dp,), f32), p2=z((Dp, Dp), f32), p2b=z((Dp,), f32),
-                      out=z((self.Cp, Dp), f32), outb=z((self.Cp,), f32))
-        self.G = dict(h=[z((Dp, Dp), f32) for _ in range(n)], zg=[z((Dp, n * Dp), f32) for _ in range(n)],
-                      p1=z((Dp, Dp), f32), p1b=z((Dp,), f32), p2=z((Dp, Dp), f32), p2b=z((Dp,), f32),
-                      out=z((self.Cp, Dp), f32), outb=z((self.Cp,), f32))
+        mk = lambda: dict(h=[z((Dp, Dp), f32) for _ in range(n)], zg=[z((Dp, n * Dp), f32) for _ in range(n)])
+        self.W, self.G = mk(), mk()
+        if not gate_only:
+            for d in (self.W, self.G):
+                d.update(p1=z((Dp, Dp), f32), p1b=z((Dp,), f32), p2=z((Dp, Dp), f32), p2b=z((Dp,), f32),
+                         out=z((self.Cp, Dp), f32), outb=z((self.Cp,), f32))
         self.arena = Arena(ops)
+
+    def _hn(self, i):
+        return "%shiddens.%d.weight" % (self.prefix, i) if self.list_names else "%shidden%d.weight" % (self.prefix, i + 1)
+
+    def _zn(self, i):
+        return "%sx_gates.%d.weight" % (self.prefix, i) if self.list_names else "%sx%d_gate.weight" % (self.prefix, i + 1)
 
     def param_shapes(self):
         D, n, s = self.D, self.n_in, {}
         for i in range(n):
-            s["gmu.hidden%d.weight" % (i + 1)] = (D, D)
+            s[self._hn(i)] = (D, D)
         for i in range(n):
-            s["gmu.x%d_gate.weight" % (i + 1)] = (D, n * D)
-        s.update({"proj1.weight": (D, D), "proj1.bias": (D,), "proj2.weight": (D, D), "proj2.bias": (D,),
-                  "out_layer.weight": (self.C, D), "out_layer.bias": (self.C,)})
+            s[self._zn(i)] = (D, n * D)
+        if not self.gate_only:
+            s.update({"proj1.weight": (D, D), "proj1.bias": (D,), "proj2.weight": (D, D), "proj2.bias": (D,),
+                      "out_layer.weight": (self.C, D), "out_layer.bias": (self.C,)})
         return s
 
     def pack(self, params):
         o, W = self.ops, self.W
         for i in range(self.n_in):
-            o.pack_matrix(params["gmu.hidden%d.weight" % (i + 1)], W["h"][i])
-            o.pack_matrix(params["gmu.x%d_gate.weight" % (i + 1)], W["zg"][i], col_map=(self.D, self.Dp))
+            o.pack_matrix(params[self._hn(i)], W["h"][i])
+            o.pack_matrix(params[self._zn(i)], W["zg"][i], col_map=(self.D, self.Dp))
+        if self.gate_only:
+            return
         o.pack_matrix(params["proj1.weight"], W["p1"]); o.pack_matrix(params["proj1.bias"].view(1, -1), W["p1b"].view(1, -1))
         o.pack_matrix(params["proj2.weight"], W["p2"]); o.pack_matrix(params["proj2.bias"].view(1, -1), W["p2b"].view(1, -1))
         o.pack_matrix(params["out_layer.weight"], W["out"]); o.pack_matrix(params["out_layer.bias"].view(1, -1), W["outb"].view(1, -1))
@@ -711,8 +724,10 @@ class HeadEngine:
     def unpack_grads(self, grads, accumulate=False):
         o, G = self.ops, self.G
         for i in range(self.n_in):
-            o.unpack_matrix(G["h"][i], grads["gmu.hidden%d.weight" % (i + 1)], accumulate=accumulate)
-            o.unpack_matrix(G["zg"][i], grads["gmu.x%d_gate.weight" % (i + 1)], col_map=(self.D, self.Dp), accumulate=accumulate)
+            o.unpack_matrix(G["h"][i], grads[self._hn(i)], accumulate=accumulate)
+            o.unpack_matrix(G["zg"][i], grads[self._zn(i)], col_map=(self.D, self.Dp), accumulate=accumulate)
+        if self.gate_only:
+            return
         o.unpack_matrix(G["p1"], grads["proj1.weight"], accumulate=accumulate)
         o.unpack_matrix(G["p1b"].view(1, -1), grads["proj1.bias"].view(1, -1), accumulate=accumulate)
         o.unpack_matrix(G["p2"], grads["proj2.weight"], accumulate=accumulate)

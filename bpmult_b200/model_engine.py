@@ -20,6 +20,11 @@ TARGETS = {"l": ("v_with_a", "a_with_v", "l_with_a2v", "l_with_v2a"),      # mmt
            "a": ("l_with_v", "v_with_l", "a_with_v2l", "a_with_l2v"),      # mmtr.py:810-830
            "v": ("l_with_a", "a_with_l", "v_with_a2l", "v_with_l2a")}      # mmtr.py:832-852
 HEAD_ORDER = ["l", "v", "a"]                                               # gmu([last_h_l, last_h_v, last_h_a]) :857
+# hybrid = True (mmtr.py:631, 662, 680-689, 765-775, 854-855): per modality a bias-free Linear over the time axis (n_vec -> LOW_DIM
+# steps), a self-attention encoder of max(layers, 3) layers, first + last step pooling; gmu_early fuses (l, v, a); the result is the
+# fourth input of the final TextShiftingNLayer.  The two gate call sites are read as what their callees accept (list vs varargs).
+LOW_DIM = 32
+EARLY = ["l_early", "v_early", "a_early"]                                   # ctor order :681-683; gmu_early(l, v, a) :775
 
 
 class Lanes:
@@ -89,11 +94,22 @@ class MMTrVatEngine:
                                         biprojection=False, dtype=dtype, uid=i + 1, shared=self.lane_shared[self.lane_of[n]])
         self.gmu = {}
         self.mod_lane = {m: i % self.lanes.n for i, m in enumerate(HEAD_ORDER)}      # lane of a modality's staging / gated units
+        self.hybrid = bool(getattr(args, "hybrid", False))
+        self.enc_names = ENC_NAMES + (EARLY if self.hybrid else [])
+        if self.hybrid:
+            for i, n in enumerate(EARLY):                     # get_network('*_mem', layers=3): every early stack uses attn_dropout (:699-707)
+                self.enc[n] = EncoderEngine(ops, D, H, max(L, 3), attn_dropout=args.attn_dropout, relu_dropout=args.relu_dropout,
+                                            res_dropout=args.res_dropout, embed_dropout=args.embed_dropout, attn_mask=args.attn_mask,
+                                            biprojection=False, dtype=dtype, uid=len(ENC_NAMES) + 1 + i,
+                                            shared=self.lane_shared[self.mod_lane[n[0]]])
+            self.We = {m: ops.zeros((LOW_DIM, n_vec), torch.float32) for m in "lva"}          # proj_{m}_e.weight, reference layout
+            self.Ge = {m: ops.zeros((LOW_DIM, n_vec), torch.float32) for m in "lva"}
+            self.gate_early = HeadEngine(ops, D, 3, args.n_classes, prefix="gmu_early.", gate_only=True)
         for m in "lav":
             sh = self.lane_shared[self.mod_lane[m]]
             self.gmu[m + "_m"] = SeqGmuEngine(ops, D, dtype, True, sh, "gmu_%s_m" % m)
             self.gmu[m] = SeqGmuEngine(ops, D, dtype, True, sh, "gmu_%s" % m)
-        self.head = HeadEngine(ops, D, 3, args.n_classes, out_dropout=args.out_dropout)
+        self.head = HeadEngine(ops, D, 4 if self.hybrid else 3, args.n_classes, out_dropout=args.out_dropout, list_names=self.hybrid)
         z = ops.zeros
         self.Wproj = {m: (z((self.d.Dp, self.Kp[m]), dtype) if self.orig[m] != D else None) for m in "lav"}
         self.Gproj = {m: (z((self.d.Dp, self.Kp[m]), torch.float32) if self.orig[m] != D else None) for m in "lav"}
@@ -107,10 +123,14 @@ class MMTrVatEngine:
                 s["gmu_%s.%s" % (m, k)] = v
         for m in "lva":
             s["proj_%s.weight" % m] = (D, self.orig[m], 1)
-        for n in ENC_NAMES:
+        for n in self.enc_names:
             for k, v in self.enc[n].param_shapes().items():
                 s["trans_%s.%s" % (n, k)] = v
         s.update(self.head.param_shapes())
+        if self.hybrid:
+            s.update(self.gate_early.param_shapes())
+            for m in "lva":
+                s["proj_%s_e.weight" % m] = (LOW_DIM, self.n_vec)
         return s
 
     def unused_params(self):
@@ -122,7 +142,7 @@ class MMTrVatEngine:
     def pack(self, params):
         o = self.ops
         o.batch_begin("pack", "model")                        # ONE launch for all ~1400 parameter tensors
-        for n in ENC_NAMES:
+        for n in self.enc_names:
             self.enc[n].pack(params, "trans_%s." % n)
         for m, g in self.gmu.items():
             g.pack(params, "gmu_%s." % m)
@@ -131,6 +151,10 @@ class MMTrVatEngine:
             if self.Wproj[m] is not None:
                 w = params["proj_%s.weight" % m]
                 o.pack_matrix(w.view(w.shape[0], w.shape[1]), self.Wproj[m])
+        if self.hybrid:
+            self.gate_early.pack(params)
+            for m in "lva":
+                o.pack_matrix(params["proj_%s_e.weight" % m], self.We[m])
         o.batch_end()
 
     def zero_grads(self):
@@ -149,24 +173,14 @@ class MMTrVatEngine:
         for m in "lav":
             if self.Gproj[m] is not None:
                 self.ops.zero_(self.Gproj[m])
+        if self.hybrid:
+            self.gate_early.zero_grads()
+            for m in "lva":
+                self.ops.zero_(self.Ge[m])
 
-    def unpack_grads(self, grads, accumulate=False):
-        self.ops.batch_begin("unpack", "model")
-        for n in ENC_NAMES:
-            self.enc[n].unpack_grads(grads, "trans_%s." % n, accumulate)
-        for m, g in self.gmu.items():
-            g.unpack_grads(grads, "gmu_%s." % m, accumulate)
-        self.head.unpack_grads(grads, accumulate)
-        for m in "lav":
-            if self.Gproj[m] is not None:
-                gw = grads["proj_%s.weight" % m]
-                self.ops.unpack_matrix(self.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=accumulate)
-        self.ops.batch_end()
-
-    def unpack_misc(self, grads, accumulate=False):
-        """gradients of everything but the encoders (the encoders' leave per bucket during backward, see Trainer)"""
+    def _unpack_rest(self, grads, accumulate):
+        """everything but the encoders, inside an open unpack batch"""
         o = self.ops
-        o.batch_begin("unpack", "misc")
         for m, g in self.gmu.items():
             g.unpack_grads(grads, "gmu_%s." % m, accumulate=accumulate)
         self.head.unpack_grads(grads, accumulate=accumulate)
@@ -174,6 +188,23 @@ class MMTrVatEngine:
             if self.Gproj[m] is not None:
                 gw = grads["proj_%s.weight" % m]
                 o.unpack_matrix(self.Gproj[m], gw.view(gw.shape[0], gw.shape[1]), accumulate=accumulate)
+        if self.hybrid:
+            self.gate_early.unpack_grads(grads, accumulate=accumulate)
+            for m in "lva":
+                o.unpack_matrix(self.Ge[m], grads["proj_%s_e.weight" % m], accumulate=accumulate)
+
+    def unpack_grads(self, grads, accumulate=False):
+        self.ops.batch_begin("unpack", "model")
+        for n in self.enc_names:
+            self.enc[n].unpack_grads(grads, "trans_%s." % n, accumulate)
+        self._unpack_rest(grads, accumulate)
+        self.ops.batch_end()
+
+    def unpack_misc(self, grads, accumulate=False):
+        """gradients of everything but the encoders (the encoders' leave per bucket during backward, see Trainer)"""
+        o = self.ops
+        o.batch_begin("unpack", "misc")
+        self._unpack_rest(grads, accumulate)
         o.batch_end()
 
     # ---------------------------------------------------------------- forward
@@ -205,6 +236,17 @@ class MMTrVatEngine:
         self.P = P
         h = {}
         ln.barrier()
+        if self.hybrid:                                                          # "parallel fusion" (:765-775), one lane per modality
+            cat_e = self.gate_early.cat_buf(B)
+            self.Pe = {}
+            for ci, n in enumerate(EARLY):
+                m = n[0]
+                with ln.on(self.mod_lane[m]):
+                    pe = A.get("Pe_" + m, (B * LOW_DIM, d.Dp), self.T_)
+                    o.timelin_fwd(P[m], self.We[m], None, pe, B, nv, LOW_DIM, d.D)       # proj_m_e over the time axis (:767-769)
+                    self.Pe[m] = pe
+                    he = self.enc[n].forward(pe, B, LOW_DIM, training=training, seed=seed, seed_ptr=seed_ptr)
+                    o.pool_fwd(he, B, LOW_DIM, cat_e, ci * d.Dp)                          # h[0] + h[-1] (:772-774)
         for n, (qm, km) in WAVE1.items():
             with ln.on(self.lane_of[n]):
                 h[n] = self.enc[n].forward(P[qm], B, nv, src_k=P[km], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
@@ -232,6 +274,9 @@ class MMTrVatEngine:
                 o.pool_fwd(top, B, nv, cat, ci * d.Dp)                               # h[0] + h[-1] (:808)
         ln.join()
         self.h = h
+        if self.hybrid:
+            fused_e, _ = self.gate_early.gate_forward(B)                          # gmu_early (:775); its gates are not returned
+            cat[:, 3 * d.Dp:4 * d.Dp].copy_(fused_e)                              # fourth input of the final gate (:855)
         logits, z = self.head.forward(B, training, seed, seed_ptr)
         return logits, z
 
@@ -257,7 +302,27 @@ class MMTrVatEngine:
         dtop = {m: A.get("dtop_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
         da1 = {m: A.get("da1_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
         da2 = {m: A.get("da2_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
+        dcat_e = None
+        if self.hybrid:
+            dfe = A.get("dfused_e", (B, d.Dp), f32)
+            dfe.copy_(dcat[:, 3 * d.Dp:4 * d.Dp])
+            dcat_e = self.gate_early.gate_backward(dfe)                           # [B, 3 * Dp]: d(last_h*_early)
         ln.fork()
+        if self.hybrid:
+            for ci, n in reversed(list(enumerate(EARLY))):
+                m = n[0]
+                k = self.mod_lane[m]
+                with ln.on(k):
+                    dhe = A.get("dhe_" + m, (B * LOW_DIM, d.Dp), f32)
+                    dpe = A.get("dpe_" + m, (B * LOW_DIM, d.Dp), f32)
+                    o.zero_(dhe)
+                    o.zero_(dpe)
+                    o.pool_bwd(dcat_e, ci * d.Dp, B, LOW_DIM, dhe)
+                    self.enc[n].backward(dhe, dpe)
+                    if on_done:
+                        on_done(n)
+                    # back through the time-axis Linear: d proj_x_m += W^T d, d W += d x^T
+                    o.timelin_bwd(dpe, self.P[m], self.We[m], dPl[k][m], True, self.Ge[m], None, B, nv, LOW_DIM, d.D)
         for ci, m in reversed(list(enumerate(HEAD_ORDER))):                      # gated fusion units of the three targets: one lane each
             u, w, pn, qn = TARGETS[m]
             with ln.on(self.mod_lane[m]):
@@ -304,7 +369,7 @@ class MMTrVatEngine:
 
     def backward_order(self):
         """encoder names in the order their gradients complete during backward (bucket launch order)"""
-        order = []
+        order = list(reversed(EARLY)) if self.hybrid else []
         for m in reversed(HEAD_ORDER):
             u, w, pn, qn = TARGETS[m]
             order += [qn, pn]

@@ -699,14 +699,19 @@ class MultiprojectionMMTransformer3DGMUClf(nn.Module):
         self.vonly, self.lonly, self.aonly = args.vonly, args.lonly, args.aonly
         if not (self.vonly and self.lonly and self.aonly):
             raise NotImplementedError("the reference forward itself requires lonly = aonly = vonly (last_h_* undefined otherwise, mmtr.py:857)")
-        if getattr(args, "hybrid", False):
-            raise NotImplementedError("hybrid=True is broken in the reference (list-vs-varargs call sites, mmtr.py:572,855); not implemented")
+        # hybrid = True: the reference's branch (mmtr.py:631, 662, 680-689, 765-775, 854-855) fails at its two gate call sites as shipped
+        # (`gmu_early(a, b, c)` on a forward(xs: list), `gmu([a, b, c, d])` on a forward(*xs)); it is implemented with those two calls
+        # read as what the callees accept -- the semantics the oracle is pinned to (oracle/ref_shim.py shim 6).
+        self.hybrid = bool(getattr(args, "hybrid", False))
+        self.low_dim = 32
         self.num_heads, self.layers_n = args.num_heads, args.layers
         self.precision = precision
         self.enc = FeatureEncoder(args)
         mk = lambda: GatedMultimodalLayerFeatures(D, D, D)
         self.gmu_l_m, self.gmu_v_m, self.gmu_a_m = mk(), mk(), mk()          # construction order = reference (same RNG stream)
         self.gmu_l, self.gmu_v, self.gmu_a = mk(), mk(), mk()
+        if self.hybrid:
+            self.gmu_early = TextShifting3Layer(D, D, D, D)
         self.proj_l = nn.Conv1d(self.orig_d_l, D, kernel_size=1, padding=0, bias=False)
         self.proj_v = nn.Conv1d(self.orig_d_v, D, kernel_size=1, padding=0, bias=False)
         self.proj_a = nn.Conv1d(self.orig_d_a, D, kernel_size=1, padding=0, bias=False)
@@ -715,12 +720,20 @@ class MultiprojectionMMTransformer3DGMUClf(nn.Module):
         self.proj1 = nn.Linear(D, D)
         self.proj2 = nn.Linear(D, D)
         self.out_layer = nn.Linear(D, args.n_classes)
-        self.gmu = TextShifting3Layer(D, D, D, D)
+        self.gmu = TextShiftingNLayer([D] * 4, D) if self.hybrid else TextShifting3Layer(D, D, D, D)
         self.num_vectors_l = self.num_vectors_a = self.num_vectors_v = 512
         self.transfm_a2l = nn.Linear(512, 512)                                  # present (unused) in the reference: kept for
         self.transfm_v2l = nn.Linear(512, 512)                                  # state_dict compatibility
         self.transfm_l2a = nn.Linear(512, 512)
         self.transfm_l2v = nn.Linear(512, 512)
+        if self.hybrid:                                                         # mmtr.py:680-686 (construction order kept)
+            mem = lambda: TransformerEncoder(embed_dim=D, num_heads=args.num_heads, layers=max(args.layers, 3), attn_dropout=args.attn_dropout,
+                                             relu_dropout=args.relu_dropout, res_dropout=args.res_dropout, embed_dropout=args.embed_dropout,
+                                             attn_mask=args.attn_mask)
+            self.trans_l_early, self.trans_v_early, self.trans_a_early = mem(), mem(), mem()
+            self.proj_l_e = nn.Linear(512, self.low_dim, bias=False)
+            self.proj_v_e = nn.Linear(512, self.low_dim, bias=False)
+            self.proj_a_e = nn.Linear(512, self.low_dim, bias=False)
         self._eng = None
         _handle(self)
 
@@ -787,13 +800,16 @@ def _model_bwd(mod, gen, g, need, shapes):
 
 @torch.library.custom_op("bpmult_b200::mmtrvat", mutates_args=())
 def _mmtrvat_op(handle: int, training: bool, txt: Tensor, img: Tensor, audio: Tensor, params: List[Tensor]) -> Tuple[Tensor, Tensor]:
-    return _model_fwd(_mod(handle), training, (txt, img, audio), params, 3)
+    mod = _mod(handle)
+    return _model_fwd(mod, training, (txt, img, audio), params, 4 if mod.hybrid else 3)
 
 
 @_mmtrvat_op.register_fake
 def _(handle, training, txt, img, audio, params):
-    a = _mod(handle).args
-    return txt.new_empty((txt.shape[0], a.n_classes), dtype=torch.float32), txt.new_empty((txt.shape[0], 3 * a.hidden_sz), dtype=torch.float32)
+    mod = _mod(handle)
+    a = mod.args
+    return (txt.new_empty((txt.shape[0], a.n_classes), dtype=torch.float32),
+            txt.new_empty((txt.shape[0], (4 if mod.hybrid else 3) * a.hidden_sz), dtype=torch.float32))
 
 
 @torch.library.custom_op("bpmult_b200::mmtrvat_bwd", mutates_args=())

@@ -191,9 +191,14 @@ def _pad_time(x, n):
 
 
 def mmtrvat_forward(sd, cfg, txt, img, audio, n_vec=512, return_intermediates=False):
-    """models/mmtr.py:735-866 MultiprojectionMMTransformer3DGMUClf.forward, hybrid = False, dropout = 0,
-    BERT bypassed (txt is float (B, L, orig_d_l)).  cfg: hidden_sz, num_heads, layers, attn_mask, orig_d_*."""
+    """models/mmtr.py:735-866 MultiprojectionMMTransformer3DGMUClf.forward, dropout = 0, BERT bypassed (txt is float
+    (B, L, orig_d_l)).  cfg: hidden_sz, num_heads, layers, attn_mask, orig_d_*, hybrid.
+    hybrid (:765-775, :854-855; ctor :631, :662, :680-689), with the two gate call sites read as what their callees accept
+    (oracle/ref_shim.py shim 6): every projected stream goes through a bias-free Linear over its TIME axis (512 -> 32 steps), a
+    SELF-attention encoder of max(layers, 3) layers, first + last step pooling; gmu_early fuses the three; the result is the fourth
+    input of the final TextShiftingNLayer."""
     D, H, L, am = cfg.hidden_sz, cfg.num_heads, cfg.layers, cfg.attn_mask
+    hybrid = bool(getattr(cfg, "hybrid", False))
 
     def proj(x, key, orig_d):                                              # :742-753
         x = x.transpose(1, 2)
@@ -205,6 +210,14 @@ def mmtrvat_forward(sd, cfg, txt, img, audio, n_vec=512, return_intermediates=Fa
     p_a = proj(audio, "proj_a.weight", cfg.orig_d_a)
     p_v = proj(img, "proj_v.weight", cfg.orig_d_v)
     enc = lambda name, q, kv: transformer_encoder(sd, "trans_%s." % name, q, kv, kv, H, L, am)
+    last_early = None
+    if hybrid:                                                             # :765-775
+        pooled = []
+        for m, p in (("l", p_l), ("v", p_v), ("a", p_a)):
+            pe = F.linear(p.permute(2, 1, 0), sd["proj_%s_e.weight" % m]).permute(2, 1, 0)          # (32, B, D)
+            he = transformer_encoder(sd, "trans_%s_early." % m, pe, None, None, H, max(L, 3), am)
+            pooled.append(he[0] + he[-1])
+        last_early, _ = text_shifting(sd, "gmu_early.", pooled)
     h = {}
     h["v_with_a"] = enc("v_with_a", p_v, p_a)                              # :779-786
     h["a_with_v"] = enc("a_with_v", p_a, p_v)
@@ -235,7 +248,10 @@ def mmtrvat_forward(sd, cfg, txt, img, audio, n_vec=512, return_intermediates=Fa
     top_v = top + mid
     last_v = top_v[0] + top_v[-1]
     # head (:857-866)
-    fused, z = text_shifting(sd, "gmu.", [last_l, last_v, last_a])
+    if hybrid:
+        fused, z = text_shifting_n(sd, "gmu.", [last_l, last_v, last_a, last_early])                  # :854-855
+    else:
+        fused, z = text_shifting(sd, "gmu.", [last_l, last_v, last_a])
     y = F.linear(F.relu(F.linear(fused, sd["proj1.weight"], sd["proj1.bias"])),
                  sd["proj2.weight"], sd["proj2.bias"]) + fused
     logits = F.linear(y, sd["out_layer.weight"], sd["out_layer.bias"])

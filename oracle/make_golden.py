@@ -269,6 +269,8 @@ def main():
     torch.save(run_mmtrvat(ref, cfg, 2, 50, 60, 40, 78, False), os.path.join(OUT, "mmtrvat_d96.pt"))
     cfg = synth.tiny_cfg(layers=1, n_classes=13, orig_d_p=48)
     torch.save(run_mmtrvapt(ref, cfg, 2, 20, 30, 25, 79), os.path.join(OUT, "mmtrvapt_tiny.pt"))
+    # hybrid = True (mmtrvat): the reference's own branch with the two gate call sites accepted in either convention (ref_shim shim 6)
+    torch.save(run_mmtrvat(ref, synth.tiny_cfg(layers=1, hybrid=True), 2, 10, 30, 25, 81, True), os.path.join(OUT, "mmtrvat_tiny_hybrid.pt"))
     # state_dict contract: key names + shapes of the reference model, and its init under the default seed
     import json
     from oracle.ref_shim import mmtrvat_args

@@ -8,6 +8,8 @@ with the five monkey-patch shims it needs to run on torch 2.11 / CPU (SURVEY.md 
   shim 3  in-place `q *= scaling` on a chunk() view in the self-attn path (multihead_attention.py:72,86,138)
   shim 4  hard-coded `.cuda()` in transfm_2dim                            (mmtr.py:434-438,725-729)
   shim 5  TextShifting3Layer called with 4 ctor args instead of 5         (mmtr.py:199 vs :663)
+  shim 6  hybrid branch of mmtrvat: `gmu_early(a, b, c)` on a forward(xs: list) and `gmu([a, b, c, d])` on a forward(*xs)
+          (mmtr.py:775 vs :211, :855 vs :258): both gates accept either calling convention; nothing else changes
   bypass  BertEncoder -> identity on float features                       (mmtr.py:144-158)
 
 Only `tests/`, `oracle/make_golden.py` and `bench.py --impl reference` may use this.
@@ -66,6 +68,10 @@ def load_reference(patch_cuda=True):
             d, e = 0, d
         _ts3_init(self, a, b, c, d, e)
     mmtr.TextShifting3Layer.__init__ = _ts3_fixed
+
+    _ts3_fwd, _tsn_fwd = mmtr.TextShifting3Layer.forward, mmtr.TextShiftingNLayer.forward     # shim 6
+    mmtr.TextShifting3Layer.forward = lambda self, *xs: _ts3_fwd(self, list(xs[0]) if len(xs) == 1 else list(xs))
+    mmtr.TextShiftingNLayer.forward = lambda self, *xs: _tsn_fwd(self, *(xs[0] if len(xs) == 1 and isinstance(xs[0], (list, tuple)) else xs))
 
     class FeatEnc(torch.nn.Module):                                              # BERT bypass
         def __init__(self, args):

@@ -47,13 +47,28 @@ def mmtrvat_shapes(cfg, n_vec=512):
     s["proj1.weight"] = (D, D); s["proj1.bias"] = (D,)
     s["proj2.weight"] = (D, D); s["proj2.bias"] = (D,)
     s["out_layer.weight"] = (C, D); s["out_layer.bias"] = (C,)
-    for i in (1, 2, 3):
-        s["gmu.hidden%d.weight" % i] = (D, D)
-    for i in (1, 2, 3):
-        s["gmu.x%d_gate.weight" % i] = (D, 3 * D)
+    hybrid = bool(getattr(cfg, "hybrid", False))
+    if hybrid:                                                             # TextShiftingNLayer([D] * 4, D), mmtr.py:662
+        for i in range(4):
+            s["gmu.hiddens.%d.weight" % i] = (D, D)
+        for i in range(4):
+            s["gmu.x_gates.%d.weight" % i] = (D, 4 * D)
+    else:
+        for i in (1, 2, 3):
+            s["gmu.hidden%d.weight" % i] = (D, D)
+        for i in (1, 2, 3):
+            s["gmu.x%d_gate.weight" % i] = (D, 3 * D)
     for n in ("a2l", "v2l", "l2a", "l2v"):                                 # unused by forward (no grad)
         s["transfm_%s.weight" % n] = (n_vec, n_vec)
         s["transfm_%s.bias" % n] = (n_vec,)
+    if hybrid:                                                             # mmtr.py:631, 680-689
+        for i in (1, 2, 3):
+            s["gmu_early.hidden%d.weight" % i] = (D, D)
+        for i in (1, 2, 3):
+            s["gmu_early.x%d_gate.weight" % i] = (D, 3 * D)
+        for m in "lva":
+            s.update(encoder_shapes(D, max(cfg.layers, 3), False, "trans_%s_early." % m))
+            s["proj_%s_e.weight" % m] = (32, n_vec)
     return s
 
 

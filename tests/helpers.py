@@ -72,7 +72,8 @@ def run_model_engine(ops, rec, dtype=torch.float32, full=True, sd=None):
     grads = {n: torch.zeros(s, device=dev) for n, s in eng.param_shapes().items()}
     eng.unpack_grads(grads)
     D, Dp, C = cfg.hidden_sz, eng.d.Dp, cfg.n_classes
-    zz = z.view(B, 3, Dp)[:, :, :D].reshape(B, 3 * D)
+    ng = 4 if getattr(cfg, "hybrid", False) else 3
+    zz = z.view(B, ng, Dp)[:, :, :D].reshape(B, ng * D)
     return logits[:, :C].cpu(), zz.cpu(), loss.cpu(), dtxt.cpu(), {n: v.cpu() for n, v in grads.items()}, eng
 
 

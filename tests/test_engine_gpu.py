@@ -179,6 +179,29 @@ def test_time_axis_linears_on_tensor_cores_match_the_definition(ops, D):
         assert Fn.max_rel(eng.Gt[name][0].cpu(), dW_e) < 1e-5 and Fn.max_rel(eng.Gt[name][1].cpu(), db_e) < 1e-5, name
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_mmtrvat_hybrid_vs_reference_golden(ops, dtype):
+    """hybrid = True: time-axis Linear 512 -> 32, three self-attention encoders of 3 layers on 32 steps, gmu_early, 4-input
+    final gate -- against the reference's own branch (golden generated with the two gate call sites accepted in either convention)"""
+    rec = load_gold("mmtrvat_tiny_hybrid.pt")
+    logits, z, loss, dtxt, grads, eng = run_model_engine(ops, rec, dtype=dtype)
+    torch.cuda.synchronize()
+    assert eng.hybrid and z.shape[1] == 4 * rec["cfg"]["hidden_sz"]
+    if dtype == torch.float32:
+        assert Fn.max_rel(logits, rec["logits"]) < 1e-4 and Fn.max_rel(z, rec["z"]) < 1e-4
+        assert abs(loss.item() - rec["loss"].item()) < 1e-5
+        assert Fn.rel_l2(dtxt, rec["dtxt"]) < 2e-4
+        worst = max((Fn.rel_l2(grads[n], ref), n) for n, ref in rec["pgrads"].items())
+        print("fp32 worst param grad:", worst)
+        assert worst[0] < 2e-4, worst
+    else:
+        e = Fn.max_rel(logits, rec["logits"])
+        print("bf16 logits max-rel %.3e, dtxt rel-l2 %.3e" % (e, Fn.rel_l2(dtxt, rec["dtxt"])))
+        assert e < 5e-2 and abs(loss.item() - rec["loss"].item()) < 2e-2           # toy width: sanity bars (see the non-hybrid test)
+        errs = {n: Fn.rel_l2(grads[n], ref) for n, ref in rec["pgrads"].items()}
+        assert sorted(errs.values())[len(errs) // 2] < 2.5e-1 and max(errs.values()) < 7e-1, max(errs.items(), key=lambda kv: kv[1])
+
+
 @pytest.mark.parametrize("lanes", ["1", "3"])
 def test_mmtrvat_lane_counts_agree_with_the_golden(ops, lanes, monkeypatch):
     """the encoder lanes (side streams, per-lane scratch and projection-gradient accumulators) are a scheduling choice only: a

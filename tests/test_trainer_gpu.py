@@ -271,3 +271,33 @@ def test_evaluate_between_graph_replays_matches_eval_mode_forward_and_the_oracle
     assert arrays["preds"].shape == (4, 6) and arrays["gates"].shape == (4, 3 * cfg.hidden_sz) and "auc_pr_samples" in metrics
     a.close()
     b.close()
+
+
+def test_hybrid_model_trains_under_graph_replay_and_matches_autograd():
+    """hybrid = True through the drop-in module's autograd and through the graph-captured Trainer: same losses"""
+    from bpmult_b200 import MultiprojectionMMTransformer3DGMUClf, Trainer
+    cfg = synth.tiny_cfg(layers=1, hybrid=True)
+    sd = synth.make_state_dict(synth.mmtrvat_shapes(cfg), 5)
+
+    def mk():
+        m = MultiprojectionMMTransformer3DGMUClf(Namespace(**vars(cfg)), precision="fp32")
+        m.load_state_dict(sd, strict=False)
+        return m.cuda().train()
+    txt, img, audio, tgt = [t.cuda() for t in synth.mmtrvat_inputs(cfg, 2, 10, 30, 25)]
+    a, b = mk(), mk()
+    opt = torch.optim.Adam([p for p in a.parameters()], lr=1e-3)
+    tr = Trainer(b, lr=1e-3)
+    la, lb = [], []
+    for _ in range(5):
+        opt.zero_grad()
+        out, z = a(txt, None, None, img, audio, True)
+        loss = torch.nn.BCEWithLogitsLoss()(out, tgt)
+        loss.backward()
+        opt.step()
+        la.append(float(loss))
+        lb.append(float(tr.step_device(txt, img, audio, tgt)[0]))
+    assert z.shape == (2, 4 * cfg.hidden_sz)
+    assert tr.graph is not None and [x[0] for x in tr.buckets][:3] == ["a_early", "v_early", "l_early"]
+    assert max(abs(x - y) for x, y in zip(la, lb)) < 2e-5, (la, lb)
+    assert la[-1] < la[0]
+    tr.close()
