@@ -196,6 +196,24 @@ def test_mmtrvat_benchmark_shape(ops, regime, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_mmtrvat_hybrid_at_the_benchmark_width(ops, dtype):
+    """hybrid = True at D=300, H=12, T=512 with 3 layers per stack (the early stacks have max(layers, 3) = 3): the
+    32-step self-attention encoders, the time-axis Linears and the two extra gates at full width, reference initialisation"""
+    cfg = synth.tiny_cfg(hidden_sz=300, num_heads=12, layers=3, orig_d_l=768, orig_d_v=35, orig_d_a=74, n_classes=6, hybrid=True)
+    rec = dict(cfg=vars(cfg), dims=(2, 50, 500, 500), seed=4243, pos_weight=torch.ones(6))
+    sd = _weights(rec, False, "init")
+    logits, z, loss, dtxt, grads, eng = run_model_engine(ops, rec, dtype=dtype, sd=sd)
+    torch.cuda.synchronize()
+    assert eng.hybrid and z.shape[1] == 4 * 300
+    ours = (logits, z, float(loss), dtxt, grads)
+    del eng
+    torch.cuda.empty_cache()
+    ref32 = _oracle(rec, False, False, sd, probe=dtype == torch.float32)
+    refac = _oracle(rec, True, False, sd) if dtype == torch.bfloat16 else None
+    _check("mmtrvat hybrid D=300 H=12 L=3 T=512 B=2", dtype, ours, ref32, refac, "init")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("regime", ["init", "trained"])
 def test_mmtrvapt_benchmark_shape(ops, regime, dtype):
     """mmtr.py:444-583 at the cfg-3 shape (head dim 128: the tensor-core attention for dh = 128 in bf16 mode)"""
