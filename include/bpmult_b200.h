@@ -20,6 +20,18 @@
  *    keep(e) <=> half-word >= round(p * 65536); kept values are scaled by 1/(1-p) (exact definition: csrc/bpm_common.cuh).
  *    `seed_ptr` (device, may be NULL) overrides `seed` when non-NULL so a captured graph can be replayed with a new seed.
  *    Backward kernels regenerate masks from (seed, site); nothing is stored except the optional attention keep bits.
+ *
+ * Entry-point families named in SURVEY section 8b and where they live here (one forward and one backward entry per family):
+ *    embed / projection     bpm_stage_rows + bpm_gemm (Conv1d k=1 as a row GEMM), bpm_embed_fwd / bpm_embed_bwd
+ *    layernorm              bpm_layernorm_fwd / bpm_layernorm_bwd, bpm_layernorm_bwd_cast (fused operand emission); the residual add is the
+ *                           producing GEMM's epilogue (bpm_gemm_t.residual)
+ *    gemm fwd/dgrad/wgrad   bpm_gemm with ta / tb / accumulate / colsum_out and the epilogue fields of bpm_gemm_t
+ *    xattn                  bpm_xattn_fwd / bpm_xattn_bwd, workspace query bpm_xattn_bwd_workspace
+ *    seq GMU                bpm_gemm x 3 + bpm_gmu_fwd / bpm_gmu_bwd
+ *    head GMU + BCE         bpm_pool_fwd / bpm_pool_bwd, bpm_tsgate_fwd / bpm_tsgate_bwd, bpm_bce_fwd_bwd
+ *    optimizer              bpm_adam_step
+ *    4-modality extras      bpm_timelin_fwd / bpm_timelin_bwd, bpm_conv1d_im2col / col2im, bpm_adaptive_pool_fwd / bwd
+ *    parameter staging      bpm_pack_matrix / bpm_unpack_matrix, bpm_remap_batch / bpm_remap_units, bpm_ln_fold_*
  */
 #ifndef BPMULT_B200_H
 #define BPMULT_B200_H
