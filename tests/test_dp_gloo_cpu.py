@@ -23,13 +23,13 @@ def _build(cfg):
     return m.train()
 
 
-def _worker(rank, world, initfile, out):
+def _worker(rank, world, initfile, out, hybrid=False):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     torch.set_num_threads(2)
     dist.init_process_group("gloo", init_method="file://" + initfile, rank=rank, world_size=world)
     from bpmult_b200.trainer import Trainer
-    cfg = synth.tiny_cfg(layers=1)
+    cfg = synth.tiny_cfg(layers=1, hybrid=hybrid)
     m = _build(cfg)
     tr = Trainer(m, lr=1e-2, use_graph=False)
     txt, img, audio, tgt = synth.mmtrvat_inputs(cfg, 4, 8, 12, 10)
@@ -40,15 +40,16 @@ def _worker(rank, world, initfile, out):
 
 
 @pytest.mark.timeout(600)
-def test_two_gloo_ranks_match_full_batch_step():
+@pytest.mark.parametrize("hybrid", [False, True], ids=["plain", "hybrid"])
+def test_two_gloo_ranks_match_full_batch_step(hybrid):
     with tempfile.TemporaryDirectory() as d:
         initfile, out = os.path.join(d, "init"), os.path.join(d, "r%d.pt")
-        mp.spawn(_worker, args=(2, initfile, out), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, initfile, out, hybrid), nprocs=2, join=True)
         r0, r1 = torch.load(out % 0, weights_only=False), torch.load(out % 1, weights_only=False)
     assert torch.equal(r0["p"], r1["p"])                          # replicas stay bit-identical
     # single process, full batch
     from bpmult_b200.trainer import Trainer
-    cfg = synth.tiny_cfg(layers=1)
+    cfg = synth.tiny_cfg(layers=1, hybrid=hybrid)
     tr = Trainer(_build(cfg), lr=1e-2, use_graph=False)
     txt, img, audio, tgt = synth.mmtrvat_inputs(cfg, 4, 8, 12, 10)
     losses = [tr.step(txt, img, audio, tgt) for _ in range(2)]
@@ -57,5 +58,9 @@ def test_two_gloo_ranks_match_full_batch_step():
     assert rel < 2e-4, rel
     # bucket order = backward completion order: wave-2 encoders first, misc last, contiguous cover of the flat buffer
     names = [b[0] for b in r0["buckets"]]
+    if hybrid:                                                    # the early-fusion stacks finish their backward first
+        assert names[:3] == ["a_early", "v_early", "l_early"]
+        names = names[3:]
     assert names[0] in ("a_with_l2v", "a_with_v2l") and names[-1] == "misc" and len(names) == 13
-    assert all(r0["buckets"][i][2] == r0["buckets"][i + 1][1] for i in range(12))
+    nb = len(r0["buckets"])
+    assert all(r0["buckets"][i][2] == r0["buckets"][i + 1][1] for i in range(nb - 1))
