@@ -361,6 +361,8 @@ def run_ours(opt):
     from bpmult_b200 import MultiprojectionMMTransformer3DGMUClf, MultiprojectionMMTransformerGMUClf, Trainer
     cfg = make_config(opt.config, opt.layers, opt.batch)
     args, B = cfg["args"], cfg["B"]
+    if opt.prune:
+        os.environ["BPM_PRUNE"] = "1"
     torch.manual_seed(1234)                                   # reference default seed (train.py:61)
     cls = MultiprojectionMMTransformerGMUClf if args.model == "mmtrvapt" else MultiprojectionMMTransformer3DGMUClf
     model = cls(args, precision=opt.precision).to(dev)
@@ -432,6 +434,7 @@ def run_ours(opt):
                         "blocking": {"value": world * B * opt.steps / (ms_blk * 1e-3), "ms_per_step": ms_blk / opt.steps,
                                      "api": "Trainer.step(pinned host tensors) -> float, nothing overlapped"}},
                 "gpu_launches": int(getattr(tr, "launches_per_step", 0)) * opt.steps, "launches_per_step": int(getattr(tr, "launches_per_step", 0)),
+                "pruned_rows": bool(getattr(tr.eng, "prune", False)),
                 "cuda_graph": bool(tr.use_graph), "loss": loss_dev, "params": tr.n_params, "ms_per_step_after_e2e": ms_again / opt.steps,
                 "clocks": sampler.summary() if sampler else None}
         fl = flops_per_sample_train(cfg) * B
@@ -474,6 +477,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--prune", action="store_true",
+                    help="mmtrvat only, NOT the headline: wave-2 query side and gated units on the two time steps that reach the head "
+                         "(identical logits and gradients; the reference computes all rows, and so does the default)")
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (0 = the config's own: 64 / 8 / 6)")
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])

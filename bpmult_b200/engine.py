@@ -114,6 +114,10 @@ class EncoderEngine:
         self.arena = Arena(ops)
         self.shared = shared if shared is not None else Arena(ops)     # scratch shared between encoders (backward temporaries)
         self.pe = None
+        # pruned query rows (crossmodal stacks only; see MMTrVatEngine): the T rows handed to forward() are rows `prune_pos` (0-based time
+        # steps) of a longer sequence -- they take those positions' embeddings, attend without the index mask, and, under the future
+        # mask of the full sequence (|S - T_full| = 0), row 0 sees key 0 alone: its attention output is the (dropout-scaled) value row 0.
+        self.prune_pos, self.prune_row0 = None, False
         self._alloc_weights()
 
     # ---------------------------------------------------------------- weights
@@ -265,6 +269,8 @@ class EncoderEngine:
         # models/transformer.py:209-216: masked iff j - i >= 1 + |S - T|  <=>  visible iff j <= i + |S - T|
         if self._mask_override is not None:
             return self._mask_override
+        if self.prune_pos is not None:
+            return -1                                       # the visible set of the pruned rows is handled in _attn_fwd / _attn_bwd
         return abs(S - T) if self.attn_mask else -1
 
     # ---------------------------------------------------------------- attention block (in-proj, attention, out-proj + residual)
@@ -289,10 +295,20 @@ class EncoderEngine:
         adrop = self._drop(self.p_attn, l, 10 + (blk == "x"))
         bits = A.get(key + "bits", (B * d.H * T * ((S + 31) // 32),), torch.int32) if adrop is not None else None
         o.xattn_fwd(q, k, v, a, lse, B, T, S, d.H, d.dh, d.dhp, mask_off=self._mask_off(T, S), drop=adrop, drop_bits=bits)
+        keep0 = None
+        if self.prune_row0 and blk == "x":
+            # time step 0 under the future mask sees key 0 only: softmax = 1, output = dropout(1) * v[key 0] per head
+            keep0 = A.get(key + "keep0", (B, d.H, 1), torch.float32)
+            if adrop is not None:
+                keep0.copy_((torch.rand(B, d.H, 1, device=keep0.device) >= self.p_attn).float() / (1.0 - self.p_attn))
+            else:
+                keep0.fill_(1.0)
+            v0 = v.view(B, S, d.H, d.dhp)[:, 0].float() * keep0
+            a.view(B, T, d.HP)[:, 0].copy_(v0.view(B, d.HP))
         # x_out = x_res + dropout(a Wo^T + bo)                                   (transformer.py:174-175)
         o.gemm(a, w["Wo"], x_out, M, d.Dp, d.HP, bias=w["bo"], drop=self._drop(self.p_res if res_drop else 0.0, l, 20 + (blk == "x")),
                residual=x_res)
-        return dict(q=q, k=k, v=v, a=a, lse=lse, q_in=q_in, k_in=k_in, v_in=v_in, S=S, bits=bits, folded=folded)
+        return dict(q=q, k=k, v=v, a=a, lse=lse, q_in=q_in, k_in=k_in, v_in=v_in, S=S, bits=bits, folded=folded, keep0=keep0)
 
     def _attn_bwd(self, l, blk, sv, B, T, gx, res_drop=True, dkv=None):
         """gx: fp32 [M, Dp] gradient wrt the block output x_out (= also flows to x_res unchanged).
@@ -320,8 +336,18 @@ class EncoderEngine:
             dv = Sh.get("dv", (Ms, d.HP), self.T_)
         # [0] rowsum(dO*O), [1] lse*log2e (+ the fp32 dQ accumulator of the head-dim-128 tensor-core backward)
         delta = Sh.get("delta", (o.xattn_bwd_workspace(self.T_, B, T, S, d.H, d.dh, d.dhp),), torch.float32)
+        g0 = None
+        if sv.get("keep0") is not None:
+            # row 0 (single visible key): no gradient reaches the scores; its output gradient goes to value row 0 alone.  With that row
+            # of dO cleared the kernel adds nothing for it (dP = 0, delta = 0 => dS = 0).
+            da0 = da.view(B, T, d.HP)[:, 0]
+            g0 = da0.float().view(B, d.H, d.dhp) * sv["keep0"]
+            da0.zero_()
         o.xattn_bwd(sv["q"], sv["k"], sv["v"], sv["a"], da, sv["lse"], delta, dq, d.scaling, dk, dv, B, T, S, d.H, d.dh, d.dhp,
                     mask_off=self._mask_off(T, S), drop=self._drop(self.p_attn, l, 10 + (blk == "x")), drop_bits=sv["bits"])
+        if g0 is not None:
+            dv0 = dv.view(B, S, d.HP)[:, 0]
+            dv0.copy_((dv0.float() + g0.view(B, d.HP)).to(dv.dtype))
         # dq already carries the dh^-0.5 factor => it is the gradient wrt (x Wq^T + bq)
         o.gemm(dq, sv["q_in"], gWq, d.HP, d.Dp, M, ta=1, tb=1, accumulate=True, colsum=gbq)
         dq_in = Sh.get("dq_in", (M, d.Dp), self.T_)
@@ -400,7 +426,7 @@ class EncoderEngine:
         self.cross = src_k is not None
         M = B * T
         Ms = B * S if self.cross else 0
-        need = max(T, S or 0) + 1
+        need = max(T, S or 0, (max(self.prune_pos) + 1) if self.prune_pos is not None else 0) + 1
         if self.pe is None or self.pe.shape[0] < need:
             self.pe = sinusoid_table(need, d.D, d.Dp, src_q.device)
         scale = math.sqrt(d.D)
@@ -415,7 +441,14 @@ class EncoderEngine:
                 self.kv_shared = src_v is None or src_v is src_k
                 xv = xk if self.kv_shared else src_v
         else:
-            o.embed_fwd(src_q, self.pe, B, T, d.D, scale, xs[0], self._drop(self.p_embed, -1, 1))
+            pe_q = self.pe
+            if self.prune_pos is not None:                                       # row t of a sample sits at time step prune_pos[t]
+                assert self.cross and not self.biproj and len(self.prune_pos) == T
+                if getattr(self, "_pe_q_key", None) != (tuple(self.prune_pos), self.pe.shape[0]):
+                    self.pe_q = torch.cat([self.pe[:1]] + [self.pe[p + 1:p + 2] for p in self.prune_pos], 0).contiguous()
+                    self._pe_q_key = (tuple(self.prune_pos), self.pe.shape[0])
+                pe_q = self.pe_q
+            o.embed_fwd(src_q, pe_q, B, T, d.D, scale, xs[0], self._drop(self.p_embed, -1, 1))
         if self.cross and self.with_embed:
             xk = A.get("xk", (Ms, d.Dp), self.T_)
             o.embed_fwd(src_k, self.pe, B, S, d.D, scale, xk, self._drop(self.p_embed, -1, 2))

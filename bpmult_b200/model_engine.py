@@ -72,8 +72,14 @@ def attn_dropout_for(name, args):
 
 
 class MMTrVatEngine:
-    def __init__(self, ops, args, dtype=torch.bfloat16, n_vec=512):
+    def __init__(self, ops, args, dtype=torch.bfloat16, n_vec=512, prune=None):
+        """prune (default: environment BPM_PRUNE=1, else off): the wave-2 stacks are crossmodal only -- a query row attends to the K/V
+        stream, never to other query rows -- the gated units are row-wise, and only time steps 0 and n_vec-1 of their output reach the
+        head (mmtr.py:808,830,852).  With prune the query side of the six wave-2 stacks and the gated units run on those two rows per
+        sample: identical logits and gradients (every other row has a zero gradient and no reader), about a third of the step gone.
+        The reference computes all rows; so does the default, and so does every headline number."""
         self.ops, self.args, self.T_, self.n_vec = ops, args, dtype, n_vec
+        self.prune = bool(int(os.environ.get("BPM_PRUNE", "0"))) if prune is None else bool(prune)
         D, H, L = args.hidden_sz, args.num_heads, args.layers
         self.d = Dims(D, H)
         self.orig = {"l": args.orig_d_l, "a": args.orig_d_a, "v": args.orig_d_v}
@@ -92,6 +98,11 @@ class MMTrVatEngine:
             self.enc[n] = EncoderEngine(ops, D, H, L, attn_dropout=attn_dropout_for(n, args), relu_dropout=args.relu_dropout,
                                         res_dropout=args.res_dropout, embed_dropout=args.embed_dropout, attn_mask=args.attn_mask,
                                         biprojection=False, dtype=dtype, uid=i + 1, shared=self.lane_shared[self.lane_of[n]])
+        if self.prune:
+            for m in HEAD_ORDER:
+                for n in TARGETS[m][2:]:
+                    self.enc[n].prune_pos = (0, n_vec - 1)
+                    self.enc[n].prune_row0 = bool(args.attn_mask)     # future mask of the full sequence: step 0 sees key 0 only
         self.gmu = {}
         self.mod_lane = {m: i % self.lanes.n for i, m in enumerate(HEAD_ORDER)}      # lane of a modality's staging / gated units
         self.hybrid = bool(getattr(args, "hybrid", False))
@@ -251,12 +262,30 @@ class MMTrVatEngine:
             with ln.on(self.lane_of[n]):
                 h[n] = self.enc[n].forward(P[qm], B, nv, src_k=P[km], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
         ln.barrier()                                                            # wave 2 reads wave-1 outputs of either lane
+        # rows of the wave-2 query side and of the gated units: all n_vec, or (prune) time steps 0 and n_vec - 1 as rows b * 2 + {0, 1}
+        Tq = 2 if self.prune else nv
+        Mq = B * Tq
+
+        def two_rows(key, x):
+            y = A.get(key, (Mq, d.Dp), x.dtype)
+            xv_, yv_ = x.view(B, nv, d.Dp), y.view(B, 2, d.Dp)
+            yv_[:, 0].copy_(xv_[:, 0])
+            yv_[:, 1].copy_(xv_[:, nv - 1])
+            return y
         for m in HEAD_ORDER:
             u, w, pn, qn = TARGETS[m]
+            Pq = P[m]
+            if self.prune:
+                with ln.on(self.lane_of[pn]):
+                    Pq = two_rows("Pq_" + m, P[m])
+                if ln.streams:                                                    # the other lane reads it too
+                    ev = torch.cuda.Event()
+                    ev.record(ln.streams[self.lane_of[pn] % ln.n])
+                    ln.streams[self.lane_of[qn] % ln.n].wait_event(ev)
             with ln.on(self.lane_of[pn]):
-                h[pn] = self.enc[pn].forward(P[m], B, nv, src_k=h[u], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
+                h[pn] = self.enc[pn].forward(Pq, B, Tq, src_k=h[u], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
             with ln.on(self.lane_of[qn]):
-                h[qn] = self.enc[qn].forward(P[m], B, nv, src_k=h[w], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
+                h[qn] = self.enc[qn].forward(Pq, B, Tq, src_k=h[w], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
         ln.barrier()
         cat = self.head.cat_buf(B)
         self.tops = {}
@@ -264,14 +293,15 @@ class MMTrVatEngine:
             u, w, pn, qn = TARGETS[m]
             hp, hq = h[pn], h[qn]
             with ln.on(self.mod_lane[m]):
-                mid = self.gmu[m + "_m"].forward(h[u], h[w], M)                    # "GMU middle"
-                a1 = A.get("a1_" + m, (M, d.Dp), self.T_)
-                a2 = A.get("a2_" + m, (M, d.Dp), self.T_)
-                o.add(hp, h[u], a1)                                                  # residual level 1 -> 2 (:799-800)
-                o.add(hq, h[w], a2)
-                top = self.gmu[m].forward(a1, a2, M, addend=mid)                     # "GMU top" + residual level 1 -> 3 (:803-806)
+                hu, hw = (two_rows("u2_" + m, h[u]), two_rows("w2_" + m, h[w])) if self.prune else (h[u], h[w])
+                mid = self.gmu[m + "_m"].forward(hu, hw, Mq)                       # "GMU middle"
+                a1 = A.get("a1_" + m, (Mq, d.Dp), self.T_)
+                a2 = A.get("a2_" + m, (Mq, d.Dp), self.T_)
+                o.add(hp, hu, a1)                                                    # residual level 1 -> 2 (:799-800)
+                o.add(hq, hw, a2)
+                top = self.gmu[m].forward(a1, a2, Mq, addend=mid)                    # "GMU top" + residual level 1 -> 3 (:803-806)
                 self.tops[m] = top
-                o.pool_fwd(top, B, nv, cat, ci * d.Dp)                               # h[0] + h[-1] (:808)
+                o.pool_fwd(top, B, Tq, cat, ci * d.Dp)                               # h[0] + h[-1] (:808)
         ln.join()
         self.h = h
         if self.hybrid:
@@ -299,9 +329,16 @@ class MMTrVatEngine:
         dh = {n: A.get("dh_" + n, (M, d.Dp), f32) for n in WAVE1}
         for t in [t for k in range(ln.n) for t in dPl[k].values()] + list(dh.values()):
             o.zero_(t)
-        dtop = {m: A.get("dtop_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
-        da1 = {m: A.get("da1_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
-        da2 = {m: A.get("da2_" + m, (M, d.Dp), f32) for m in HEAD_ORDER}
+        Tq = 2 if self.prune else nv
+        Mq = B * Tq
+        dtop = {m: A.get("dtop_" + m, (Mq, d.Dp), f32) for m in HEAD_ORDER}
+        da1 = {m: A.get("da1_" + m, (Mq, d.Dp), f32) for m in HEAD_ORDER}
+        da2 = {m: A.get("da2_" + m, (Mq, d.Dp), f32) for m in HEAD_ORDER}
+
+        def add_two_rows(src2, dst):                                             # dst[time steps 0, n_vec - 1] += the two rows of src2
+            sv_, dv_ = src2.view(B, 2, d.Dp), dst.view(B, nv, d.Dp)
+            dv_[:, 0] += sv_[:, 0]
+            dv_[:, nv - 1] += sv_[:, 1]
         dcat_e = None
         if self.hybrid:
             dfe = A.get("dfused_e", (B, d.Dp), f32)
@@ -327,19 +364,37 @@ class MMTrVatEngine:
             u, w, pn, qn = TARGETS[m]
             with ln.on(self.mod_lane[m]):
                 o.zero_(dtop[m])
-                o.pool_bwd(dcat, ci * d.Dp, B, nv, dtop[m])
+                o.pool_bwd(dcat, ci * d.Dp, B, Tq, dtop[m])
                 o.zero_(da1[m])
                 o.zero_(da2[m])
                 self.gmu[m].backward(dtop[m], da1[m], da2[m])                    # d(p+u), d(q+w)
-                self.gmu[m + "_m"].backward(dtop[m], dh[u], dh[w])               # mid consumes u, w directly
-                o.axpy_f32(da1[m], dh[u], True)
-                o.axpy_f32(da2[m], dh[w], True)
+                if self.prune:
+                    du2 = A.get("du2_" + m, (Mq, d.Dp), f32)
+                    dw2 = A.get("dw2_" + m, (Mq, d.Dp), f32)
+                    o.zero_(du2)
+                    o.zero_(dw2)
+                    self.gmu[m + "_m"].backward(dtop[m], du2, dw2)
+                    o.axpy_f32(da1[m], du2, True)
+                    o.axpy_f32(da2[m], dw2, True)
+                    add_two_rows(du2, dh[u])
+                    add_two_rows(dw2, dh[w])
+                else:
+                    self.gmu[m + "_m"].backward(dtop[m], dh[u], dh[w])           # mid consumes u, w directly
+                    o.axpy_f32(da1[m], dh[u], True)
+                    o.axpy_f32(da2[m], dh[w], True)
         ln.barrier()
         for m in reversed(HEAD_ORDER):
             u, w, pn, qn = TARGETS[m]
             for n, da, dsrc in ((qn, da2[m], dh[w]), (pn, da1[m], dh[u])):
-                with ln.on(self.lane_of[n]):
-                    self.enc[n].backward(da, dPl[self.lane_of[n]][m], dsrc)
+                k = self.lane_of[n]
+                with ln.on(k):
+                    if self.prune:
+                        dq2 = A.get("dq2_" + n, (Mq, d.Dp), f32)
+                        o.zero_(dq2)
+                        self.enc[n].backward(da, dq2, dsrc)
+                        add_two_rows(dq2, dPl[k][m])
+                    else:
+                        self.enc[n].backward(da, dPl[k][m], dsrc)
                     if on_done:
                         on_done(n)
         ln.barrier()                                                            # wave 1 consumes dh written on either lane

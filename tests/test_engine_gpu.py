@@ -202,6 +202,27 @@ def test_mmtrvat_hybrid_vs_reference_golden(ops, dtype):
         assert sorted(errs.values())[len(errs) // 2] < 2.5e-1 and max(errs.values()) < 7e-1, max(errs.items(), key=lambda kv: kv[1])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("gold", ["mmtrvat_tiny.pt", "mmtrvat_tiny_hybrid.pt"])
+def test_pruned_mode_vs_reference_golden(ops, gold, dtype, monkeypatch):
+    """BPM_PRUNE=1: wave-2 query side and gated units on time steps 0 and 511 only (2-row attention launches, row 0 = value row 0) -- same
+    logits and gradients as the reference's full computation"""
+    monkeypatch.setenv("BPM_PRUNE", "1")
+    rec = load_gold(gold)
+    logits, z, loss, dtxt, grads, eng = run_model_engine(ops, rec, dtype=dtype)
+    torch.cuda.synchronize()
+    assert eng.prune and eng.enc["a_with_l2v"].T == 2
+    if dtype == torch.float32:
+        assert Fn.max_rel(logits, rec["logits"]) < 1e-4 and Fn.max_rel(z, rec["z"]) < 1e-4
+        assert abs(loss.item() - rec["loss"].item()) < 1e-5 and Fn.rel_l2(dtxt, rec["dtxt"]) < 2e-4
+        worst = max((Fn.rel_l2(grads[n], ref), n) for n, ref in rec["pgrads"].items())
+        assert worst[0] < 2e-4, worst
+    else:
+        assert Fn.max_rel(logits, rec["logits"]) < 5e-2 and abs(loss.item() - rec["loss"].item()) < 2e-2
+        errs = {n: Fn.rel_l2(grads[n], ref) for n, ref in rec["pgrads"].items()}
+        assert sorted(errs.values())[len(errs) // 2] < 2.5e-1 and max(errs.values()) < 7e-1, max(errs.items(), key=lambda kv: kv[1])
+
+
 @pytest.mark.parametrize("lanes", ["1", "3"])
 def test_mmtrvat_lane_counts_agree_with_the_golden(ops, lanes, monkeypatch):
     """the encoder lanes (side streams, per-lane scratch and projection-gradient accumulators) are a scheduling choice only: a

@@ -301,3 +301,22 @@ def test_hybrid_model_trains_under_graph_replay_and_matches_autograd():
     assert max(abs(x - y) for x, y in zip(la, lb)) < 2e-5, (la, lb)
     assert la[-1] < la[0]
     tr.close()
+
+
+def test_pruned_trainer_under_graph_replay_follows_the_full_one(monkeypatch):
+    """BPM_PRUNE=1 through the captured Trainer (dropout off so that both draw nothing): the same losses and parameters as the full model"""
+    from bpmult_b200 import Trainer
+    cfg = synth.tiny_cfg()
+    batch = [t.cuda() for t in synth.mmtrvat_inputs(cfg, 2, 10, 30, 25)]
+    full = Trainer(_model(cfg, "fp32"), lr=1e-3)
+    monkeypatch.setenv("BPM_PRUNE", "1")
+    pr = Trainer(_model(cfg, "fp32"), lr=1e-3)
+    assert pr.eng.prune and not full.eng.prune
+    lf = [float(full.step_device(*batch)[0]) for _ in range(5)]
+    lp = [float(pr.step_device(*batch)[0]) for _ in range(5)]
+    assert pr.graph is not None and max(abs(a - b) for a, b in zip(lf, lp)) < 2e-5, (lf, lp)
+    rel = ((full.flat_p - pr.flat_p).double().norm() / full.flat_p.double().norm()).item()
+    assert rel < 2e-4, rel
+    assert pr.launches_per_step < full.launches_per_step + 200
+    full.close()
+    pr.close()
