@@ -1,8 +1,8 @@
 """Evaluation loop of the reference (train.py:165-280 `model_eval`, :140-163 `weighted_acc`) over the drop-in: the device half is
 `Trainer.evaluate` (eval-mode forward, loss, sigmoid, 0.5 threshold); this module is the host half -- stacking the batches and
 computing the metrics dictionary the reference logs and selects checkpoints by (`metrics[...]` keys per task, train.py:191-262,
-tuning metric train.py:404-407).  Multilabel tasks of the two fusion models only (cmu-mosei for mmtrvat; moviescope, mmimdb for
-mmtrvapt); the regression / single-label tasks of the reference's other models are outside SURVEY section 8.
+tuning metric train.py:404-407).  Multilabel tasks of the two fusion models only (cmu-mosei, counseling for mmtrvat; moviescope, mmimdb
+for mmtrvapt); the regression / single-label tasks of the reference's other models are outside SURVEY section 8.
 
 The key -> metric assignment deliberately follows the reference, including where a key's name and its content disagree (mmimdb's
 "micro_f1" holds the micro average precision, cmu-mosei's "auc_pr_micro" the mean weighted accuracy, ...): checkpoints are selected on
@@ -64,8 +64,17 @@ def multilabel_metrics(task, tgts, preds, raw_preds, losses):
         metrics["f1_emos"] = float(np.average(f1s))
         metrics["wacc_emos"] = _ap("micro")(tgts, preds, raw)
         metrics["auc_pr_micro"] = float(np.average(accs))
+    elif task == "counseling":
+        # train.py:208-231: two labels; f1_low / f1_high end up as the eps-smoothed F1 of label 1 / label 0 (the sklearn values assigned
+        # first are overwritten), acc = subset accuracy, auc_pr_micro = micro average precision
+        from sklearn.metrics import accuracy_score
+        per = [weighted_acc(preds[:, c], tgts[:, c]) for c in range(2)]
+        metrics["f1_low"] = per[1][1]
+        metrics["f1_high"] = per[0][1]
+        metrics["acc"] = accuracy_score(tgts, preds)
+        metrics["auc_pr_micro"] = _ap("micro")(tgts, preds, raw)
     else:
-        raise ValueError("multilabel_metrics: task %r is not one of moviescope, mmimdb, cmu-mosei" % (task,))
+        raise ValueError("multilabel_metrics: task %r is not one of moviescope, mmimdb, cmu-mosei, counseling" % (task,))
     return metrics
 
 

@@ -64,6 +64,11 @@ def test_metric_keys_and_values_per_task():
     assert abs(m["f1_emos"] - np.mean([f for _, f in per])) < 1e-12
     assert abs(m["auc_pr_micro"] - np.mean([a for a, _ in per])) < 1e-12          # train.py:261: the mean weighted accuracy lives under this key
     assert m["wacc_emos"] == average_precision_score(tgts, raw, average="micro")  # train.py:260
+    from sklearn.metrics import accuracy_score
+    m = multilabel_metrics("counseling", tgts[:, :2], preds[:, :2], raw[:, :2], [1.0])
+    assert list(m) == ["loss", "f1_low", "f1_high", "acc", "auc_pr_micro"]
+    assert abs(m["f1_low"] - per[1][1]) < 1e-12 and abs(m["f1_high"] - per[0][1]) < 1e-12          # train.py:229-230 (overwrite the sklearn values)
+    assert m["acc"] == accuracy_score(tgts[:, :2], preds[:, :2]) and m["auc_pr_micro"] == average_precision_score(tgts[:, :2], raw[:, :2], average="micro")
     try:
         multilabel_metrics("cmu-mosi", tgts, preds, raw, [1.0])
         assert False
