@@ -10,11 +10,12 @@ def run(dbg, steps):
     ops = CudaOps()
     ops.lib.bpm_debug_set(1, dbg)
     torch.manual_seed(1234)
-    args = bench.cfg2_args()
+    cfg = bench.make_config("cfg2")
+    args = cfg["args"]
     dev = torch.device("cuda", 0)
     model = MultiprojectionMMTransformer3DGMUClf(args, precision="bf16").to(dev).train()
     tr = Trainer(model, lr=1e-3, seed=1234)
-    host = [t.to(dev) for t in bench.synth_batch(args, 64, 2024)]
+    host = [t.to(dev) for t in bench.synth_batch(cfg, 64, 2024)]
     out = []
     for i in range(steps):
         out.append(float(tr.step_device(*host)[0]))

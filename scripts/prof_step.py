@@ -13,14 +13,15 @@ from bpmult_b200 import MultiprojectionMMTransformer3DGMUClf  # noqa: E402
 from bpmult_b200 import Trainer  # noqa: E402
 
 torch.manual_seed(0)
-args = bench.cfg2_args()
+cfg = bench.make_config(os.environ.get("PROF_CFG", "cfg2"))
+args = cfg["args"]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = torch.device("cuda", 0)
 model = MultiprojectionMMTransformer3DGMUClf(args, precision="bf16").to(dev)
 model.train()
 tr = Trainer(model, lr=1e-3)
 g = torch.Generator().manual_seed(2024)
-host = list(bench.synth_batch(args, B, 2024))
+host = list(bench.synth_batch(cfg, B, 2024))
 devb = [t.to(dev) for t in host]
 for _ in range(5):
     tr.step_device(*devb)
