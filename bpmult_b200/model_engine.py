@@ -101,7 +101,10 @@ class MMTrVatEngine:
         if self.prune:
             for m in HEAD_ORDER:
                 for n in TARGETS[m][2:]:
-                    self.enc[n].prune_pos = (0, n_vec - 1)
+                    # rows b * 4 + {0, 1, 2, 3}: time step 0, then three copies of step n_vec - 1 (the attention backward runs on tensor
+                    # cores for T % 4 == 0 only; with 2 rows it fell back to the fp32-math kernels: 20 ms of 98 ms summed device time).
+                    # pool_fwd / pool_bwd read and feed the FIRST and LAST row of a sample: rows 1 and 2 never receive a gradient.
+                    self.enc[n].prune_pos = (0, n_vec - 1, n_vec - 1, n_vec - 1)
                     self.enc[n].prune_row0 = bool(args.attn_mask)     # future mask of the full sequence: step 0 sees key 0 only
         self.gmu = {}
         self.mod_lane = {m: i % self.lanes.n for i, m in enumerate(HEAD_ORDER)}      # lane of a modality's staging / gated units
@@ -262,15 +265,15 @@ class MMTrVatEngine:
             with ln.on(self.lane_of[n]):
                 h[n] = self.enc[n].forward(P[qm], B, nv, src_k=P[km], S=nv, training=training, seed=seed, seed_ptr=seed_ptr)
         ln.barrier()                                                            # wave 2 reads wave-1 outputs of either lane
-        # rows of the wave-2 query side and of the gated units: all n_vec, or (prune) time steps 0 and n_vec - 1 as rows b * 2 + {0, 1}
-        Tq = 2 if self.prune else nv
+        # rows of the wave-2 query side and of the gated units: all n_vec, or (prune) time step 0 and three copies of step n_vec - 1
+        Tq = 4 if self.prune else nv
         Mq = B * Tq
 
         def two_rows(key, x):
             y = A.get(key, (Mq, d.Dp), x.dtype)
-            xv_, yv_ = x.view(B, nv, d.Dp), y.view(B, 2, d.Dp)
+            xv_, yv_ = x.view(B, nv, d.Dp), y.view(B, 4, d.Dp)
             yv_[:, 0].copy_(xv_[:, 0])
-            yv_[:, 1].copy_(xv_[:, nv - 1])
+            yv_[:, 1:].copy_(xv_[:, nv - 1:nv].expand(B, 3, d.Dp))
             return y
         for m in HEAD_ORDER:
             u, w, pn, qn = TARGETS[m]
@@ -329,16 +332,16 @@ class MMTrVatEngine:
         dh = {n: A.get("dh_" + n, (M, d.Dp), f32) for n in WAVE1}
         for t in [t for k in range(ln.n) for t in dPl[k].values()] + list(dh.values()):
             o.zero_(t)
-        Tq = 2 if self.prune else nv
+        Tq = 4 if self.prune else nv
         Mq = B * Tq
         dtop = {m: A.get("dtop_" + m, (Mq, d.Dp), f32) for m in HEAD_ORDER}
         da1 = {m: A.get("da1_" + m, (Mq, d.Dp), f32) for m in HEAD_ORDER}
         da2 = {m: A.get("da2_" + m, (Mq, d.Dp), f32) for m in HEAD_ORDER}
 
-        def add_two_rows(src2, dst):                                             # dst[time steps 0, n_vec - 1] += the two rows of src2
-            sv_, dv_ = src2.view(B, 2, d.Dp), dst.view(B, nv, d.Dp)
+        def add_two_rows(src4, dst):                               # dst[time steps 0, n_vec - 1] += rows 0 and 3 (rows 1, 2 carry zeros)
+            sv_, dv_ = src4.view(B, 4, d.Dp), dst.view(B, nv, d.Dp)
             dv_[:, 0] += sv_[:, 0]
-            dv_[:, nv - 1] += sv_[:, 1]
+            dv_[:, nv - 1] += sv_[:, 3]
         dcat_e = None
         if self.hybrid:
             dfe = A.get("dfused_e", (B, d.Dp), f32)

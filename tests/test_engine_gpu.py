@@ -211,7 +211,7 @@ def test_pruned_mode_vs_reference_golden(ops, gold, dtype, monkeypatch):
     rec = load_gold(gold)
     logits, z, loss, dtxt, grads, eng = run_model_engine(ops, rec, dtype=dtype)
     torch.cuda.synchronize()
-    assert eng.prune and eng.enc["a_with_l2v"].T == 2
+    assert eng.prune and eng.enc["a_with_l2v"].T == 4
     if dtype == torch.float32:
         assert Fn.max_rel(logits, rec["logits"]) < 1e-4 and Fn.max_rel(z, rec["z"]) < 1e-4
         assert abs(loss.item() - rec["loss"].item()) < 1e-5 and Fn.rel_l2(dtxt, rec["dtxt"]) < 2e-4

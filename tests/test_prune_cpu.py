@@ -42,8 +42,8 @@ def _run(rec, prune, sd=None, cfg_over=None, training=True):
 def test_pruned_engine_reproduces_the_reference_golden(gold):
     rec = load_gold(gold)
     logits, z, loss, dtxt, dimg, grads, eng = _run(rec, True)
-    assert eng.prune and eng.enc["l_with_a2v"].prune_pos == (0, 511) and eng.enc["l_with_a2v"].prune_row0
-    assert eng.enc["l_with_a2v"].T == 2 and eng.enc["l_with_a"].T == 512
+    assert eng.prune and eng.enc["l_with_a2v"].prune_pos == (0, 511, 511, 511) and eng.enc["l_with_a2v"].prune_row0
+    assert eng.enc["l_with_a2v"].T == 4 and eng.enc["l_with_a"].T == 512
     assert Fn.max_rel(logits, rec["logits"]) < 2e-5 and Fn.max_rel(z, rec["z"]) < 2e-5
     assert abs(loss - rec["loss"].item()) < 1e-5
     assert Fn.max_rel(dtxt, rec["dtxt"]) < 1e-4
